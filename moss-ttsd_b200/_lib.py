@@ -1,0 +1,87 @@
+"""ctypes binding of libmtts.so (the C-ABI declared in include/mtts.h).
+
+There is deliberately no fallback: if the shared library cannot be loaded the import of any op raises,
+so a GPU run can never silently execute something other than the CUDA path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmtts.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "mtts.h")
+
+_lib = None
+_lock = threading.Lock()
+
+c_void_p, c_int, c_ll, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t, ctypes.c_float
+c_double = ctypes.c_double
+c_u64 = ctypes.c_ulonglong
+
+# name -> (restype, argtypes). Kept in the same order as include/mtts.h; tests/test_abi.py checks that every
+# symbol the header declares is listed here and exported by the .so.
+SIGNATURES = {
+    "mtts_last_error": (ctypes.c_char_p, []),
+    "mtts_version": (c_int, []),
+    "mtts_init": (c_int, []),
+    "mtts_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "mtts_gemm": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int,
+                          c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_size_t, c_void_p]),
+    "mtts_gemm_simt": (c_int, [c_void_p, c_int, c_ll, c_ll, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int,
+                               c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "mtts_rvq_codebook_norms": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mtts_rvq_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    "mtts_rvq_decode": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+}
+
+
+class MttsError(RuntimeError):
+    pass
+
+
+def header_symbols(path: str = HEADER_PATH):
+    """Function names declared in include/mtts.h."""
+    with open(path) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mtts_[a-z0-9_]+)\s*\(", text)))
+
+
+def load(build_if_missing: bool = True):
+    """Load libmtts.so, building it in-tree with nvcc first if it is absent."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if not build_if_missing:
+                raise MttsError(f"{LIB_PATH} is missing; run `python moss-ttsd_b200/build.py`")
+            from . import build as _build
+            _build.build(verbose=False)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header/.so mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().mtts_last_error()
+        raise MttsError(f"libmtts error {rc}: {msg.decode() if msg else '?'}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,43 @@
+// Error plumbing and device attribute cache for libmtts.
+#include "common.cuh"
+#include "mtts_internal.h"
+#include <string.h>
+
+static thread_local char g_err[1024] = "";
+
+int mtts_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int g_num_sms[64] = {0};
+
+int mtts_num_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (g_num_sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    g_num_sms[dev] = n;
+  }
+  return g_num_sms[dev];
+}
+
+extern "C" const char* mtts_last_error(void) { return g_err; }
+extern "C" int mtts_version(void) { return MTTS_VERSION; }
+
+extern "C" int mtts_init(void) {
+  int dev = 0;
+  MTTS_CUDA_CHECK(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  MTTS_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  MTTS_CUDA_CHECK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10)
+    return mtts_set_error(MTTS_ERR_UNSUPPORTED, "libmtts is built for sm_100a only; device %d is sm_%d%d", dev, major,
+                          minor);
+  (void)mtts_num_sms();
+  return MTTS_OK;
+}

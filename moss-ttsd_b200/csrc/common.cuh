@@ -1,0 +1,126 @@
+// Shared device/host helpers for libmtts (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libmtts is written for sm_100a (B200) only"
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Error reporting: every C-ABI entry point returns 0 or a negative code and records a message in a
+// thread-local buffer that mtts_last_error() hands back.
+// ---------------------------------------------------------------------------------------------
+#define MTTS_OK 0
+#define MTTS_ERR_ARG (-1)
+#define MTTS_ERR_CUDA (-2)
+#define MTTS_ERR_UNSUPPORTED (-3)
+
+int mtts_set_error(int code, const char* fmt, ...);
+
+#define MTTS_REQUIRE(cond, ...)                                   \
+  do {                                                            \
+    if (!(cond)) return mtts_set_error(MTTS_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define MTTS_CUDA_CHECK(expr)                                                                \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return mtts_set_error(MTTS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                   \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+  } while (0)
+
+#define MTTS_LAUNCH_CHECK()                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess)                                                                   \
+      return mtts_set_error(MTTS_ERR_CUDA, "kernel launch failed: %s (%s:%d)",               \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                     \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+int mtts_num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+// ---------------------------------------------------------------------------------------------
+// Small device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32). `red` must hold 33 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? red[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// 16-byte streaming load that does not pollute L1 (weights / KV are read once per step).
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ld_nc_v2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+
+// two packed bf16 -> two floats (exact: bf16 is the top half of fp32)
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  bf162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+#endif  // __CUDACC__

@@ -1,0 +1,120 @@
+"""tcgen05 GEMM (mtts_gemm) and the exact-fp32 CUDA-core GEMM (mtts_gemm_simt) against a torch fp64 product."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, w, bias=None, gelu=False, gamma=None, residual=None, out_dtype=torch.float32):
+    v = x.double() @ w.double().t()
+    if bias is not None:
+        v = v + bias.double()
+    if gelu:
+        v = torch.nn.functional.gelu(v)
+    if out_dtype == torch.bfloat16:
+        v = v.to(torch.bfloat16).double()
+    if gamma is not None:
+        v = v * gamma.double()
+    if residual is not None:
+        v = residual.double() + v
+    return v
+
+
+SHAPES = [
+    (1, 256, 128), (1, 2048, 2048), (3, 1000, 512), (16, 4096, 2048), (17, 384, 6144), (64, 2048, 6144),
+    (100, 130, 200), (128, 768, 3072), (300, 1025, 2048), (257, 962, 512), (1000, 512, 560),
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_tc_bf16(M, N, K):
+    from moss_ttsd_b200 import ops
+    K = (K + 7) // 8 * 8
+    g = torch.Generator(device="cuda").manual_seed(M * 7919 + N * 31 + K)
+    x = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    out = ops.gemm(x, w, out_dtype=torch.float32)
+    ref = _ref(x, w)
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * max(scale, 1.0), (err, scale)
+    out2 = ops.gemm(x, w, out_dtype=torch.float32)
+    assert torch.equal(out, out2), "split-K reduction must be deterministic"
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_tc_tf32(M, N, K):
+    from moss_ttsd_b200 import ops
+    K = (K + 3) // 4 * 4
+    g = torch.Generator(device="cuda").manual_seed(M * 7919 + N * 31 + K + 1)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    out = ops.gemm(x, w)
+    ref = _ref(x, w)
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 4e-3 * max(scale, 1.0), (err, scale)  # tf32: 10-bit mantissa operands
+
+
+@pytest.mark.parametrize("M,N,K", [(5, 256, 512), (64, 2048, 2048), (200, 700, 768)])
+def test_gemm_tc_epilogues_bf16(M, N, K):
+    from moss_ttsd_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1234 + M)
+    x = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.03).to(torch.bfloat16)
+    res = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    out = ops.gemm(x, w, residual=res)
+    ref = _ref(x, w, residual=res, out_dtype=torch.bfloat16)
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 0.05, err
+    # SwiGLU: interleaved gate/up rows
+    gate, up = w[: N // 2], w[N // 2:]
+    wi = torch.stack([gate, up], dim=1).reshape(N, K).contiguous()
+    h = ops.gemm(x, wi, swiglu=True)
+    gq = (x.double() @ gate.double().t()).to(torch.bfloat16).float()
+    uq = (x.double() @ up.double().t()).to(torch.bfloat16).float()
+    href = (torch.nn.functional.silu(gq).to(torch.bfloat16).float() * uq).to(torch.bfloat16)
+    assert h.shape == (M, N // 2)
+    bad = ((h.float() - href.float()).abs() > 0.02 * (1 + href.float().abs())).float().mean().item()
+    assert bad < 1e-3, bad
+
+
+@pytest.mark.parametrize("M,N,K", [(7, 300, 512), (1500, 768, 3072)])
+def test_gemm_tc_epilogues_f32(M, N, K):
+    from moss_ttsd_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(99 + M)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.03
+    b = torch.randn(N, device="cuda", generator=g)
+    gm = torch.rand(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    out = ops.gemm(x, w, bias=b, gelu=True)
+    ref = _ref(x, w, bias=b, gelu=True)
+    assert (out.double() - ref).abs().max().item() <= 5e-3 * max(ref.abs().max().item(), 1)
+    out = ops.gemm(x, w, bias=b, gamma=gm, residual=res)
+    ref = _ref(x, w, bias=b, gamma=gm, residual=res)
+    assert (out.double() - ref).abs().max().item() <= 5e-3 * max(ref.abs().max().item(), 1)
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 64, 64), (33, 130, 77), (375, 512, 3072)])
+def test_gemm_simt_exact_fp32(M, N, K):
+    from moss_ttsd_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5 + M)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) * 0.05
+    b = torch.randn(N, device="cuda", generator=g)
+    out = ops.gemm_simt(x, w, bias=b)
+    ref = _ref(x, w, bias=b)
+    assert (out.double() - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1)
+    # channel-major activations (B, K, T) read in place
+    B, T = 3, 50
+    xc = torch.randn(B, K, T, device="cuda", generator=g)
+    out = ops.gemm_simt(xc, w, x_layout=(T, K * T, 1, T), M=B * T)
+    ref = _ref(xc.permute(0, 2, 1).reshape(B * T, K), w)
+    assert (out.double() - ref).abs().max().item() <= 2e-5 * max(ref.abs().max().item(), 1)
+
+
+def test_gemm_rejects_cpu_tensors():
+    from moss_ttsd_b200 import ops, _lib
+    with pytest.raises(_lib.MttsError):
+        ops.gemm(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(8, 64, dtype=torch.bfloat16))
