@@ -95,6 +95,82 @@ int mtts_rvq_encode(const float* z, const uint8_t* valid, const float* codebooks
 int mtts_rvq_decode(const long long* codes, long long codes_ld, const float* codebooks, int N, int nq,
                     int codebook_size, int dim, float* out, int* err_flag, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Qwen3-style decoder step (bf16).  Reference: HF Qwen3Model invoked at modeling_asteroid.py:226,273-284,
+ * arithmetic and rounding points per SURVEY.md Appendix B.
+ * ---------------------------------------------------------------------------------------------- */
+/* out[r,:] = sum_c bf16 tables[c][ids[r,c],:] with a bf16 rounding after every add
+ * (AsteroidTTSModel._prepare_multi_modal_inputs, modeling_asteroid.py:235-250).
+ * ids [rows, channels] int64; tables_host: HOST array of `channels` device pointers ([vocab_c, hidden] bf16);
+ * out [rows, hidden] bf16. Out-of-range ids set *err_flag = 1 and contribute zero. */
+int mtts_embed_sum8(const long long* ids, int rows, int channels, const void* const* tables_host,
+                    const int* vocab_sizes_host, int hidden, void* out, int* err_flag, void* stream);
+
+/* Qwen3RMSNorm: fp32 mean-square, cast to bf16, then bf16 multiply by w. x/out [rows, hidden] bf16. */
+int mtts_rmsnorm(const void* x, long long ldx, const void* w, void* out, long long ldo, int rows, int hidden, float eps,
+                 void* stream);
+
+/* Per-head RMSNorm of q and k, rotate-half RoPE, and the KV-cache append (replaces DynamicCache.update's torch.cat).
+ *   qkv [rows, (Hq+2Hkv)*128] bf16; q_out [rows, Hq*128]; pools [num_pages, Hkv, page_size, 128] bf16;
+ *   positions[r] = RoPE position = slot in the sequence's cache; row_seq[r] = sequence (NULL: r);
+ *   block_table [num_seqs, max_pages] int32 or NULL for a contiguous cache (page = seq*max_pages + pos/page_size);
+ *   inv_freq [64] fp32 = theta^(-2i/128). */
+int mtts_qknorm_rope_kvappend(const void* qkv, long long ld_qkv, const void* q_norm_w, const void* k_norm_w,
+                              const float* inv_freq, const int* positions, const int* row_seq, void* q_out,
+                              void* k_pool, void* v_pool, const int* block_table, int max_pages, int page_size,
+                              int num_pages, int rows, int num_q_heads, int num_kv_heads, int head_dim, float eps,
+                              int* err_flag, void* stream);
+
+/* Causal GQA attention over the paged/contiguous cache; decode (rows_per_tile = 1, tile arrays NULL) and prefill
+ * (rows_per_tile = 4: tile t covers query rows tile_row0[t] .. +tile_nrows[t] of ONE sequence, consecutive positions).
+ * Row r attends keys 0..positions[r] of sequence row_seq[r]. out [rows, Hq*128] bf16. nsplit > 1 splits the keys
+ * across CTAs (small batches); workspace from mtts_gqa_attention_workspace_bytes, first 64 KiB zero before first use. */
+size_t mtts_gqa_attention_workspace_bytes(int tiles, int num_kv_heads, int group, int rows_per_tile, int nsplit);
+int mtts_gqa_attention(const void* q, const void* k_pool, const void* v_pool, const int* block_table, int max_pages,
+                       int page_size, const int* tile_row0, const int* tile_nrows, const int* row_seq,
+                       const int* positions, void* out, int tiles, int rows_per_tile, int num_q_heads,
+                       int num_kv_heads, int head_dim, int nsplit, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Delay-pattern sampler (CustomMixin._sample, modeling_asteroid.py:52-197).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mtts_sampler_config {
+  int channels;            /* 8 */
+  int vocab[8];            /* logits per channel: 152697, 1025 x7 */
+  int logit_offset[8];     /* column of channel c's first logit in the fused-head output row */
+  int do_sample[8];        /* generation_config.do_samples */
+  int has_rep[8];   float rep_penalty[8];   /* RepetitionPenaltyLogitsProcessor */
+  int has_temp[8];  float temperature[8];   /* TemperatureLogitsWarper */
+  int top_k[8];                             /* TopKLogitsWarper, 0 = absent */
+  int has_top_p[8]; float top_p[8];         /* TopPLogitsWarper */
+  int seen_offset_words[8];  /* per-channel offset (32-bit words) inside one row of the history bitmap */
+  int seen_words_per_row;
+  int pad_token;           /* 1024    (modeling_asteroid.py:126) */
+  int eos_mask_token;      /* 152694  (modeling_asteroid.py:128) */
+} mtts_sampler_config;
+
+/* Mark every token of ids[:, :rows, c] (int64 [B, *, channels], batch stride row_stride_b elements) in the
+ * per-(row, channel) history bitmap `seen` (zeroed by the caller). History includes left-pad rows, as in the reference. */
+int mtts_sampler_init_history(const long long* ids, int B, int rows, long long row_stride_b,
+                              const mtts_sampler_config* cfg, uint32_t* seen, void* stream);
+
+/* One draw per (row, channel) from the bf16 fused-head logits [B, ld]: masks -> repetition penalty -> temperature ->
+ * top-k -> top-p -> multinomial (Philox, stream = (seed, step, row, channel)) or argmax. out_tokens [B, channels] int64.
+ * *step_ptr is the device-resident step counter s (0 = first generated row). */
+int mtts_sample8(const void* logits, long long ld, int B, const mtts_sampler_config* cfg, const uint32_t* seen,
+                 const int* step_ptr, unsigned long long seed, long long* out_tokens, int* err_flag, void* stream);
+
+/* The per-row state machine after the draw: wind-down trigger, teacher forcing (tf_tail [B, channels-1, channels] =
+ * prompt[:, P:P+channels-1, :]), wind-down fill, finished fill, append to sequences [B, max_len_rows, channels] at row
+ * P + s, history bitmap update, counters/stopping, positions[b] += 1, unfinished_hist[s] = #unfinished rows,
+ * finish_len[b] = length at which row b finished, and finally *step_ptr += 1. tokens [B, channels] is updated in place
+ * and is the next step's input_ids. B <= 1024. */
+int mtts_delay_step(long long* tokens, const long long* tf_tail, long long* sequences, long long max_len_rows,
+                    int* unfinished, int* needs_steps, int* positions, uint32_t* seen, int* step_ptr,
+                    int* unfinished_hist, int* finish_len, int B, int prompt_rows, int max_length, int speech_lo,
+                    int speech_hi, int eos_token, int has_eos_criteria, const mtts_sampler_config* cfg, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

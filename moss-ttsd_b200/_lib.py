@@ -21,6 +21,22 @@ c_void_p, c_int, c_ll, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, ctypes
 c_double = ctypes.c_double
 c_u64 = ctypes.c_ulonglong
 
+class SamplerConfig(ctypes.Structure):
+    """Mirror of `mtts_sampler_config` (include/mtts.h)."""
+    _fields_ = [
+        ("channels", c_int),
+        ("vocab", c_int * 8), ("logit_offset", c_int * 8), ("do_sample", c_int * 8),
+        ("has_rep", c_int * 8), ("rep_penalty", c_float * 8),
+        ("has_temp", c_int * 8), ("temperature", c_float * 8),
+        ("top_k", c_int * 8),
+        ("has_top_p", c_int * 8), ("top_p", c_float * 8),
+        ("seen_offset_words", c_int * 8), ("seen_words_per_row", c_int),
+        ("pad_token", c_int), ("eos_mask_token", c_int),
+    ]
+
+
+_cfg_p = ctypes.POINTER(SamplerConfig)
+
 # name -> (restype, argtypes). Kept in the same order as include/mtts.h; tests/test_abi.py checks that every
 # symbol the header declares is listed here and exported by the .so.
 SIGNATURES = {
@@ -36,6 +52,20 @@ SIGNATURES = {
     "mtts_rvq_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
     "mtts_rvq_decode": (c_int, [c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "mtts_embed_sum8": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int), c_int, c_void_p,
+                                c_void_p, c_void_p]),
+    "mtts_rmsnorm": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_void_p]),
+    "mtts_qknorm_rope_kvappend": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          c_float, c_void_p, c_void_p]),
+    "mtts_gqa_attention_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "mtts_gqa_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
+                                   c_void_p]),
+    "mtts_sampler_init_history": (c_int, [c_void_p, c_int, c_int, c_ll, _cfg_p, c_void_p, c_void_p]),
+    "mtts_sample8": (c_int, [c_void_p, c_ll, c_int, _cfg_p, c_void_p, c_void_p, c_u64, c_void_p, c_void_p, c_void_p]),
+    "mtts_delay_step": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _cfg_p, c_void_p]),
 }
 
 

@@ -39,5 +39,13 @@ extern "C" int mtts_init(void) {
     return mtts_set_error(MTTS_ERR_UNSUPPORTED, "libmtts is built for sm_100a only; device %d is sm_%d%d", dev, major,
                           minor);
   (void)mtts_num_sms();
+  static bool configured[64] = {false};
+  if (dev < 64 && !configured[dev]) {
+    int rc = 0;
+    if ((rc = mtts_configure_gemm_tc())) return rc;
+    if ((rc = mtts_configure_attention())) return rc;
+    if ((rc = mtts_configure_rvq())) return rc;
+    configured[dev] = true;
+  }
   return MTTS_OK;
 }

@@ -1,0 +1,301 @@
+// Causal GQA attention over a paged (or contiguous) bf16 KV cache — decode (1 query row per sequence) and
+// prefill (tiles of QT consecutive query rows of one sequence) share one kernel.
+//
+// Replaces HF Qwen3Attention's attention call (installed modeling_qwen3.py:184-219,273-288, selected by
+// `attn_implementation` in generation_utils.py:15 / inference.py:29) and DynamicCache's torch.cat growth.
+// Left-pad rows of the reference batch are simply not stored: every sequence's cache is compact and RoPE
+// positions come from cumsum(mask)-1 (last paragraph), which leaves every real
+// token's result unchanged.
+//
+// The op is HBM/L2-bandwidth bound (2 FMA per byte of K/V): CUDA cores with 16-byte streaming loads, fp32
+// online softmax, split-KV across CTAs for small batches with a last-arriver combine (no spin waits).
+// Thread layout: 16 lanes cover one 128-wide K/V row (8 dims each); the two half-warps of each of the 4
+// warps walk different keys, so one CTA consumes 8 keys per step.
+#include "common.cuh"
+#include "mtts_internal.h"
+
+namespace {
+
+constexpr int kD = 128;
+constexpr int kThreads = 128;
+constexpr int kGroups = 8;  // half-warps per CTA
+constexpr int kUnroll = 4;
+
+struct AttnParams {
+  const bf16* q;    // [rows, Hq, 128]
+  const bf16* k_pool;
+  const bf16* v_pool;  // [num_pages, Hkv, page_size, 128]
+  const int* block_table;
+  int max_pages, page_shift;
+  const int* tile_row0;   // [tiles] first query row of the tile (NULL: tile index, 1 row per tile)
+  const int* tile_nrows;  // [tiles] rows in the tile (<= QT)
+  const int* row_seq;     // [rows]  sequence of each row (NULL: row index)
+  const int* positions;   // [rows]  position of each query row (it attends keys 0..pos)
+  bf16* out;              // [rows, Hq * 128]
+  int Hq, Hkv;
+  float scale_log2;  // head_dim^-0.5 * log2(e)
+  int nsplit;
+  float* ws;       // split partials
+  int* counters;   // [tiles * Hkv]
+};
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+
+template <int QT, int G>
+__global__ void __launch_bounds__(kThreads) gqa_attn_kernel(const AttnParams p) {
+  constexpr int NQ = QT * G;  // query vectors handled per CTA
+  extern __shared__ float sm[];
+  float* sm_m = sm;                       // [kGroups][NQ]
+  float* sm_l = sm_m + kGroups * NQ;      // [kGroups][NQ]
+  float* sm_o = sm_l + kGroups * NQ;      // [kGroups][NQ][128]
+  __shared__ int s_is_last;
+
+  const int tile = blockIdx.x, hk = blockIdx.y, split = blockIdx.z;
+  const int row0 = p.tile_row0 ? p.tile_row0[tile] : tile;
+  const int nrows = p.tile_nrows ? p.tile_nrows[tile] : 1;
+  const int seq = p.row_seq ? p.row_seq[row0] : row0;
+  const int pos0 = p.positions[row0];
+  const int kv_len = pos0 + nrows;  // keys 0 .. kv_len-1; row i sees keys <= pos0 + i
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4, l16 = lane & 15;
+  const int group = warp * 2 + half;
+  const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+
+  // split-KV range (multiples of kGroups keys)
+  int k_begin = 0, k_end = kv_len;
+  if (p.nsplit > 1) {
+    const int per = ((kv_len + p.nsplit - 1) / p.nsplit + kGroups - 1) / kGroups * kGroups;
+    k_begin = min(kv_len, split * per);
+    k_end = min(kv_len, k_begin + per);
+  }
+
+  // q fragments (pre-scaled): qf[i][8]
+  float qf[NQ][8];
+#pragma unroll
+  for (int t = 0; t < QT; ++t)
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (t < nrows) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p.q + ((long long)(row0 + t) * p.Hq + hk * G + g) * kD + l16 * 8);
+        unpack8(u, qf[t * G + g]);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) qf[t * G + g][d] *= p.scale_log2;
+      } else {
+#pragma unroll
+        for (int d = 0; d < 8; ++d) qf[t * G + g][d] = 0.f;
+      }
+    }
+
+  float m[NQ], l[NQ], acc[NQ][8];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    m[i] = -1e30f;
+    l[i] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[i][d] = 0.f;
+  }
+
+  const int page_mask = (1 << p.page_shift) - 1;
+  const long long head_off = ((long long)hk << p.page_shift) * kD;
+  const long long page_stride = ((long long)p.Hkv << p.page_shift) * kD;
+
+  for (int kb = k_begin + group; kb < k_end; kb += kGroups * kUnroll) {
+    uint4 kv[kUnroll], vv[kUnroll];
+    int key[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      key[u] = kb + u * kGroups;
+      if (key[u] < k_end) {
+        const int lp = key[u] >> p.page_shift;
+        const int page = p.block_table ? __ldg(p.block_table + (long long)seq * p.max_pages + lp) : seq * p.max_pages + lp;
+        const long long off = (long long)page * page_stride + head_off + (long long)(key[u] & page_mask) * kD + l16 * 8;
+        kv[u] = ld_nc_v4(p.k_pool + off);
+        vv[u] = ld_nc_v4(p.v_pool + off);
+      } else {
+        kv[u] = make_uint4(0, 0, 0, 0);
+        vv[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      if (key[u] >= k_end) continue;  // uniform across the half-warp
+      float kf[8], vf[8];
+      unpack8(kv[u], kf);
+      unpack8(vv[u], vf);
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) s = fmaf(qf[i][d], kf[d], s);
+        s += __shfl_xor_sync(hmask, s, 8);
+        s += __shfl_xor_sync(hmask, s, 4);
+        s += __shfl_xor_sync(hmask, s, 2);
+        s += __shfl_xor_sync(hmask, s, 1);
+        if (QT > 1 && key[u] > pos0 + i / G) s = -INFINITY;  // causal mask inside the tile
+        const float mn = fmaxf(m[i], s);
+        const float corr = exp2f(m[i] - mn);
+        const float pr = exp2f(s - mn);
+        m[i] = mn;
+        l[i] = l[i] * corr + pr;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc[i][d] = fmaf(pr, vf[d], acc[i][d] * corr);
+      }
+    }
+  }
+
+  // ---- combine the 8 half-warp states of this CTA
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    if (l16 == 0) {
+      sm_m[group * NQ + i] = m[i];
+      sm_l[group * NQ + i] = l[i];
+    }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) sm_o[(group * NQ + i) * kD + l16 * 8 + d] = acc[i][d];
+  }
+  __syncthreads();
+
+  const int unit = tile * p.Hkv + hk;
+  // each thread finalises one (query vector, dim) pair at a time: NQ * 128 outputs
+  float* wsb = p.ws ? p.ws + ((long long)unit * p.nsplit) * NQ * (kD + 2) : nullptr;
+  for (int o = threadIdx.x; o < NQ * kD; o += kThreads) {
+    const int i = o / kD, d = o % kD;
+    float M = -1e30f;
+#pragma unroll
+    for (int gq = 0; gq < kGroups; ++gq) M = fmaxf(M, sm_m[gq * NQ + i]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int gq = 0; gq < kGroups; ++gq) {
+      const float w = exp2f(sm_m[gq * NQ + i] - M);
+      L = fmaf(sm_l[gq * NQ + i], w, L);
+      O = fmaf(sm_o[(gq * NQ + i) * kD + d], w, O);
+    }
+    if (p.nsplit == 1) {
+      const int t = i / G, g = i % G;
+      if (t < nrows)
+        p.out[((long long)(row0 + t) * p.Hq + hk * G + g) * kD + d] = __float2bfloat16_rn(O / L);
+    } else {
+      float* w0 = wsb + (long long)split * NQ * (kD + 2) + i * (kD + 2);
+      __stcg(w0 + 2 + d, O);
+      if (d == 0) {
+        __stcg(w0, M);
+        __stcg(w0 + 1, L);
+      }
+    }
+  }
+  if (p.nsplit == 1) return;
+
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(p.counters + unit, 1);
+    const int last = prev == p.nsplit - 1;
+    if (last) p.counters[unit] = 0;
+    s_is_last = last;
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  for (int o = threadIdx.x; o < NQ * kD; o += kThreads) {
+    const int i = o / kD, d = o % kD;
+    float M = -1e30f;
+    for (int s = 0; s < p.nsplit; ++s) M = fmaxf(M, __ldcg(wsb + ((long long)s * NQ + i) * (kD + 2)));
+    float L = 0.f, O = 0.f;
+    for (int s = 0; s < p.nsplit; ++s) {
+      const float* w0 = wsb + ((long long)s * NQ + i) * (kD + 2);
+      const float w = exp2f(__ldcg(w0) - M);
+      L = fmaf(__ldcg(w0 + 1), w, L);
+      O = fmaf(__ldcg(w0 + 2 + d), w, O);
+    }
+    const int t = i / G, g = i % G;
+    if (t < nrows) p.out[((long long)(row0 + t) * p.Hq + hk * G + g) * kD + d] = __float2bfloat16_rn(O / L);
+  }
+}
+
+template <int QT, int G>
+int launch_attn(const AttnParams& p, int tiles, cudaStream_t stream) {
+  constexpr int NQ = QT * G;
+  const size_t smem = sizeof(float) * (size_t)kGroups * NQ * (kD + 2);
+  dim3 grid(tiles, p.Hkv, p.nsplit);
+  gqa_attn_kernel<QT, G><<<grid, kThreads, smem, stream>>>(p);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+template <int QT, int G>
+int configure_attn() {
+  const size_t smem = sizeof(float) * (size_t)kGroups * QT * G * (kD + 2);
+  if (smem > 48 * 1024)
+    MTTS_CUDA_CHECK(cudaFuncSetAttribute(gqa_attn_kernel<QT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return MTTS_OK;
+}
+
+}  // namespace
+
+int mtts_configure_attention() {
+  int rc = 0;
+  if ((rc = configure_attn<1, 1>())) return rc;
+  if ((rc = configure_attn<1, 2>())) return rc;
+  if ((rc = configure_attn<1, 4>())) return rc;
+  if ((rc = configure_attn<4, 1>())) return rc;
+  if ((rc = configure_attn<4, 2>())) return rc;
+  if ((rc = configure_attn<4, 4>())) return rc;
+  return MTTS_OK;
+}
+
+static constexpr size_t kAttnCounterBytes = 65536;
+
+extern "C" size_t mtts_gqa_attention_workspace_bytes(int tiles, int num_kv_heads, int group, int rows_per_tile,
+                                                     int nsplit) {
+  if (nsplit <= 1) return kAttnCounterBytes;
+  return kAttnCounterBytes + (size_t)tiles * num_kv_heads * nsplit * rows_per_tile * group * (kD + 2) * sizeof(float);
+}
+
+extern "C" int mtts_gqa_attention(const void* q, const void* k_pool, const void* v_pool, const int* block_table,
+                                  int max_pages, int page_size, const int* tile_row0, const int* tile_nrows,
+                                  const int* row_seq, const int* positions, void* out, int tiles, int rows_per_tile,
+                                  int num_q_heads, int num_kv_heads, int head_dim, int nsplit, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(head_dim == kD, "mtts_gqa_attention: head_dim must be 128 (got %d)", head_dim);
+  MTTS_REQUIRE(num_kv_heads > 0 && num_q_heads % num_kv_heads == 0, "mtts_gqa_attention: bad head counts");
+  const int G = num_q_heads / num_kv_heads;
+  MTTS_REQUIRE(G == 1 || G == 2 || G == 4, "mtts_gqa_attention: GQA group must be 1, 2 or 4 (got %d)", G);
+  MTTS_REQUIRE(rows_per_tile == 1 || rows_per_tile == 4, "mtts_gqa_attention: rows_per_tile must be 1 or 4");
+  MTTS_REQUIRE(page_size > 0 && (page_size & (page_size - 1)) == 0, "mtts_gqa_attention: page_size must be a power of two");
+  MTTS_REQUIRE(nsplit >= 1 && nsplit <= 64, "mtts_gqa_attention: nsplit out of range");
+  if (tiles <= 0) return MTTS_OK;
+  MTTS_REQUIRE(q && k_pool && v_pool && positions && out, "mtts_gqa_attention: null pointer");
+  AttnParams p;
+  p.q = reinterpret_cast<const bf16*>(q); p.k_pool = reinterpret_cast<const bf16*>(k_pool);
+  p.v_pool = reinterpret_cast<const bf16*>(v_pool); p.block_table = block_table; p.max_pages = max_pages;
+  int shift = 0;
+  while ((1 << shift) < page_size) ++shift;
+  p.page_shift = shift; p.tile_row0 = tile_row0; p.tile_nrows = tile_nrows; p.row_seq = row_seq; p.positions = positions;
+  p.out = reinterpret_cast<bf16*>(out); p.Hq = num_q_heads; p.Hkv = num_kv_heads;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
+  p.nsplit = nsplit; p.ws = nullptr; p.counters = nullptr;
+  if (nsplit > 1) {
+    const size_t need = mtts_gqa_attention_workspace_bytes(tiles, num_kv_heads, G, rows_per_tile, nsplit);
+    MTTS_REQUIRE(workspace && workspace_bytes >= need, "mtts_gqa_attention: workspace too small (%zu < %zu)",
+                 workspace_bytes, need);
+    MTTS_REQUIRE((size_t)tiles * num_kv_heads * sizeof(int) <= kAttnCounterBytes,
+                 "mtts_gqa_attention: too many tiles for split-KV");
+    p.counters = reinterpret_cast<int*>(workspace);
+    p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kAttnCounterBytes);
+  }
+#define MTTS_ATTN_CASE(QT_, G_) \
+  if (rows_per_tile == QT_ && G == G_) return launch_attn<QT_, G_>(p, tiles, stream);
+  MTTS_ATTN_CASE(1, 1)
+  MTTS_ATTN_CASE(1, 2)
+  MTTS_ATTN_CASE(1, 4)
+  MTTS_ATTN_CASE(4, 1)
+  MTTS_ATTN_CASE(4, 2)
+  MTTS_ATTN_CASE(4, 4)
+#undef MTTS_ATTN_CASE
+  return mtts_set_error(MTTS_ERR_UNSUPPORTED, "mtts_gqa_attention: unsupported configuration");
+}

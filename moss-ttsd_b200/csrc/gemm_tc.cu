@@ -357,12 +357,6 @@ int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int 
 template <typename T, int BN, int kStages>
 int launch(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, dim3 grid, cudaStream_t stream) {
   constexpr int smem = smem_bytes<BN, kStages>();
-  static bool configured = false;  // per instantiation; attribute is per-function and sticky
-  if (!configured) {
-    MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<T, BN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem));
-    configured = true;
-  }
   gemm_tc_kernel<T, BN, kStages><<<grid, kNumThreads, smem, stream>>>(tw, tx, p);
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
@@ -380,7 +374,30 @@ int dispatch(int bn, const CUtensorMap& tw, const CUtensorMap& tx, const GemmPar
   }
 }
 
+template <typename T, int BN, int kStages>
+int configure_one() {
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<T, BN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       smem_bytes<BN, kStages>()));
+  return MTTS_OK;
+}
+
 }  // namespace
+
+// Opt every instantiation into its dynamic shared-memory size (called from mtts_init, outside any graph capture).
+int mtts_configure_gemm_tc() {
+  int rc = 0;
+  if ((rc = configure_one<bf16, 16, 8>())) return rc;
+  if ((rc = configure_one<bf16, 32, 8>())) return rc;
+  if ((rc = configure_one<bf16, 64, 6>())) return rc;
+  if ((rc = configure_one<bf16, 128, 3>())) return rc;
+  if ((rc = configure_one<bf16, 256, 4>())) return rc;
+  if ((rc = configure_one<float, 16, 8>())) return rc;
+  if ((rc = configure_one<float, 32, 8>())) return rc;
+  if ((rc = configure_one<float, 64, 6>())) return rc;
+  if ((rc = configure_one<float, 128, 3>())) return rc;
+  if ((rc = configure_one<float, 256, 4>())) return rc;
+  return MTTS_OK;
+}
 
 int mtts_gemm_tc_pick_bn(int M) {
   if (M <= 16) return 16;

@@ -1,0 +1,251 @@
+// Small bandwidth-bound ops of the Qwen3-style decoder step (bf16 activations, fp32 statistics).
+// Every rounding point mirrors the reference's bf16 eager path so that
+// teacher-forced logits stay within bf16 noise of it.
+#include "common.cuh"
+#include "mtts_internal.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// 8-table embedding gather + sum.   modeling_asteroid.py:235-250 (_prepare_multi_modal_inputs):
+//   acc = zeros(bf16); for i in range(8): acc += E_i[ids[..., i]]      (bf16 rounding after every add)
+// ------------------------------------------------------------------------------------------------
+struct EmbedParams {
+  const long long* ids;  // [rows, channels]
+  const bf16* tables[8];
+  int vocab[8];
+  int rows, channels, hidden;
+  bf16* out;  // [rows, hidden]
+  int* err_flag;
+};
+
+__global__ void embed_sum_kernel(const EmbedParams p) {
+  const int vec_per_row = p.hidden >> 3;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = gid / vec_per_row;
+  if (row >= p.rows) return;
+  const int col = static_cast<int>(gid % vec_per_row) * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int c = 0; c < p.channels; ++c) {
+    const long long id = p.ids[row * p.channels + c];
+    if (id < 0 || id >= p.vocab[c]) {
+      if (p.err_flag) *p.err_flag = 1;
+      continue;
+    }
+    const uint4 v = *reinterpret_cast<const uint4*>(p.tables[c] + id * p.hidden + col);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[2 * j] = bf16_round(acc[2 * j] + bf16lo(u[j]));
+      acc[2 * j + 1] = bf16_round(acc[2 * j + 1] + bf16hi(u[j]));
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16(acc[0], acc[1]);
+  o.y = pack_bf16(acc[2], acc[3]);
+  o.z = pack_bf16(acc[4], acc[5]);
+  o.w = pack_bf16(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(p.out + row * p.hidden + col) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm (HF Qwen3RMSNorm, installed modeling_qwen3.py:50-66; used at every decoder layer and as
+// the final norm, invoked via modeling_asteroid.py:273-284):
+//   v = mean(x.float()^2); y = (x.float() * rsqrt(v + eps)).to(bf16); out = w * y   (bf16 multiply)
+// One CTA per row; hidden <= 8 * 1024 elements.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, long long ldx,
+                                                      const bf16* __restrict__ w, bf16* __restrict__ out,
+                                                      long long ldo, int hidden, float eps) {
+  __shared__ float red[33];
+  const long long row = blockIdx.x;
+  const bf16* xr = x + row * ldx;
+  const int nvec = hidden >> 3;
+  float ss = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + v * 8);
+    const uint32_t a[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lo = bf16lo(a[j]), hi = bf16hi(a[j]);
+      ss = fmaf(lo, lo, ss);
+      ss = fmaf(hi, hi, ss);
+    }
+  }
+  ss = block_sum(ss, red);
+  const float inv = rsqrtf(ss / (float)hidden + eps);
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(xr + v * 8);
+    const uint4 wv = *reinterpret_cast<const uint4*>(w + v * 8);
+    const uint32_t a[4] = {u.x, u.y, u.z, u.w};
+    const uint32_t b[4] = {wv.x, wv.y, wv.z, wv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lo = bf16_round(bf16lo(a[j]) * inv) * bf16lo(b[j]);
+      const float hi = bf16_round(bf16hi(a[j]) * inv) * bf16hi(b[j]);
+      o[j] = pack_bf16(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(out + row * ldo + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-head q/k RMSNorm + RoPE + KV-cache append (HF Qwen3Attention.forward, installed
+// modeling_qwen3.py:236-271; apply_rotary_pos_emb :86-181; DynamicCache.update replaced by an in-place
+// paged store). One warp per (row, head); head_dim == 128: lane l owns elements {2l, 2l+1} and their
+// rotate-half partners {64+2l, 65+2l}.
+//   qkv   [rows, (Hq + 2*Hkv) * 128] bf16 (output of the fused q/k/v projection)
+//   q_out [rows, Hq * 128] bf16
+//   k_pool/v_pool [num_pages, Hkv, page_size, 128] bf16; page = block_table[seq * max_pages + pos / page_size]
+//                 (block_table == NULL: page = seq * max_pages + pos / page_size, i.e. a contiguous cache)
+// cos/sin are evaluated in fp32 from pos * inv_freq and rounded to bf16 before use, products and the sum
+// are rounded to bf16 one by one, as the bf16 eager reference does.
+// ------------------------------------------------------------------------------------------------
+struct RopeParams {
+  const bf16* qkv;
+  long long ld_qkv;
+  const bf16* q_norm_w;
+  const bf16* k_norm_w;
+  const float* inv_freq;  // [64]
+  const int* positions;   // [rows]
+  const int* row_seq;     // [rows] sequence index of each row (NULL: row index)
+  bf16* q_out;
+  bf16* k_pool;
+  bf16* v_pool;
+  const int* block_table;
+  int max_pages, page_shift, num_pages;
+  int rows, Hq, Hkv;
+  float eps;
+  int* err_flag;
+};
+
+__global__ void __launch_bounds__(256) qknorm_rope_kv_kernel(const RopeParams p) {
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int heads = p.Hq + 2 * p.Hkv;
+  const int row = warp_global / heads;
+  const int h = warp_global % heads;
+  if (row >= p.rows) return;
+  const bf16* src = p.qkv + (long long)row * p.ld_qkv + h * 128;
+  const uint32_t a = *reinterpret_cast<const uint32_t*>(src + 2 * lane);        // elements 2l, 2l+1
+  const uint32_t b = *reinterpret_cast<const uint32_t*>(src + 64 + 2 * lane);   // elements 64+2l, 65+2l
+  const int pos = p.positions[row];
+  const int seq = p.row_seq ? p.row_seq[row] : row;
+
+  bf16* dst;
+  if (h < p.Hq) {
+    dst = p.q_out + ((long long)row * p.Hq + h) * 128;
+  } else {
+    const int hk = (h - p.Hq) % p.Hkv;
+    const bool is_v = (h - p.Hq) >= p.Hkv;
+    const int lp = pos >> p.page_shift;
+    int page = -1;
+    if (pos >= 0 && lp < p.max_pages) page = p.block_table ? p.block_table[(long long)seq * p.max_pages + lp] : seq * p.max_pages + lp;
+    if (page < 0 || page >= p.num_pages) {
+      if (p.err_flag && lane == 0) *p.err_flag = 2;
+      return;
+    }
+    bf16* pool = is_v ? p.v_pool : p.k_pool;
+    const int slot = pos & ((1 << p.page_shift) - 1);
+    dst = pool + (((long long)page * p.Hkv + hk) << p.page_shift) * 128 + (long long)slot * 128;
+    if (is_v) {  // V: plain copy
+      *reinterpret_cast<uint32_t*>(dst + 2 * lane) = a;
+      *reinterpret_cast<uint32_t*>(dst + 64 + 2 * lane) = b;
+      return;
+    }
+  }
+  const bf16* nw = (h < p.Hq) ? p.q_norm_w : p.k_norm_w;
+  float x0 = bf16lo(a), x1 = bf16hi(a), x2 = bf16lo(b), x3 = bf16hi(b);
+  float ss = x0 * x0;
+  ss = fmaf(x1, x1, ss);
+  ss = fmaf(x2, x2, ss);
+  ss = fmaf(x3, x3, ss);
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
+  const uint32_t wa = *reinterpret_cast<const uint32_t*>(nw + 2 * lane);
+  const uint32_t wb = *reinterpret_cast<const uint32_t*>(nw + 64 + 2 * lane);
+  // normed = w * bf16(x * inv), rounded to bf16 (it is a bf16 tensor in the reference)
+  x0 = bf16_round(bf16lo(wa) * bf16_round(x0 * inv));
+  x1 = bf16_round(bf16hi(wa) * bf16_round(x1 * inv));
+  x2 = bf16_round(bf16lo(wb) * bf16_round(x2 * inv));
+  x3 = bf16_round(bf16hi(wb) * bf16_round(x3 * inv));
+  // RoPE: angle index i = 2l, 2l+1 (shared by element i and i+64)
+  const float f0 = (float)pos * p.inv_freq[2 * lane];
+  const float f1 = (float)pos * p.inv_freq[2 * lane + 1];
+  const float c0 = bf16_round(cosf(f0)), s0 = bf16_round(sinf(f0));
+  const float c1 = bf16_round(cosf(f1)), s1 = bf16_round(sinf(f1));
+  // out[i] = bf16(x[i]*cos) + bf16(-x[i+64]*sin) ; out[i+64] = bf16(x[i+64]*cos) + bf16(x[i]*sin)
+  const float o0 = bf16_round(x0 * c0) + bf16_round(-x2 * s0);
+  const float o1 = bf16_round(x1 * c1) + bf16_round(-x3 * s1);
+  const float o2 = bf16_round(x2 * c0) + bf16_round(x0 * s0);
+  const float o3 = bf16_round(x3 * c1) + bf16_round(x1 * s1);
+  *reinterpret_cast<uint32_t*>(dst + 2 * lane) = pack_bf16(o0, o1);
+  *reinterpret_cast<uint32_t*>(dst + 64 + 2 * lane) = pack_bf16(o2, o3);
+}
+
+}  // namespace
+
+extern "C" int mtts_embed_sum8(const long long* ids, int rows, int channels, const void* const* tables_host,
+                               const int* vocab_sizes_host, int hidden, void* out, int* err_flag, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(channels >= 1 && channels <= 8, "mtts_embed_sum8: channels must be in [1,8], got %d", channels);
+  MTTS_REQUIRE(hidden > 0 && hidden % 8 == 0, "mtts_embed_sum8: hidden must be a multiple of 8");
+  if (rows <= 0) return MTTS_OK;
+  MTTS_REQUIRE(ids && tables_host && vocab_sizes_host && out, "mtts_embed_sum8: null pointer");
+  EmbedParams p;
+  p.ids = ids;
+  for (int c = 0; c < 8; ++c) {
+    p.tables[c] = c < channels ? reinterpret_cast<const bf16*>(tables_host[c]) : nullptr;
+    p.vocab[c] = c < channels ? vocab_sizes_host[c] : 0;
+  }
+  p.rows = rows; p.channels = channels; p.hidden = hidden;
+  p.out = reinterpret_cast<bf16*>(out);
+  p.err_flag = err_flag;
+  const long long total = (long long)rows * (hidden / 8);
+  embed_sum_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(p);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_rmsnorm(const void* x, long long ldx, const void* w, void* out, long long ldo, int rows, int hidden,
+                            float eps, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(hidden > 0 && hidden % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0,
+               "mtts_rmsnorm: hidden and strides must be multiples of 8");
+  if (rows <= 0) return MTTS_OK;
+  MTTS_REQUIRE(x && w && out, "mtts_rmsnorm: null pointer");
+  rmsnorm_kernel<<<rows, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(w),
+                                          reinterpret_cast<bf16*>(out), ldo, hidden, eps);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_qknorm_rope_kvappend(const void* qkv, long long ld_qkv, const void* q_norm_w, const void* k_norm_w,
+                                         const float* inv_freq, const int* positions, const int* row_seq, void* q_out,
+                                         void* k_pool, void* v_pool, const int* block_table, int max_pages,
+                                         int page_size, int num_pages, int rows, int num_q_heads, int num_kv_heads,
+                                         int head_dim, float eps, int* err_flag, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(head_dim == 128, "mtts_qknorm_rope_kvappend: head_dim must be 128 (got %d)", head_dim);
+  MTTS_REQUIRE(page_size > 0 && (page_size & (page_size - 1)) == 0, "mtts_qknorm_rope_kvappend: page_size must be a power of two");
+  if (rows <= 0) return MTTS_OK;
+  MTTS_REQUIRE(qkv && q_norm_w && k_norm_w && inv_freq && positions && q_out && k_pool && v_pool,
+               "mtts_qknorm_rope_kvappend: null pointer");
+  RopeParams p;
+  p.qkv = reinterpret_cast<const bf16*>(qkv); p.ld_qkv = ld_qkv;
+  p.q_norm_w = reinterpret_cast<const bf16*>(q_norm_w); p.k_norm_w = reinterpret_cast<const bf16*>(k_norm_w);
+  p.inv_freq = inv_freq; p.positions = positions; p.row_seq = row_seq;
+  p.q_out = reinterpret_cast<bf16*>(q_out); p.k_pool = reinterpret_cast<bf16*>(k_pool);
+  p.v_pool = reinterpret_cast<bf16*>(v_pool); p.block_table = block_table; p.max_pages = max_pages;
+  int shift = 0;
+  while ((1 << shift) < page_size) ++shift;
+  p.page_shift = shift; p.num_pages = num_pages; p.rows = rows; p.Hq = num_q_heads; p.Hkv = num_kv_heads; p.eps = eps;
+  p.err_flag = err_flag;
+  const long long warps = (long long)rows * (num_q_heads + 2 * num_kv_heads);
+  qknorm_rope_kv_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, stream>>>(p);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}

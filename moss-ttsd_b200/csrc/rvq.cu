@@ -266,6 +266,11 @@ __global__ void rvq_decode_kernel(const long long* __restrict__ codes, long long
 
 }  // namespace
 
+int mtts_configure_rvq() {
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+  return MTTS_OK;
+}
+
 extern "C" int mtts_rvq_codebook_norms(const float* codebooks, int nq, int codebook_size, int dim, float* norms,
                                        void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -290,11 +295,6 @@ extern "C" int mtts_rvq_encode(const float* z, const uint8_t* valid, const float
   MTTS_REQUIRE((reinterpret_cast<uintptr_t>(z) & 15) == 0 && (reinterpret_cast<uintptr_t>(codebooks) & 15) == 0,
                "mtts_rvq_encode: z and codebooks must be 16-byte aligned");
   const size_t smem = sizeof(float) * (kTV * (dim + 4) + 2 * kTC * kCPitch + 2 * kTV) + sizeof(int) * 2 * kTV;
-  static bool configured = false;
-  if (!configured) {
-    MTTS_CUDA_CHECK(cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    configured = true;
-  }
   rvq_encode_kernel<<<ceil_div(N, kTV), kThreads, smem, stream>>>(z, valid, codebooks, norms, N, nq, codebook_size,
                                                                   dim, codes, zq, residual_out);
   MTTS_LAUNCH_CHECK();

@@ -1,0 +1,424 @@
+"""Decoder engine: HBM layout of the LM weights, the (paged or contiguous) KV cache, and the launch sequence of
+one prefill / one decode step. All arithmetic is in libmtts kernels; torch only owns memory, streams and the
+CUDA graph that replays the ~230 launches of a decode step.
+
+Reference behaviour being replaced: AsteroidTTSInstruct.forward + HF Qwen3Model (modeling_asteroid.py:252-285,
+337-426) and the per-step part of CustomMixin._sample (modeling_asteroid.py:110-169).
+
+HBM layout (one replica per GPU):
+  heads   [Vpad, H] bf16   the 8 LM heads stacked (each head's rows padded to a multiple of 8); when the
+                           checkpoint ties heads and embedding tables (tie_weights, modeling_asteroid.py:315-317)
+                           the 8 embedding tables are views into this buffer
+  layer l : wqkv [(Hq+2Hkv)*D, H]   q|k|v rows stacked -> one GEMM
+            wo   [H, Hq*D]
+            wgu  [2I, H]            gate/up rows interleaved (2j = gate_j, 2j+1 = up_j) -> SwiGLU in the epilogue
+            wd   [H, I]
+            ln1, ln2 [H], q_norm, k_norm [D]
+  KV pool per layer: k, v [num_pages, Hkv, page_size, D] bf16; left-pad rows are never stored.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import check, ptr, stream_ptr
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+@dataclass
+class LMShape:
+    hidden_size: int = 2048
+    intermediate_size: int = 6144
+    num_hidden_layers: int = 28
+    num_attention_heads: int = 16
+    num_key_value_heads: int = 8
+    head_dim: int = 128
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 1e6
+    vocab_size: int = 152697
+    speech_vocab_size: int = 1025
+    channels: int = 8
+
+    @classmethod
+    def from_config(cls, cfg):
+        g = lambda k, d=None: getattr(cfg, k, d)
+        hd = g("head_dim") or g("hidden_size") // g("num_attention_heads")
+        rope_theta = g("rope_theta")
+        if rope_theta is None:
+            rp = g("rope_parameters") or {}
+            rope_theta = rp.get("rope_theta", 1e6) if isinstance(rp, dict) else 1e6
+        return cls(g("hidden_size"), g("intermediate_size"), g("num_hidden_layers"), g("num_attention_heads"),
+                   g("num_key_value_heads"), hd, g("rms_norm_eps", 1e-6), float(rope_theta), g("vocab_size"),
+                   g("speech_vocab_size", 1025), g("channels", 8))
+
+    @property
+    def vocabs(self) -> List[int]:
+        return [self.vocab_size] + [self.speech_vocab_size] * (self.channels - 1)
+
+    @property
+    def head_offsets(self) -> List[int]:
+        offs, o = [], 0
+        for v in self.vocabs:
+            offs.append(o)
+            o += _pad8(v)
+        return offs
+
+    @property
+    def vpad(self) -> int:
+        return sum(_pad8(v) for v in self.vocabs)
+
+
+class LMWeights:
+    """Weights in the kernel layout, built from a state dict that uses the reference's key names."""
+
+    def __init__(self, shape: LMShape, device):
+        self.shape = shape
+        self.device = torch.device(device)
+        s = shape
+        bf = dict(dtype=torch.bfloat16, device=self.device)
+        self.heads = torch.zeros((s.vpad, s.hidden_size), **bf)
+        self.embeds: Optional[torch.Tensor] = None  # separate tables when not tied
+        self.tied = True
+        self.layers = []
+        for _ in range(s.num_hidden_layers):
+            self.layers.append(dict(
+                ln1=torch.ones(s.hidden_size, **bf), ln2=torch.ones(s.hidden_size, **bf),
+                q_norm=torch.ones(s.head_dim, **bf), k_norm=torch.ones(s.head_dim, **bf),
+                wqkv=torch.empty(((s.num_attention_heads + 2 * s.num_key_value_heads) * s.head_dim, s.hidden_size), **bf),
+                wo=torch.empty((s.hidden_size, s.num_attention_heads * s.head_dim), **bf),
+                wgu=torch.empty((2 * s.intermediate_size, s.hidden_size), **bf),
+                wd=torch.empty((s.hidden_size, s.intermediate_size), **bf)))
+        self.final_norm = torch.ones(s.hidden_size, **bf)
+        # inv_freq exactly as HF computes it (fp32 pow on the host), modeling_qwen3.py rotary embedding init
+        inv = 1.0 / (s.rope_theta ** (torch.arange(0, s.head_dim, 2, dtype=torch.int64).float() / s.head_dim))
+        self.inv_freq = inv.to(self.device, torch.float32).contiguous()
+
+    # ---- views
+    def head_view(self, c: int) -> torch.Tensor:
+        o, v = self.shape.head_offsets[c], self.shape.vocabs[c]
+        return self.heads[o:o + v]
+
+    def embed_view(self, c: int) -> torch.Tensor:
+        if self.embeds is None:
+            return self.head_view(c)
+        o, v = self.shape.head_offsets[c], self.shape.vocabs[c]
+        return self.embeds[o:o + v]
+
+    def nbytes(self) -> int:
+        n = self.heads.numel() + (self.embeds.numel() if self.embeds is not None else 0) + self.final_norm.numel()
+        for L in self.layers:
+            n += sum(t.numel() for t in L.values())
+        return n * 2
+
+    def load_state_dict(self, sd: dict, tie_word_embeddings: Optional[bool] = None):
+        """Accepts the reference's keys: model.embedding_list.{i}.weight, model.language_model.layers.{l}.*,
+        model.language_model.norm.weight, lm_heads.{i}.weight (SURVEY.md §5 checkpoint row)."""
+        s = self.shape
+        dev = self.device
+
+        def get(k):
+            t = sd[k]
+            return t.to(dev, torch.bfloat16) if isinstance(t, torch.Tensor) else torch.as_tensor(t).to(dev, torch.bfloat16)
+
+        have_heads = all(f"lm_heads.{c}.weight" in sd for c in range(s.channels))
+        have_emb = all(f"model.embedding_list.{c}.weight" in sd for c in range(s.channels))
+        if not (have_heads or have_emb):
+            raise KeyError("state dict has neither lm_heads.* nor model.embedding_list.*")
+        if tie_word_embeddings is None:
+            tie_word_embeddings = not (have_heads and have_emb) or all(
+                sd[f"lm_heads.{c}.weight"].data_ptr() == sd[f"model.embedding_list.{c}.weight"].data_ptr()
+                for c in range(s.channels))
+        self.tied = bool(tie_word_embeddings)
+        for c in range(s.channels):
+            hk = f"lm_heads.{c}.weight" if have_heads else f"model.embedding_list.{c}.weight"
+            self.head_view(c).copy_(get(hk))
+        if not self.tied:
+            self.embeds = torch.zeros_like(self.heads)
+            for c in range(s.channels):
+                self.embed_view(c).copy_(get(f"model.embedding_list.{c}.weight"))
+        else:
+            self.embeds = None
+        pre = "model.language_model."
+        for l, L in enumerate(self.layers):
+            b = f"{pre}layers.{l}."
+            L["ln1"].copy_(get(b + "input_layernorm.weight"))
+            L["ln2"].copy_(get(b + "post_attention_layernorm.weight"))
+            L["q_norm"].copy_(get(b + "self_attn.q_norm.weight"))
+            L["k_norm"].copy_(get(b + "self_attn.k_norm.weight"))
+            nq = s.num_attention_heads * s.head_dim
+            nk = s.num_key_value_heads * s.head_dim
+            L["wqkv"][:nq].copy_(get(b + "self_attn.q_proj.weight"))
+            L["wqkv"][nq:nq + nk].copy_(get(b + "self_attn.k_proj.weight"))
+            L["wqkv"][nq + nk:].copy_(get(b + "self_attn.v_proj.weight"))
+            L["wo"].copy_(get(b + "self_attn.o_proj.weight"))
+            L["wgu"][0::2].copy_(get(b + "mlp.gate_proj.weight"))
+            L["wgu"][1::2].copy_(get(b + "mlp.up_proj.weight"))
+            L["wd"].copy_(get(b + "mlp.down_proj.weight"))
+        self.final_norm.copy_(get(pre + "norm.weight"))
+        return self
+
+    def init_random_(self, seed: int = 0, std: float = 0.02):
+        """Seeded random init directly on the device (bench / smoke only; parity tests load reference weights)."""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        self.heads.normal_(0.0, std, generator=g)
+        for c in range(self.shape.channels):  # padding rows between heads stay zero
+            o, v = self.shape.head_offsets[c], self.shape.vocabs[c]
+            self.heads[o + v:o + _pad8(v)].zero_()
+        for L in self.layers:
+            for k in ("wqkv", "wo", "wgu", "wd"):
+                L[k].normal_(0.0, std, generator=g)
+        return self
+
+
+class KVCache:
+    """bf16 K/V pools for all layers plus the page mapping of one batch."""
+
+    def __init__(self, shape: LMShape, batch: int, max_tokens: int, device, paged: bool = False, page_size: int = 64,
+                 shuffle_pages: bool = False):
+        s = shape
+        self.page_size = page_size
+        self.max_pages = (max_tokens + page_size - 1) // page_size
+        self.num_pages = batch * self.max_pages
+        self.paged = paged
+        shp = (s.num_hidden_layers, self.num_pages, s.num_key_value_heads, page_size, s.head_dim)
+        self.k = torch.empty(shp, dtype=torch.bfloat16, device=device)
+        self.v = torch.empty(shp, dtype=torch.bfloat16, device=device)
+        self.block_table = None
+        if paged:
+            # every sequence gets its pages up front from one pool; `shuffle_pages` scatters them to exercise
+            # the indirection (an on-demand allocator only changes which integers are written here)
+            ids = np.arange(self.num_pages, dtype=np.int32)
+            if shuffle_pages:
+                np.random.default_rng(0).shuffle(ids)
+            self.block_table = torch.from_numpy(ids.reshape(batch, self.max_pages)).to(device)
+
+    def nbytes(self):
+        return self.k.numel() * 4
+
+
+class SamplerSetup:
+    """Host-side description of the per-channel processors -> `mtts_sampler_config`."""
+
+    def __init__(self, shape: LMShape, do_samples, layers, pad_token=1024, eos_mask_token=152694):
+        cfg = _lib.SamplerConfig()
+        cfg.channels = shape.channels
+        off_words = 0
+        for c in range(shape.channels):
+            cfg.vocab[c] = shape.vocabs[c]
+            cfg.logit_offset[c] = shape.head_offsets[c]
+            cfg.do_sample[c] = 1 if do_samples[c] else 0
+            lc = layers[c] if layers is not None and c < len(layers) else {}
+            rp, tp, tk, pp = lc.get("repetition_penalty"), lc.get("temperature"), lc.get("top_k"), lc.get("top_p")
+            cfg.has_rep[c] = 0 if rp is None else 1
+            cfg.rep_penalty[c] = 1.0 if rp is None else float(rp)
+            cfg.has_temp[c] = 0 if tp is None else 1
+            cfg.temperature[c] = 1.0 if tp is None else float(tp)
+            cfg.top_k[c] = 0 if tk is None else int(tk)
+            cfg.has_top_p[c] = 0 if pp is None else 1
+            cfg.top_p[c] = 1.0 if pp is None else float(pp)
+            cfg.seen_offset_words[c] = off_words
+            off_words += (shape.vocabs[c] + 31) // 32
+        cfg.seen_words_per_row = off_words
+        cfg.pad_token = pad_token
+        cfg.eos_mask_token = eos_mask_token
+        self.cfg = cfg
+        self.words_per_row = off_words
+
+
+class DecoderEngine:
+    """Runs prefill and decode steps for one batch on one GPU."""
+
+    def __init__(self, weights: LMWeights):
+        self.w = weights
+        self.s = weights.shape
+        self.dev = weights.device
+        self.L = _lib.load()
+        check(self.L.mtts_init())
+        s = self.s
+        self._tables = (ctypes.c_void_p * 8)(*[weights.embed_view(c).data_ptr() for c in range(s.channels)],
+                                             *([None] * (8 - s.channels)))
+        self._vocabs = (ctypes.c_int * 8)(*s.vocabs, *([0] * (8 - s.channels)))
+        self.err = torch.zeros(4, dtype=torch.int32, device=self.dev)
+        self.use_graph = os.environ.get("MTTS_NO_GRAPH", "0") != "1"
+
+    # ------------------------------------------------------------------ primitive launches
+    def _embed(self, ids, out):
+        rows = ids.shape[0]
+        check(self.L.mtts_embed_sum8(ptr(ids), rows, self.s.channels, self._tables, self._vocabs, self.s.hidden_size,
+                                     ptr(out), ptr(self.err), stream_ptr()))
+
+    def _rmsnorm(self, x, w, out):
+        check(self.L.mtts_rmsnorm(ptr(x), x.stride(0), ptr(w), ptr(out), out.stride(0), x.shape[0], x.shape[1],
+                                  self.s.rms_norm_eps, stream_ptr()))
+
+    def _rope_kv(self, qkv, lw, positions, row_seq, q_out, cache: KVCache, layer: int):
+        s = self.s
+        check(self.L.mtts_qknorm_rope_kvappend(
+            ptr(qkv), qkv.stride(0), ptr(lw["q_norm"]), ptr(lw["k_norm"]), ptr(self.w.inv_freq), ptr(positions),
+            ptr(row_seq), ptr(q_out), ptr(cache.k[layer]), ptr(cache.v[layer]), ptr(cache.block_table), cache.max_pages,
+            cache.page_size, cache.num_pages, qkv.shape[0], s.num_attention_heads, s.num_key_value_heads, s.head_dim,
+            s.rms_norm_eps, ptr(self.err), stream_ptr()))
+
+    def _attention(self, q, cache: KVCache, layer: int, positions, row_seq, out, tiles, rows_per_tile, tile_row0,
+                   tile_nrows, nsplit, ws):
+        s = self.s
+        check(self.L.mtts_gqa_attention(
+            ptr(q), ptr(cache.k[layer]), ptr(cache.v[layer]), ptr(cache.block_table), cache.max_pages, cache.page_size,
+            ptr(tile_row0), ptr(tile_nrows), ptr(row_seq), ptr(positions), ptr(out), tiles, rows_per_tile,
+            s.num_attention_heads, s.num_key_value_heads, s.head_dim, nsplit, ptr(ws), ws.numel() if ws is not None else 0,
+            stream_ptr()))
+
+    def _attn_workspace(self, tiles, rows_per_tile, nsplit):
+        s = self.s
+        n = self.L.mtts_gqa_attention_workspace_bytes(tiles, s.num_key_value_heads,
+                                                      s.num_attention_heads // s.num_key_value_heads, rows_per_tile,
+                                                      nsplit)
+        return torch.zeros(n, dtype=torch.uint8, device=self.dev)
+
+    # ------------------------------------------------------------------ layer stack over R packed rows
+    def _alloc_acts(self, R):
+        s = self.s
+        bf = dict(dtype=torch.bfloat16, device=self.dev)
+        nqkv = (s.num_attention_heads + 2 * s.num_key_value_heads) * s.head_dim
+        return dict(x=torch.empty((R, s.hidden_size), **bf), xn=torch.empty((R, s.hidden_size), **bf),
+                    qkv=torch.empty((R, nqkv), **bf), q=torch.empty((R, s.num_attention_heads * s.head_dim), **bf),
+                    ao=torch.empty((R, s.num_attention_heads * s.head_dim), **bf),
+                    h=torch.empty((R, s.intermediate_size), **bf))
+
+    def _gemm_ws(self, R):
+        s = self.s
+        need = 0
+        nqkv = (s.num_attention_heads + 2 * s.num_key_value_heads) * s.head_dim
+        for (n, k) in ((nqkv, s.hidden_size), (s.hidden_size, s.num_attention_heads * s.head_dim),
+                       (2 * s.intermediate_size, s.hidden_size), (s.hidden_size, s.intermediate_size),
+                       (s.vpad, s.hidden_size)):
+            need = max(need, self.L.mtts_gemm_workspace_bytes(R, n, k, ops.BF16))
+        return torch.zeros(need, dtype=torch.uint8, device=self.dev)
+
+    def _layers(self, a, cache, positions, row_seq, attn_kw, gws):
+        x, xn, qkv, q, ao, h = a["x"], a["xn"], a["qkv"], a["q"], a["ao"], a["h"]
+        for l, lw in enumerate(self.w.layers):
+            self._rmsnorm(x, lw["ln1"], xn)
+            ops.gemm(xn, lw["wqkv"], out=qkv, workspace=gws)
+            self._rope_kv(qkv, lw, positions, row_seq, q, cache, l)
+            self._attention(q, cache, l, positions, row_seq, ao, **attn_kw)
+            ops.gemm(ao, lw["wo"], out=x, residual=x, workspace=gws)
+            self._rmsnorm(x, lw["ln2"], xn)
+            ops.gemm(xn, lw["wgu"], out=h, swiglu=True, workspace=gws)
+            ops.gemm(h, lw["wd"], out=x, residual=x, workspace=gws)
+        self._rmsnorm(x, self.w.final_norm, xn)
+        return xn
+
+    # ------------------------------------------------------------------ prefill
+    def prefill(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, cache: KVCache, all_logits: bool = False):
+        """input_ids (B, P, C) int64, attention_mask (B, P). Real tokens (mask != 0) are packed; their positions
+        are cumsum(mask) - 1. Returns (logits bf16 [B, Vpad] of each sequence's last real token, lengths [B]) or,
+        with all_logits, the logits of every packed row plus the packing index."""
+        B, P, C = input_ids.shape
+        mask = (attention_mask != 0)
+        lens = mask.sum(1).to(torch.int64)
+        lens_h = lens.cpu().numpy()
+        R = int(lens_h.sum())
+        flat_idx = mask.reshape(-1).nonzero(as_tuple=False).squeeze(1)          # packing is pure index plumbing
+        ids = input_ids.reshape(B * P, C).index_select(0, flat_idx).contiguous()
+        cu = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(lens_h, out=cu[1:])
+        pos_h = np.concatenate([np.arange(n, dtype=np.int32) for n in lens_h]) if R else np.zeros(0, np.int32)
+        seq_h = np.repeat(np.arange(B, dtype=np.int32), lens_h)
+        row0_h, nrows_h = [], []
+        for b in range(B):
+            for t in range(0, int(lens_h[b]), 4):
+                row0_h.append(cu[b] + t)
+                nrows_h.append(min(4, int(lens_h[b]) - t))
+        positions = torch.from_numpy(pos_h).to(self.dev)
+        row_seq = torch.from_numpy(seq_h).to(self.dev)
+        tile_row0 = torch.tensor(row0_h, dtype=torch.int32, device=self.dev)
+        tile_nrows = torch.tensor(nrows_h, dtype=torch.int32, device=self.dev)
+        a = self._alloc_acts(R)
+        gws = self._gemm_ws(R)
+        self._embed(ids, a["x"])
+        attn_kw = dict(tiles=len(row0_h), rows_per_tile=4, tile_row0=tile_row0, tile_nrows=tile_nrows, nsplit=1, ws=None)
+        xn = self._layers(a, cache, positions, row_seq, attn_kw, gws)
+        if all_logits:
+            logits = torch.empty((R, self.s.vpad), dtype=torch.bfloat16, device=self.dev)
+            ops.gemm(xn, self.w.heads, out=logits, workspace=gws)
+            return logits, flat_idx, lens
+        last = torch.from_numpy(cu[1:] - 1).to(self.dev)
+        hl = xn.index_select(0, last).contiguous()
+        logits = torch.empty((B, self.s.vpad), dtype=torch.bfloat16, device=self.dev)
+        ops.gemm(hl, self.w.heads, out=logits, workspace=self._gemm_ws(B))
+        return logits, lens
+
+    # ------------------------------------------------------------------ decode
+    def make_decode_state(self, B: int, cache: KVCache, sampler: SamplerSetup, seed: int, prompt_rows: int,
+                          max_length: int, max_len_rows: int, speech_range, eos_token: int, has_eos_criteria: bool):
+        st = dict(B=B, cache=cache, sampler=sampler, seed=seed, P=prompt_rows, max_length=max_length,
+                  max_len_rows=max_len_rows, speech=speech_range, eos=eos_token, has_eos=has_eos_criteria)
+        i32 = dict(dtype=torch.int32, device=self.dev)
+        st["tokens"] = torch.zeros((B, self.s.channels), dtype=torch.int64, device=self.dev)
+        st["positions"] = torch.zeros(B, **i32)
+        st["unfinished"] = torch.ones(B, **i32)
+        st["needs"] = torch.full((B,), -1, **i32)
+        st["finish_len"] = torch.zeros(B, **i32)
+        st["step"] = torch.zeros(1, **i32)
+        st["hist"] = torch.full((max(max_len_rows, 8) + 16,), -1, **i32)
+        st["seen"] = torch.zeros((B, sampler.words_per_row), dtype=torch.int32, device=self.dev)
+        st["sequences"] = torch.zeros((B, max_len_rows, self.s.channels), dtype=torch.int64, device=self.dev)
+        st["logits"] = torch.empty((B, self.s.vpad), dtype=torch.bfloat16, device=self.dev)
+        st["acts"] = self._alloc_acts(B)
+        st["gws"] = self._gemm_ws(B)
+        s = self.s
+        nsplit = max(1, min(32, (2 * 148) // max(1, B * s.num_key_value_heads)))
+        st["nsplit"] = nsplit
+        st["attn_ws"] = self._attn_workspace(B, 1, nsplit)
+        st["graph"] = None
+        return st
+
+    def sample_and_advance(self, st, logits):
+        """Draw 8 tokens per row from `logits` and run the delay-pattern state machine (one step)."""
+        sm = st["sampler"]
+        check(self.L.mtts_sample8(ptr(logits), logits.stride(0), st["B"], ctypes.byref(sm.cfg), ptr(st["seen"]),
+                                  ptr(st["step"]), st["seed"], ptr(st["tokens"]), ptr(self.err), stream_ptr()))
+        check(self.L.mtts_delay_step(ptr(st["tokens"]), ptr(st["tf_tail"]), ptr(st["sequences"]), st["max_len_rows"],
+                                     ptr(st["unfinished"]), ptr(st["needs"]), ptr(st["positions"]), ptr(st["seen"]),
+                                     ptr(st["step"]), ptr(st["hist"]), ptr(st["finish_len"]), st["B"], st["P"],
+                                     st["max_length"], st["speech"][0], st["speech"][1], st["eos"],
+                                     1 if st["has_eos"] else 0, ctypes.byref(sm.cfg), stream_ptr()))
+
+    def _decode_body(self, st):
+        a = st["acts"]
+        self._embed(st["tokens"], a["x"])
+        attn_kw = dict(tiles=st["B"], rows_per_tile=1, tile_row0=None, tile_nrows=None, nsplit=st["nsplit"],
+                       ws=st["attn_ws"] if st["nsplit"] > 1 else None)
+        xn = self._layers(a, st["cache"], st["positions"], None, attn_kw, st["gws"])
+        ops.gemm(xn, self.w.heads, out=st["logits"], workspace=st["gws"])
+        self.sample_and_advance(st, st["logits"])
+
+    def decode_step(self, st):
+        """Feed the row appended by the previous step, sample the next one. Replays a CUDA graph after the
+        first call (launch-bound otherwise: ~230 kernels per step)."""
+        if not self.use_graph:
+            self._decode_body(st)
+            return
+        if st["graph"] is None:
+            # warm-up launch outside capture would advance the state, so capture directly; all buffers are
+            # preallocated and every kernel argument that changes per step lives in device memory.
+            g = torch.cuda.CUDAGraph()
+            cap_stream = torch.cuda.Stream(device=self.dev)
+            cap_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap_stream):
+                with torch.cuda.graph(g, stream=cap_stream):
+                    self._decode_body(st)
+            torch.cuda.current_stream().wait_stream(cap_stream)
+            st["graph"] = g
+        st["graph"].replay()

@@ -1,0 +1,369 @@
+"""Drop-in mirror of the reference's `modeling_asteroid.py` for the inference path.
+
+Same names, argument meaning and error behaviour as /root/reference/modeling_asteroid.py:
+  AsteroidTTSConfig (:17-28), AsteroidTTSOutputWithPast (:31-39), GenerateDecoderOnlyOutput (:42-49),
+  AsteroidTTSInstruct (:288-426) with .generate (HF GenerationMixin.generate -> CustomMixin._sample :52-197),
+  .forward (:337-426, inference branch), .is_speech_token (:311-312), .set_weights (:334-335).
+What differs is what runs underneath: libmtts CUDA kernels driven by `lm_engine.DecoderEngine`, one CUDA graph
+replay per generated frame, no host sync inside the step. Training (`labels=`) is out of scope and raises.
+"""
+from __future__ import annotations
+
+import copy
+import json
+import os
+from dataclasses import dataclass
+from typing import List, Optional, Tuple, Union
+
+import torch
+
+from .lm_engine import DecoderEngine, KVCache, LMShape, LMWeights, SamplerSetup
+
+
+class AsteroidTTSConfig:
+    """Qwen3-style decoder config plus the four TTS fields of the reference (modeling_asteroid.py:17-28)."""
+    model_type = "asteroid_tts"
+
+    def __init__(self, channels=8, speech_pad_token=1024, speech_vocab_size=1025, speech_token_range=None, **kwargs):
+        defaults = dict(vocab_size=151936, hidden_size=4096, intermediate_size=22016, num_hidden_layers=32,
+                        num_attention_heads=32, num_key_value_heads=32, head_dim=128, hidden_act="silu",
+                        max_position_embeddings=32768, rms_norm_eps=1e-6, rope_theta=10000.0, attention_bias=False,
+                        tie_word_embeddings=False, pad_token_id=None, bos_token_id=None, eos_token_id=None,
+                        output_attentions=False, output_hidden_states=False, use_return_dict=True)
+        defaults.update(kwargs)
+        for k, v in defaults.items():
+            setattr(self, k, v)
+        self.channels = channels
+        self.speech_pad_token = speech_pad_token
+        self.speech_vocab_size = speech_vocab_size
+        self.speech_token_range = list(speech_token_range) if speech_token_range is not None else []
+
+    @classmethod
+    def from_pretrained(cls, path, **kwargs):
+        with open(os.path.join(path, "config.json")) as f:
+            d = json.load(f)
+        d.update(kwargs)
+        return cls(**d)
+
+    def to_dict(self):
+        return dict(self.__dict__)
+
+
+class GenerationConfig:
+    """The subset of HF GenerationConfig the sampler reads, with HF's defaults, plus the reference's custom
+    fields `do_samples` and `layers` (modeling_asteroid.py:95-106)."""
+
+    def __init__(self, **kwargs):
+        self.max_length = 20
+        self.max_new_tokens = None
+        self.do_sample = False
+        self.temperature = 1.0
+        self.top_k = 50
+        self.top_p = 1.0
+        self.repetition_penalty = 1.0
+        self.eos_token_id = None
+        self.pad_token_id = None
+        self.return_dict_in_generate = False
+        self.output_scores = False
+        self.output_logits = False
+        self.output_attentions = False
+        self.output_hidden_states = False
+        self.do_samples = None
+        self.layers = None
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @classmethod
+    def from_pretrained(cls, path):
+        p = os.path.join(path, "generation_config.json")
+        if not os.path.exists(p):
+            return cls()
+        with open(p) as f:
+            return cls(**json.load(f))
+
+    def update(self, **kwargs):
+        unused = {}
+        for k, v in kwargs.items():
+            if hasattr(self, k):
+                setattr(self, k, v)
+            else:
+                unused[k] = v
+        return unused
+
+
+@dataclass
+class AsteroidTTSOutputWithPast:
+    loss: Optional[torch.Tensor] = None
+    logits: Optional[torch.Tensor] = None
+    loss_all: Optional[Tuple[torch.Tensor]] = None
+    logits_all: Optional[Tuple[torch.Tensor]] = None
+    past_key_values: Optional[object] = None
+    hidden_states: Optional[Tuple[torch.Tensor, ...]] = None
+    attentions: Optional[Tuple[torch.Tensor, ...]] = None
+
+
+@dataclass
+class GenerateDecoderOnlyOutput:
+    sequences: Optional[torch.Tensor] = None
+    scores: Optional[tuple] = None
+    logits: Optional[tuple] = None
+    attentions: Optional[tuple] = None
+    hidden_states: Optional[tuple] = None
+    past_key_values: Optional[object] = None
+
+
+class AsteroidTTSInstruct:
+    """Inference-only drop-in for the reference class of the same name."""
+
+    def __init__(self, config: AsteroidTTSConfig, device: Union[str, torch.device, None] = None):
+        self.config = config
+        self.channels = config.channels
+        self.weights = [1 for _ in range(self.channels)]
+        self.vocab_size = config.vocab_size
+        self.generation_config = GenerationConfig(eos_token_id=config.eos_token_id, pad_token_id=config.pad_token_id)
+        self.shape = LMShape.from_config(config)
+        self.device = torch.device(device) if device is not None else None
+        self._w: Optional[LMWeights] = None
+        self._engine: Optional[DecoderEngine] = None
+        self.training = False
+        self.dtype = torch.bfloat16
+        # knobs of the B200 engine (not in the reference)
+        self.kv_paged = False
+        self.kv_page_size = 64
+        self.sync_every = 8
+        if self.device is not None and self.device.type == "cuda":
+            self._materialize()
+
+    # ------------------------------------------------------------------ construction / loading
+    def _materialize(self):
+        if self._w is None:
+            if self.device is None or self.device.type != "cuda":
+                raise RuntimeError("AsteroidTTSInstruct runs on CUDA only (no CPU path); call .to('cuda') first")
+            self._w = LMWeights(self.shape, self.device)
+            self._engine = None
+
+    @property
+    def engine(self) -> DecoderEngine:
+        self._materialize()
+        if self._engine is None:
+            self._engine = DecoderEngine(self._w)
+        return self._engine
+
+    def to(self, device=None, dtype=None, **kw):
+        if dtype is not None and dtype != torch.bfloat16:
+            raise ValueError("the B200 decoder path computes in bf16 (north_star); got dtype %s" % dtype)
+        if device is not None:
+            device = torch.device(device)
+            if self._w is not None and device != self.device:
+                raise RuntimeError("moving an already materialised model between devices is not supported")
+            self.device = device
+            if device.type == "cuda":
+                self._pending = getattr(self, "_pending", None)
+                self._materialize()
+                if self._pending is not None:
+                    self._w.load_state_dict(self._pending, self.config.tie_word_embeddings or None)
+                    self._pending = None
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", device if device is not None else torch.cuda.current_device()))
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def load_state_dict(self, sd, strict=True, tie_word_embeddings=None):
+        if self._w is None:
+            if self.device is not None and self.device.type == "cuda":
+                self._materialize()
+            else:
+                self._pending = sd
+                return self
+        self._w.load_state_dict(sd, tie_word_embeddings)
+        self._engine = None
+        return self
+
+    def init_random_weights(self, seed=0):
+        self._materialize()
+        self._w.init_random_(seed)
+        self._engine = None
+        return self
+
+    @classmethod
+    def from_pretrained(cls, model_path, torch_dtype=torch.bfloat16, attn_implementation=None, device=None, **kwargs):
+        """Local directory with config.json (+ generation_config.json) and *.safetensors / pytorch_model*.bin.
+        `attn_implementation` is accepted for signature compatibility and ignored: attention always runs in the
+        libmtts kernel."""
+        if torch_dtype not in (torch.bfloat16, None):
+            raise ValueError("the B200 decoder path computes in bf16 only")
+        config = AsteroidTTSConfig.from_pretrained(model_path)
+        model = cls(config, device=device)
+        model.generation_config = GenerationConfig.from_pretrained(model_path)
+        if model.generation_config.eos_token_id is None:
+            model.generation_config.eos_token_id = config.eos_token_id
+        sd = {}
+        files = sorted(os.listdir(model_path))
+        st_files = [f for f in files if f.endswith(".safetensors")]
+        if st_files:
+            from safetensors.torch import load_file
+            for f in st_files:
+                sd.update(load_file(os.path.join(model_path, f)))
+        else:
+            for f in files:
+                if f.endswith(".bin") or f.endswith(".pt"):
+                    sd.update(torch.load(os.path.join(model_path, f), map_location="cpu"))
+        if not sd:
+            raise FileNotFoundError(f"no weights found under {model_path}")
+        model.load_state_dict(sd, tie_word_embeddings=config.tie_word_embeddings or None)
+        return model
+
+    # ------------------------------------------------------------------ small API of the reference class
+    def can_generate(self):
+        return True
+
+    def is_speech_token(self, tokens):
+        return (tokens >= self.config.speech_token_range[0]) & (tokens < self.config.speech_token_range[1])
+
+    def set_weights(self, weights):
+        self.weights = weights
+
+    # ------------------------------------------------------------------ forward (teacher-forced logits)
+    @torch.no_grad()
+    def forward(self, input_ids: torch.LongTensor = None, attention_mask: Optional[torch.Tensor] = None,
+                position_ids=None, past_key_values=None, inputs_embeds=None, labels=None, use_cache=None,
+                output_attentions=None, output_hidden_states=None, return_dict=None, cache_position=None,
+                skip_logits=None, **kwargs):
+        if (input_ids is None) ^ (inputs_embeds is not None):
+            raise ValueError("You must specify exactly one of input_ids or inputs_embeds")
+        if inputs_embeds is not None:
+            raise NotImplementedError("inputs_embeds is not supported by the B200 path (the embedding sum is fused)")
+        if labels is not None:
+            raise NotImplementedError("training loss is out of scope of the B200 inference path")
+        if past_key_values is not None:
+            raise NotImplementedError("forward() is the teacher-forced full-sequence pass; use generate() for decoding")
+        B, S, C = input_ids.shape
+        if C != self.config.channels:
+            raise ValueError(f"Expected {self.config.channels} channels, got {C}")
+        eng = self.engine
+        input_ids = input_ids.to(self.device)
+        if attention_mask is None:
+            attention_mask = torch.ones((B, S), device=self.device)
+        attention_mask = attention_mask.to(self.device)
+        cache = KVCache(self.shape, B, S, self.device, paged=self.kv_paged, page_size=self.kv_page_size)
+        logits, flat_idx, _ = eng.prefill(input_ids, attention_mask, cache, all_logits=True)
+        self._check_err()
+        full = torch.zeros((B * S, self.shape.vpad), dtype=torch.bfloat16, device=self.device)
+        full.index_copy_(0, flat_idx, logits)
+        full = full.view(B, S, -1)
+        logits_all = tuple(full[..., o:o + v] for o, v in zip(self.shape.head_offsets, self.shape.vocabs))
+        return AsteroidTTSOutputWithPast(loss=None, logits=logits_all[0], loss_all=None, logits_all=logits_all)
+
+    __call__ = forward
+
+    def _check_err(self):
+        e = self.engine.err.cpu().tolist()
+        if any(e):
+            self.engine.err.zero_()
+            raise RuntimeError(f"libmtts device-side error flags {e} (1: token id out of range, 2: KV page out of range, "
+                               f"3: sampler candidate overflow)")
+
+    # ------------------------------------------------------------------ generate
+    def _sampler_setup(self, gc: GenerationConfig) -> SamplerSetup:
+        C = self.channels
+        if gc.do_samples is not None:
+            do_samples = list(gc.do_samples)
+            layers = [dict(l) for l in (gc.layers or [])] + [{} for _ in range(C - len(gc.layers or []))]
+        else:
+            # shared processor list as HF builds it (modeling_asteroid.py:107-109): repetition penalty always (if != 1),
+            # warpers only when sampling
+            do_samples = [bool(gc.do_sample)] * C
+            lc = {}
+            if gc.repetition_penalty is not None and gc.repetition_penalty != 1.0:
+                lc["repetition_penalty"] = gc.repetition_penalty
+            if gc.do_sample:
+                if gc.temperature is not None and gc.temperature != 1.0:
+                    lc["temperature"] = gc.temperature
+                if gc.top_k is not None and gc.top_k != 0:
+                    lc["top_k"] = gc.top_k
+                if gc.top_p is not None and gc.top_p < 1.0:
+                    lc["top_p"] = gc.top_p
+            layers = [dict(lc) for _ in range(C)]
+        return SamplerSetup(self.shape, do_samples, layers, pad_token=1024, eos_mask_token=152694)
+
+    @torch.no_grad()
+    def generate(self, input_ids: torch.LongTensor = None, attention_mask: Optional[torch.Tensor] = None,
+                 generation_config: Optional[GenerationConfig] = None, streamer=None, seed: Optional[int] = None,
+                 **kwargs):
+        """input_ids (B, T, 8) int64 — the delay-shifted, left-padded prompt grid whose last 7 rows are the
+        teacher-forced tail; attention_mask (B, T). Returns LongTensor (B, T - 7 + G, 8) (or
+        GenerateDecoderOnlyOutput with return_dict_in_generate), exactly the rows CustomMixin._sample returns."""
+        gc = copy.deepcopy(generation_config if generation_config is not None else self.generation_config)
+        gc.update(**kwargs)
+        if gc.output_attentions or gc.output_hidden_states or gc.output_scores or gc.output_logits:
+            raise NotImplementedError("per-step scores/attentions capture is not supported by the fused decode step")
+        B, T, C = input_ids.shape
+        if C != self.config.channels:
+            raise ValueError(f"Expected {self.config.channels} channels, got {C}")
+        if T < C:
+            raise ValueError("prompt grid must include the (channels-1) delay rows")
+        dev = self.device
+        eng = self.engine
+        input_ids = input_ids.to(dev).contiguous()
+        if attention_mask is None:
+            attention_mask = torch.ones((B, T), device=dev)
+        attention_mask = attention_mask.to(dev)
+        P = T - (C - 1)
+        max_length = T + gc.max_new_tokens if gc.max_new_tokens is not None else gc.max_length
+        eos = gc.eos_token_id
+        if isinstance(eos, (list, tuple)):
+            eos = eos[0] if len(eos) else None
+        has_eos = eos is not None
+        eos_fill = self.config.eos_token_id if self.config.eos_token_id is not None else (eos if eos is not None else 0)
+        if isinstance(eos_fill, (list, tuple)):
+            eos_fill = eos_fill[0]
+        # A row in wind-down ignores max_length for up to C-2 extra rows; allocate for it.
+        max_rows = max(max_length, P + 1) + C + self.sync_every
+        sampler = self._sampler_setup(gc)
+        if seed is None:
+            seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)  # follows torch.manual_seed / accelerate set_seed
+        cache = KVCache(self.shape, B, max_rows + 1, dev, paged=self.kv_paged, page_size=self.kv_page_size)
+        st = eng.make_decode_state(B, cache, sampler, seed, P, max_length, max_rows,
+                                   tuple(self.config.speech_token_range), int(eos_fill), has_eos)
+        st["sequences"][:, :P].copy_(input_ids[:, :P])
+        st["tf_tail"] = input_ids[:, P:].contiguous()
+        from . import _lib
+        import ctypes
+        _lib.check(eng.L.mtts_sampler_init_history(input_ids.data_ptr(), B, P, input_ids.stride(0), ctypes.byref(sampler.cfg),
+                                                   st["seen"].data_ptr(), _lib.stream_ptr()))
+        # ---- step 0: prefill the prompt, sample from its last position
+        logits, lens = eng.prefill(input_ids[:, :P], attention_mask[:, :P], cache)
+        st["positions"].copy_((lens - 1).to(torch.int32))
+        eng.sample_and_advance(st, logits)
+        if streamer is not None:
+            streamer.put(st["tokens"][:, 0].cpu())
+        # ---- steps 1..: one graph replay per frame; the host looks at the stop flag every `sync_every` steps
+        steps_done = 1
+        final_len = None
+        hist_host = None
+        while True:
+            if steps_done % self.sync_every == 0 or streamer is not None or steps_done == 1:
+                hist_host = st["hist"][:steps_done].cpu()
+                zero = (hist_host == 0).nonzero()
+                if zero.numel():
+                    final_len = P + int(zero[0]) + 1
+                    break
+            if P + steps_done >= max_rows:  # cannot happen unless the stop logic is broken
+                final_len = max_rows
+                break
+            eng.decode_step(st)
+            steps_done += 1
+            if streamer is not None:
+                streamer.put(st["tokens"][:, 0].cpu())
+        self._check_err()
+        if streamer is not None:
+            streamer.end()
+        out = st["sequences"][:, :final_len].clone()
+        self._last_state = st
+        if gc.return_dict_in_generate:
+            return GenerateDecoderOnlyOutput(sequences=out, past_key_values=None)
+        return out

@@ -22,10 +22,22 @@ def _dt(t: torch.Tensor) -> int:
     raise TypeError(f"unsupported dtype {t.dtype}")
 
 
+_inited = set()
+
+
+def ensure_init():
+    """mtts_init() once per device (sets kernel attributes; must happen outside CUDA-graph capture)."""
+    d = torch.cuda.current_device()
+    if d not in _inited:
+        check(_lib.load().mtts_init())
+        _inited.add(d)
+
+
 def _cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise _lib.MttsError("libmtts ops need CUDA tensors; there is no CPU path")
+    ensure_init()
 
 
 _workspaces: dict = {}

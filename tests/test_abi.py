@@ -1,0 +1,44 @@
+"""The C-ABI library loads and exports every symbol include/mtts.h declares (no GPU needed, no compute calls)."""
+import ctypes
+import os
+
+from moss_ttsd_b200 import _lib
+
+
+def test_header_symbols_are_bound_and_exported():
+    syms = _lib.header_symbols()
+    assert len(syms) >= 15
+    assert set(syms) == set(_lib.SIGNATURES), (set(syms) ^ set(_lib.SIGNATURES))
+    lib = _lib.load()
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert lib.mtts_version() == 100
+    assert isinstance(lib.mtts_last_error(), bytes)
+
+
+def test_no_torch_types_in_the_abi():
+    import re
+    with open(_lib.HEADER_PATH) as f:
+        code = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)  # declarations only, comments stripped
+    assert "torch" not in code.lower() and "at::" not in code and "c10" not in code and "Tensor" not in code
+
+
+def test_workspace_queries_work_without_a_device():
+    lib = _lib.load()
+    assert lib.mtts_gemm_workspace_bytes(1, 4096, 2048, 0) >= 16384
+    assert lib.mtts_gqa_attention_workspace_bytes(4, 8, 2, 1, 8) > 65536
+
+
+def test_product_never_imports_oracle():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "moss-ttsd_b200")
+    for dp, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dp, f)) as fh:
+                    src = fh.read()
+                assert "import oracle" not in src and "from oracle" not in src, os.path.join(dp, f)
+
+
+def test_sampler_config_struct_size_matches_header():
+    # 1 + 8*11 arrays of 4-byte fields + 3 trailing ints = 92 ints
+    assert ctypes.sizeof(_lib.SamplerConfig) == 4 * (1 + 8 * 11 + 1 + 2)
