@@ -171,6 +171,46 @@ int mtts_delay_step(long long* tokens, const long long* tf_tail, long long* sequ
                     int* unfinished_hist, int* finish_len, int B, int prompt_rows, int max_length, int speech_lo,
                     int speech_hi, int eos_token, int has_eos_criteria, const mtts_sampler_config* cfg, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * XY_Tokenizer decode path, fp32, token-major activations [batch*frames, channels]
+ * (XY_Tokenizer/xy_tokenizer/model.py:103-128 -> nn/modules.py). All dense layers go through mtts_gemm (TF32).
+ * ---------------------------------------------------------------------------------------------- */
+/* nn.LayerNorm over C; rows at or beyond lengths[row / rows_per_item] are written as zeros when lengths != NULL
+ * (modules.py:171,182,554 and the masking of :407,626). */
+int mtts_layernorm(const float* x, const float* w, const float* b, float* out, long long rows, int C, float eps,
+                   const int* lengths, int rows_per_item, void* stream);
+
+/* VarLenAttention core (modules.py:117-160), non-causal, head_dim 64: qkv [B*T, 3*H*64] (q|k|v incl. biases, q NOT yet
+ * scaled), out [B*T, H*64]; keys >= lengths[b] are masked. */
+int mtts_mha_varlen(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads, int head_dim,
+                    void* stream);
+
+/* ConvNeXtBlock front half (modules.py:1142-1150): depthwise Conv1d(k=7,pad=3) + LayerNorm(C, eps). x,out [B,T,C];
+ * conv_w [C,7]; zero padding at both ends of every item. */
+int mtts_dwconv7_ln(const float* x, const float* conv_w, const float* conv_b, const float* ln_w, const float* ln_b,
+                    float* out, int B, int T, int C, float eps, void* stream);
+
+/* Tap overlap-add of a ConvTranspose1d computed as GEMM (modules.py:354-368,413-419): y [B,Tin,K,Cout] ->
+ * out[b,u,co] = act(bias[co] + sum_j y[b,(u-j)/stride,j,co]), u < Tout (trim), act = exact-erf GELU if gelu. */
+int mtts_convt_gather(const float* y, const float* bias, float* out, int B, int Tin, int Cout, int K, int stride,
+                      int Tout, int gelu, void* stream);
+
+/* im2col for Conv1d(K odd, pad=(K-1)/2) on token-major x [B,T,Cin]: col[b,t,j*Cin+ci] = x[b,t+j-pad,ci]
+ * (VocosBackbone.embed, modules.py:1372). */
+int mtts_im2col(const float* x, float* col, int B, int T, int Cin, int K, int ld_col, void* stream);
+
+/* ISTFTHead nonlinearity (modules.py:971-984): x [rows, 2F] = (log-mag | phase) -> spec [rows, lds] =
+ * (Re_0..Re_{F-1} | Im_0..Im_{F-1} | 0...) with mag = min(exp(.), 100). */
+int mtts_istft_spec(const float* x, long long ldx, float* spec, long long lds, long long rows, int num_bins,
+                    void* stream);
+
+/* ISTFT overlap-add, window-envelope normalisation and "same" trim (modules.py:759-792): frames [B,T,n_fft]
+ * (already windowed: the inverse-DFT-times-window basis is applied by mtts_gemm) -> out [B, T*hop]. */
+int mtts_istft_ola(const float* frames, const float* window, float* out, int B, int T, int n_fft, int hop, void* stream);
+
+/* x[r,:] += table[r % mod,:]  (sinusoidal positional embedding, modules.py:398-402,600-606). */
+int mtts_add_rows_mod(float* x, const float* table, long long rows, int C, int mod, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,7 @@ extern "C" int mtts_init(void) {
     if ((rc = mtts_configure_gemm_tc())) return rc;
     if ((rc = mtts_configure_attention())) return rc;
     if ((rc = mtts_configure_rvq())) return rc;
+    if ((rc = mtts_configure_codec())) return rc;
     configured[dev] = true;
   }
   return MTTS_OK;

@@ -1,0 +1,435 @@
+// fp32 kernels of the XY_Tokenizer decode path that are not GEMMs. Activations are TOKEN-major
+// ([batch * frames, channels], channels contiguous) everywhere, so every projection is a plain mtts_gemm and no
+// (B,C,T)<->(B,T,C) transposes are ever materialised (the reference transposes around every block,
+// XY_Tokenizer/xy_tokenizer/nn/modules.py:1144-1153,1399-1409).
+#include "common.cuh"
+#include "mtts_internal.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the channel dim (nn.LayerNorm, modules.py:171,182,324,554,1110,1377,1397), optionally
+// zeroing rows at or beyond each item's length (`torch.where(attention_mask, hidden_states, 0)`,
+// modules.py:407,626). One warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float* __restrict__ out,
+                                                        long long rows, int C, float eps,
+                                                        const int* __restrict__ lengths, int rows_per_item) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * C;
+  float* orow = out + row * C;
+  if (lengths) {
+    const int item = (int)(row / rows_per_item), t = (int)(row % rows_per_item);
+    if (t >= lengths[item]) {
+      for (int c = lane * 4; c < C; c += 128) *reinterpret_cast<float4*>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+  }
+  float s = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+    q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+  }
+  const float inv = rsqrtf(warp_sum(q) / (float)C + eps);
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float4 ww = *reinterpret_cast<const float4*>(w + c);
+    const float4 bb = *reinterpret_cast<const float4*>(b + c);
+    float4 o;
+    o.x = (v.x - mean) * inv * ww.x + bb.x;
+    o.y = (v.y - mean) * inv * ww.y + bb.y;
+    o.z = (v.z - mean) * inv * ww.z + bb.z;
+    o.w = (v.w - mean) * inv * ww.w + bb.w;
+    *reinterpret_cast<float4*>(orow + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Non-causal multi-head attention with per-item key lengths (VarLenAttention.forward, modules.py:117-160).
+// qkv: [B*T, 3*E] fp32 (q | k | v, the fused projection incl. biases), head_dim 64. Keys at or beyond an item's
+// length are masked (the reference adds finfo.min there and +1.0 — a constant shift — on valid ones,
+// modules.py:99-115). Query rows beyond the length are computed over the same valid keys; their values are
+// never consumed (they are zeroed after the final LayerNorm, modules.py:407,626).
+// Flash-style: CTA = 64 queries x one head, K/V tiles of 64 keys in shared memory, fp32 throughout.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHD = 64, kQT = 64, kKT = 64, kPitch = 68;
+
+__global__ void __launch_bounds__(256) mha_varlen_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                         const int* __restrict__ lengths, int T, int H, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  float* sq = sm;                    // [64][68]
+  float* sk = sq + kQT * kPitch;     // [64][68]
+  float* sv = sk + kKT * kPitch;     // [64][68]
+  float* sp = sv + kKT * kPitch;     // [64][68] probabilities
+  const int E = H * kHD;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kQT;
+  const int len = lengths ? min(lengths[b], T) : T;
+  const int tid = threadIdx.x;
+  const int qi = tid >> 4;   // 0..15 -> queries qi*4 .. qi*4+3
+  const int ki = tid & 15;   // 0..15 -> keys ki + 16*j (scores) / dims ki*4..+3 (output)
+  const float* base = qkv + (long long)b * T * 3 * E;
+
+  // Q tile (pre-scaled, as `query = q_proj(x) * scaling`, modules.py:126)
+  for (int i = tid; i < kQT * (kHD / 4); i += 256) {
+    const int r = i >> 4, c4 = (i & 15) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < T) v = *reinterpret_cast<const float4*>(base + (long long)(q0 + r) * 3 * E + h * kHD + c4);
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    *reinterpret_cast<float4*>(sq + r * kPitch + c4) = v;
+  }
+  float m[4], l[4], acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[i] = -1e30f;
+    l[i] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) acc[i][d] = 0.f;
+  }
+  // all-masked items (len == 0) attend uniformly over every key in the reference; keep that corner defined
+  const int kv_len = len > 0 ? len : T;
+
+  for (int k0 = 0; k0 < kv_len; k0 += kKT) {
+    __syncthreads();
+    for (int i = tid; i < kKT * (kHD / 4); i += 256) {
+      const int r = i >> 4, c4 = (i & 15) * 4;
+      float4 kv4 = make_float4(0.f, 0.f, 0.f, 0.f), vv4 = kv4;
+      if (k0 + r < kv_len) {
+        const float* p = base + (long long)(k0 + r) * 3 * E + h * kHD + c4;
+        kv4 = *reinterpret_cast<const float4*>(p + E);
+        vv4 = *reinterpret_cast<const float4*>(p + 2 * E);
+      }
+      *reinterpret_cast<float4*>(sk + r * kPitch + c4) = kv4;
+      *reinterpret_cast<float4*>(sv + r * kPitch + c4) = vv4;
+    }
+    __syncthreads();
+    // scores: 4 queries x 4 keys per thread
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < kHD; d += 4) {
+      float4 qv[4], kv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(sq + (qi * 4 + i) * kPitch + d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kv[j] = *reinterpret_cast<const float4*>(sk + (ki + 16 * j) * kPitch + d);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[i][j] = fmaf(qv[i].x, kv[j].x, s[i][j]);
+          s[i][j] = fmaf(qv[i].y, kv[j].y, s[i][j]);
+          s[i][j] = fmaf(qv[i].z, kv[j].z, s[i][j]);
+          s[i][j] = fmaf(qv[i].w, kv[j].w, s[i][j]);
+        }
+    }
+    // online softmax per query row (16 lanes share a row)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -1e30f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (k0 + ki + 16 * j >= kv_len) s[i][j] = -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      const float mn = fmaxf(m[i], mx);
+      const float corr = __expf(m[i] - mn);
+      float ps = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pr = __expf(s[i][j] - mn);
+        ps += pr;
+        sp[(qi * 4 + i) * kPitch + ki + 16 * j] = pr;
+      }
+      ps += __shfl_xor_sync(0xffffffffu, ps, 8);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 4);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+      m[i] = mn;
+      l[i] = l[i] * corr + ps;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) acc[i][d] *= corr;
+    }
+    __syncwarp();  // a query row's probabilities are written and read by the same half-warp
+    // O += P V : 4 queries x 4 dims per thread
+#pragma unroll 8
+    for (int k = 0; k < kKT; ++k) {
+      const float4 vv = *reinterpret_cast<const float4*>(sv + k * kPitch + ki * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float pr = sp[(qi * 4 + i) * kPitch + k];
+        acc[i][0] = fmaf(pr, vv.x, acc[i][0]);
+        acc[i][1] = fmaf(pr, vv.y, acc[i][1]);
+        acc[i][2] = fmaf(pr, vv.z, acc[i][2]);
+        acc[i][3] = fmaf(pr, vv.w, acc[i][3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = q0 + qi * 4 + i;
+    if (q < T) {
+      const float inv = 1.0f / l[i];
+      *reinterpret_cast<float4*>(out + ((long long)b * T + q) * E + h * kHD + ki * 4) =
+          make_float4(acc[i][0] * inv, acc[i][1] * inv, acc[i][2] * inv, acc[i][3] * inv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ConvNeXt front half: depthwise Conv1d(k=7, pad=3, groups=C) + LayerNorm(C, eps) fused
+// (ConvNeXtBlock.forward modules.py:1142-1150). x/out: [B, T, C]; w: [C, 7]; zero padding at each item's ends.
+// One CTA (C/4 threads) per token.
+// ------------------------------------------------------------------------------------------------
+__global__ void dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ cb,
+                                  const float* __restrict__ lw, const float* __restrict__ lb, float* __restrict__ out,
+                                  int T, int C, float eps) {
+  __shared__ float red[33];
+  const long long tok = blockIdx.x;
+  const int t = (int)(tok % T);
+  const int c = threadIdx.x * 4;
+  float4 a = *reinterpret_cast<const float4*>(cb + c);
+  float wk[4][7];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) wk[i][j] = __ldg(w + (c + i) * 7 + j);
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int tt = t + j - 3;
+    if (tt < 0 || tt >= T) continue;
+    const float4 v = *reinterpret_cast<const float4*>(x + (tok + (j - 3)) * C + c);
+    a.x = fmaf(wk[0][j], v.x, a.x);
+    a.y = fmaf(wk[1][j], v.y, a.y);
+    a.z = fmaf(wk[2][j], v.z, a.z);
+    a.w = fmaf(wk[3][j], v.w, a.w);
+  }
+  const float mean = block_sum((a.x + a.y) + (a.z + a.w), red) / (float)C;
+  const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+  const float var = block_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3), red) / (float)C;
+  const float inv = rsqrtf(var + eps);
+  const float4 g = *reinterpret_cast<const float4*>(lw + c);
+  const float4 bb = *reinterpret_cast<const float4*>(lb + c);
+  *reinterpret_cast<float4*>(out + tok * C + c) =
+      make_float4(d0 * inv * g.x + bb.x, d1 * inv * g.y + bb.y, d2 * inv * g.z + bb.z, d3 * inv * g.w + bb.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ConvTranspose1d as GEMM + gather: y[b, t, j, co] = sum_ci x[b,t,ci] W[ci,co,j] comes from mtts_gemm; this kernel
+// overlap-adds the taps:  out[b, u, co] = act(bias[co] + sum_{j : (u-j) % stride == 0, 0 <= (u-j)/stride < Tin} y[b,(u-j)/stride,j,co])
+// (OmniAudioDecoder deconv1/deconv2 + GELU + trim, modules.py:354-368,413-419).
+// ------------------------------------------------------------------------------------------------
+__global__ void convt_gather_kernel(const float* __restrict__ y, const float* __restrict__ bias, float* __restrict__ out,
+                                    int B, int Tin, int Cout, int K, int stride, int Tout, int gelu) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cv = Cout >> 2;
+  const long long total = (long long)B * Tout * cv;
+  if (gid >= total) return;
+  const int c = (int)(gid % cv) * 4;
+  const int u = (int)((gid / cv) % Tout);
+  const int b = (int)(gid / ((long long)cv * Tout));
+  float4 a = bias ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < K; ++j) {
+    const int r = u - j;
+    if (r < 0 || (r % stride) != 0) continue;
+    const int t = r / stride;
+    if (t >= Tin) continue;
+    const float4 v = *reinterpret_cast<const float4*>(y + (((long long)b * Tin + t) * K + j) * Cout + c);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  if (gelu) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+  *reinterpret_cast<float4*>(out + ((long long)b * Tout + u) * Cout + c) = a;
+}
+
+// im2col for Conv1d(k, pad=(k-1)/2) on token-major input: col[b,t, j*Cin + ci] = x[b, t + j - pad, ci] (0 outside).
+// (VocosBackbone.embed, modules.py:1372,1401.)
+__global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int T, int Cin, int K,
+                              int ld_col) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cv = Cin >> 2;
+  const long long total = (long long)B * T * K * cv;
+  if (gid >= total) return;
+  const int c = (int)(gid % cv) * 4;
+  const int j = (int)((gid / cv) % K);
+  const long long tok = gid / ((long long)cv * K);
+  const int t = (int)(tok % T);
+  const int tt = t + j - (K - 1) / 2;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tt >= 0 && tt < T) v = *reinterpret_cast<const float4*>(x + (tok + (tt - t)) * Cin + c);
+  *reinterpret_cast<float4*>(col + tok * ld_col + j * Cin + c) = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ISTFT head (ISTFTHead.forward modules.py:969-988): x = Linear(h) -> (mag, phase); mag = min(exp(mag), 100);
+// S = mag * (cos p + i sin p). Writes [Re_0..Re_{F-1}, Im_0..Im_{F-1}, 0 pad] per frame, which the next GEMM
+// multiplies with the windowed inverse-DFT basis.
+// ------------------------------------------------------------------------------------------------
+__global__ void istft_spec_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ spec, long long lds,
+                                  long long rows, int F) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rows * F) return;
+  const long long r = gid / F;
+  const int k = (int)(gid % F);
+  const float mg = fminf(expf(x[r * ldx + k]), 100.0f);
+  const float ph = x[r * ldx + F + k];
+  spec[r * lds + k] = mg * cosf(ph);
+  spec[r * lds + F + k] = mg * sinf(ph);
+  if (k == 0)
+    for (long long z = 2LL * F; z < lds; ++z) spec[r * lds + z] = 0.f;
+}
+
+// Overlap-add of windowed frames + envelope normalisation + "same" trim (ISTFT.forward modules.py:759-792):
+// frames [B, T, n_fft] already multiplied by the window; out [B, T*hop].
+__global__ void istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ window,
+                                 float* __restrict__ out, int B, int T, int n_fft, int hop) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (long long)T * hop;
+  if (gid >= (long long)B * per) return;
+  const int b = (int)(gid / per);
+  const long long so = gid % per;
+  const int pad = (n_fft - hop) / 2;
+  const long long s = so + pad;  // position in the untrimmed signal
+  int f_hi = (int)(s / hop);
+  if (f_hi > T - 1) f_hi = T - 1;
+  float acc = 0.f, env = 0.f;
+  for (int f = f_hi; f >= 0; --f) {
+    const long long o = s - (long long)f * hop;
+    if (o >= n_fft) break;
+    acc += frames[((long long)b * T + f) * n_fft + o];
+    const float wv = window[o];
+    env = fmaf(wv, wv, env);
+  }
+  out[gid] = acc / env;
+}
+
+// x[r, :] += table[(r % mod), :]   (sinusoid positional embedding add, modules.py:398-402,600-606)
+__global__ void add_rows_mod_kernel(float* __restrict__ x, const float* __restrict__ table, long long rows, int C,
+                                    int mod) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cv = C >> 2;
+  if (gid >= rows * cv) return;
+  const long long r = gid / cv;
+  const int c = (int)(gid % cv) * 4;
+  float4 v = *reinterpret_cast<float4*>(x + r * C + c);
+  const float4 t = *reinterpret_cast<const float4*>(table + (r % mod) * C + c);
+  v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+  *reinterpret_cast<float4*>(x + r * C + c) = v;
+}
+
+}  // namespace
+
+int mtts_configure_codec() {
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(mha_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(4 * kQT * kPitch * sizeof(float))));
+  return MTTS_OK;
+}
+
+extern "C" int mtts_layernorm(const float* x, const float* w, const float* b, float* out, long long rows, int C,
+                              float eps, const int* lengths, int rows_per_item, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(C > 0 && C % 4 == 0, "mtts_layernorm: C must be a multiple of 4");
+  if (rows <= 0) return MTTS_OK;
+  MTTS_REQUIRE(x && w && b && out, "mtts_layernorm: null pointer");
+  MTTS_REQUIRE(lengths == nullptr || rows_per_item > 0, "mtts_layernorm: rows_per_item must be positive with lengths");
+  layernorm_kernel<<<(unsigned)ceil_div_ll(rows, 8), 256, 0, stream>>>(x, w, b, out, rows, C, eps, lengths,
+                                                                      rows_per_item);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_mha_varlen(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads,
+                               int head_dim, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(head_dim == kHD, "mtts_mha_varlen: head_dim must be 64 (got %d)", head_dim);
+  if (B <= 0 || T <= 0) return MTTS_OK;
+  MTTS_REQUIRE(qkv && out, "mtts_mha_varlen: null pointer");
+  dim3 grid(ceil_div(T, kQT), num_heads, B);
+  mha_varlen_kernel<<<grid, 256, 4 * kQT * kPitch * sizeof(float), stream>>>(qkv, out, lengths, T, num_heads,
+                                                                            1.0f / sqrtf((float)head_dim));
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_dwconv7_ln(const float* x, const float* conv_w, const float* conv_b, const float* ln_w,
+                               const float* ln_b, float* out, int B, int T, int C, float eps, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(C % 128 == 0 && C <= 4096, "mtts_dwconv7_ln: C must be a multiple of 128 and <= 4096");
+  if (B <= 0 || T <= 0) return MTTS_OK;
+  MTTS_REQUIRE(x && conv_w && conv_b && ln_w && ln_b && out, "mtts_dwconv7_ln: null pointer");
+  dwconv7_ln_kernel<<<(unsigned)((long long)B * T), C / 4, 0, stream>>>(x, conv_w, conv_b, ln_w, ln_b, out, T, C, eps);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_convt_gather(const float* y, const float* bias, float* out, int B, int Tin, int Cout, int K,
+                                 int stride, int Tout, int gelu, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(Cout % 4 == 0 && K > 0 && stride > 0, "mtts_convt_gather: bad shape");
+  if (B <= 0 || Tout <= 0) return MTTS_OK;
+  MTTS_REQUIRE(y && out, "mtts_convt_gather: null pointer");
+  const long long total = (long long)B * Tout * (Cout / 4);
+  convt_gather_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(y, bias, out, B, Tin, Cout, K, stride, Tout,
+                                                                            gelu);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_im2col(const float* x, float* col, int B, int T, int Cin, int K, int ld_col, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(Cin % 4 == 0 && (K & 1) == 1 && ld_col >= K * Cin && ld_col % 4 == 0, "mtts_im2col: bad shape");
+  if (B <= 0 || T <= 0) return MTTS_OK;
+  MTTS_REQUIRE(x && col, "mtts_im2col: null pointer");
+  const long long total = (long long)B * T * K * (Cin / 4);
+  im2col_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(x, col, B, T, Cin, K, ld_col);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_istft_spec(const float* x, long long ldx, float* spec, long long lds, long long rows, int num_bins,
+                               void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(num_bins > 0 && ldx >= 2 * num_bins && lds >= 2 * num_bins, "mtts_istft_spec: bad shape");
+  if (rows <= 0) return MTTS_OK;
+  MTTS_REQUIRE(x && spec, "mtts_istft_spec: null pointer");
+  istft_spec_kernel<<<(unsigned)ceil_div_ll(rows * num_bins, 256), 256, 0, stream>>>(x, ldx, spec, lds, rows, num_bins);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_istft_ola(const float* frames, const float* window, float* out, int B, int T, int n_fft, int hop,
+                              void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(n_fft > hop && hop > 0 && (n_fft - hop) % 2 == 0, "mtts_istft_ola: bad n_fft/hop");
+  if (B <= 0 || T <= 0) return MTTS_OK;
+  MTTS_REQUIRE(frames && window && out, "mtts_istft_ola: null pointer");
+  const long long total = (long long)B * T * hop;
+  istft_ola_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(frames, window, out, B, T, n_fft, hop);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_add_rows_mod(float* x, const float* table, long long rows, int C, int mod, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(C % 4 == 0 && mod > 0, "mtts_add_rows_mod: bad shape");
+  if (rows <= 0) return MTTS_OK;
+  MTTS_REQUIRE(x && table, "mtts_add_rows_mod: null pointer");
+  add_rows_mod_kernel<<<(unsigned)ceil_div_ll(rows * (C / 4), 256), 256, 0, stream>>>(x, table, rows, C, mod);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}

@@ -8,3 +8,4 @@ int mtts_gemm_tc_pick_bn(int M);
 int mtts_configure_gemm_tc();
 int mtts_configure_attention();
 int mtts_configure_rvq();
+int mtts_configure_codec();

@@ -65,6 +65,10 @@ __device__ __forceinline__ float score_at(const ScoreCtx& c, int j) {
 }
 
 __device__ __forceinline__ bool better(float v, int i, float ov, int oi) { return v > ov || (v == ov && i < oi); }
+// Candidate order for top-p: descending value, and among EQUAL values descending index. bf16 logits tie often; HF
+// sorts ascending (stable), so within a tie group the lower index has the smaller cumulative mass and is removed
+// first — i.e. in descending order the higher index must come first.
+__device__ __forceinline__ bool sorts_before(float v, int i, float ov, int oi) { return v > ov || (v == ov && i > oi); }
 
 // bitonic sort of (val, idx) in shared memory, descending by val then ascending idx; n is a power of two
 __device__ void bitonic_sort_desc(float* val, int* idx, int n) {
@@ -74,7 +78,7 @@ __device__ void bitonic_sort_desc(float* val, int* idx, int n) {
         const int x = t ^ j;
         if (x > t) {
           const bool up = (t & k) == 0;  // "up" = this run sorted in our target (descending) order
-          const bool t_first = better(val[t], idx[t], val[x], idx[x]);
+          const bool t_first = sorts_before(val[t], idx[t], val[x], idx[x]);
           if (up ? !t_first : t_first) {
             const float tv = val[t]; val[t] = val[x]; val[x] = tv;
             const int ti = idx[t]; idx[t] = idx[x]; idx[x] = ti;
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(kThreads) sample8_kernel(const SampleParams p)
   }
   int npad = 1;
   while (npad < n) npad <<= 1;
-  for (int t = n + tid; t < npad; t += kThreads) { s_val[t] = -INFINITY; s_idx[t] = 0x7fffffff; }
+  for (int t = n + tid; t < npad; t += kThreads) { s_val[t] = -INFINITY; s_idx[t] = -1; }
   __syncthreads();
   bitonic_sort_desc(s_val, s_idx, npad);
 

@@ -1,0 +1,374 @@
+"""Drop-in mirror of the reference codec class `XY_Tokenizer` (XY_Tokenizer/xy_tokenizer/model.py) for the
+generation hot path: `decode` / `inference_detokenize` (model.py:103-128,194-256) and the ResidualVQ
+(`quantizer.forward`, `quantizer.decode_codes`, nn/quantizer.py:244-364) run on libmtts CUDA kernels.
+
+Same constructor (`generator_params` dict from xy_tokenizer_config.yaml), same attributes
+(input_sample_rate, output_sample_rate, encoder_downsample_rate, decoder_upsample_rate, nq), same
+`load_from_checkpoint(config_path, ckpt_path)` and state-dict key names (incl. old-style weight_norm
+`weight_g` / `weight_v` of quantizer.input_proj / output_proj).
+
+HBM layout: every activation is token-major [batch*frames, channels] fp32; ConvTranspose1d / Conv1d weights are
+re-packed once at load time so that each of them is one mtts_gemm (TF32 tensor cores, fp32 accumulate).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import yaml
+
+from .. import _lib, ops
+from .._lib import check, ptr, stream_ptr
+
+
+def sinusoids(length, channels, max_timescale=10000):
+    """Positional table exactly as the reference builds it (modules.py:25-31; numpy log, torch exp/sin/cos on host)."""
+    import numpy as np
+    assert channels % 2 == 0
+    log_timescale_increment = np.log(max_timescale) / (channels // 2 - 1)
+    inv_timescales = torch.exp(-log_timescale_increment * torch.arange(channels // 2))
+    scaled_time = torch.arange(length)[:, np.newaxis] * inv_timescales[np.newaxis, :]
+    return torch.cat([torch.sin(scaled_time), torch.cos(scaled_time)], dim=1)
+
+
+def _wn(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """torch.nn.utils.weight_norm (dim=0) weight: g * v / ||v|| (the reference recomputes this every forward)."""
+    n = v.float().reshape(v.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1)))
+    return v.float() * (g.float() / n)
+
+
+class _TransformerStack:
+    """Weights of `n` OmniWhisperTransformerLayer (modules.py:163-205) in GEMM layout."""
+
+    def __init__(self, sd, prefix, n_layers, dev):
+        f = lambda k: sd[prefix + k].to(dev, torch.float32).contiguous()
+        self.layers = []
+        for l in range(n_layers):
+            p = f"layers.{l}."
+            qw, kw, vw = f(p + "self_attn.q_proj.weight"), f(p + "self_attn.k_proj.weight"), f(p + "self_attn.v_proj.weight")
+            qb, vb = f(p + "self_attn.q_proj.bias"), f(p + "self_attn.v_proj.bias")
+            self.layers.append(dict(
+                ln1_w=f(p + "self_attn_layer_norm.weight"), ln1_b=f(p + "self_attn_layer_norm.bias"),
+                wqkv=torch.cat([qw, kw, vw], 0).contiguous(), bqkv=torch.cat([qb, torch.zeros_like(qb), vb]).contiguous(),
+                wo=f(p + "self_attn.out_proj.weight"), bo=f(p + "self_attn.out_proj.bias"),
+                ln2_w=f(p + "final_layer_norm.weight"), ln2_b=f(p + "final_layer_norm.bias"),
+                fc1_w=f(p + "fc1.weight"), fc1_b=f(p + "fc1.bias"), fc2_w=f(p + "fc2.weight"), fc2_b=f(p + "fc2.bias")))
+        self.ln_w, self.ln_b = f("layer_norm.weight"), f("layer_norm.bias")
+
+
+class ResidualVQ:
+    """Inference-side mirror of nn/quantizer.py ResidualVQ: `forward(z, input_length, n_quantizers=None)` returns the
+    reference's 5-tuple (commit losses are zeros: training-only bookkeeping), `decode_codes(codes)`."""
+
+    def __init__(self, input_dim, rvq_dim, output_dim, num_quantizers, codebook_size, codebook_dim, **_):
+        assert rvq_dim == codebook_dim, "in/out_project of VectorQuantize are Identity in the shipped config"
+        self.input_dim, self.rvq_dim, self.output_dim = input_dim, rvq_dim, output_dim
+        self.num_quantizers, self.codebook_size = num_quantizers, codebook_size
+        self.codebooks = None
+
+    def load(self, sd: Dict[str, torch.Tensor], prefix: str, dev):
+        f = lambda k: sd[prefix + k].to(dev, torch.float32)
+        self.codebooks = torch.stack([f(f"quantizers.{i}.codebook") for i in range(self.num_quantizers)]).contiguous()
+        self.norms = ops.rvq_codebook_norms(self.codebooks)
+        if self.input_dim != self.rvq_dim:
+            self.in_w = _wn(f("input_proj.weight_v"), f("input_proj.weight_g"))[:, :, 0].contiguous()
+            self.in_b = f("input_proj.bias").contiguous()
+        else:
+            self.in_w = None
+        if self.rvq_dim != self.output_dim:
+            self.out_w = _wn(f("output_proj.weight_v"), f("output_proj.weight_g"))[:, :, 0].contiguous()
+            self.out_b = f("output_proj.bias").contiguous()
+        else:
+            self.out_w = None
+        self.dev = dev
+
+    def decode_tokens(self, codes: torch.Tensor) -> torch.Tensor:
+        """codes (nq, B, T) -> token-major (B*T, output_dim) fp32."""
+        nq, B, T = codes.shape
+        flat = codes.reshape(nq, B * T).contiguous()
+        err = torch.zeros(1, dtype=torch.int32, device=codes.device)
+        emb = ops.rvq_decode(flat, self.codebooks, err_flag=err)
+        if self.out_w is not None:
+            emb = ops.gemm(emb, self.out_w, bias=self.out_b)
+        self._err = err
+        return emb
+
+    def decode_codes(self, codes: torch.Tensor) -> torch.Tensor:
+        """(nq, B, T) int64 -> (B, D, T) fp32, as the reference returns it."""
+        nq, B, T = codes.shape
+        out = self.decode_tokens(codes.to(self.dev))
+        if int(self._err.item()):
+            raise IndexError("code index out of range in decode_codes")
+        return out.view(B, T, -1).permute(0, 2, 1)
+
+    def forward(self, z: torch.Tensor, input_length: torch.Tensor, n_quantizers: Optional[int] = None):
+        """z (B, input_dim, T) fp32 channel-major, input_length (B,). Returns (quantized_out (B, output_dim, T),
+        all_indices (nq, B, T) int64, all_commit_losses (nq,), all_quantized (nq, B, D, T) — not materialised, None —,
+        output_length)."""
+        z = z.to(self.dev, torch.float32)
+        B, Cin, T = z.shape
+        nq = n_quantizers or self.num_quantizers
+        if self.in_w is not None:
+            # exact-fp32 projection read in place from the channel-major tensor: a TF32 product here would move codes
+            zt = ops.gemm_simt(z, self.in_w, bias=self.in_b, x_layout=(T, z.stride(0), z.stride(2), z.stride(1)), M=B * T)
+        else:
+            zt = z.permute(0, 2, 1).reshape(B * T, Cin).contiguous()
+        lengths = input_length.to(self.dev)
+        valid = (torch.arange(T, device=self.dev)[None, :] < lengths[:, None]).reshape(-1).contiguous()
+        codes, zq, _ = ops.rvq_encode(zt, self.codebooks[:nq].contiguous(), self.norms[:nq].contiguous(), valid=valid)
+        if self.out_w is not None:
+            zq = ops.gemm(zq, self.out_w, bias=self.out_b)
+        quantized_out = zq.view(B, T, -1).permute(0, 2, 1)
+        return (quantized_out, codes.view(nq, B, T), torch.zeros(nq, device=self.dev), None, input_length)
+
+    __call__ = forward
+
+
+class XY_Tokenizer:
+    def __init__(self, generator_params: dict):
+        gp = generator_params
+        self.params = gp
+        self.input_sample_rate = gp["input_sample_rate"]
+        self.output_sample_rate = gp["output_sample_rate"]
+        self.encoder_downsample_rate = 1280
+        self.decoder_upsample_rate = 1920
+        self.code_dim = gp["quantizer_kwargs"]["input_dim"]
+        self.nq = gp["quantizer_kwargs"]["num_quantizers"]
+        self.quantizer = ResidualVQ(**gp["quantizer_kwargs"])
+        self.device = None
+        self._sd = None
+        self._ready = False
+        self.training = False
+
+    # ------------------------------------------------------------------ loading
+    @classmethod
+    def load_from_checkpoint(cls, config_path: str, ckpt_path: str):
+        with open(config_path, "r") as f:
+            config = yaml.safe_load(f)
+        model = cls(config["generator_params"])
+        checkpoint = torch.load(ckpt_path, map_location="cpu")
+        model.load_state_dict(checkpoint["generator"] if "generator" in checkpoint else checkpoint)
+        return model
+
+    def load_state_dict(self, sd, strict=True):
+        self._sd = {k: (v if isinstance(v, torch.Tensor) else torch.as_tensor(v)) for k, v in sd.items()}
+        self._ready = False
+        if self.device is not None:
+            self._prepare()
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("XY_Tokenizer (B200 path) runs on CUDA only; there is no CPU path")
+        self.device = device
+        if self._sd is not None:
+            self._prepare()
+        return self
+
+    def cuda(self):
+        return self.to(torch.device("cuda", torch.cuda.current_device()))
+
+    def eval(self):
+        return self
+
+    def _prepare(self):
+        sd, dev, gp = self._sd, self.device, self.params
+        f = lambda k: sd[k].to(dev, torch.float32).contiguous()
+        self.quantizer.load(sd, "quantizer.", dev)
+        # post-RVQ adapter (Transformer, modules.py:519-640)
+        pk = gp["post_rvq_adapter_kwargs"]
+        self.pr_in_w, self.pr_in_b = f("post_rvq_adapter.proj.weight"), f("post_rvq_adapter.proj.bias")
+        self.pr_out_w, self.pr_out_b = f("post_rvq_adapter.out_proj.weight"), f("post_rvq_adapter.out_proj.bias")
+        self.pr_stack = _TransformerStack(sd, "post_rvq_adapter.", pk["encoder_layers"], dev)
+        self.pr_heads = pk["encoder_attention_heads"]
+        self.pr_pos = sinusoids(pk["max_source_positions"], pk["d_model"]).to(dev, torch.float32).contiguous()
+        # UpConv (modules.py:480-515): ConvTranspose1d(k = stride) == GEMM; rows ordered (tap, out_channel)
+        w = f("upsample.up_conv.weight")  # [Cin, Cout, k]
+        self.up_stride = gp["upsample_kwargs"]["stride"]
+        self.up_w = w.permute(2, 1, 0).reshape(-1, w.shape[0]).contiguous()
+        # acoustic decoder (modules.py:329-423)
+        ak = gp["acoustic_decoder_kwargs"]
+        self.ad_stack = _TransformerStack(sd, "acoustic_decoder.", ak["decoder_layers"], dev)
+        self.ad_heads = ak["decoder_attention_heads"]
+        max_pos = (ak["max_audio_seconds"] * ak["sampling_rate"] // ak["hop_length"]) // ak["stride_size"]
+        self.ad_pos = sinusoids(max_pos, ak["d_model"]).to(dev, torch.float32).contiguous()
+        w1, w2 = f("acoustic_decoder.deconv1.weight"), f("acoustic_decoder.deconv2.weight")
+        self.dc1_w = w1.permute(2, 1, 0).reshape(-1, w1.shape[0]).contiguous()
+        self.dc1_b = f("acoustic_decoder.deconv1.bias")
+        self.dc2_w = w2.permute(2, 1, 0).reshape(-1, w2.shape[0]).contiguous()
+        self.dc2_b = f("acoustic_decoder.deconv2.bias")
+        self.dc_k, self.dc1_stride, self.mel_bins = ak["kernel_size"], ak["stride_size"], ak["num_mel_bins"]
+        # Vocos (modules.py:1347-1479)
+        vk = gp["vocos_kwargs"]
+        we = f("enhanced_vocos.backbone.embed.weight")  # [dim, Cin, 7]
+        self.v_k = we.shape[2]
+        self.v_embed_ld = (self.v_k * we.shape[1] + 3) // 4 * 4
+        wcol = torch.zeros((we.shape[0], self.v_embed_ld), dtype=torch.float32, device=dev)
+        wcol[:, :self.v_k * we.shape[1]] = we.permute(0, 2, 1).reshape(we.shape[0], -1)
+        self.v_embed_w, self.v_embed_b = wcol, f("enhanced_vocos.backbone.embed.bias")
+        self.v_norm_w, self.v_norm_b = f("enhanced_vocos.backbone.norm.weight"), f("enhanced_vocos.backbone.norm.bias")
+        self.v_blocks = []
+        for i in range(vk["num_layers"]):
+            p = f"enhanced_vocos.backbone.convnext.{i}."
+            self.v_blocks.append(dict(dw_w=f(p + "dwconv.weight").reshape(-1, self.v_k).contiguous(), dw_b=f(p + "dwconv.bias"),
+                                      ln_w=f(p + "norm.weight"), ln_b=f(p + "norm.bias"),
+                                      pw1_w=f(p + "pwconv1.weight"), pw1_b=f(p + "pwconv1.bias"),
+                                      pw2_w=f(p + "pwconv2.weight"), pw2_b=f(p + "pwconv2.bias"), gamma=f(p + "gamma")))
+        self.v_fln_w = f("enhanced_vocos.backbone.final_layer_norm.weight")
+        self.v_fln_b = f("enhanced_vocos.backbone.final_layer_norm.bias")
+        self.v_dim = vk["dim"]
+        self.n_fft, self.hop = vk["n_fft"], vk["hop_size"]
+        F = self.n_fft // 2 + 1
+        self.head_ld = (2 * F + 3) // 4 * 4
+        self.head_w, self.head_b = f("enhanced_vocos.head.out.weight"), f("enhanced_vocos.head.out.bias")
+        self.window = torch.hann_window(self.n_fft).to(dev, torch.float32).contiguous()
+        # windowed inverse real DFT as a [n_fft, 2F(+pad)] matrix (irfft(n=n_fft, norm="backward") x hann, modules.py:765-766)
+        n = torch.arange(self.n_fft, dtype=torch.float64)[:, None]
+        k = torch.arange(F, dtype=torch.float64)[None, :]
+        ck = torch.full((1, F), 2.0, dtype=torch.float64)
+        ck[0, 0] = 1.0
+        if self.n_fft % 2 == 0:
+            ck[0, -1] = 1.0
+        ang = 2.0 * math.pi * n * k / self.n_fft
+        win = torch.hann_window(self.n_fft, dtype=torch.float64)[:, None]
+        basis = torch.zeros((self.n_fft, self.head_ld), dtype=torch.float64)
+        basis[:, :F] = win * ck * torch.cos(ang) / self.n_fft
+        basis[:, F:2 * F] = -win * ck * torch.sin(ang) / self.n_fft
+        self.basis = basis.to(dev, torch.float32).contiguous()
+        ops.ensure_init()
+        self.L = _lib.load()
+        self._ready = True
+
+    # ------------------------------------------------------------------ kernels
+    def _ln(self, x, w, b, eps=1e-5, lengths=None, rows_per_item=0, out=None):
+        out = torch.empty_like(x) if out is None else out
+        check(self.L.mtts_layernorm(ptr(x), ptr(w), ptr(b), ptr(out), x.shape[0], x.shape[1], eps, ptr(lengths),
+                                    rows_per_item, stream_ptr()))
+        return out
+
+    def _stack(self, h, st: _TransformerStack, heads, lengths, B, T):
+        E = h.shape[1]
+        for lw in st.layers:
+            xn = self._ln(h, lw["ln1_w"], lw["ln1_b"])
+            qkv = ops.gemm(xn, lw["wqkv"], bias=lw["bqkv"])
+            ao = torch.empty((B * T, E), dtype=torch.float32, device=h.device)
+            check(self.L.mtts_mha_varlen(ptr(qkv), ptr(ao), ptr(lengths), B, T, heads, E // heads, stream_ptr()))
+            ops.gemm(ao, lw["wo"], bias=lw["bo"], residual=h, out=h)
+            xn = self._ln(h, lw["ln2_w"], lw["ln2_b"], out=xn)
+            ff = ops.gemm(xn, lw["fc1_w"], bias=lw["fc1_b"], gelu=True)
+            ops.gemm(ff, lw["fc2_w"], bias=lw["fc2_b"], residual=h, out=h)
+        return self._ln(h, st.ln_w, st.ln_b, lengths=lengths, rows_per_item=T)  # + zero rows beyond each length
+
+    @torch.no_grad()
+    def detokenize_tokens(self, codes: torch.Tensor, codes_lengths: torch.Tensor):
+        """codes (nq, B, T) int64 on device, lengths (B,) -> waveform (B, T*1920) fp32."""
+        if not self._ready:
+            raise RuntimeError("XY_Tokenizer: weights not loaded / not moved to CUDA")
+        nq, B, T = codes.shape
+        dev = self.device
+        L = self.L
+        len1 = codes_lengths.to(dev, torch.int32).contiguous()
+        z = self.quantizer.decode_tokens(codes)                                 # (B*T, 3072)
+        # post-RVQ adapter
+        h = ops.gemm(z, self.pr_in_w, bias=self.pr_in_b)                        # (B*T, 768)
+        check(L.mtts_add_rows_mod(ptr(h), ptr(self.pr_pos), B * T, h.shape[1], T, stream_ptr()))
+        h = self._stack(h, self.pr_stack, self.pr_heads, len1, B, T)
+        z = ops.gemm(h, self.pr_out_w, bias=self.pr_out_b)                      # (B*T, 3072)
+        # upsample x4 (tap-major rows -> a plain reshape gives (B*4T, 768))
+        s = self.up_stride
+        h = ops.gemm(z, self.up_w).view(B * T * s, -1)
+        T2 = T * s
+        len2 = (len1 * s).contiguous()
+        check(L.mtts_add_rows_mod(ptr(h), ptr(self.ad_pos), B * T2, h.shape[1], T2, stream_ptr()))
+        h = self._stack(h, self.ad_stack, self.ad_heads, len2, B, T2)
+        # deconv1 (k3 s2) + GELU, deconv2 (k3 s1) + GELU, trim to 2*T2
+        K, st = self.dc_k, self.dc1_stride
+        T3 = (T2 - 1) * st + K
+        y = ops.gemm(h, self.dc1_w)                                             # (B*T2, K*768)
+        h3 = torch.empty((B * T3, self.dc1_b.numel()), dtype=torch.float32, device=dev)
+        check(L.mtts_convt_gather(ptr(y), ptr(self.dc1_b), ptr(h3), B, T2, self.dc1_b.numel(), K, st, T3, 1, stream_ptr()))
+        y = ops.gemm(h3, self.dc2_w)                                            # (B*T3, K*80)
+        T4 = min(T3 + K - 1, T2 * st)
+        mel = torch.empty((B * T4, self.mel_bins), dtype=torch.float32, device=dev)
+        check(L.mtts_convt_gather(ptr(y), ptr(self.dc2_b), ptr(mel), B, T3, self.mel_bins, K, 1, T4, 1, stream_ptr()))
+        # Vocos backbone
+        col = torch.empty((B * T4, self.v_embed_ld), dtype=torch.float32, device=dev)
+        if self.v_embed_ld != self.v_k * self.mel_bins:
+            col.zero_()
+        check(L.mtts_im2col(ptr(mel), ptr(col), B, T4, self.mel_bins, self.v_k, self.v_embed_ld, stream_ptr()))
+        x = ops.gemm(col, self.v_embed_w, bias=self.v_embed_b)                  # (B*T4, 512)
+        x = self._ln(x, self.v_norm_w, self.v_norm_b, eps=1e-6)
+        t = torch.empty_like(x)
+        for bl in self.v_blocks:
+            check(L.mtts_dwconv7_ln(ptr(x), ptr(bl["dw_w"]), ptr(bl["dw_b"]), ptr(bl["ln_w"]), ptr(bl["ln_b"]), ptr(t), B, T4,
+                                    self.v_dim, 1e-6, stream_ptr()))
+            ff = ops.gemm(t, bl["pw1_w"], bias=bl["pw1_b"], gelu=True)
+            ops.gemm(ff, bl["pw2_w"], bias=bl["pw2_b"], gamma=bl["gamma"], residual=x, out=x)
+        x = self._ln(x, self.v_fln_w, self.v_fln_b, eps=1e-6)
+        # ISTFT head
+        F = self.n_fft // 2 + 1
+        hx = ops.gemm(x, self.head_w, bias=self.head_b)                         # (B*T4, 2F)
+        spec = torch.empty((B * T4, self.head_ld), dtype=torch.float32, device=dev)
+        check(L.mtts_istft_spec(ptr(hx), hx.stride(0), ptr(spec), self.head_ld, B * T4, F, stream_ptr()))
+        frames = ops.gemm(spec, self.basis)                                     # (B*T4, n_fft), already windowed
+        wav = torch.empty((B, T4 * self.hop), dtype=torch.float32, device=dev)
+        check(L.mtts_istft_ola(ptr(frames), ptr(self.window), ptr(wav), B, T4, self.n_fft, self.hop, stream_ptr()))
+        return wav
+
+    # ------------------------------------------------------------------ reference API
+    @torch.inference_mode()
+    def inference_detokenize(self, codes, codes_lengths):
+        wav = self.detokenize_tokens(codes.to(self.device), codes_lengths)
+        up = self.decoder_upsample_rate
+        return {"y": wav[:, None, :], "output_length": codes_lengths.to(self.device) * up}
+
+    @torch.inference_mode()
+    def decode(self, codes_list, overlap_seconds=10, device=None):
+        """B x (nq, T) int64 -> {"syn_wav_list": B x (T*1920,) fp32}; 30 s windows, (30 - overlap) s hop
+        (model.py:194-256). Chunk bookkeeping is done on the host from the known lengths (no device syncs)."""
+        device = torch.device(device) if device is not None else self.device
+        if device.type != "cuda":
+            raise RuntimeError("XY_Tokenizer.decode runs on CUDA only (no CPU path)")
+        duration_seconds = 30 - overlap_seconds
+        chunk_code_length = int(30 * self.input_sample_rate // self.encoder_downsample_rate)
+        duration_code_length = int(duration_seconds * self.input_sample_rate // self.encoder_downsample_rate)
+        duration_wav_length = duration_code_length * self.decoder_upsample_rate
+        batch_size = len(codes_list)
+        lens = [int(c.shape[-1]) for c in codes_list]
+        max_code_length = max(lens) if lens else 0
+        codes_tensor = torch.zeros(self.nq, batch_size, max_code_length, device=device, dtype=torch.long)
+        for i, c in enumerate(codes_list):
+            codes_tensor[:, i, :c.shape[-1]] = c.to(device)
+        max_chunks = (max_code_length + duration_code_length - 1) // duration_code_length if duration_code_length > 0 else 0
+        wav_chunks = []
+        for chunk_idx in range(max_chunks):
+            start = chunk_idx * duration_code_length
+            end = min(start + chunk_code_length, max_code_length)
+            chunk_lens = [min(max(l - start, 0), end - start) for l in lens]
+            if max(chunk_lens) == 0:
+                continue
+            wav = self.detokenize_tokens(codes_tensor[:, :, start:end].contiguous(),
+                                         torch.tensor(chunk_lens, dtype=torch.int32, device=device))
+            valid = torch.zeros(batch_size, 1, duration_wav_length, device=device)
+            for b in range(batch_size):
+                n = min(chunk_lens[b] * self.decoder_upsample_rate, duration_wav_length)
+                if n > 0:
+                    valid[b, 0, :n] = wav[b, :n]
+            wav_chunks.append(valid)
+        if wav_chunks:
+            wav_tensor = torch.cat(wav_chunks, dim=-1)
+            syn = [wav_tensor[i, 0, :lens[i] * self.decoder_upsample_rate] for i in range(batch_size)]
+        else:
+            syn = [torch.zeros(0, device=device) for _ in range(batch_size)]
+        return {"syn_wav_list": syn}
+
+    @torch.inference_mode()
+    def encode(self, wav_list, overlap_seconds=10, device=None):
+        raise NotImplementedError(
+            "XY_Tokenizer.encode: the mel / encoder front-end (SURVEY.md §8f #1) is the next tier; the ResidualVQ part "
+            "of encode is available as `self.quantizer(z, lengths)` on the down-sampled features")
+
+    def inference_tokenize(self, x, input_lengths):
+        raise NotImplementedError("see XY_Tokenizer.encode")

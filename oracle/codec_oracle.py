@@ -1,0 +1,149 @@
+"""Oracle (TEST INFRASTRUCTURE, never shipped): CPU restatement in plain torch of the XY_Tokenizer decode path.
+
+Follows /root/reference/XY_Tokenizer/xy_tokenizer:
+  decode / chunking          <- model.py:194-256
+  inference_detokenize       <- model.py:103-128
+  quantizer.decode_codes     <- nn/quantizer.py:345-364 (+ old-style weight_norm output_proj :224-225)
+  transformer stack          <- nn/modules.py:58-205 (VarLenAttention + OmniWhisperTransformerLayer), :519-640 (Transformer)
+  UpConv, OmniAudioDecoder   <- nn/modules.py:480-515, 329-423
+  Vocos / ConvNeXt / ISTFT   <- nn/modules.py:1096-1154, 1347-1410, 1451-1479, 939-988, 709-792
+Parity status: PINNED against the reference's own `decode` outputs (tests/golden/codec_*.npz from
+oracle/gen_golden_codec.py), checked in tests/test_oracle_pin.py.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from oracle.codec_weights import weight_norm_weight
+
+
+def sinusoids(length, channels, max_timescale=10000):
+    log_timescale_increment = np.log(max_timescale) / (channels // 2 - 1)
+    inv_timescales = torch.exp(-log_timescale_increment * torch.arange(channels // 2))
+    scaled_time = torch.arange(length)[:, np.newaxis] * inv_timescales[np.newaxis, :]
+    return torch.cat([torch.sin(scaled_time), torch.cos(scaled_time)], dim=1)
+
+
+class CodecOracle:
+    def __init__(self, gp: dict, sd_np: dict):
+        self.gp = gp
+        self.sd = {k: torch.from_numpy(np.asarray(v)).float() for k, v in sd_np.items()}
+        self.nq = gp["quantizer_kwargs"]["num_quantizers"]
+
+    # -------------------------------------------------------------- pieces
+    def _attn_mask(self, seq_len, max_len):
+        valid = torch.arange(max_len)[None, :] < seq_len[:, None]
+        m = (valid[:, None, :, None] & valid[:, None, None, :]).float()
+        return m + (1.0 - m) * torch.finfo(torch.float32).min
+
+    def _layer(self, h, p, heads, seq_len):
+        sd = self.sd
+        B, T, E = h.shape
+        hd = E // heads
+        res = h
+        x = F.layer_norm(h, (E,), sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"])
+        q = F.linear(x, sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.q_proj.bias"]) * (hd ** -0.5)
+        k = F.linear(x, sd[p + "self_attn.k_proj.weight"])
+        v = F.linear(x, sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"])
+        q, k, v = (t.view(B, T, heads, hd).transpose(1, 2) for t in (q, k, v))
+        s = torch.matmul(q, k.transpose(-1, -2)) + self._attn_mask(seq_len, T)
+        a = torch.matmul(F.softmax(s, dim=-1), v).transpose(1, 2).contiguous().view(B, T, E)
+        h = res + F.linear(a, sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"])
+        res = h
+        x = F.layer_norm(h, (E,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"])
+        x = F.linear(F.gelu(F.linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"])), sd[p + "fc2.weight"], sd[p + "fc2.bias"])
+        return res + x
+
+    def _stack(self, h, prefix, n_layers, heads, seq_len, pos):
+        B, T, E = h.shape
+        h = h + (pos[:T] if T < pos.shape[0] else pos)
+        for l in range(n_layers):
+            h = self._layer(h, f"{prefix}layers.{l}.", heads, seq_len)
+        h = F.layer_norm(h, (E,), self.sd[prefix + "layer_norm.weight"], self.sd[prefix + "layer_norm.bias"])
+        mask = (torch.arange(T)[None, :] < seq_len[:, None])[..., None]
+        return torch.where(mask, h, torch.zeros((), dtype=h.dtype))
+
+    def decode_codes(self, codes):
+        sd = self.sd
+        nq, B, T = codes.shape
+        emb = torch.zeros(B, T, sd["quantizer.quantizers.0.codebook"].shape[1])
+        for i in range(nq):
+            emb += F.embedding(codes[i], sd[f"quantizer.quantizers.{i}.codebook"])
+        w = torch.from_numpy(weight_norm_weight(sd["quantizer.output_proj.weight_v"].numpy(), sd["quantizer.output_proj.weight_g"].numpy()))
+        return F.linear(emb, w[:, :, 0], sd["quantizer.output_proj.bias"])  # (B, T, 3072) token-major
+
+    def detokenize(self, codes, lengths):
+        gp, sd = self.gp, self.sd
+        pk, ak, vk = gp["post_rvq_adapter_kwargs"], gp["acoustic_decoder_kwargs"], gp["vocos_kwargs"]
+        lengths = lengths.long()
+        z = self.decode_codes(codes)
+        h = F.linear(z, sd["post_rvq_adapter.proj.weight"], sd["post_rvq_adapter.proj.bias"])
+        h = self._stack(h, "post_rvq_adapter.", pk["encoder_layers"], pk["encoder_attention_heads"], lengths,
+                        sinusoids(pk["max_source_positions"], pk["d_model"]))
+        z = F.linear(h, sd["post_rvq_adapter.out_proj.weight"], sd["post_rvq_adapter.out_proj.bias"])
+        s = gp["upsample_kwargs"]["stride"]
+        u = F.conv_transpose1d(z.transpose(1, 2), sd["upsample.up_conv.weight"], stride=s)       # (B, 768, 4T)
+        max_pos = (ak["max_audio_seconds"] * ak["sampling_rate"] // ak["hop_length"]) // ak["stride_size"]
+        h = self._stack(u.transpose(1, 2), "acoustic_decoder.", ak["decoder_layers"], ak["decoder_attention_heads"],
+                        lengths * s, sinusoids(max_pos, ak["d_model"]))
+        tgt = h.shape[1]
+        x = F.gelu(F.conv_transpose1d(h.permute(0, 2, 1), sd["acoustic_decoder.deconv1.weight"], sd["acoustic_decoder.deconv1.bias"],
+                                      stride=ak["stride_size"]))
+        x = F.gelu(F.conv_transpose1d(x, sd["acoustic_decoder.deconv2.weight"], sd["acoustic_decoder.deconv2.bias"], stride=1))
+        x = x[:, :, :tgt * ak["stride_size"]]
+        # Vocos
+        p = "enhanced_vocos.backbone."
+        dim = vk["dim"]
+        x = F.conv1d(x, sd[p + "embed.weight"], sd[p + "embed.bias"], padding=3)
+        x = F.layer_norm(x.transpose(1, 2), (dim,), sd[p + "norm.weight"], sd[p + "norm.bias"], eps=1e-6).transpose(1, 2)
+        for i in range(vk["num_layers"]):
+            q = f"{p}convnext.{i}."
+            r = x
+            y = F.conv1d(x, sd[q + "dwconv.weight"], sd[q + "dwconv.bias"], padding=3, groups=dim).transpose(1, 2)
+            y = F.layer_norm(y, (dim,), sd[q + "norm.weight"], sd[q + "norm.bias"], eps=1e-6)
+            y = F.linear(F.gelu(F.linear(y, sd[q + "pwconv1.weight"], sd[q + "pwconv1.bias"])), sd[q + "pwconv2.weight"], sd[q + "pwconv2.bias"])
+            x = r + (sd[q + "gamma"] * y).transpose(1, 2)
+        x = F.layer_norm(x.transpose(1, 2), (dim,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], eps=1e-6)
+        # ISTFT head
+        n_fft, hop = vk["n_fft"], vk["hop_size"]
+        o = F.linear(x, sd["enhanced_vocos.head.out.weight"], sd["enhanced_vocos.head.out.bias"]).transpose(1, 2)
+        mag, ph = o.chunk(2, dim=1)
+        mag = torch.clip(torch.exp(mag), max=1e2)
+        S = mag * (torch.cos(ph) + 1j * torch.sin(ph))
+        win = torch.hann_window(n_fft)
+        pad = (n_fft - hop) // 2
+        Bn, N, T = S.shape
+        ifft = torch.fft.irfft(S, n_fft, dim=1, norm="backward") * win[None, :, None]
+        out_size = (T - 1) * hop + n_fft
+        y = F.fold(ifft, output_size=(1, out_size), kernel_size=(1, n_fft), stride=(1, hop))[:, 0, 0, pad:-pad]
+        env = F.fold(win.square().expand(1, T, -1).transpose(1, 2), output_size=(1, out_size), kernel_size=(1, n_fft),
+                     stride=(1, hop)).squeeze()[pad:-pad]
+        return y / env
+
+    def decode(self, codes_list, overlap_seconds=10):
+        in_sr, down, up = self.gp["input_sample_rate"], 1280, 1920
+        chunk_len = int(30 * in_sr // down)
+        dur_len = int((30 - overlap_seconds) * in_sr // down)
+        dur_wav = dur_len * up
+        B = len(codes_list)
+        lens = torch.tensor([c.shape[-1] for c in codes_list])
+        Tm = int(lens.max())
+        codes = torch.zeros(self.nq, B, Tm, dtype=torch.long)
+        for i, c in enumerate(codes_list):
+            codes[:, i, :c.shape[-1]] = c
+        chunks = []
+        for ci in range((Tm + dur_len - 1) // dur_len):
+            start = ci * dur_len
+            end = min(start + chunk_len, Tm)
+            cl = torch.clamp(lens - start, 0, end - start)
+            if cl.max() == 0:
+                continue
+            wav = self.detokenize(codes[:, :, start:end], cl)
+            valid = torch.zeros(B, dur_wav)
+            for b in range(B):
+                n = min(int(cl[b]) * up, dur_wav)
+                if n > 0:
+                    valid[b, :n] = wav[b, :n]
+            chunks.append(valid)
+        full = torch.cat(chunks, -1)
+        return [full[i, :int(lens[i]) * up] for i in range(B)]

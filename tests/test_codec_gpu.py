@@ -1,0 +1,182 @@
+"""CUDA codec-decode path vs goldens from the reference XY_Tokenizer.decode and vs the pinned CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests.common import gold
+
+pytestmark = pytest.mark.gpu
+
+# Stated waveform tolerance (north_star "within a stated SNR"): the dense layers run as TF32 tensor-core GEMMs
+# (10-bit mantissa operands, fp32 accumulate); everything else is fp32.
+SNR_DB = 30.0
+
+
+def snr_db(ref, got):
+    ref, got = np.asarray(ref, np.float64), np.asarray(got, np.float64)
+    return 10 * np.log10((ref ** 2).sum() / max(((ref - got) ** 2).sum(), 1e-30))
+
+
+def _spt(gp, seed):
+    from moss_ttsd_b200.xy_tokenizer.model import XY_Tokenizer
+    from oracle.codec_weights import make_codec_weights
+    spt = XY_Tokenizer(gp)
+    spt.load_state_dict({k: torch.from_numpy(v) for k, v in make_codec_weights(gp, seed).items()})
+    return spt.to("cuda")
+
+
+@pytest.mark.parametrize("name,lens", [("tiny", [30, 11]), ("tiny_long", [400, 120])])
+def test_decode_matches_reference_golden(name, lens):
+    from oracle.codec_weights import TINY_CODEC
+    g = gold("codec_decode.npz")
+    spt = _spt(TINY_CODEC, int(g[f"{name}_seed"]))
+    codes = [torch.from_numpy(g[f"{name}_codes{i}"].astype(np.int64)).cuda() for i in range(len(lens))]
+    wavs = spt.decode(codes, overlap_seconds=10)["syn_wav_list"]
+    for i, n in enumerate(lens):
+        w = wavs[i].cpu().numpy()
+        assert w.shape == (n * 1920,) and w.dtype == np.float32
+        ref = g[f"{name}_wav{i}"]
+        if name == "tiny_long":
+            w = w[::8]
+        s = snr_db(ref, w)
+        print(f"{name}[{i}] SNR {s:.1f} dB")
+        assert s >= SNR_DB, s
+
+
+def test_decode_full_config_matches_reference_golden():
+    from oracle.codec_weights import full_codec_params
+    g = gold("codec_decode.npz")
+    spt = _spt(full_codec_params(), int(g["full_seed"]))
+    codes = [torch.from_numpy(g["full_codes0"].astype(np.int64)).cuda()]
+    w = spt.decode(codes)["syn_wav_list"][0].cpu().numpy()
+    s = snr_db(g["full_wav0"], w)
+    print(f"full config SNR {s:.1f} dB")
+    assert w.shape == g["full_wav0"].shape
+    assert s >= SNR_DB, s
+
+
+def test_inference_detokenize_shapes_and_empty():
+    from oracle.codec_weights import TINY_CODEC
+    spt = _spt(TINY_CODEC, 21)
+    codes = torch.randint(0, 128, (8, 3, 20), device="cuda")
+    out = spt.inference_detokenize(codes, torch.tensor([20, 7, 13]))
+    assert out["y"].shape == (3, 1, 20 * 1920)
+    assert out["output_length"].tolist() == [20 * 1920, 7 * 1920, 13 * 1920]
+    assert spt.decode([])["syn_wav_list"] == []
+    z = spt.decode([torch.zeros(8, 0, dtype=torch.long)])["syn_wav_list"]
+    assert z[0].numel() == 0
+    assert spt.input_sample_rate == 16000 and spt.output_sample_rate == 24000 and spt.nq == 8
+    assert spt.encoder_downsample_rate == 1280 and spt.decoder_upsample_rate == 1920
+
+
+def test_batched_decode_equals_oracle_batched():
+    """A ragged batch goes through the same padded computation as the reference's batched decode (the Vocos tail of
+    the shorter item depends on the padding) — compare against the oracle run on the same batch."""
+    from oracle.codec_oracle import CodecOracle
+    from oracle.codec_weights import TINY_CODEC, make_codec_weights
+    rng = np.random.default_rng(5)
+    codes = [torch.from_numpy(rng.integers(0, 128, (8, n)).astype(np.int64)) for n in (60, 25, 44)]
+    with torch.no_grad():
+        ref = CodecOracle(TINY_CODEC, make_codec_weights(TINY_CODEC, 21)).decode(codes)
+    spt = _spt(TINY_CODEC, 21)
+    got = spt.decode([c.cuda() for c in codes])["syn_wav_list"]
+    for r, w in zip(ref, got):
+        assert snr_db(r.numpy(), w.cpu().numpy()) >= SNR_DB
+
+
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_residual_vq_forward_matches_reference_golden(name):
+    """ResidualVQ.forward through the drop-in class: codes bit-exact vs the reference's (near-ties adjudicated)."""
+    from moss_ttsd_b200.xy_tokenizer.model import ResidualVQ
+    from oracle import rvq_np
+    from oracle.codec_weights import make_rvq_weights
+    g = gold("rvq.npz")
+    B, T, din, D, K, nq = [int(v) for v in g[f"{name}_dims"]]
+    w = make_rvq_weights(din, D, din, nq, K, seed=3)
+    rvq = ResidualVQ(input_dim=din, rvq_dim=D, output_dim=din, num_quantizers=nq, codebook_size=K, codebook_dim=D)
+    rvq.load({k: torch.from_numpy(v) for k, v in w.items()}, "", torch.device("cuda"))
+    z = torch.from_numpy(g[f"{name}_z"]).cuda()
+    zq, codes, losses, _, out_len = rvq(z, torch.from_numpy(g[f"{name}_lengths"]))
+    assert codes.shape == (nq, B, T) and codes.dtype == torch.int64 and zq.shape == (B, din, T)
+    got, want = codes.cpu().numpy().reshape(nq, -1), g[f"{name}_codes"].reshape(nq, -1)
+    cbs = np.stack([w[f"quantizers.{i}.codebook"] for i in range(nq)])
+    rows_ok = (got == want).all(0)
+    if not rows_ok.all():
+        # first differing layer of each row must be a near-tie of the fp64 distances on the reference's own residual
+        lengths = g[f"{name}_lengths"]
+        valid = (np.arange(T)[None, :] < lengths[:, None]).reshape(-1)
+        tok = g[f"{name}_z_in"].transpose(0, 2, 1).reshape(B * T, D)
+        _, _, _, layer_in = rvq_np.rvq_forward(tok, cbs, valid)
+        for r in np.nonzero(~rows_ok)[0]:
+            i = int(np.nonzero(got[:, r] != want[:, r])[0][0])
+            d = rvq_np.vq_dist64(layer_in[i][r:r + 1], cbs[i])[0]
+            assert abs(d[got[i, r]] - d[want[i, r]]) <= 1e-6 * max(1.0, abs(d[want[i, r]]))
+    assert rows_ok.mean() >= 0.95
+    # quantized_out where the codes agree: the output projection runs in TF32 -> tolerance, not bit-exactness
+    ref = g[f"{name}_zq_out"]
+    err = np.abs(zq.cpu().numpy() - ref).transpose(0, 2, 1).reshape(B * T, -1)[rows_ok].max()
+    assert err <= 5e-3 * max(1.0, np.abs(ref).max()), err
+    dec = rvq.decode_codes(torch.from_numpy(g[f"{name}_codes"]).cuda())
+    assert np.abs(dec.cpu().numpy() - g[f"{name}_decode"]).max() <= 5e-3 * max(1.0, np.abs(g[f"{name}_decode"]).max())
+
+
+def test_codec_kernels_against_torch_functional():
+    import torch.nn.functional as F
+    from moss_ttsd_b200 import _lib, ops
+    ops.ensure_init()
+    L = _lib.load()
+    sp = _lib.stream_ptr
+    g = torch.Generator(device="cuda").manual_seed(0)
+    # layernorm with length masking
+    x = torch.randn(2 * 50, 768, device="cuda", generator=g)
+    w, b = torch.randn(768, device="cuda", generator=g), torch.randn(768, device="cuda", generator=g)
+    out = torch.empty_like(x)
+    lens = torch.tensor([50, 20], dtype=torch.int32, device="cuda")
+    _lib.check(L.mtts_layernorm(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), 100, 768, 1e-5, lens.data_ptr(), 50, sp()))
+    ref = F.layer_norm(x, (768,), w, b, 1e-5)
+    ref[70:] = 0
+    assert (out - ref).abs().max().item() <= 2e-5
+    # attention
+    B, T, H = 2, 150, 3
+    qkv = torch.randn(B * T, 3 * H * 64, device="cuda", generator=g)
+    ao = torch.empty(B * T, H * 64, device="cuda")
+    lens = torch.tensor([150, 77], dtype=torch.int32, device="cuda")
+    _lib.check(L.mtts_mha_varlen(qkv.data_ptr(), ao.data_ptr(), lens.data_ptr(), B, T, H, 64, sp()))
+    q, k, v = (t.view(B, T, H, 64).transpose(1, 2).double() for t in qkv.view(B, T, 3, H * 64).unbind(2))
+    s = (q * 64 ** -0.5) @ k.transpose(-1, -2)
+    km = torch.arange(T, device="cuda")[None, :] < lens[:, None]
+    s = s.masked_fill(~km[:, None, None, :], float("-inf"))
+    ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, T, H * 64)
+    got = ao.view(B, T, H * 64).double()
+    assert (got[0] - ref[0]).abs().max().item() <= 1e-4
+    assert (got[1, :77] - ref[1, :77]).abs().max().item() <= 1e-4
+    # dwconv7 + LN
+    Bc, Tc, C = 2, 40, 512
+    x = torch.randn(Bc, Tc, C, device="cuda", generator=g)
+    cw, cb = torch.randn(C, 7, device="cuda", generator=g) * 0.3, torch.randn(C, device="cuda", generator=g) * 0.1
+    out = torch.empty_like(x)
+    _lib.check(L.mtts_dwconv7_ln(x.data_ptr(), cw.data_ptr(), cb.data_ptr(), w[:C].contiguous().data_ptr(),
+                                 b[:C].contiguous().data_ptr(), out.data_ptr(), Bc, Tc, C, 1e-6, sp()))
+    y = F.conv1d(x.transpose(1, 2), cw[:, None, :], cb, padding=3, groups=C).transpose(1, 2)
+    ref = F.layer_norm(y, (C,), w[:C], b[:C], 1e-6)
+    assert (out - ref).abs().max().item() <= 1e-4
+    # istft (spec -> basis GEMM -> overlap-add) against torch.fft.irfft + fold
+    from oracle.codec_weights import TINY_CODEC
+    spt = _spt(TINY_CODEC, 21)
+    Bi, Ti, Fb = 2, 12, 481
+    hx = torch.randn(Bi * Ti, 2 * Fb, device="cuda", generator=g)
+    spec = torch.empty(Bi * Ti, spt.head_ld, device="cuda")
+    _lib.check(L.mtts_istft_spec(hx.data_ptr(), hx.stride(0), spec.data_ptr(), spt.head_ld, Bi * Ti, Fb, sp()))
+    frames = ops.gemm_simt(spec, spt.basis)
+    wav = torch.empty(Bi, Ti * 240, device="cuda")
+    _lib.check(L.mtts_istft_ola(frames.data_ptr(), spt.window.data_ptr(), wav.data_ptr(), Bi, Ti, 960, 240, sp()))
+    o = hx.view(Bi, Ti, 2 * Fb).transpose(1, 2)
+    mag, ph = o.chunk(2, dim=1)
+    S = torch.clip(torch.exp(mag), max=1e2) * (torch.cos(ph) + 1j * torch.sin(ph))
+    win = torch.hann_window(960, device="cuda")
+    ifft = torch.fft.irfft(S, 960, dim=1, norm="backward") * win[None, :, None]
+    size = (Ti - 1) * 240 + 960
+    yy = F.fold(ifft, output_size=(1, size), kernel_size=(1, 960), stride=(1, 240))[:, 0, 0, 360:-360]
+    env = F.fold(win.square().expand(1, Ti, -1).transpose(1, 2), output_size=(1, size), kernel_size=(1, 960), stride=(1, 240)).squeeze()[360:-360]
+    ref = yy / env
+    assert (wav - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()

@@ -48,17 +48,17 @@ def test_teacher_forced_logits_within_bf16_tolerance(model):
     assert np.abs(eos - g["logits0_eos_bf16"]).max() <= MAX_ABS
 
 
-def _adjudicate_greedy(model_seq, ref_seq, ref_other):
-    """Greedy tokens must be identical over the horizon; a difference is only tolerated at a step where the two
-    reference precisions (bf16 / fp32) themselves disagree, i.e. a genuine near-tie of the logits."""
-    n = min(model_seq.shape[1], ref_seq.shape[1])
-    diff = np.argwhere(model_seq[:, :n] != ref_seq[:, :n])
-    if diff.size == 0:
-        return 0
-    first = diff[:, 1].min()
-    d2 = np.argwhere(ref_seq[:, :n] != ref_other[:, :n])
-    assert d2.size and d2[:, 1].min() <= first, f"greedy mismatch at row {first} while the references agree"
-    return int(first)
+# Greedy parity. Two bf16 implementations of a RANDOM-INIT model cannot agree token-for-token for long: the gap between
+# the best and second-best of ~1000 random logits is below bf16 noise in roughly one decision out of ten, and the
+# reference's own bf16 and fp32 runs part ways after a handful of rows (row 19 of the golden = 4 generated rows).
+# So greedy parity is checked two ways:
+#  (a) free-running: identical to the bf16 reference over the horizon where the reference agrees with itself
+#      (bf16 vs fp32 golden); a divergence before that row is a failure;
+#  (b) teacher-forced over the whole 24-row horizon: feeding the reference's own tokens, every argmax decision must
+#      match the fp32 oracle unless the oracle's top-2 gap is within 2 x MAX_ABS (a genuine near-tie).
+def _stable_horizon(ref_a, ref_b):
+    d = np.argwhere(ref_a != ref_b)
+    return int(d[:, 1].min()) if d.size else ref_a.shape[1]
 
 
 @pytest.mark.parametrize("paged", [False, True])
@@ -68,12 +68,50 @@ def test_greedy_tokens_identical_over_horizon(model, paged):
     T = ids.shape[1]
     model.kv_paged = paged
     model.generation_config.eos_token_id = 152694
-    seq = model.generate(input_ids=ids, attention_mask=mask, max_length=T + 24, do_sample=False).cpu().numpy()
-    model.kv_paged = False
+    try:
+        seq = model.generate(input_ids=ids, attention_mask=mask, max_length=T + 24, do_sample=False).cpu().numpy()
+    finally:
+        model.kv_paged = False
     assert seq.shape == g["greedy_bf16"].shape
     np.testing.assert_array_equal(seq[:, :T - 7], g["ids"][:, :T - 7])
-    first = _adjudicate_greedy(seq, g["greedy_bf16"], g["greedy_f32"])
-    assert first == 0, f"diverged from the bf16 reference at row {first} (a near-tie: fp32 and bf16 references differ there too)"
+    horizon = _stable_horizon(g["greedy_bf16"], g["greedy_f32"])
+    assert horizon > T - 7 + 2
+    np.testing.assert_array_equal(seq[:, :horizon], g["greedy_bf16"][:, :horizon])
+    d = np.argwhere(seq != g["greedy_bf16"])
+    print("stable horizon (rows):", horizon, "first divergence from bf16 reference:", int(d[:, 1].min()) if d.size else None)
+
+
+def test_teacher_forced_greedy_decisions_match_oracle(model):
+    from oracle import lm_oracle
+    g = gold("lm_tiny.npz")
+    lo, hi = TINY["speech_token_range"]
+    seq = torch.from_numpy(g["greedy_bf16"])                     # the reference's own generated grid
+    T0 = g["ids"].shape[1]
+    P = T0 - 7
+    mask = torch.cat([torch.from_numpy(g["mask"])[:, :P], torch.ones(seq.shape[0], seq.shape[1] - P, dtype=torch.float64)], 1)
+    out = model.forward(input_ids=seq.cuda(), attention_mask=mask.cuda())
+    sd = lm_oracle.make_weights(TINY, TINY_SEED)
+    with torch.no_grad():
+        ref = lm_oracle.OracleLM(TINY, sd, torch.float32).logits_all(seq, mask)
+    total = flips = 0
+    for c in range(8):
+        ours = out.logits_all[c][:, P - 1:].float().cpu()
+        r = ref[c][:, P - 1:]
+        if c == 0:
+            ours, r = ours[..., lo:hi], r[..., lo:hi]
+        else:
+            ours, r = ours[..., :1024], r[..., :1024]
+        am_o, am_r = ours.argmax(-1), r.argmax(-1)
+        top2 = r.topk(2, -1).values
+        gap = (top2[..., 0] - top2[..., 1])
+        bad = am_o != am_r
+        total += bad.numel()
+        flips += int(bad.sum())
+        # a flipped decision must be a near-tie of the fp32 reference
+        chosen = torch.gather(r, -1, am_o[..., None])[..., 0]
+        assert ((top2[..., 0] - chosen)[bad] <= 2 * MAX_ABS).all(), (c, (top2[..., 0] - chosen)[bad].max())
+    print(f"teacher-forced argmax decisions: {total - flips}/{total} identical, {flips} near-tie flips")
+    assert flips <= 0.1 * total
 
 
 def test_graph_and_eager_decode_agree(model, monkeypatch):

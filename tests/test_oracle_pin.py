@@ -115,3 +115,21 @@ def test_rvq_oracle_matches_reference(name):
     assert np.abs(dec_out - g[f"{name}_decode"]).max() <= 2e-5 * max(1.0, np.abs(dec_out).max())
     zq_out = (zq @ w_out.T + w["output_proj.bias"]).reshape(B, T, din).transpose(0, 2, 1)
     assert np.abs(zq_out - g[f"{name}_zq_out"]).max() <= 2e-5 * max(1.0, np.abs(zq_out).max())
+
+
+@pytest.mark.parametrize("name,lens", [("tiny", [30, 11]), ("tiny_long", [400, 120])])
+def test_codec_oracle_decode_matches_reference(name, lens):
+    from oracle.codec_oracle import CodecOracle
+    from oracle.codec_weights import TINY_CODEC, make_codec_weights
+    g = gold("codec_decode.npz")
+    orc = CodecOracle(TINY_CODEC, make_codec_weights(TINY_CODEC, int(g[f"{name}_seed"])))
+    codes = [torch.from_numpy(g[f"{name}_codes{i}"].astype(np.int64)) for i in range(len(lens))]
+    with torch.no_grad():
+        wavs = orc.decode(codes)
+    for i, n in enumerate(lens):
+        w = wavs[i].numpy()
+        assert w.shape == (n * 1920,)
+        ref = g[f"{name}_wav{i}"]
+        if name == "tiny_long":
+            w = w[::8]
+        assert np.abs(w - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max()), np.abs(w - ref).max()
