@@ -47,6 +47,8 @@ const char* mtts_last_error(void);
 int mtts_version(void);
 /* Caches per-device attributes for the current device. Safe to call repeatedly. */
 int mtts_init(void);
+/* Number of kernels this library has launched (or recorded into a CUDA graph under capture) in this process. */
+long long mtts_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense projections (tcgen05 / TMEM / TMA).   out[M,N] = epi(x[M,K] . w[N,K]^T)

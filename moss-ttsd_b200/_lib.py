@@ -43,6 +43,7 @@ SIGNATURES = {
     "mtts_last_error": (ctypes.c_char_p, []),
     "mtts_version": (c_int, []),
     "mtts_init": (c_int, []),
+    "mtts_launch_count": (c_ll, []),
     "mtts_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mtts_gemm": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_size_t, c_void_p]),

@@ -26,6 +26,11 @@ int mtts_num_sms() {
   return g_num_sms[dev];
 }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void mtts_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long mtts_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
 extern "C" const char* mtts_last_error(void) { return g_err; }
 extern "C" int mtts_version(void) { return MTTS_VERSION; }
 

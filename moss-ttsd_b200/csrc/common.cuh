@@ -34,8 +34,11 @@ int mtts_set_error(int code, const char* fmt, ...);
                             cudaGetErrorString(_e), __FILE__, __LINE__);                     \
   } while (0)
 
+void mtts_count_launch();  // bumps the process-wide launch counter (bench.py reports it as gpu_launches)
+
 #define MTTS_LAUNCH_CHECK()                                                                  \
   do {                                                                                       \
+    mtts_count_launch();                                                                     \
     cudaError_t _e = cudaGetLastError();                                                     \
     if (_e != cudaSuccess)                                                                   \
       return mtts_set_error(MTTS_ERR_CUDA, "kernel launch failed: %s (%s:%d)",               \

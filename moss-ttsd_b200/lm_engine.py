@@ -167,13 +167,24 @@ class LMWeights:
         self.final_norm.copy_(get(pre + "norm.weight"))
         return self
 
-    def init_random_(self, seed: int = 0, std: float = 0.02):
-        """Seeded random init directly on the device (bench / smoke only; parity tests load reference weights)."""
+    def init_random_(self, seed: int = 0, std: float = 0.02, tied: bool = True, speech_only_head0=None):
+        """Seeded random init directly on the device (bench / smoke only; parity tests load reference weights).
+        `speech_only_head0=(lo, hi)` zeroes the non-speech rows of head 0 so that greedy decoding of a random-init
+        model stays inside the speech range and never emits EOS."""
         g = torch.Generator(device=self.device).manual_seed(seed)
         self.heads.normal_(0.0, std, generator=g)
+        self.tied = tied
+        if not tied:
+            self.embeds = torch.empty_like(self.heads).normal_(0.0, std, generator=g)
+        else:
+            self.embeds = None
         for c in range(self.shape.channels):  # padding rows between heads stay zero
             o, v = self.shape.head_offsets[c], self.shape.vocabs[c]
             self.heads[o + v:o + _pad8(v)].zero_()
+        if speech_only_head0 is not None:
+            lo, hi = speech_only_head0
+            self.heads[:lo].zero_()
+            self.heads[hi:self.shape.vocabs[0]].zero_()
         for L in self.layers:
             for k in ("wqkv", "wo", "wgu", "wd"):
                 L[k].normal_(0.0, std, generator=g)
@@ -250,6 +261,7 @@ class DecoderEngine:
         self._vocabs = (ctypes.c_int * 8)(*s.vocabs, *([0] * (8 - s.channels)))
         self.err = torch.zeros(4, dtype=torch.int32, device=self.dev)
         self.use_graph = os.environ.get("MTTS_NO_GRAPH", "0") != "1"
+        self.graph_replayed_launches = 0  # kernels executed through graph replays (not seen by mtts_launch_count)
 
     # ------------------------------------------------------------------ primitive launches
     def _embed(self, ids, out):
@@ -414,6 +426,7 @@ class DecoderEngine:
             # warm-up launch outside capture would advance the state, so capture directly; all buffers are
             # preallocated and every kernel argument that changes per step lives in device memory.
             g = torch.cuda.CUDAGraph()
+            n0 = self.L.mtts_launch_count()
             cap_stream = torch.cuda.Stream(device=self.dev)
             cap_stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(cap_stream):
@@ -421,4 +434,6 @@ class DecoderEngine:
                     self._decode_body(st)
             torch.cuda.current_stream().wait_stream(cap_stream)
             st["graph"] = g
+            st["graph_nodes"] = self.L.mtts_launch_count() - n0
         st["graph"].replay()
+        self.graph_replayed_launches += st["graph_nodes"]

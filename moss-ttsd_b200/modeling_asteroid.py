@@ -183,9 +183,10 @@ class AsteroidTTSInstruct:
         self._engine = None
         return self
 
-    def init_random_weights(self, seed=0):
+    def init_random_weights(self, seed=0, tied=True, speech_only_head0=False):
         self._materialize()
-        self._w.init_random_(seed)
+        rng = tuple(self.config.speech_token_range) if speech_only_head0 else None
+        self._w.init_random_(seed, tied=tied, speech_only_head0=rng)
         self._engine = None
         return self
 

@@ -158,6 +158,79 @@ class XY_Tokenizer:
             self._prepare()
         return self
 
+    def param_shapes(self):
+        """(name, shape, fan_in) of every decode-side tensor under the reference's state-dict names."""
+        gp = self.params
+        out = []
+
+        def layer(p, d, ffn):
+            for nm in ("self_attn_layer_norm", "final_layer_norm"):
+                out.extend([(p + nm + ".weight", (d,), 0), (p + nm + ".bias", (d,), -1)])
+            for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+                out.append((p + f"self_attn.{nm}.weight", (d, d), d))
+                if nm != "k_proj":
+                    out.append((p + f"self_attn.{nm}.bias", (d,), -1))
+            out.extend([(p + "fc1.weight", (ffn, d), d), (p + "fc1.bias", (ffn,), -1),
+                        (p + "fc2.weight", (d, ffn), ffn), (p + "fc2.bias", (d,), -1)])
+
+        qk = gp["quantizer_kwargs"]
+        for i in range(qk["num_quantizers"]):
+            out.append((f"quantizer.quantizers.{i}.codebook", (qk["codebook_size"], qk["codebook_dim"]), -2))
+        for nm, (o, i) in (("input_proj", (qk["rvq_dim"], qk["input_dim"])), ("output_proj", (qk["output_dim"], qk["rvq_dim"]))):
+            out.extend([(f"quantizer.{nm}.weight_v", (o, i, 1), i), (f"quantizer.{nm}.weight_g", (o, 1, 1), 0),
+                        (f"quantizer.{nm}.bias", (o,), -1)])
+        pk = gp["post_rvq_adapter_kwargs"]
+        d = pk["d_model"]
+        out.extend([("post_rvq_adapter.proj.weight", (d, pk["input_dim"]), pk["input_dim"]), ("post_rvq_adapter.proj.bias", (d,), -1)])
+        for l in range(pk["encoder_layers"]):
+            layer(f"post_rvq_adapter.layers.{l}.", d, pk["encoder_ffn_dim"])
+        out.extend([("post_rvq_adapter.layer_norm.weight", (d,), 0), ("post_rvq_adapter.layer_norm.bias", (d,), -1),
+                    ("post_rvq_adapter.out_proj.weight", (pk["output_dim"], d), d), ("post_rvq_adapter.out_proj.bias", (pk["output_dim"],), -1)])
+        uk = gp["upsample_kwargs"]
+        out.append(("upsample.up_conv.weight", (uk["stride"] * uk["d_model"], uk["d_model"], uk["stride"]), uk["stride"] * uk["d_model"]))
+        ak = gp["acoustic_decoder_kwargs"]
+        d = ak["d_model"]
+        out.extend([("acoustic_decoder.deconv1.weight", (d, d, ak["kernel_size"]), d), ("acoustic_decoder.deconv1.bias", (d,), -1),
+                    ("acoustic_decoder.deconv2.weight", (d, ak["num_mel_bins"], ak["kernel_size"]), d),
+                    ("acoustic_decoder.deconv2.bias", (ak["num_mel_bins"],), -1)])
+        for l in range(ak["decoder_layers"]):
+            layer(f"acoustic_decoder.layers.{l}.", d, ak["decoder_ffn_dim"])
+        out.extend([("acoustic_decoder.layer_norm.weight", (d,), 0), ("acoustic_decoder.layer_norm.bias", (d,), -1)])
+        vk = gp["vocos_kwargs"]
+        dim, inter, p = vk["dim"], vk["intermediate_dim"], "enhanced_vocos.backbone."
+        out.extend([(p + "embed.weight", (dim, vk["input_channels"], 7), 7 * vk["input_channels"]), (p + "embed.bias", (dim,), -1),
+                    (p + "norm.weight", (dim,), 0), (p + "norm.bias", (dim,), -1)])
+        for i in range(vk["num_layers"]):
+            q = f"{p}convnext.{i}."
+            out.extend([(q + "gamma", (dim,), -3), (q + "dwconv.weight", (dim, 1, 7), 7), (q + "dwconv.bias", (dim,), -1),
+                        (q + "norm.weight", (dim,), 0), (q + "norm.bias", (dim,), -1),
+                        (q + "pwconv1.weight", (inter, dim), dim), (q + "pwconv1.bias", (inter,), -1),
+                        (q + "pwconv2.weight", (dim, inter), inter), (q + "pwconv2.bias", (dim,), -1)])
+        out.extend([(p + "final_layer_norm.weight", (dim,), 0), (p + "final_layer_norm.bias", (dim,), -1),
+                    ("enhanced_vocos.head.out.weight", (vk["n_fft"] + 2, dim), dim), ("enhanced_vocos.head.out.bias", (vk["n_fft"] + 2,), -1)])
+        return out
+
+    def init_random_weights(self, seed=0, device="cuda"):
+        """Seeded random decode-side weights generated on the device (bench / smoke; no parity role)."""
+        dev = torch.device(device)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        sd = {}
+        for name, shape, fan in self.param_shapes():
+            t = torch.empty(shape, dtype=torch.float32, device=dev).normal_(0.0, 1.0, generator=g)
+            if fan > 0:
+                t *= fan ** -0.5
+            elif fan == 0:
+                t = 1.0 + 0.1 * t
+            elif fan == -1:
+                t *= 0.02
+            elif fan == -2:
+                t *= 0.1
+            else:
+                t = 0.1 + 0.02 * t
+            sd[name] = t
+        self.device = dev
+        return self.load_state_dict(sd)
+
     def to(self, device):
         device = torch.device(device)
         if device.type != "cuda":

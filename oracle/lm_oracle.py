@@ -249,3 +249,112 @@ def sample_loop(logits_fn, input_ids, max_length, speech_range, eos_token_id=152
         if unfinished.max() == 0:
             break
     return ids
+
+
+# ------------------------------------------------------------------------------------------------ cached decode
+class OracleCachedLM(OracleLM):
+    """The same arithmetic with a per-layer K/V cache (what the reference does through HF DynamicCache): used as the
+    timed CPU baseline in bench.py and pinned against the full-recompute path in tests/test_oracle_pin.py."""
+
+    def __init__(self, shape, sd, dtype=torch.float32):
+        super().__init__(shape, sd, dtype)
+        self.k, self.v, self.mask = None, None, None
+
+    def reset(self):
+        self.k, self.v, self.mask = None, None, None
+
+    def step(self, ids, attention_mask):
+        """ids (B, S, 8): the new rows; attention_mask (B, past + S) over everything so far -> last-position logits."""
+        s, sd = self.s, self.sd
+        B, S, _ = ids.shape
+        am = attention_mask.long()
+        total = am.shape[1]
+        past = total - S
+        pos = (am.cumsum(-1) - 1).masked_fill(am == 0, 1)[:, past:]
+        freqs = pos[:, :, None].float() * self.inv_freq[None, None, :].float()
+        emb = torch.cat((freqs, freqs), dim=-1)
+        cos, sin = emb.cos().to(self.dtype)[:, None], emb.sin().to(self.dtype)[:, None]
+        minv = torch.finfo(self.dtype).min
+        qi = torch.arange(past, total)[:, None]
+        ki = torch.arange(total)[None, :]
+        allowed = (ki <= qi)[None, None] & (am[:, None, None, :] != 0)
+        add_mask = torch.zeros(B, 1, S, total, dtype=self.dtype).masked_fill(~allowed, minv)
+        x = self.embed_sum(ids)
+        Hq, Hkv, D = s["num_attention_heads"], s["num_key_value_heads"], s["head_dim"]
+        eps = s["rms_norm_eps"]
+        p = "model.language_model."
+        L = s["num_hidden_layers"]
+        if self.k is None:
+            self.k, self.v = [None] * L, [None] * L
+        for l in range(L):
+            b = f"{p}layers.{l}."
+            res = x
+            h = rmsnorm(x, sd[b + "input_layernorm.weight"], eps)
+            q = rmsnorm(F.linear(h, sd[b + "self_attn.q_proj.weight"]).view(B, S, Hq, D), sd[b + "self_attn.q_norm.weight"], eps).transpose(1, 2)
+            k = rmsnorm(F.linear(h, sd[b + "self_attn.k_proj.weight"]).view(B, S, Hkv, D), sd[b + "self_attn.k_norm.weight"], eps).transpose(1, 2)
+            v = F.linear(h, sd[b + "self_attn.v_proj.weight"]).view(B, S, Hkv, D).transpose(1, 2)
+            q = (q * cos) + (rotate_half(q) * sin)
+            k = (k * cos) + (rotate_half(k) * sin)
+            self.k[l] = k if self.k[l] is None else torch.cat([self.k[l], k], dim=2)
+            self.v[l] = v if self.v[l] is None else torch.cat([self.v[l], v], dim=2)
+            g = Hq // Hkv
+            kr = self.k[l][:, :, None].expand(B, Hkv, g, total, D).reshape(B, Hq, total, D)
+            vr = self.v[l][:, :, None].expand(B, Hkv, g, total, D).reshape(B, Hq, total, D)
+            w = torch.matmul(q, kr.transpose(2, 3)) * (D ** -0.5) + add_mask
+            w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
+            ao = torch.matmul(w, vr).transpose(1, 2).contiguous().reshape(B, S, Hq * D)
+            x = res + F.linear(ao, sd[b + "self_attn.o_proj.weight"])
+            res = x
+            h = rmsnorm(x, sd[b + "post_attention_layernorm.weight"], eps)
+            h = F.linear(F.silu(F.linear(h, sd[b + "mlp.gate_proj.weight"])) * F.linear(h, sd[b + "mlp.up_proj.weight"]),
+                         sd[b + "mlp.down_proj.weight"])
+            x = res + h
+        hl = rmsnorm(x, sd[p + "norm.weight"], eps)[:, -1]
+        return [F.linear(hl, sd[f"lm_heads.{c}.weight"]) for c in range(s["channels"])]
+
+    def generate(self, input_ids, attention_mask, max_length, speech_range, **kw):
+        """Greedy/sampled generation with the cache, driving `sample_loop` (the restated `_sample`)."""
+        self.reset()
+        P = input_ids.shape[1] - (self.s["channels"] - 1)
+        state = dict(fed=0)
+
+        def logits_fn(cur):
+            am = torch.cat([attention_mask[:, :P], torch.ones(cur.shape[0], cur.shape[1] - P, dtype=attention_mask.dtype)], 1)
+            new = cur[:, state["fed"]:]
+            state["fed"] = cur.shape[1]
+            with torch.no_grad():
+                return self.step(new, am)
+
+        return sample_loop(logits_fn, input_ids, max_length, speech_range, **kw)
+
+
+def random_weights_fast(shape: dict, seed: int = 0, std: float = 0.02, dtype=torch.float32):
+    """Full-size random weights for the timed CPU baseline (torch RNG, no parity role)."""
+    g = torch.Generator().manual_seed(seed)
+    H, I, L = shape["hidden_size"], shape["intermediate_size"], shape["num_hidden_layers"]
+    Hq, Hkv, D = shape["num_attention_heads"], shape["num_key_value_heads"], shape["head_dim"]
+    V, Vs, C = shape["vocab_size"], shape["speech_vocab_size"], shape["channels"]
+    n = lambda *s: (torch.randn(*s, generator=g, dtype=torch.float32) * std).to(dtype)
+    sd = {}
+    for c in range(C):
+        sd[f"lm_heads.{c}.weight"] = n(V if c == 0 else Vs, H)
+        sd[f"model.embedding_list.{c}.weight"] = sd[f"lm_heads.{c}.weight"]
+    lo, hi = shape["speech_token_range"]
+    sd["lm_heads.0.weight"][:lo] = 0
+    sd["lm_heads.0.weight"][hi:] = 0
+    p = "model.language_model."
+    for l in range(L):
+        b = f"{p}layers.{l}."
+        sd[b + "input_layernorm.weight"] = torch.ones(H, dtype=dtype)
+        sd[b + "post_attention_layernorm.weight"] = torch.ones(H, dtype=dtype)
+        sd[b + "self_attn.q_norm.weight"] = torch.ones(D, dtype=dtype)
+        sd[b + "self_attn.k_norm.weight"] = torch.ones(D, dtype=dtype)
+        sd[b + "self_attn.q_proj.weight"] = n(Hq * D, H)
+        sd[b + "self_attn.k_proj.weight"] = n(Hkv * D, H)
+        sd[b + "self_attn.v_proj.weight"] = n(Hkv * D, H)
+        sd[b + "self_attn.o_proj.weight"] = n(H, Hq * D)
+        sd[b + "mlp.gate_proj.weight"] = n(I, H)
+        sd[b + "mlp.up_proj.weight"] = n(I, H)
+        sd[b + "mlp.down_proj.weight"] = n(H, I)
+    sd[p + "norm.weight"] = torch.ones(H, dtype=dtype)
+    return sd

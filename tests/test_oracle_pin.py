@@ -133,3 +133,11 @@ def test_codec_oracle_decode_matches_reference(name, lens):
         if name == "tiny_long":
             w = w[::8]
         assert np.abs(w - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max()), np.abs(w - ref).max()
+
+
+def test_cached_oracle_equals_reference_greedy(lm_gold, sd):
+    """The KV-cached oracle (the timed CPU baseline) reproduces the reference's `_sample` output too."""
+    m = lm_oracle.OracleCachedLM(TINY, sd, torch.float32)
+    ids, mask = torch.from_numpy(lm_gold["ids"]), torch.from_numpy(lm_gold["mask"])
+    seq = m.generate(ids, mask, max_length=ids.shape[1] + 24, speech_range=TINY["speech_token_range"])
+    np.testing.assert_array_equal(seq.numpy(), lm_gold["greedy_f32"])
