@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(kThreads) sample8_kernel(const SampleParams p)
       nk = max(cnt, 1);
     }
     const float vmax = s_val[0];
+    __syncwarp();  // every lane has read the maximum before lane 0 overwrites it below
     // probabilities (unnormalised), stored in place
     float part = 0.f;
     const int chunk = (nk + 31) / 32;

@@ -221,9 +221,21 @@ def test_sampler_support_and_distribution_vs_oracle(model, cfg):
                 assert torch.equal(draws[0, :, c], sc.argmax(-1))
                 continue
             probs = torch.softmax(sc, -1)
+            # Support check. Two things are NOT defined by the reference and are therefore not compared: (i) which
+            # members of a group of EQUAL scores survive the top-p cut (torch.sort's order among ties is unspecified:
+            # stable on CUDA, not on CPU — and bf16 logits tie all the time), and (ii) a token sitting exactly on the
+            # cut (fp32 summation order). So a draw is legal iff its processed score is >= the smallest score the
+            # oracle keeps with top_p widened by 1e-3.
+            loose = dict(cfg)
+            if "top_p" in loose:
+                loose["top_p"] = min(1.0, loose["top_p"] + 1e-3)
+            kept = _processed_scores_oracle(logits[:, o:o + v].cpu(), hist[c], loose, 1024 if c > 0 else None)
+            base_cfg = {k_: v_ for k_, v_ in cfg.items() if k_ in ("repetition_penalty", "temperature")}
+            base = _processed_scores_oracle(logits[:, o:o + v].cpu(), hist[c], base_cfg, 1024 if c > 0 else None)
             for b in range(B):
                 d = draws[:, b, c]
-                assert (probs[b, d] > 0).all(), "drew a token outside the reference's filtered support"
+                vmin = kept[b][kept[b] > -float("inf")].min()
+                assert (base[b, d] >= vmin).all(), "drew a token outside the reference's filtered support"
                 top = probs[b].topk(5)
                 for pv, pi in zip(top.values.tolist(), top.indices.tolist()):
                     freq = (d == pi).float().mean().item()
