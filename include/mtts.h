@@ -57,7 +57,7 @@ long long mtts_launch_count(void);
  * (XY_Tokenizer/xy_tokenizer/nn/modules.py:84-87,181-182,494-500,1111-1115,957).
  * in_dtype BF16: bf16 operands; F32: fp32 storage multiplied as TF32. fp32 accumulation either way.
  * bias/gamma are fp32 [N]; residual has the output dtype. Row strides in ELEMENTS.
- * workspace: mtts_gemm_workspace_bytes() bytes whose first 16 KiB are ZERO before the first use.
+ * workspace: unused since split-K partials moved to distributed shared memory (kept for ABI stability; may be NULL).
  * ---------------------------------------------------------------------------------------------- */
 size_t mtts_gemm_workspace_bytes(int M, int N, int K, int in_dtype);
 int mtts_gemm(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo, int M, int N,
@@ -159,9 +159,12 @@ int mtts_sampler_init_history(const long long* ids, int B, int rows, long long r
 
 /* One draw per (row, channel) from the bf16 fused-head logits [B, ld]: masks -> repetition penalty -> temperature ->
  * top-k -> top-p -> multinomial (Philox, stream = (seed, step, row, channel)) or argmax. out_tokens [B, channels] int64.
- * *step_ptr is the device-resident step counter s (0 = first generated row). */
+ * *step_ptr is the device-resident step counter s (0 = first generated row). `workspace`: mtts_sample8_workspace_bytes()
+ * bytes, zero-filled once by the caller (the kernels leave it clean); logits rows and per-channel offsets 16-byte aligned. */
+size_t mtts_sample8_workspace_bytes(int B, int channels);
 int mtts_sample8(const void* logits, long long ld, int B, const mtts_sampler_config* cfg, const uint32_t* seen,
-                 const int* step_ptr, unsigned long long seed, long long* out_tokens, int* err_flag, void* stream);
+                 const int* step_ptr, unsigned long long seed, long long* out_tokens, int* err_flag, void* workspace,
+                 size_t workspace_bytes, void* stream);
 
 /* The per-row state machine after the draw: wind-down trigger, teacher forcing (tf_tail [B, channels-1, channels] =
  * prompt[:, P:P+channels-1, :]), wind-down fill, finished fill, append to sequences [B, max_len_rows, channels] at row

@@ -64,7 +64,9 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
                                    c_void_p]),
     "mtts_sampler_init_history": (c_int, [c_void_p, c_int, c_int, c_ll, _cfg_p, c_void_p, c_void_p]),
-    "mtts_sample8": (c_int, [c_void_p, c_ll, c_int, _cfg_p, c_void_p, c_void_p, c_u64, c_void_p, c_void_p, c_void_p]),
+    "mtts_sample8_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mtts_sample8": (c_int, [c_void_p, c_ll, c_int, _cfg_p, c_void_p, c_void_p, c_u64, c_void_p, c_void_p, c_void_p, c_size_t,
+                             c_void_p]),
     "mtts_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p, c_int, c_void_p]),
     "mtts_mha_varlen": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mtts_dwconv7_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,

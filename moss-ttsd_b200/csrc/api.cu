@@ -13,6 +13,16 @@ int mtts_set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+#include <stdlib.h>
+bool mtts_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTTS_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int g_num_sms[64] = {0};
 
 int mtts_num_sms() {

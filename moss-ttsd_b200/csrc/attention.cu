@@ -19,7 +19,7 @@ namespace {
 constexpr int kD = 128;
 constexpr int kThreads = 128;
 constexpr int kGroups = 8;  // half-warps per CTA
-constexpr int kUnroll = 4;
+
 
 struct AttnParams {
   const bf16* q;    // [rows, Hq, 128]
@@ -47,6 +47,8 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 template <int QT, int G>
 __global__ void __launch_bounds__(kThreads) gqa_attn_kernel(const AttnParams p) {
   constexpr int NQ = QT * G;  // query vectors handled per CTA
+  constexpr int kUnroll = (QT > 1) ? 4 : 8;  // keys in flight per half-warp (decode: 16 x 16 B loads per lane)
+  pdl_launch_dependents();    // the o_proj GEMM may start streaming its weights while attention runs
   extern __shared__ float sm[];
   float* sm_m = sm;                       // [kGroups][NQ]
   float* sm_l = sm_m + kGroups * NQ;      // [kGroups][NQ]
@@ -105,14 +107,13 @@ __global__ void __launch_bounds__(kThreads) gqa_attn_kernel(const AttnParams p) 
 
   for (int kb = k_begin + group; kb < k_end; kb += kGroups * kUnroll) {
     uint4 kv[kUnroll], vv[kUnroll];
-    int key[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      key[u] = kb + u * kGroups;
-      if (key[u] < k_end) {
-        const int lp = key[u] >> p.page_shift;
+      const int key = kb + u * kGroups;
+      if (key < k_end) {
+        const int lp = key >> p.page_shift;
         const int page = p.block_table ? __ldg(p.block_table + (long long)seq * p.max_pages + lp) : seq * p.max_pages + lp;
-        const long long off = (long long)page * page_stride + head_off + (long long)(key[u] & page_mask) * kD + l16 * 8;
+        const long long off = (long long)page * page_stride + head_off + (long long)(key & page_mask) * kD + l16 * 8;
         kv[u] = ld_nc_v4(p.k_pool + off);
         vv[u] = ld_nc_v4(p.v_pool + off);
       } else {
@@ -120,12 +121,13 @@ __global__ void __launch_bounds__(kThreads) gqa_attn_kernel(const AttnParams p) 
         vv[u] = make_uint4(0, 0, 0, 0);
       }
     }
+    // scores of the batch: s[u][i] (replicated over the 16 lanes of the half-warp after the butterfly)
+    float sc[kUnroll][NQ];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-      if (key[u] >= k_end) continue;  // uniform across the half-warp
-      float kf[8], vf[8];
+      float kf[8];
       unpack8(kv[u], kf);
-      unpack8(vv[u], vf);
+      const int key = kb + u * kGroups;
 #pragma unroll
       for (int i = 0; i < NQ; ++i) {
         float s = 0.f;
@@ -135,15 +137,37 @@ __global__ void __launch_bounds__(kThreads) gqa_attn_kernel(const AttnParams p) 
         s += __shfl_xor_sync(hmask, s, 4);
         s += __shfl_xor_sync(hmask, s, 2);
         s += __shfl_xor_sync(hmask, s, 1);
-        if (QT > 1 && key[u] > pos0 + i / G) s = -INFINITY;  // causal mask inside the tile
-        const float mn = fmaxf(m[i], s);
-        const float corr = exp2f(m[i] - mn);
-        const float pr = exp2f(s - mn);
-        m[i] = mn;
-        l[i] = l[i] * corr + pr;
-#pragma unroll
-        for (int d = 0; d < 8; ++d) acc[i][d] = fmaf(pr, vf[d], acc[i][d] * corr);
+        // beyond the range, or (prefill tiles) beyond this query's causal horizon
+        if (key >= k_end || (QT > 1 && key > pos0 + i / G)) s = -INFINITY;
+        sc[u][i] = s;
       }
+    }
+    // one online-softmax update per batch of kUnroll keys
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+      float mx = m[i];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) mx = fmaxf(mx, sc[u][i]);
+      const float corr = exp2f(m[i] - mx);
+      m[i] = mx;
+      float ps = 0.f;
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        sc[u][i] = exp2f(sc[u][i] - mx);
+        ps += sc[u][i];
+      }
+      l[i] = l[i] * corr + ps;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) acc[i][d] *= corr;
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      float vf[8];
+      unpack8(vv[u], vf);
+#pragma unroll
+      for (int i = 0; i < NQ; ++i)
+#pragma unroll
+        for (int d = 0; d < 8; ++d) acc[i][d] = fmaf(sc[u][i], vf[d], acc[i][d]);
     }
   }
 

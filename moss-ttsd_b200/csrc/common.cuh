@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "libmtts is written for sm_100a (B200) only"
@@ -44,6 +45,55 @@ void mtts_count_launch();  // bumps the process-wide launch counter (bench.py re
       return mtts_set_error(MTTS_ERR_CUDA, "kernel launch failed: %s (%s:%d)",               \
                             cudaGetErrorString(_e), __FILE__, __LINE__);                     \
   } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). Every kernel of the decode step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: it may start while its predecessor is still running,
+// does whatever does not depend on the predecessor (barrier/TMEM setup, and for the GEMM: streaming its WEIGHTS
+// into the shared-memory ring), and only then executes griddepcontrol.wait, which returns once the predecessor
+// grid has completed and its writes are visible. Each kernel also fires griddepcontrol.launch_dependents at its
+// top so that its own successor can do the same. Kernels must not touch predecessor-dependent memory (reads or
+// writes) before pdl_wait().
+// ---------------------------------------------------------------------------------------------
+bool mtts_pdl_enabled();  // false when MTTS_NO_PDL=1
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mtts_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                              cudaStream_t stream, int cluster_z, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (mtts_pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster_z > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = cluster_z;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mtts_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      Args... args) {
+  return mtts_launch_cluster(kernel, grid, block, smem, stream, 1, args...);
+}
+#endif
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

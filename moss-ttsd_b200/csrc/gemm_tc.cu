@@ -13,11 +13,18 @@
 //     issues full 128-lane MMAs and the kernel degenerates to a pure weight-streaming pass that is
 //     HBM-bound; large M (prefill, codec) uses BN = 128/256.
 //   * operands arrive by TMA (cp.async.bulk.tensor, 128B swizzle) into a kStages-deep mbarrier ring;
-//     one elected thread issues tcgen05.mma; accumulators live in TMEM; four epilogue warps read
-//     them back with tcgen05.ld and apply the fused epilogue (bias / GELU / layer-scale / residual /
-//     SwiGLU / bf16 rounding points of the reference).
-//   * split-K (grid.z) keeps all 148 SMs pulling weights when N/128 tiles are few; the partial sums
-//     are reduced in fixed split order by the last CTA to arrive (no spin-waits, deterministic).
+//     one elected thread issues tcgen05.mma; accumulators live in TMEM; four epilogue warps read them
+//     back with tcgen05.ld, stage the tile (shared memory, or the split-K workspace) and run a row-major,
+//     16-byte-vectorised epilogue (bias / GELU / layer-scale / residual / SwiGLU / the reference's bf16
+//     rounding points).
+//   * split-K (grid.z) keeps all SMs pulling weights when N/128 tiles are few. The splits of one output tile
+//     form a thread-block CLUSTER: every CTA stages its partial tile in its own shared memory, and after one
+//     cluster barrier each CTA reduces a slice of the rows by reading its peers' tiles over distributed shared
+//     memory in fixed rank order (bitwise deterministic; no workspace, no atomics, no global round trips).
+//   * PDL: the kernel starts while its predecessor in the stream is still running and streams its WEIGHT
+//     tiles (which never depend on the predecessor) into the ring before griddepcontrol.wait; activations,
+//     residual reads and all global writes happen after it. The ring is sized so that two CTAs (this GEMM's
+//     and the next one's) fit on an SM.
 #include "common.cuh"
 #include "sm100.cuh"
 #include "mtts_internal.h"
@@ -26,6 +33,7 @@
 #include <unordered_map>
 #include <string>
 #include <string.h>
+#include <stdlib.h>
 
 using namespace sm100;
 
@@ -48,8 +56,7 @@ struct GemmParams {
   const void* residual;
   long long ldr;
   int flags;
-  float* ws;      // split-K partials [splits][tiles][BN][128]
-  int* counters;  // one per output tile, zero on entry, zero on exit
+  int vec_ok;     // output / residual rows allow 4-wide vector access
 };
 
 template <typename T>
@@ -73,17 +80,80 @@ constexpr int smem_bytes() {
   return kStages * (kBlockW * kSwizzleBytes + BN * kSwizzleBytes) + 1024 /*align slack*/ + 256 /*barriers*/;
 }
 
-__device__ __forceinline__ float apply_epilogue_scalar(float v, int n, int m, const GemmParams& p) {
-  if (p.flags & MTTS_EPI_BIAS) v += __ldg(p.bias + n);
-  if (p.flags & MTTS_EPI_GELU) v = gelu_erf(v);
-  if (p.out_bf16) v = bf16_round(v);  // the reference materialises the bf16 linear output first
-  if (p.flags & MTTS_EPI_GAMMA) v *= __ldg(p.gamma + n);
-  if (p.flags & MTTS_EPI_RESIDUAL) {
-    float r = p.out_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p.residual)[(long long)m * p.ldr + n])
-                         : reinterpret_cast<const float*>(p.residual)[(long long)m * p.ldr + n];
-    v = r + v;
+// One output row segment of 4 consecutive n for row m: the fused epilogue on a float4 of accumulators.
+__device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int n, float4 a) {
+  float v[4] = {a.x, a.y, a.z, a.w};
+  if (p.flags & MTTS_EPI_SWIGLU) {
+    // rows interleaved (2j = gate_j, 2j+1 = up_j); rounding points of Qwen3MLP in bf16:
+    // bf16(gate), bf16(silu), bf16(up), bf16(product)
+    float o2[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float g = v[2 * h], u = v[2 * h + 1];
+      if (p.out_bf16) { g = bf16_round(g); u = bf16_round(u); }
+      float s = silu_f(g);
+      if (p.out_bf16) s = bf16_round(s);
+      o2[h] = s * u;
+    }
+    const long long o = (long long)m * p.ldo + (n >> 1);
+    if (p.out_bf16) {
+      bf16* op = reinterpret_cast<bf16*>(p.out) + o;
+      if (n + 1 < p.N) op[0] = __float2bfloat16_rn(o2[0]);
+      if (n + 3 < p.N) op[1] = __float2bfloat16_rn(o2[1]);
+    } else {
+      float* op = reinterpret_cast<float*>(p.out) + o;
+      if (n + 1 < p.N) op[0] = o2[0];
+      if (n + 3 < p.N) op[1] = o2[1];
+    }
+    return;
   }
-  return v;
+  const bool full = p.vec_ok && (n + 3 < p.N);
+  float r[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.flags & MTTS_EPI_RESIDUAL) {
+    const long long ri = (long long)m * p.ldr + n;
+    if (full) {
+      if (p.out_bf16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p.residual) + ri);
+        r[0] = bf16lo(u.x); r[1] = bf16hi(u.x); r[2] = bf16lo(u.y); r[3] = bf16hi(u.y);
+      } else {
+        const float4 u = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + ri);
+        r[0] = u.x; r[1] = u.y; r[2] = u.z; r[3] = u.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < p.N)
+          r[j] = p.out_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p.residual)[ri + j])
+                            : reinterpret_cast<const float*>(p.residual)[ri + j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (n + j >= p.N) break;
+    float x = v[j];
+    if (p.flags & MTTS_EPI_BIAS) x += __ldg(p.bias + n + j);
+    if (p.flags & MTTS_EPI_GELU) x = gelu_erf(x);
+    if (p.out_bf16) x = bf16_round(x);  // the reference materialises the bf16 linear output first
+    if (p.flags & MTTS_EPI_GAMMA) x *= __ldg(p.gamma + n + j);
+    if (p.flags & MTTS_EPI_RESIDUAL) x = r[j] + x;
+    v[j] = x;
+  }
+  const long long o = (long long)m * p.ldo + n;
+  if (full) {
+    if (p.out_bf16)
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+    else
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < p.N) {
+        if (p.out_bf16)
+          reinterpret_cast<bf16*>(p.out)[o + j] = __float2bfloat16_rn(v[j]);
+        else
+          reinterpret_cast<float*>(p.out)[o + j] = v[j];
+      }
+  }
 }
 
 template <typename T, int BN, int kStages>
@@ -96,6 +166,7 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
   constexpr uint32_t kBBytes = BN * kSwizzleBytes;
   constexpr uint32_t kCols = tmem_cols<BN>();
   constexpr uint32_t kIdesc = make_idesc(Traits<T>::kFmt, kBlockW, BN);
+  static_assert(kStages * (kABytes + kBBytes) >= BN * kBlockW * 4, "ring too small to stage the accumulator tile");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -105,7 +176,6 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  int* is_last_smem = reinterpret_cast<int*>(tmem_ptr_smem + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -113,6 +183,8 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
   const int kb_begin = split * p.kb_per_split;
   const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
   const int num_kb = kb_end - kb_begin;  // host guarantees >= 1
+
+  pdl_launch_dependents();  // let the next kernel in the stream start its own prologue / weight prefetch
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_w);
@@ -141,7 +213,17 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
       // weights are streamed once per launch when M fits one tile; keep activations resident in L2.
       const uint64_t pol_w = (gridDim.y == 1) ? kEvictFirst : kEvictNormal;
       const uint64_t pol_x = kEvictLast;
-      for (int it = 0; it < num_kb; ++it) {
+      // (1) weights of the first ring fill do not depend on the previous kernel: issue them before the PDL wait
+      const int pre = min(num_kb, kStages);
+      for (int it = 0; it < pre; ++it) {
+        mbar_arrive_expect_tx(&full_bar[it], kABytes + kBBytes);
+        tma_load_2d(smem_a + it * kABytes, &tmap_w, &full_bar[it], (kb_begin + it) * BK, n_tile * kBlockW, pol_w);
+      }
+      pdl_wait();
+      // (2) activations are the predecessor's output
+      for (int it = 0; it < pre; ++it)
+        tma_load_2d(smem_b + it * kBBytes, &tmap_x, &full_bar[it], (kb_begin + it) * BK, m_tile * BN, pol_x);
+      for (int it = pre; it < num_kb; ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
@@ -178,94 +260,76 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
     // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
     const int quarter = warp & 3;
     const int n_local = quarter * 32 + lane;
-    const int n = n_tile * kBlockW + n_local;
-    const int epi_tid = threadIdx.x - 64;
+    const int epi_tid = threadIdx.x - 64;  // 0..127
+    const int m_base = m_tile * BN;
+    const int mv = min(BN, p.M - m_base);  // valid activation rows in this tile
+    pdl_wait();  // residual reads and output writes below depend on / conflict with the predecessor
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const int m_base = m_tile * BN;
-    const int tile_id = m_tile * gridDim.x + n_tile;
-    const int num_tiles = gridDim.x * gridDim.y;
-    bool do_final = true;
-
-    if (p.splits > 1) {
-      float* wsp = p.ws + ((long long)(split * num_tiles + tile_id) * BN) * kBlockW + n_local;
+    // ---- stage the fp32 accumulator (partial) tile as [m][128 n] in the now idle smem ring
+    float* stage = reinterpret_cast<float*>(smem);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(taddr + c, r);
-        tmem_ld_wait();
+    for (int c = 0; c < mv; c += 16) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(taddr + c, r);
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) __stcg(wsp + (c + j) * kBlockW, __uint_as_float(r[j]));
-      }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (epi_tid == 0) {
-        const int prev = atomicAdd(p.counters + tile_id, 1);
-        const int last = (prev == p.splits - 1);
-        if (last) p.counters[tile_id] = 0;  // leave the counter clean for the next launch
-        *is_last_smem = last;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      do_final = (*is_last_smem != 0);
-      if (do_final) __threadfence();
+      for (int j = 0; j < 16; ++j) stage[(c + j) * kBlockW + n_local] = __uint_as_float(r[j]);
     }
+    if (p.splits == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
 
-    if (do_final) {
+  // ---- split-K: all partial tiles of this cluster are staged
+  __syncwarp();  // reconverge the single-lane producer / MMA warps: barrier.cluster is warp-aligned
+  if (p.splits > 1) cluster_sync_all();
+
+  if (warp >= 2) {
+    const int epi_tid = threadIdx.x - 64;
+    const int m_base = m_tile * BN;
+    const int mv = min(BN, p.M - m_base);
+    const int n4 = (epi_tid & 31) * 4;
+    const int n = n_tile * kBlockW + n4;
+    const float* stage = reinterpret_cast<const float*>(smem);
+    if (n < p.N) {
+      if (p.splits > 1) {
+        // this CTA finalises rows [r0, r1) of the tile; thread -> 4 consecutive n, rows r0 + (epi_tid / 32) + 4 i
+        const int rank = (int)cluster_ctarank();
+        const int per = (mv + p.splits - 1) / p.splits;
+        const int r0 = rank * per, r1 = min(mv, r0 + per);
+        const uint32_t sbase = smem_u32(stage) + n4 * 4;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
-        float acc[16];
-        if (p.splits > 1) {
+        for (int ml = r0 + (epi_tid >> 5); ml < r1; ml += 8) {
+          float4 v[2][8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-          for (int s = 0; s < p.splits; ++s) {  // fixed order -> bitwise deterministic
-            const float* wsp = p.ws + ((long long)(s * num_tiles + tile_id) * BN) * kBlockW + n_local;
+          for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] += __ldcg(wsp + (c + j) * kBlockW);
+            for (int s = 0; s < 8; ++s)
+              v[i][s] = (s < p.splits && ml + 4 * i < r1) ? ld_dsmem_f4(sbase + (ml + 4 * i) * kBlockW * 4, s)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float4 acc = v[i][0];
+#pragma unroll
+            for (int s = 1; s < 8; ++s) {  // fixed rank order -> bitwise deterministic
+              acc.x += v[i][s].x; acc.y += v[i][s].y; acc.z += v[i][s].z; acc.w += v[i][s].w;
+            }
+            if (ml + 4 * i < r1) epilogue_store4(p, m_base + ml + 4 * i, n, acc);
           }
-        } else {
-          uint32_t r[16];
-          tmem_ld_32x32b_x16(taddr + c, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
         }
-        if (p.flags & MTTS_EPI_SWIGLU) {
-          // weight rows are interleaved (2j = gate_j, 2j+1 = up_j): neighbouring lanes pair up.
-          // Rounding points follow Qwen3MLP in bf16: bf16(gate), bf16(silu), bf16(up), bf16(product).
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = m_base + c + j;
-            float v = p.out_bf16 ? bf16_round(acc[j]) : acc[j];
-            float other = __shfl_xor_sync(0xffffffffu, v, 1);
-            if ((lane & 1) == 0 && m < p.M && n < p.N) {
-              float s = silu_f(v);
-              if (p.out_bf16) s = bf16_round(s);
-              float h = s * other;
-              const long long o = (long long)m * p.ldo + (n >> 1);
-              if (p.out_bf16)
-                reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(h);
-              else
-                reinterpret_cast<float*>(p.out)[o] = h;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = m_base + c + j;
-            if (m < p.M && n < p.N) {
-              float v = apply_epilogue_scalar(acc[j], n, m, p);
-              const long long o = (long long)m * p.ldo + n;
-              if (p.out_bf16)
-                reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(v);
-              else
-                reinterpret_cast<float*>(p.out)[o] = v;
-            }
-          }
+      } else {
+#pragma unroll 2
+        for (int ml = epi_tid >> 5; ml < mv; ml += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(stage + ml * kBlockW + n4);
+          epilogue_store4(p, m_base + ml, n, a);
         }
       }
     }
   }
+
+  // nobody may exit (and have its shared memory reassigned) while a peer is still reading it
+  __syncwarp();
+  if (p.splits > 1) cluster_sync_all();
 
   tc_fence_before();
   __syncthreads();
@@ -354,10 +418,21 @@ int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int 
   return MTTS_OK;
 }
 
-template <typename T, int BN, int kStages>
+// Stage counts: the small-BN (decode) variants keep the ring <= ~100 KB so that this GEMM's CTA and the next
+// kernel's (PDL) fit on one SM together; the large-BN (prefill / codec) variants use the full 200 KB.
+template <int BN> struct Stages;
+template <> struct Stages<16> { static constexpr int v = 5; };   //  90 KB
+template <> struct Stages<32> { static constexpr int v = 5; };   // 100 KB
+template <> struct Stages<64> { static constexpr int v = 4; };   //  96 KB
+template <> struct Stages<128> { static constexpr int v = 3; };  //  96 KB
+template <> struct Stages<256> { static constexpr int v = 4; };  // 192 KB
+
+template <typename T, int BN>
 int launch(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int kStages = Stages<BN>::v;
   constexpr int smem = smem_bytes<BN, kStages>();
-  gemm_tc_kernel<T, BN, kStages><<<grid, kNumThreads, smem, stream>>>(tw, tx, p);
+  MTTS_CUDA_CHECK(mtts_launch_cluster(gemm_tc_kernel<T, BN, kStages>, grid, dim3(kNumThreads), smem, stream, (int)grid.z,
+                                      tw, tx, p));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }
@@ -366,18 +441,18 @@ template <typename T>
 int dispatch(int bn, const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, dim3 grid,
              cudaStream_t stream) {
   switch (bn) {
-    case 16: return launch<T, 16, 8>(tw, tx, p, grid, stream);
-    case 32: return launch<T, 32, 8>(tw, tx, p, grid, stream);
-    case 64: return launch<T, 64, 6>(tw, tx, p, grid, stream);
-    case 128: return launch<T, 128, 3>(tw, tx, p, grid, stream);
-    default: return launch<T, 256, 4>(tw, tx, p, grid, stream);
+    case 16: return launch<T, 16>(tw, tx, p, grid, stream);
+    case 32: return launch<T, 32>(tw, tx, p, grid, stream);
+    case 64: return launch<T, 64>(tw, tx, p, grid, stream);
+    case 128: return launch<T, 128>(tw, tx, p, grid, stream);
+    default: return launch<T, 256>(tw, tx, p, grid, stream);
   }
 }
 
-template <typename T, int BN, int kStages>
+template <typename T, int BN>
 int configure_one() {
-  MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<T, BN, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       smem_bytes<BN, kStages>()));
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<T, BN, Stages<BN>::v>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       smem_bytes<BN, Stages<BN>::v>()));
   return MTTS_OK;
 }
 
@@ -386,16 +461,16 @@ int configure_one() {
 // Opt every instantiation into its dynamic shared-memory size (called from mtts_init, outside any graph capture).
 int mtts_configure_gemm_tc() {
   int rc = 0;
-  if ((rc = configure_one<bf16, 16, 8>())) return rc;
-  if ((rc = configure_one<bf16, 32, 8>())) return rc;
-  if ((rc = configure_one<bf16, 64, 6>())) return rc;
-  if ((rc = configure_one<bf16, 128, 3>())) return rc;
-  if ((rc = configure_one<bf16, 256, 4>())) return rc;
-  if ((rc = configure_one<float, 16, 8>())) return rc;
-  if ((rc = configure_one<float, 32, 8>())) return rc;
-  if ((rc = configure_one<float, 64, 6>())) return rc;
-  if ((rc = configure_one<float, 128, 3>())) return rc;
-  if ((rc = configure_one<float, 256, 4>())) return rc;
+  if ((rc = configure_one<bf16, 16>())) return rc;
+  if ((rc = configure_one<bf16, 32>())) return rc;
+  if ((rc = configure_one<bf16, 64>())) return rc;
+  if ((rc = configure_one<bf16, 128>())) return rc;
+  if ((rc = configure_one<bf16, 256>())) return rc;
+  if ((rc = configure_one<float, 16>())) return rc;
+  if ((rc = configure_one<float, 32>())) return rc;
+  if ((rc = configure_one<float, 64>())) return rc;
+  if ((rc = configure_one<float, 128>())) return rc;
+  if ((rc = configure_one<float, 256>())) return rc;
   return MTTS_OK;
 }
 
@@ -407,32 +482,25 @@ int mtts_gemm_tc_pick_bn(int M) {
   return 256;
 }
 
-// Split-K heuristic: about one CTA per SM (the small-BN variants keep ~145 KB of TMA loads in flight per CTA,
-// which is what saturates HBM), each split keeping at least 4 k-blocks so the ring still pipelines.
+// Split-K heuristic for the weight-streaming (small-M) variants: aim at `target` CTAs (default: two per SM), cluster
+// sizes 1/2/4/8, each split keeping at least 2 k-blocks.
 static int pick_splits(int tiles, int kb_total, int bn) {
   if (bn > 64) return 1;
-  int target = mtts_num_sms();
-  int s = target / tiles;
-  if (s < 1) s = 1;
-  int max_by_k = kb_total / 4;
-  if (max_by_k < 1) max_by_k = 1;
-  if (s > max_by_k) s = max_by_k;
-  if (s > 16) s = 16;
+  static int target_env = -1;
+  if (target_env < 0) {
+    const char* e = getenv("MTTS_GEMM_TARGET_CTAS");
+    target_env = e ? atoi(e) : 0;
+  }
+  const int target = target_env > 0 ? target_env : 2 * mtts_num_sms();  // two ring buffers fit per SM
+  int s = 1;
+  while (s < 8 && tiles * (s * 2) <= target && kb_total / (s * 2) >= 2) s *= 2;
   return s;
 }
 
-// Workspace layout: [kCounterBytes of per-tile arrival counters | split-K partial sums].
-// The counter area must be zero before the first launch (the caller allocates it zeroed once); every
-// launch leaves it zero again, so one workspace can be shared by all GEMMs issued on one stream.
-static constexpr size_t kCounterBytes = 16384;
-
+// Kept for ABI stability: split-K partials now live in distributed shared memory, so no workspace is needed.
 extern "C" size_t mtts_gemm_workspace_bytes(int M, int N, int K, int dtype) {
-  int bn = mtts_gemm_tc_pick_bn(M);
-  long long tiles = (long long)ceil_div(N, kBlockW) * ceil_div(M, bn);
-  int bk = dtype == MTTS_DTYPE_BF16 ? 64 : 32;
-  int splits = pick_splits((int)tiles, ceil_div(K, bk), bn);
-  size_t ws = splits > 1 ? (size_t)splits * tiles * bn * kBlockW * sizeof(float) : 0;
-  return kCounterBytes + ws;
+  (void)M; (void)N; (void)K; (void)dtype;
+  return 256;
 }
 
 extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long ldw, void* out, long long ldo,
@@ -452,7 +520,7 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   if (flags & MTTS_EPI_GAMMA) MTTS_REQUIRE(gamma != nullptr, "mtts_gemm: EPI_GAMMA without gamma");
   if (flags & MTTS_EPI_RESIDUAL) MTTS_REQUIRE(residual != nullptr, "mtts_gemm: EPI_RESIDUAL without residual");
   if (flags & MTTS_EPI_SWIGLU)
-    MTTS_REQUIRE((N % 2) == 0 && !(flags & ~MTTS_EPI_SWIGLU), "mtts_gemm: SWIGLU needs even N and no other flags");
+    MTTS_REQUIRE((N % 4) == 0 && !(flags & ~MTTS_EPI_SWIGLU), "mtts_gemm: SWIGLU needs N % 4 == 0 and no other flags");
 
   const int bn = mtts_gemm_tc_pick_bn(M);
   const int bk = kSwizzleBytes / eb;
@@ -464,22 +532,17 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   const int tiles = tiles_n * tiles_m;
   int splits = pick_splits(tiles, p.kb_total, bn);
   p.kb_per_split = ceil_div(p.kb_total, splits);
-  splits = ceil_div(p.kb_total, p.kb_per_split);  // every slice gets >= 1 k-block
+  while (splits > 1 && (splits - 1) * p.kb_per_split >= p.kb_total) {  // every slice must get >= 1 k-block
+    splits /= 2;
+    p.kb_per_split = ceil_div(p.kb_total, splits);
+  }
   p.splits = splits;
   p.out = out; p.ldo = ldo; p.out_bf16 = out_dtype == MTTS_DTYPE_BF16;
   p.bias = bias; p.gamma = gamma; p.residual = residual; p.ldr = ldr; p.flags = flags;
-  if (splits > 1 && (size_t)tiles * sizeof(int) > kCounterBytes) {
-    splits = 1;
-    p.splits = 1;
-    p.kb_per_split = p.kb_total;
-  }
-  if (splits > 1) {
-    const size_t ws_need = kCounterBytes + (size_t)splits * tiles * bn * kBlockW * sizeof(float);
-    MTTS_REQUIRE(workspace != nullptr && workspace_bytes >= ws_need,
-                 "mtts_gemm: workspace too small (%zu given, %zu needed)", workspace_bytes, ws_need);
-    p.counters = reinterpret_cast<int*>(workspace);
-    p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCounterBytes);
-  }
+  const int oeb = p.out_bf16 ? 2 : 4;
+  p.vec_ok = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) % (4 * oeb)) == 0) &&
+             (!(flags & MTTS_EPI_RESIDUAL) || ((ldr % 4 == 0) && (reinterpret_cast<uintptr_t>(residual) % (4 * oeb)) == 0));
+  (void)workspace; (void)workspace_bytes;
   CUtensorMap tw, tx;
   int rc = get_tmap(w, N, K, ldw, kBlockW, eb, &tw);
   if (rc) return rc;

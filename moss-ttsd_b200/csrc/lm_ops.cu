@@ -20,6 +20,7 @@ struct EmbedParams {
 };
 
 __global__ void embed_sum_kernel(const EmbedParams p) {
+  pdl_launch_dependents();  // the GEMM that follows may start streaming its weights now
   const int vec_per_row = p.hidden >> 3;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long row = gid / vec_per_row;
@@ -59,6 +60,7 @@ __global__ void embed_sum_kernel(const EmbedParams p) {
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x, long long ldx,
                                                       const bf16* __restrict__ w, bf16* __restrict__ out,
                                                       long long ldo, int hidden, float eps) {
+  pdl_launch_dependents();  // the GEMM that follows may start streaming its weights now
   __shared__ float red[33];
   const long long row = blockIdx.x;
   const bf16* xr = x + row * ldx;
@@ -123,6 +125,7 @@ struct RopeParams {
 };
 
 __global__ void __launch_bounds__(256) qknorm_rope_kv_kernel(const RopeParams p) {
+  pdl_launch_dependents();
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int heads = p.Hq + 2 * p.Hkv;

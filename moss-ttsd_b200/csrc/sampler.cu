@@ -2,7 +2,7 @@
 // machine of CustomMixin._sample, all on the device (the reference needs ~60 launches and two host syncs
 // per step for this, modeling_asteroid.py:123-169).
 //
-//   sample8_kernel     one CTA per (row, channel): masks (modeling_asteroid.py:124-128), repetition penalty ->
+//   sample_scan/finish one CTA per (row, channel, 4096-logit slice): masks (modeling_asteroid.py:124-128), repetition penalty ->
 //                      temperature -> top-k -> top-p in HF's order and semantics (:95-106,129; HF
 //                      RepetitionPenaltyLogitsProcessor / TemperatureLogitsWarper / TopKLogitsWarper /
 //                      TopPLogitsWarper), then multinomial draw or argmax (:131-138).
@@ -15,22 +15,12 @@
 // k-th largest score, so one more pass collects the (few) candidates above it and only those are sorted.
 #include "common.cuh"
 #include "mtts_internal.h"
+#include <string.h>
 
 namespace {
 
 constexpr int kThreads = 512;
 constexpr int kCap = 2048;  // candidate list capacity
-
-struct SampleParams {
-  const bf16* logits;
-  long long ld;
-  mtts_sampler_config cfg;
-  const uint32_t* seen;
-  const int* step_ptr;
-  unsigned long long seed;
-  long long* out_tokens;  // [B, channels]
-  int* err_flag;
-};
 
 // ---- Philox4x32-10 (counter-based; one independent stream per (step, row, channel))
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t (&k)[2]) {
@@ -90,96 +80,235 @@ __device__ void bitonic_sort_desc(float* val, int* idx, int n) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads) sample8_kernel(const SampleParams p) {
-  __shared__ float s_val[kCap];
-  __shared__ int s_idx[kCap];
-  __shared__ float s_red[33];
-  __shared__ int s_count;
-  __shared__ float s_thr;
-  __shared__ int s_keep;
-  __shared__ float s_zkeep;
+// ------------------------------------------------------------------------------------------------
+// The 152,697-wide channel-0 row is cut into slices of kSlice logits, one CTA each, so that a batch-1 step is not a
+// single CTA crawling over 300 KB (that cost 180 us); small channels are one slice. Two phases, each finished by
+// the last CTA of a (row, channel) to arrive (atomic ticket, no spinning):
+//   scan    every slice computes its per-thread maxima. Greedy channels: slice argmax -> last arriver reduces -> token.
+//           Sampled channels: each slice reports its kReport largest thread maxima; the k-th largest of all reported
+//           values is a lower bound of the k-th largest score -> threshold.
+//   finish  (sampled channels only) every slice pushes its scores >= threshold into a small global candidate list;
+//           the last arriver sorts it and applies top-k (ties kept) / top-p / the Philox draw.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSlice = kThreads * 8;  // 4096 logits per CTA, 16-byte loads
+constexpr int kReport = 64;
+constexpr int kMaxSlices = 64;
 
-  const int b = blockIdx.x, c = blockIdx.y;
+struct SampleWs {
+  float* slice_val;   // [B][C][kMaxSlices]
+  int* slice_idx;     // [B][C][kMaxSlices]
+  float* reported;    // [B][C][kMaxSlices * kReport]
+  float* thr;         // [B][C]
+  int* tickets;       // [B][C][2]  (scan, finish) zero between launches
+  int* cand_count;    // [B][C]     zero between launches
+  float* cand_val;    // [B][C][kCap]
+  int* cand_idx;      // [B][C][kCap]
+};
+
+struct SampleParams2 {
+  const bf16* logits;
+  long long ld;
+  mtts_sampler_config cfg;
+  const uint32_t* seen;
+  const int* step_ptr;
+  unsigned long long seed;
+  long long* out_tokens;
+  int* err_flag;
+  SampleWs ws;
+  int total_slices;
+  unsigned char slice_channel[kMaxSlices];
+  unsigned char slice_index[kMaxSlices];
+  unsigned char slices_of[8];
+};
+
+__device__ __forceinline__ ScoreCtx make_ctx(const SampleParams2& p, int b, int c, int step) {
   const mtts_sampler_config& cfg = p.cfg;
-  const int V = cfg.vocab[c];
-  const int step = *p.step_ptr;
   ScoreCtx sc;
   sc.lg = p.logits + (long long)b * p.ld + cfg.logit_offset[c];
   sc.seen = p.seen + (long long)b * cfg.seen_words_per_row + cfg.seen_offset_words[c];
   sc.mask_idx = -1;
-  if (c != 0 && step >= c) sc.mask_idx = cfg.pad_token;             // channel c is live: pad is illegal
-  if (c == 0 && step <= cfg.channels - 2) sc.mask_idx = cfg.eos_mask_token;  // no EOS while the prompt tail is forced
+  if (c != 0 && step >= c) sc.mask_idx = cfg.pad_token;                        // channel c is live: pad is illegal
+  if (c == 0 && step <= cfg.channels - 2) sc.mask_idx = cfg.eos_mask_token;    // no EOS while the prompt tail is forced
   sc.has_rep = cfg.has_rep[c] != 0;
   sc.pen = cfg.rep_penalty[c];
   sc.has_temp = cfg.has_temp[c] != 0;
   sc.temp = cfg.temperature[c];
-  const int tid = threadIdx.x;
+  return sc;
+}
 
-  // ---------------- pass 1: per-thread maximum (also the greedy answer)
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int j = tid; j < V; j += kThreads) {
-    const float s = score_at(sc, j);
-    if (better(s, j, bv, bi)) { bv = s; bi = j; }
+// processed scores of logits j0 .. j0+7 (j0 % 8 == 0); entries at or beyond V come back as -inf
+__device__ __forceinline__ void scores8(const ScoreCtx& c, int j0, int V, float (&s)[8]) {
+  if (j0 >= V) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = -INFINITY;
+    return;
   }
-  if (!cfg.do_sample[c]) {
-    // block argmax, lowest index on ties (torch.argmax)
+  if (j0 + 8 <= V) {
+    const uint4 u = *reinterpret_cast<const uint4*>(c.lg + j0);
+    s[0] = bf16lo(u.x); s[1] = bf16hi(u.x); s[2] = bf16lo(u.y); s[3] = bf16hi(u.y);
+    s[4] = bf16lo(u.z); s[5] = bf16hi(u.z); s[6] = bf16lo(u.w); s[7] = bf16hi(u.w);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = (j0 + e < V) ? __bfloat162float(c.lg[j0 + e]) : -INFINITY;
+  }
+  const uint32_t bits = c.has_rep ? (c.seen[j0 >> 5] >> (j0 & 31)) & 0xffu : 0u;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float v = s[e];
+    if (j0 + e == c.mask_idx) v = -INFINITY;
+    if ((bits >> e) & 1u) v = v < 0.f ? v * c.pen : v / c.pen;
+    if (c.has_temp) v = v / c.temp;
+    s[e] = v;
+  }
+}
+
+__device__ __forceinline__ void block_argmax(float& bv, int& bi, float* s_val, int* s_idx) {
+  const int tid = threadIdx.x;
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid < 32) {
+    bv = tid < kThreads / 32 ? s_val[tid] : -INFINITY;
+    bi = tid < kThreads / 32 ? s_idx[tid] : 0x7fffffff;
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
     }
-    if ((tid & 31) == 0) { s_val[tid >> 5] = bv; s_idx[tid >> 5] = bi; }
-    __syncthreads();
-    if (tid < 32) {
-      bv = tid < kThreads / 32 ? s_val[tid] : -INFINITY;
-      bi = tid < kThreads / 32 ? s_idx[tid] : 0x7fffffff;
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-      }
-      if (tid == 0) p.out_tokens[(long long)b * cfg.channels + c] = bi == 0x7fffffff ? 0 : bi;
-    }
-    return;
   }
+}
 
-  // ---------------- candidate threshold
-  int k = cfg.top_k[c] > 0 ? min(cfg.top_k[c], V) : V;
-  if (k <= kThreads && V > kCap) {
+__global__ void __launch_bounds__(kThreads) sample_scan_kernel(const SampleParams2 p) {
+  __shared__ float s_val[kMaxSlices * kReport];
+  __shared__ int s_idx[kMaxSlices * kReport];
+  __shared__ int s_last;
+  pdl_launch_dependents();
+  const int b = blockIdx.x, c = p.slice_channel[blockIdx.y], slice = p.slice_index[blockIdx.y];
+  const mtts_sampler_config& cfg = p.cfg;
+  const int V = cfg.vocab[c], S = p.slices_of[c];
+  const int tid = threadIdx.x;
+  const int step = *p.step_ptr;
+  const ScoreCtx sc = make_ctx(p, b, c, step);
+  const int j0 = slice * kSlice + tid * 8;
+  float sv[8];
+  scores8(sc, j0, V, sv);
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (j0 + e < V && better(sv[e], j0 + e, bv, bi)) { bv = sv[e]; bi = j0 + e; }
+  const long long bc = (long long)b * cfg.channels + c;
+  const bool greedy = !cfg.do_sample[c];
+  if (greedy) {
+    block_argmax(bv, bi, s_val, s_idx);
+    if (tid == 0) {
+      p.ws.slice_val[bc * kMaxSlices + slice] = bv;
+      p.ws.slice_idx[bc * kMaxSlices + slice] = bi;
+    }
+  } else if (S > 1) {
     s_val[tid] = bv;
     s_idx[tid] = bi;
     __syncthreads();
     bitonic_sort_desc(s_val, s_idx, kThreads);
-    if (tid == 0) s_thr = s_val[k - 1];  // >= k scores are >= this value
-    __syncthreads();
-  } else {
-    if (tid == 0) s_thr = -INFINITY;
-    __syncthreads();
+    if (tid < kReport) p.ws.reported[(bc * kMaxSlices + slice) * kReport + tid] = s_val[tid];
   }
-  const float thr = s_thr;
-  if (tid == 0) s_count = 0;
+  // ---- ticket: the last slice of this (row, channel) finishes the phase
+  __threadfence();
   __syncthreads();
-
-  // ---------------- pass 2: collect candidates
-  for (int j = tid; j < V; j += kThreads) {
-    const float s = score_at(sc, j);
-    if (s >= thr) {
-      const int pos = atomicAdd(&s_count, 1);
-      if (pos < kCap) { s_val[pos] = s; s_idx[pos] = j; }
+  if (tid == 0) {
+    const int prev = atomicAdd(p.ws.tickets + bc * 2, 1);
+    s_last = (prev == S - 1);
+    if (s_last) p.ws.tickets[bc * 2] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (greedy) {
+    bv = -INFINITY;
+    bi = 0x7fffffff;
+    if (tid < S) {
+      bv = __ldcg(p.ws.slice_val + bc * kMaxSlices + tid);
+      bi = __ldcg(p.ws.slice_idx + bc * kMaxSlices + tid);
     }
+    __syncthreads();
+    block_argmax(bv, bi, s_val, s_idx);
+    if (tid == 0) p.out_tokens[bc] = bi == 0x7fffffff ? 0 : bi;  // torch.argmax: lowest index on ties
+    return;
+  }
+  // sampled channel: threshold = k-th largest reported maximum (a lower bound of the k-th largest score)
+  float thr = -INFINITY;
+  const int k = cfg.top_k[c] > 0 ? min(cfg.top_k[c], V) : V;
+  if (S > 1 && k <= S * kReport) {
+    const int n = S * kReport;
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    for (int t = tid; t < npad; t += kThreads) {
+      s_val[t] = t < n ? __ldcg(p.ws.reported + bc * kMaxSlices * kReport + t) : -INFINITY;
+      s_idx[t] = t;
+    }
+    __syncthreads();
+    bitonic_sort_desc(s_val, s_idx, npad);
+    thr = s_val[k - 1];
+  }
+  if (tid == 0) p.ws.thr[bc] = thr;
+}
+
+__global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SampleParams2 p) {
+  __shared__ float s_val[kCap];
+  __shared__ int s_idx[kCap];
+  __shared__ int s_last;
+  pdl_launch_dependents();
+  const int b = blockIdx.x, c = p.slice_channel[blockIdx.y], slice = p.slice_index[blockIdx.y];
+  const mtts_sampler_config& cfg = p.cfg;
+  if (!cfg.do_sample[c]) return;
+  const int V = cfg.vocab[c], S = p.slices_of[c];
+  const int tid = threadIdx.x;
+  const int step = *p.step_ptr;
+  const ScoreCtx sc = make_ctx(p, b, c, step);
+  const long long bc = (long long)b * cfg.channels + c;
+  const float thr = __ldcg(p.ws.thr + bc);
+  const int j0 = slice * kSlice + tid * 8;
+  float sv[8];
+  scores8(sc, j0, V, sv);
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (j0 + e < V && sv[e] >= thr) {
+      const int pos = atomicAdd(p.ws.cand_count + bc, 1);
+      if (pos < kCap) {
+        __stcg(p.ws.cand_val + bc * kCap + pos, sv[e]);
+        __stcg(p.ws.cand_idx + bc * kCap + pos, j0 + e);
+      }
+    }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(p.ws.tickets + bc * 2 + 1, 1);
+    s_last = (prev == S - 1);
+    if (s_last) p.ws.tickets[bc * 2 + 1] = 0;
   }
   __syncthreads();
-  int n = s_count;
+  if (!s_last) return;
+  __threadfence();
+  int n = __ldcg(p.ws.cand_count + bc);
+  __syncthreads();
+  if (tid == 0) p.ws.cand_count[bc] = 0;
   if (n > kCap) {
     if (tid == 0 && p.err_flag) *p.err_flag = 3;  // candidate overflow (pathological ties); truncated
     n = kCap;
   }
   int npad = 1;
   while (npad < n) npad <<= 1;
-  for (int t = n + tid; t < npad; t += kThreads) { s_val[t] = -INFINITY; s_idx[t] = -1; }
+  for (int t = tid; t < npad; t += kThreads) {
+    s_val[t] = t < n ? __ldcg(p.ws.cand_val + bc * kCap + t) : -INFINITY;
+    s_idx[t] = t < n ? __ldcg(p.ws.cand_idx + bc * kCap + t) : -1;
+  }
   __syncthreads();
   bitonic_sort_desc(s_val, s_idx, npad);
+  const int k = cfg.top_k[c] > 0 ? min(cfg.top_k[c], V) : V;
 
   // ---------------- top-k (ties with the k-th value are kept, HF: scores < kth -> -inf), top-p, draw
   if (tid < 32) {
@@ -187,7 +316,6 @@ __global__ void __launch_bounds__(kThreads) sample8_kernel(const SampleParams p)
     int nk = n;
     if (cfg.top_k[c] > 0 && k < n) {
       const float kth = s_val[k - 1];
-      // first position whose value is < kth (list is sorted descending)
       int cnt = 0;
       for (int t = lane; t < n; t += 32) cnt += (s_val[t] >= kth) ? 1 : 0;
       cnt = (int)warp_sum((float)cnt);
@@ -202,7 +330,6 @@ __global__ void __launch_bounds__(kThreads) sample8_kernel(const SampleParams p)
     }
     const float vmax = s_val[0];
     __syncwarp();  // every lane has read the maximum before lane 0 overwrites it below
-    // probabilities (unnormalised), stored in place
     float part = 0.f;
     const int chunk = (nk + 31) / 32;
     const int t0 = lane * chunk, t1 = min(nk, t0 + chunk);
@@ -211,7 +338,6 @@ __global__ void __launch_bounds__(kThreads) sample8_kernel(const SampleParams p)
       s_val[t] = e;
       part += e;
     }
-    // inclusive scan of per-lane partial sums (descending order)
     float incl = part;
     for (int o = 1; o < 32; o <<= 1) {
       const float up = __shfl_up_sync(0xffffffffu, incl, o);
@@ -223,17 +349,16 @@ __global__ void __launch_bounds__(kThreads) sample8_kernel(const SampleParams p)
       // HF: sort ascending, cum = cumsum(softmax); remove cum <= 1 - top_p; always keep the largest.
       // In descending order: position t is removed iff (mass of t and everything after it) / Z <= 1 - top_p.
       const float limit = (1.0f - cfg.top_p[c]);
-      float before = incl - part;  // mass strictly before this lane's chunk
+      float before = incl - part;
       int my_keep = 0;
       for (int t = t0; t < t1; ++t) {
-        const float tail = (Z - before) / Z;  // mass of t..end
+        const float tail = (Z - before) / Z;
         if (t == 0 || tail > limit) my_keep = t + 1;
         before += s_val[t];
       }
       for (int o = 16; o > 0; o >>= 1) my_keep = max(my_keep, __shfl_xor_sync(0xffffffffu, my_keep, o));
       keep = max(my_keep, 1);
     }
-    // mass of the kept prefix
     float kpart = 0.f;
     for (int t = t0; t < min(t1, keep); ++t) kpart += s_val[t];
     float kincl = kpart;
@@ -244,7 +369,6 @@ __global__ void __launch_bounds__(kThreads) sample8_kernel(const SampleParams p)
     const float Zk = __shfl_sync(0xffffffffu, kincl, 31);
     const float u = philox_uniform(p.seed, (uint32_t)step, (uint32_t)(b * 8 + c));
     const float target = u * Zk;
-    // the lane whose chunk contains the target walks it
     const float lo = kincl - kpart;
     int choice = -1;
     if (target >= lo && target < kincl) {
@@ -257,7 +381,7 @@ __global__ void __launch_bounds__(kThreads) sample8_kernel(const SampleParams p)
     }
     for (int o = 16; o > 0; o >>= 1) choice = max(choice, __shfl_xor_sync(0xffffffffu, choice, o));
     if (choice < 0) choice = keep - 1;  // rounding at the very end of the CDF
-    if (lane == 0) p.out_tokens[(long long)b * cfg.channels + c] = s_idx[choice];
+    if (lane == 0) p.out_tokens[bc] = s_idx[choice];
   }
 }
 
@@ -383,19 +507,72 @@ extern "C" int mtts_sampler_init_history(const long long* ids, int B, int rows, 
   return MTTS_OK;
 }
 
+static size_t sample_ws_layout(int B, int C, SampleWs* ws, uint8_t* base) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  };
+  const size_t bc = (size_t)B * C;
+  // integer state first: [tickets | cand_count] must be ZERO before the first launch (kernels leave them zero)
+  int* tickets = reinterpret_cast<int*>(take(bc * 2 * sizeof(int)));
+  int* cand_count = reinterpret_cast<int*>(take(bc * sizeof(int)));
+  float* slice_val = reinterpret_cast<float*>(take(bc * kMaxSlices * sizeof(float)));
+  int* slice_idx = reinterpret_cast<int*>(take(bc * kMaxSlices * sizeof(int)));
+  float* reported = reinterpret_cast<float*>(take(bc * kMaxSlices * kReport * sizeof(float)));
+  float* thr = reinterpret_cast<float*>(take(bc * sizeof(float)));
+  float* cand_val = reinterpret_cast<float*>(take(bc * kCap * sizeof(float)));
+  int* cand_idx = reinterpret_cast<int*>(take(bc * kCap * sizeof(int)));
+  if (ws) {
+    ws->tickets = tickets; ws->cand_count = cand_count; ws->slice_val = slice_val; ws->slice_idx = slice_idx;
+    ws->reported = reported; ws->thr = thr; ws->cand_val = cand_val; ws->cand_idx = cand_idx;
+  }
+  return off;
+}
+
+extern "C" size_t mtts_sample8_workspace_bytes(int B, int channels) {
+  return sample_ws_layout(B > 0 ? B : 1, channels > 0 ? channels : 8, nullptr, nullptr);
+}
+
 extern "C" int mtts_sample8(const void* logits, long long ld, int B, const mtts_sampler_config* cfg,
                             const uint32_t* seen, const int* step_ptr, unsigned long long seed, long long* out_tokens,
-                            int* err_flag, void* stream_) {
+                            int* err_flag, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   int rc = validate_cfg(cfg);
   if (rc) return rc;
   if (B <= 0) return MTTS_OK;
   MTTS_REQUIRE(logits && seen && step_ptr && out_tokens, "mtts_sample8: null pointer");
-  SampleParams p;
+  MTTS_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0, "mtts_sample8: logits rows must be 16-byte aligned");
+  MTTS_REQUIRE(workspace && workspace_bytes >= mtts_sample8_workspace_bytes(B, cfg->channels),
+               "mtts_sample8: workspace too small (need %zu bytes, first 4 KiB-aligned integer area zeroed once)",
+               mtts_sample8_workspace_bytes(B, cfg->channels));
+  SampleParams2 p;
+  memset(&p, 0, sizeof(p));
   p.logits = reinterpret_cast<const bf16*>(logits); p.ld = ld; p.cfg = *cfg; p.seen = seen; p.step_ptr = step_ptr;
   p.seed = seed; p.out_tokens = out_tokens; p.err_flag = err_flag;
-  sample8_kernel<<<dim3(B, cfg->channels), kThreads, 0, stream>>>(p);
+  sample_ws_layout(B, cfg->channels, &p.ws, reinterpret_cast<uint8_t*>(workspace));
+  int total = 0;
+  bool any_sample = false;
+  for (int c = 0; c < cfg->channels; ++c) {
+    MTTS_REQUIRE(cfg->logit_offset[c] % 8 == 0, "mtts_sample8: logit_offset[%d] must be a multiple of 8", c);
+    const int S = (cfg->vocab[c] + kSlice - 1) / kSlice;
+    MTTS_REQUIRE(S <= kMaxSlices && total + S <= kMaxSlices, "mtts_sample8: vocabulary too large for %d slices", kMaxSlices);
+    p.slices_of[c] = (unsigned char)S;
+    for (int s2 = 0; s2 < S; ++s2) {
+      p.slice_channel[total] = (unsigned char)c;
+      p.slice_index[total] = (unsigned char)s2;
+      ++total;
+    }
+    any_sample |= cfg->do_sample[c] != 0;
+  }
+  p.total_slices = total;
+  sample_scan_kernel<<<dim3(B, total), kThreads, 0, stream>>>(p);
   MTTS_LAUNCH_CHECK();
+  if (any_sample) {
+    sample_finish_kernel<<<dim3(B, total), kThreads, 0, stream>>>(p);
+    MTTS_LAUNCH_CHECK();
+  }
   return MTTS_OK;
 }
 

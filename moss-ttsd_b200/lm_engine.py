@@ -390,9 +390,11 @@ class DecoderEngine:
         st["acts"] = self._alloc_acts(B)
         st["gws"] = self._gemm_ws(B)
         s = self.s
-        nsplit = max(1, min(32, (2 * 148) // max(1, B * s.num_key_value_heads)))
+        nsplit = max(1, min(32, -(-(4 * 148) // max(1, B * s.num_key_value_heads))))  # >= 4 CTAs per SM
         st["nsplit"] = nsplit
         st["attn_ws"] = self._attn_workspace(B, 1, nsplit)
+        st["sample_ws"] = torch.zeros(self.L.mtts_sample8_workspace_bytes(B, self.s.channels), dtype=torch.uint8,
+                                      device=self.dev)
         st["graph"] = None
         return st
 
@@ -400,7 +402,8 @@ class DecoderEngine:
         """Draw 8 tokens per row from `logits` and run the delay-pattern state machine (one step)."""
         sm = st["sampler"]
         check(self.L.mtts_sample8(ptr(logits), logits.stride(0), st["B"], ctypes.byref(sm.cfg), ptr(st["seen"]),
-                                  ptr(st["step"]), st["seed"], ptr(st["tokens"]), ptr(self.err), stream_ptr()))
+                                  ptr(st["step"]), st["seed"], ptr(st["tokens"]), ptr(self.err), ptr(st["sample_ws"]),
+                                  st["sample_ws"].numel(), stream_ptr()))
         check(self.L.mtts_delay_step(ptr(st["tokens"]), ptr(st["tf_tail"]), ptr(st["sequences"]), st["max_len_rows"],
                                      ptr(st["unfinished"]), ptr(st["needs"]), ptr(st["positions"]), ptr(st["seen"]),
                                      ptr(st["step"]), ptr(st["hist"]), ptr(st["finish_len"]), st["B"], st["P"],

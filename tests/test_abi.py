@@ -25,7 +25,8 @@ def test_no_torch_types_in_the_abi():
 
 def test_workspace_queries_work_without_a_device():
     lib = _lib.load()
-    assert lib.mtts_gemm_workspace_bytes(1, 4096, 2048, 0) >= 16384
+    assert lib.mtts_gemm_workspace_bytes(1, 4096, 2048, 0) > 0
+    assert lib.mtts_sample8_workspace_bytes(4, 8) > 4 * 8 * 2048 * 8
     assert lib.mtts_gqa_attention_workspace_bytes(4, 8, 2, 1, 8) > 65536
 
 

@@ -206,11 +206,13 @@ def test_sampler_support_and_distribution_vs_oracle(model, cfg):
                                                    seen.data_ptr(), _lib.stream_ptr()))
         step = torch.full((1,), 9, dtype=torch.int32, device="cuda")  # step 9: pad masked on every ch>=1, EOS allowed
         toks = torch.zeros((B, C), dtype=torch.int64, device="cuda")
+        sws = torch.zeros(eng.L.mtts_sample8_workspace_bytes(B, C), dtype=torch.uint8, device="cuda")
         draws = []
         n_draws = 1 if not do_sample else 400
         for i in range(n_draws):
             _lib.check(eng.L.mtts_sample8(logits.data_ptr(), logits.stride(0), B, ctypes.byref(sm.cfg), seen.data_ptr(),
-                                          step.data_ptr(), 1000 + i, toks.data_ptr(), eng.err.data_ptr(), _lib.stream_ptr()))
+                                          step.data_ptr(), 1000 + i, toks.data_ptr(), eng.err.data_ptr(), sws.data_ptr(),
+                                          sws.numel(), _lib.stream_ptr()))
             draws.append(toks.cpu().clone())
         draws = torch.stack(draws)  # (n, B, C)
         assert eng.err.cpu().sum().item() == 0
