@@ -240,6 +240,215 @@ __global__ void __launch_bounds__(kThreads) gqa_attn_kernel(const AttnParams p) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Decode specialisation (one query row per sequence). The generic kernel above spends ~190 warp-instructions
+// per 512-byte key row because the online-softmax bookkeeping is replicated over the 16 lanes that share a row.
+// Here 8 lanes share a row (a warp instruction covers 4 rows), each lane owns dims {8l..8l+7} and {64+8l..64+8l+7}
+// so that every LDG.128 of 8 lanes is one full 128-byte line, 4 keys per lane-group are in flight per iteration
+// (16 x 16 B per lane), and the softmax state is updated once per batch with ex2.approx.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDecRows = 16;   // key rows per CTA step: 4 warps x 4 lane-groups
+constexpr int kDecU = 4;       // steps per iteration -> 64 keys per CTA iteration
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads) gqa_decode_kernel(const AttnParams p) {
+  pdl_launch_dependents();
+  extern __shared__ float sm[];
+  float* sm_m = sm;                        // [kDecRows][G]
+  float* sm_l = sm_m + kDecRows * G;       // [kDecRows][G]
+  float* sm_o = sm_l + kDecRows * G;       // [kDecRows][G][128]
+  __shared__ int s_is_last;
+
+  const int row = blockIdx.x, hk = blockIdx.y, split = blockIdx.z;
+  const int seq = p.row_seq ? p.row_seq[row] : row;
+  const int kv_len = p.positions[row] + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane >> 3, l8 = lane & 7;
+  const int rg = warp * 4 + grp;
+
+  int k_begin = 0, k_end = kv_len;
+  if (p.nsplit > 1) {
+    const int per = ((kv_len + p.nsplit - 1) / p.nsplit + kDecRows - 1) / kDecRows * kDecRows;
+    k_begin = min(kv_len, split * per);
+    k_end = min(kv_len, k_begin + per);
+  }
+
+  float qf[G][16];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const bf16* qp = p.q + ((long long)row * p.Hq + hk * G + g) * kD + l8 * 8;
+    float lo[8], hi[8];
+    unpack8(*reinterpret_cast<const uint4*>(qp), lo);
+    unpack8(*reinterpret_cast<const uint4*>(qp + 64), hi);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      qf[g][d] = lo[d] * p.scale_log2;
+      qf[g][8 + d] = hi[d] * p.scale_log2;
+    }
+  }
+  float m[G], l[G], acc[G][16];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    m[g] = -1e30f;
+    l[g] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) acc[g][d] = 0.f;
+  }
+  const int page_mask = (1 << p.page_shift) - 1;
+  const long long head_off = ((long long)hk << p.page_shift) * kD;
+  const long long page_stride = ((long long)p.Hkv << p.page_shift) * kD;
+
+  for (int kb = k_begin; kb < k_end; kb += kDecRows * kDecU) {
+    uint4 k0[kDecU], k1[kDecU], v0[kDecU], v1[kDecU];
+#pragma unroll
+    for (int u = 0; u < kDecU; ++u) {
+      const int key = min(kb + rg + kDecRows * u, k_end - 1);  // clamp: the load is always legal, the score is masked
+      const int lp = key >> p.page_shift;
+      const int page = p.block_table ? __ldg(p.block_table + (long long)seq * p.max_pages + lp) : seq * p.max_pages + lp;
+      const long long off = (long long)page * page_stride + head_off + (long long)(key & page_mask) * kD + l8 * 8;
+      k0[u] = ld_nc_v4(p.k_pool + off);
+      k1[u] = ld_nc_v4(p.k_pool + off + 64);
+      v0[u] = ld_nc_v4(p.v_pool + off);
+      v1[u] = ld_nc_v4(p.v_pool + off + 64);
+    }
+    float sc[kDecU][G];
+#pragma unroll
+    for (int u = 0; u < kDecU; ++u) {
+      float kf[16];
+      {
+        float a[8], b[8];
+        unpack8(k0[u], a);
+        unpack8(k1[u], b);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { kf[d] = a[d]; kf[8 + d] = b[d]; }
+      }
+      const bool valid = (kb + rg + kDecRows * u) < k_end;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) s = fmaf(qf[g][d], kf[d], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        sc[u][g] = valid ? s : -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float mx = m[g];
+#pragma unroll
+      for (int u = 0; u < kDecU; ++u) mx = fmaxf(mx, sc[u][g]);
+      const float corr = fast_exp2(m[g] - mx);
+      m[g] = mx;
+      float ps = 0.f;
+#pragma unroll
+      for (int u = 0; u < kDecU; ++u) {
+        sc[u][g] = fast_exp2(sc[u][g] - mx);
+        ps += sc[u][g];
+      }
+      l[g] = l[g] * corr + ps;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) acc[g][d] *= corr;
+    }
+#pragma unroll
+    for (int u = 0; u < kDecU; ++u) {
+      float vf[16];
+      {
+        float a[8], b[8];
+        unpack8(v0[u], a);
+        unpack8(v1[u], b);
+#pragma unroll
+        for (int d = 0; d < 8; ++d) { vf[d] = a[d]; vf[8 + d] = b[d]; }
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[g][d] = fmaf(sc[u][g], vf[d], acc[g][d]);
+    }
+  }
+
+  // ---- combine the 16 lane-group states of this CTA
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    if (l8 == 0) {
+      sm_m[rg * G + g] = m[g];
+      sm_l[rg * G + g] = l[g];
+    }
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      sm_o[(rg * G + g) * kD + l8 * 8 + d] = acc[g][d];
+      sm_o[(rg * G + g) * kD + 64 + l8 * 8 + d] = acc[g][8 + d];
+    }
+  }
+  __syncthreads();
+  const int unit = row * p.Hkv + hk;
+  float* wsb = p.ws ? p.ws + ((long long)unit * p.nsplit) * G * (kD + 2) : nullptr;
+  for (int o = threadIdx.x; o < G * kD; o += kThreads) {
+    const int g = o / kD, d = o % kD;
+    float M = -1e30f;
+#pragma unroll
+    for (int r = 0; r < kDecRows; ++r) M = fmaxf(M, sm_m[r * G + g]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int r = 0; r < kDecRows; ++r) {
+      const float w = fast_exp2(sm_m[r * G + g] - M);
+      L = fmaf(sm_l[r * G + g], w, L);
+      O = fmaf(sm_o[(r * G + g) * kD + d], w, O);
+    }
+    if (p.nsplit == 1) {
+      p.out[((long long)row * p.Hq + hk * G + g) * kD + d] = __float2bfloat16_rn(O / L);
+    } else {
+      float* w0 = wsb + (long long)split * G * (kD + 2) + g * (kD + 2);
+      __stcg(w0 + 2 + d, O);
+      if (d == 0) {
+        __stcg(w0, M);
+        __stcg(w0 + 1, L);
+      }
+    }
+  }
+  if (p.nsplit == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(p.counters + unit, 1);
+    const int last = prev == p.nsplit - 1;
+    if (last) p.counters[unit] = 0;
+    s_is_last = last;
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  for (int o = threadIdx.x; o < G * kD; o += kThreads) {
+    const int g = o / kD, d = o % kD;
+    float M = -1e30f;
+    for (int s = 0; s < p.nsplit; ++s) M = fmaxf(M, __ldcg(wsb + ((long long)s * G + g) * (kD + 2)));
+    float L = 0.f, O = 0.f;
+    for (int s = 0; s < p.nsplit; ++s) {
+      const float* w0 = wsb + ((long long)s * G + g) * (kD + 2);
+      const float w = fast_exp2(__ldcg(w0) - M);
+      L = fmaf(__ldcg(w0 + 1), w, L);
+      O = fmaf(__ldcg(w0 + 2 + d), w, O);
+    }
+    p.out[((long long)row * p.Hq + hk * G + g) * kD + d] = __float2bfloat16_rn(O / L);
+  }
+}
+
+template <int G>
+int launch_decode(const AttnParams& p, int rows, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * (size_t)kDecRows * G * (kD + 2);
+  dim3 grid(rows, p.Hkv, p.nsplit);
+  gqa_decode_kernel<G><<<grid, kThreads, smem, stream>>>(p);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
 template <int QT, int G>
 int launch_attn(const AttnParams& p, int tiles, cudaStream_t stream) {
   constexpr int NQ = QT * G;
@@ -311,6 +520,11 @@ extern "C" int mtts_gqa_attention(const void* q, const void* k_pool, const void*
                  "mtts_gqa_attention: too many tiles for split-KV");
     p.counters = reinterpret_cast<int*>(workspace);
     p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kAttnCounterBytes);
+  }
+  if (rows_per_tile == 1 && tile_row0 == nullptr) {
+    if (G == 1) return launch_decode<1>(p, tiles, stream);
+    if (G == 2) return launch_decode<2>(p, tiles, stream);
+    return launch_decode<4>(p, tiles, stream);
   }
 #define MTTS_ATTN_CASE(QT_, G_) \
   if (rows_per_tile == QT_ && G == G_) return launch_attn<QT_, G_>(p, tiles, stream);
