@@ -198,13 +198,22 @@ def main():
     start = T - 7
     wav_host = torch.empty((BATCH, NEW_FRAMES * 1920), dtype=torch.float32).pin_memory()
 
+    phase_ms = {"generate": 0.0, "codec": 0.0}
+
     def hot_path(ids, mask):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
         out = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=NEW_FRAMES, do_sample=False)
+        ev[1].record()
         speech = undelay(out[:, start:])
         ends = (find_max_valid_positions(speech) + 1)
         n = speech.shape[1]
         wavs = spt.decode([speech[i].permute(1, 0) for i in range(BATCH)], overlap_seconds=10)["syn_wav_list"]
+        ev[2].record()
+        hot_path.events.append(ev)
         return wavs, n, ends
+
+    hot_path.events = []
 
     def barrier():
         if world > 1:
@@ -250,7 +259,10 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    hot_path.events = []
     ms, frames, launches = timed(args.steps, step_resident)
+    gen_ms = sum(e[0].elapsed_time(e[1]) for e in hot_path.events) / max(1, len(hot_path.events))
+    codec_ms = sum(e[1].elapsed_time(e[2]) for e in hot_path.events) / max(1, len(hot_path.events))
     clk = clocks.stop() if rank == 0 else None
     value = frames * FRAME_S / (ms / 1e3)
     step_e2e()
@@ -329,6 +341,7 @@ def main():
                        "l2": "no flush needed: 3.5 GB weights + >4 GB KV per step exceed the 126 MB L2"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e / args.steps},
+            "phases_ms_per_step": {"lm_generate": gen_ms, "codec_decode": codec_ms},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }))
     if world > 1:

@@ -184,8 +184,6 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
   const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
   const int num_kb = kb_end - kb_begin;  // host guarantees >= 1
 
-  pdl_launch_dependents();  // let the next kernel in the stream start its own prologue / weight prefetch
-
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_x);
@@ -206,6 +204,9 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Only now (TMEM columns are ours) may the next kernel in the stream start its prologue / weight prefetch: a
+  // dependent that grabbed TMEM first and then sat in griddepcontrol.wait would deadlock against our allocation.
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -340,6 +341,198 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent variant for large M (prefill, codec): one CTA per SM walks the (n_tile, m_tile) list; the 512 TMEM
+// columns hold TWO 128 x 256 fp32 accumulators, so the MMA warp fills one while eight epilogue warps drain the
+// other straight from TMEM to global memory (lane = output column n: every warp store is one contiguous segment of
+// row m). The smem ring keeps streaming across tile boundaries.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPBN = 256;
+constexpr int kPStages = 4;
+constexpr int kPThreads = 320;  // warp0 TMA, warp1 MMA/TMEM, warps 2..9 epilogue
+
+__device__ __forceinline__ float epilogue_scalar(const GemmParams& p, float v, int m, int n, float bias_n, float gamma_n) {
+  if (p.flags & MTTS_EPI_BIAS) v += bias_n;
+  if (p.flags & MTTS_EPI_GELU) v = gelu_erf(v);
+  if (p.out_bf16) v = bf16_round(v);
+  if (p.flags & MTTS_EPI_GAMMA) v *= gamma_n;
+  if (p.flags & MTTS_EPI_RESIDUAL) {
+    const long long ri = (long long)m * p.ldr + n;
+    const float r = p.out_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p.residual)[ri])
+                               : reinterpret_cast<const float*>(p.residual)[ri];
+    v = r + v;
+  }
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPThreads, 1) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                                                                       const __grid_constant__ CUtensorMap tmap_x,
+                                                                       const GemmParams p, int tiles_n, int num_tiles) {
+  constexpr int BK = Traits<T>::kBlockK;
+  constexpr int UK = Traits<T>::kUmmaK;
+  constexpr uint32_t kABytes = kBlockW * kSwizzleBytes;
+  constexpr uint32_t kBBytes = kPBN * kSwizzleBytes;
+  constexpr uint32_t kIdesc = make_idesc(Traits<T>::kFmt, kBlockW, kPBN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kPStages * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kPStages * kBBytes);
+  uint64_t* empty_bar = full_bar + kPStages;
+  uint64_t* tmem_full_bar = empty_bar + kPStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = p.kb_total;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_x);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kPStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tmem_full_bar[a], 1);
+        mbar_init(&tmem_empty_bar[a], 8);  // one arrival per epilogue warp
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<512>(tmem_ptr_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();  // after the TMEM allocation (see gemm_tc_kernel)
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      pdl_wait();
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_tile = t % tiles_n, m_tile = t / tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kPStages;
+          const uint32_t ph = (it / kPStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], kABytes + kBBytes);
+          tma_load_2d(smem_a + s * kABytes, &tmap_w, &full_bar[s], kb * BK, n_tile * kBlockW, kEvictLast);
+          tma_load_2d(smem_b + s * kBBytes, &tmap_x, &full_bar[s], kb * BK, m_tile * kPBN, kEvictNormal);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int it = 0, ti = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+        const int a = ti & 1;
+        const uint32_t aph = (ti >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[a], aph ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + a * kPBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kPStages;
+          const uint32_t ph = (it / kPStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + s * kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + s * kBBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * UK * (int)sizeof(T));
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * UK * (int)sizeof(T));
+            if constexpr (sizeof(T) == 2)
+              umma_bf16(tacc, da, db, kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_tf32(tacc, da, db, kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[a]);
+      }
+    }
+  } else {
+    // ================= epilogue: 8 warps, lane quarter = warp % 4, column half = (warp - 2) / 4 =================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    pdl_wait();
+    int ti = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+      const int n_tile = t % tiles_n, m_tile = t / tiles_n;
+      const int a = ti & 1;
+      const uint32_t aph = (ti >> 1) & 1;
+      const int n = n_tile * kBlockW + quarter * 32 + lane;
+      const bool n_ok = n < p.N;
+      const float bias_n = (n_ok && (p.flags & MTTS_EPI_BIAS)) ? __ldg(p.bias + n) : 0.f;
+      const float gamma_n = (n_ok && (p.flags & MTTS_EPI_GAMMA)) ? __ldg(p.gamma + n) : 1.f;
+      mbar_wait(&tmem_full_bar[a], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + a * kPBN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int m0 = m_tile * kPBN + half * 128;
+#pragma unroll 1
+      for (int c = 0; c < 128; c += 32) {
+        if (m0 + c >= p.M) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c, r);
+        tmem_ld_wait();
+        if (p.flags & MTTS_EPI_SWIGLU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int m = m0 + c + j;
+            float v = __uint_as_float(r[j]);
+            if (p.out_bf16) v = bf16_round(v);
+            const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+            if ((lane & 1) == 0 && n_ok && m < p.M) {
+              float sg = silu_f(v);
+              if (p.out_bf16) sg = bf16_round(sg);
+              const float h = sg * other;
+              const long long o = (long long)m * p.ldo + (n >> 1);
+              if (p.out_bf16)
+                reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(h);
+              else
+                reinterpret_cast<float*>(p.out)[o] = h;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int m = m0 + c + j;
+            if (n_ok && m < p.M) {
+              const float v = epilogue_scalar(p, __uint_as_float(r[j]), m, n, bias_n, gamma_n);
+              const long long o = (long long)m * p.ldo + n;
+              if (p.out_bf16)
+                reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(v);
+              else
+                reinterpret_cast<float*>(p.out)[o] = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[a]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Host side: tensor-map cache + launch
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -445,7 +638,20 @@ int dispatch(int bn, const CUtensorMap& tw, const CUtensorMap& tx, const GemmPar
     case 32: return launch<T, 32>(tw, tx, p, grid, stream);
     case 64: return launch<T, 64>(tw, tx, p, grid, stream);
     case 128: return launch<T, 128>(tw, tx, p, grid, stream);
-    default: return launch<T, 256>(tw, tx, p, grid, stream);
+    default: {
+      static int persist = -1;
+      if (persist < 0) {
+        const char* e = getenv("MTTS_GEMM_NO_PERSIST");
+        persist = (e && e[0] == '1') ? 0 : 1;
+      }
+      if (!persist) return launch<T, 256>(tw, tx, p, grid, stream);
+      const int num_tiles = (int)(grid.x * grid.y);
+      const int ctas = num_tiles < mtts_num_sms() ? num_tiles : mtts_num_sms();
+      MTTS_CUDA_CHECK(mtts_launch(gemm_tc_persist_kernel<T>, dim3(ctas), dim3(kPThreads), smem_bytes<kPBN, kPStages>(), stream,
+                                  tw, tx, p, (int)grid.x, num_tiles));
+      MTTS_LAUNCH_CHECK();
+      return MTTS_OK;
+    }
   }
 }
 
@@ -471,6 +677,10 @@ int mtts_configure_gemm_tc() {
   if ((rc = configure_one<float, 64>())) return rc;
   if ((rc = configure_one<float, 128>())) return rc;
   if ((rc = configure_one<float, 256>())) return rc;
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persist_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       smem_bytes<kPBN, kPStages>()));
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       smem_bytes<kPBN, kPStages>()));
   return MTTS_OK;
 }
 
