@@ -200,9 +200,19 @@ int mtts_dwconv7_ln(const float* x, const float* conv_w, const float* conv_b, co
 int mtts_convt_gather(const float* y, const float* bias, float* out, int B, int Tin, int Cout, int K, int stride,
                       int Tout, int gelu, void* stream);
 
-/* im2col for Conv1d(K odd, pad=(K-1)/2) on token-major x [B,T,Cin]: col[b,t,j*Cin+ci] = x[b,t+j-pad,ci]
- * (VocosBackbone.embed, modules.py:1372). */
-int mtts_im2col(const float* x, float* col, int B, int T, int Cin, int K, int ld_col, void* stream);
+/* im2col for Conv1d(K odd, pad=(K-1)/2, stride) on token-major x [B,T,Cin]: col[b,t',j*Cin+ci] = x[b,t'*stride+j-pad,ci]
+ * (VocosBackbone.embed modules.py:1372; OmniAudioEncoder conv1/conv2 modules.py:238-240). */
+int mtts_im2col(const float* x, float* col, int B, int T, int Cin, int K, int ld_col, int stride, void* stream);
+
+/* Log-mel front end of XY_Tokenizer.encode (MelFeatureExtractor, nn/feature_extractor.py:78-104): torch.stft with a
+ * centred, reflect-padded Hann window restated as framing (this kernel) + an exact-fp32 DFT GEMM (mtts_gemm_simt);
+ * then |.|^2 (mtts_power_spectrum), the mel filter bank (mtts_gemm_simt) and log10 / per-item max-8 clamp / (x+4)/4
+ * (mtts_logmel_finish, one CTA per item, in place on [B, per_item]). wav [B, L] fp32 rows of stride ld_wav. */
+int mtts_stft_frames(const float* wav, long long ld_wav, const float* window, float* frames, int B, int T, int L, int n_fft,
+                     int hop, void* stream);
+int mtts_power_spectrum(const float* spec, long long lds, float* out, long long ldo, long long rows, int num_bins,
+                        void* stream);
+int mtts_logmel_finish(float* mel, int B, int per_item, void* stream);
 
 /* ISTFTHead nonlinearity (modules.py:971-984): x [rows, 2F] = (log-mag | phase) -> spec [rows, lds] =
  * (Re_0..Re_{F-1} | Im_0..Im_{F-1} | 0...) with mag = min(exp(.), 100). */

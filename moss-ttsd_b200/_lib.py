@@ -72,7 +72,10 @@ SIGNATURES = {
     "mtts_dwconv7_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
                                 c_void_p]),
     "mtts_convt_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "mtts_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mtts_im2col": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mtts_stft_frames": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mtts_power_spectrum": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p]),
+    "mtts_logmel_finish": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "mtts_istft_spec": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p]),
     "mtts_istft_ola": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mtts_add_rows_mod": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),

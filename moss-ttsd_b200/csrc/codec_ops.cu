@@ -260,19 +260,69 @@ __global__ void convt_gather_kernel(const float* __restrict__ y, const float* __
 // im2col for Conv1d(k, pad=(k-1)/2) on token-major input: col[b,t, j*Cin + ci] = x[b, t + j - pad, ci] (0 outside).
 // (VocosBackbone.embed, modules.py:1372,1401.)
 __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int B, int T, int Cin, int K,
-                              int ld_col) {
+                              int ld_col, int stride, int Tout) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cv = Cin >> 2;
-  const long long total = (long long)B * T * K * cv;
+  const long long total = (long long)B * Tout * K * cv;
   if (gid >= total) return;
   const int c = (int)(gid % cv) * 4;
   const int j = (int)((gid / cv) % K);
-  const long long tok = gid / ((long long)cv * K);
-  const int t = (int)(tok % T);
-  const int tt = t + j - (K - 1) / 2;
+  const long long otok = gid / ((long long)cv * K);
+  const int to = (int)(otok % Tout);
+  const long long b = otok / Tout;
+  const int tt = to * stride + j - (K - 1) / 2;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (tt >= 0 && tt < T) v = *reinterpret_cast<const float4*>(x + (tok + (tt - t)) * Cin + c);
-  *reinterpret_cast<float4*>(col + tok * ld_col + j * Cin + c) = v;
+  if (tt >= 0 && tt < T) v = *reinterpret_cast<const float4*>(x + (b * T + tt) * Cin + c);
+  *reinterpret_cast<float4*>(col + otok * ld_col + j * Cin + c) = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Log-mel front end (MelFeatureExtractor._torch_extract_fbank_features, nn/feature_extractor.py:78-104):
+// torch.stft(n_fft, hop, hann, center=True -> reflect pad n_fft/2) restated as framing + an exact-fp32 DFT GEMM.
+//   stft_frames: frames[b, t, n] = window[n] * xpad[b, t*hop + n - n_fft/2]  (reflect at both ends of the L-sample
+//                chunk, which the extractor has already zero-padded to 30 s), t < T.
+//   power:       P[r, k] = re^2 + im^2 from the GEMM output [r, (re_0..re_{F-1} | im_0..im_{F-1})]
+//   logmel_finish (one CTA per item): log10(max(mel, 1e-10)); clamp at (item max - 8); (x + 4) / 4.
+// ------------------------------------------------------------------------------------------------
+__global__ void stft_frames_kernel(const float* __restrict__ wav, long long ld_wav, const float* __restrict__ window,
+                                   float* __restrict__ frames, int B, int T, int L, int n_fft, int hop) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)B * T * n_fft;
+  if (gid >= total) return;
+  const int n = (int)(gid % n_fft);
+  const int t = (int)((gid / n_fft) % T);
+  const long long b = gid / ((long long)n_fft * T);
+  long long i = (long long)t * hop + n - n_fft / 2;
+  if (i < 0) i = -i;
+  if (i >= L) i = 2LL * (L - 1) - i;
+  frames[gid] = window[n] * wav[b * ld_wav + i];
+}
+
+__global__ void power_kernel(const float* __restrict__ spec, long long lds, float* __restrict__ out, long long ldo,
+                             long long rows, int F) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= rows * ldo) return;
+  const long long r = gid / ldo;
+  const int k = (int)(gid % ldo);
+  float v = 0.f;
+  if (k < F) {
+    const float re = spec[r * lds + k], im = spec[r * lds + F + k];
+    v = re * re + im * im;
+  }
+  out[gid] = v;
+}
+
+__global__ void __launch_bounds__(1024) logmel_finish_kernel(float* __restrict__ mel, int per_item) {
+  __shared__ float red[33];
+  float* m = mel + (long long)blockIdx.x * per_item;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < per_item; i += blockDim.x) {
+    const float v = log10f(fmaxf(m[i], 1e-10f));
+    m[i] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = block_max(mx, red);
+  for (int i = threadIdx.x; i < per_item; i += blockDim.x) m[i] = (fmaxf(m[i], mx - 8.0f) + 4.0f) / 4.0f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -390,13 +440,46 @@ extern "C" int mtts_convt_gather(const float* y, const float* bias, float* out, 
   return MTTS_OK;
 }
 
-extern "C" int mtts_im2col(const float* x, float* col, int B, int T, int Cin, int K, int ld_col, void* stream_) {
+extern "C" int mtts_im2col(const float* x, float* col, int B, int T, int Cin, int K, int ld_col, int stride, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  MTTS_REQUIRE(Cin % 4 == 0 && (K & 1) == 1 && ld_col >= K * Cin && ld_col % 4 == 0, "mtts_im2col: bad shape");
+  MTTS_REQUIRE(Cin % 4 == 0 && (K & 1) == 1 && ld_col >= K * Cin && ld_col % 4 == 0 && stride >= 1, "mtts_im2col: bad shape");
   if (B <= 0 || T <= 0) return MTTS_OK;
   MTTS_REQUIRE(x && col, "mtts_im2col: null pointer");
-  const long long total = (long long)B * T * K * (Cin / 4);
-  im2col_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(x, col, B, T, Cin, K, ld_col);
+  const int Tout = (T + 2 * ((K - 1) / 2) - K) / stride + 1;
+  const long long total = (long long)B * Tout * K * (Cin / 4);
+  im2col_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(x, col, B, T, Cin, K, ld_col, stride, Tout);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_stft_frames(const float* wav, long long ld_wav, const float* window, float* frames, int B, int T, int L,
+                                int n_fft, int hop, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(n_fft > 0 && hop > 0 && L > n_fft / 2, "mtts_stft_frames: bad shape");
+  if (B <= 0 || T <= 0) return MTTS_OK;
+  MTTS_REQUIRE(wav && window && frames, "mtts_stft_frames: null pointer");
+  const long long total = (long long)B * T * n_fft;
+  stft_frames_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(wav, ld_wav, window, frames, B, T, L, n_fft, hop);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_power_spectrum(const float* spec, long long lds, float* out, long long ldo, long long rows, int num_bins,
+                                   void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(num_bins > 0 && lds >= 2 * num_bins && ldo >= num_bins, "mtts_power_spectrum: bad shape");
+  if (rows <= 0) return MTTS_OK;
+  MTTS_REQUIRE(spec && out, "mtts_power_spectrum: null pointer");
+  power_kernel<<<(unsigned)ceil_div_ll(rows * ldo, 256), 256, 0, stream>>>(spec, lds, out, ldo, rows, num_bins);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_logmel_finish(float* mel, int B, int per_item, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (B <= 0 || per_item <= 0) return MTTS_OK;
+  MTTS_REQUIRE(mel, "mtts_logmel_finish: null pointer");
+  logmel_finish_kernel<<<B, 1024, 0, stream>>>(mel, per_item);
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }

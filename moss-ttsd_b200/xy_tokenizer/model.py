@@ -32,6 +32,37 @@ def sinusoids(length, channels, max_timescale=10000):
     return torch.cat([torch.sin(scaled_time), torch.cos(scaled_time)], dim=1)
 
 
+def mel_filter_bank_slaney(num_frequency_bins: int, num_mel_filters: int, min_frequency: float, max_frequency: float,
+                           sampling_rate: int):
+    """Slaney-scale, Slaney-normalised triangular mel filters [num_frequency_bins, num_mel_filters] (float64), the table
+    MelFeatureExtractor builds with transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney")
+    (nn/feature_extractor.py:41-49)."""
+    import numpy as np
+
+    def hz_to_mel(f):
+        f = np.asarray(f, dtype=np.float64)
+        lin = 3.0 * f / 200.0
+        logstep = 27.0 / np.log(6.4)
+        return np.where(f >= 1000.0, 15.0 + np.log(np.maximum(f, 1e-300) / 1000.0) * logstep, lin)
+
+    def mel_to_hz(m):
+        m = np.asarray(m, dtype=np.float64)
+        lin = 200.0 * m / 3.0
+        logstep = np.log(6.4) / 27.0
+        return np.where(m >= 15.0, 1000.0 * np.exp(logstep * (m - 15.0)), lin)
+
+    mel_freqs = np.linspace(hz_to_mel(min_frequency), hz_to_mel(max_frequency), num_mel_filters + 2)
+    filter_freqs = mel_to_hz(mel_freqs)
+    fft_freqs = np.linspace(0, sampling_rate // 2, num_frequency_bins)
+    diff = np.diff(filter_freqs)
+    slopes = filter_freqs[None, :] - fft_freqs[:, None]
+    down = -slopes[:, :-2] / diff[:-1]
+    up = slopes[:, 2:] / diff[1:]
+    fb = np.maximum(0.0, np.minimum(down, up))
+    fb *= (2.0 / (filter_freqs[2:num_mel_filters + 2] - filter_freqs[:num_mel_filters]))[None, :]
+    return fb
+
+
 def _wn(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     """torch.nn.utils.weight_norm (dim=0) weight: g * v / ||v|| (the reference recomputes this every forward)."""
     n = v.float().reshape(v.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1)))
@@ -101,6 +132,15 @@ class ResidualVQ:
         if int(self._err.item()):
             raise IndexError("code index out of range in decode_codes")
         return out.view(B, T, -1).permute(0, 2, 1)
+
+    def encode_tokens(self, zt: torch.Tensor, valid: torch.Tensor, n_quantizers: Optional[int] = None):
+        """Token-major entry used by XY_Tokenizer.encode: zt (N, input_dim) fp32, valid (N,) bool -> codes (nq, N)."""
+        nq = n_quantizers or self.num_quantizers
+        if self.in_w is not None:
+            zt = ops.gemm_simt(zt, self.in_w, bias=self.in_b)  # exact fp32: a TF32 product here would move codes
+        codes, _, _ = ops.rvq_encode(zt.contiguous(), self.codebooks[:nq].contiguous(), self.norms[:nq].contiguous(),
+                                     valid=valid.contiguous(), want_zq=False)
+        return codes
 
     def forward(self, z: torch.Tensor, input_length: torch.Tensor, n_quantizers: Optional[int] = None):
         """z (B, input_dim, T) fp32 channel-major, input_length (B,). Returns (quantized_out (B, output_dim, T),
@@ -313,6 +353,66 @@ class XY_Tokenizer:
         ops.ensure_init()
         self.L = _lib.load()
         self._ready = True
+        self._prepare_encoder()
+
+    def _prepare_encoder(self):
+        """Encode-side weights (semantic / acoustic encoders, adapters, gated down-conv); absent keys -> encode() unavailable."""
+        sd, dev, gp = self._sd, self.device, self.params
+        self._enc_ready = False
+        if "semantic_encoder.conv1.weight" not in sd:
+            return
+        f = lambda k: sd[k].to(dev, torch.float32).contiguous()
+
+        def conv_as_gemm(w):  # Conv1d [Cout, Cin, k] -> [Cout, k*Cin (padded to 4)]
+            co, ci, k = w.shape
+            ld = (k * ci + 3) // 4 * 4
+            out = torch.zeros((co, ld), dtype=torch.float32, device=dev)
+            out[:, :k * ci] = w.permute(0, 2, 1).reshape(co, -1)
+            return out
+
+        self.enc = {}
+        for name in ("semantic_encoder", "acoustic_encoder"):
+            kw = gp[f"{name}_kwargs"]
+            max_pos = (kw["max_audio_seconds"] * kw["sampling_rate"] // kw["hop_length"]) // kw["stride_size"]
+            self.enc[name] = dict(
+                c1_w=conv_as_gemm(f(f"{name}.conv1.weight")), c1_b=f(f"{name}.conv1.bias"),
+                c2_w=conv_as_gemm(f(f"{name}.conv2.weight")), c2_b=f(f"{name}.conv2.bias"),
+                k=kw["kernel_size"], stride=kw["stride_size"], heads=kw["encoder_attention_heads"],
+                stack=_TransformerStack(sd, f"{name}.", kw["encoder_layers"], dev),
+                pos=sinusoids(max_pos, kw["d_model"]).to(dev, torch.float32).contiguous())
+        for name in ("semantic_encoder_adapter", "pre_rvq_adapter"):
+            kw = gp[f"{name}_kwargs"]
+            self.enc[name] = dict(
+                proj_w=f(f"{name}.proj.weight") if kw["input_dim"] != kw["d_model"] else None,
+                proj_b=f(f"{name}.proj.bias") if kw["input_dim"] != kw["d_model"] else None,
+                out_w=f(f"{name}.out_proj.weight") if kw["output_dim"] != kw["d_model"] else None,
+                out_b=f(f"{name}.out_proj.bias") if kw["output_dim"] != kw["d_model"] else None,
+                heads=kw["encoder_attention_heads"], stack=_TransformerStack(sd, f"{name}.", kw["encoder_layers"], dev),
+                pos=sinusoids(kw["max_source_positions"], kw["d_model"]).to(dev, torch.float32).contiguous())
+        dk = gp["downsample_kwargs"]
+        gw, uw = f("downsample.gate_proj.weight"), f("downsample.up_proj.weight")  # [4D, D, 4]
+        g2 = gw.permute(0, 2, 1).reshape(gw.shape[0], -1)
+        u2 = uw.permute(0, 2, 1).reshape(uw.shape[0], -1)
+        self.ds_gu_w = torch.stack([g2, u2], dim=1).reshape(2 * g2.shape[0], g2.shape[1]).contiguous()  # interleaved
+        self.ds_down_w = f("downsample.down_proj.weight")
+        self.ds_ln_w, self.ds_ln_b = f("downsample.layer_norm.weight"), f("downsample.layer_norm.bias")
+        self.ds_pool = dk["avg_pooler"]
+        # log-mel front end: Hann window, real-DFT matrix (cos | -sin), Slaney mel filters
+        fk = gp["feature_extractor_kwargs"]
+        self.fe_nfft, self.fe_hop, self.fe_mels = fk["n_fft"], fk["hop_length"], fk["feature_size"]
+        self.fe_nsamples = fk["chunk_length"] * fk["sampling_rate"]
+        F = self.fe_nfft // 2 + 1
+        n = torch.arange(self.fe_nfft, dtype=torch.float64)[None, :]
+        k = torch.arange(F, dtype=torch.float64)[:, None]
+        ang = 2.0 * math.pi * k * n / self.fe_nfft
+        self.fe_dft = torch.cat([torch.cos(ang), -torch.sin(ang)], 0).to(dev, torch.float32).contiguous()  # [2F, n_fft]
+        self.fe_window = torch.hann_window(self.fe_nfft).to(dev, torch.float32).contiguous()
+        self.fe_pld = (F + 3) // 4 * 4
+        fb = torch.from_numpy(mel_filter_bank_slaney(F, self.fe_mels, 0.0, fk["sampling_rate"] / 2, fk["sampling_rate"]))
+        melw = torch.zeros((self.fe_mels, self.fe_pld), dtype=torch.float32)
+        melw[:, :F] = fb.t().to(torch.float32)
+        self.fe_melw = melw.to(dev).contiguous()
+        self._enc_ready = True
 
     # ------------------------------------------------------------------ kernels
     def _ln(self, x, w, b, eps=1e-5, lengths=None, rows_per_item=0, out=None):
@@ -370,7 +470,7 @@ class XY_Tokenizer:
         col = torch.empty((B * T4, self.v_embed_ld), dtype=torch.float32, device=dev)
         if self.v_embed_ld != self.v_k * self.mel_bins:
             col.zero_()
-        check(L.mtts_im2col(ptr(mel), ptr(col), B, T4, self.mel_bins, self.v_k, self.v_embed_ld, stream_ptr()))
+        check(L.mtts_im2col(ptr(mel), ptr(col), B, T4, self.mel_bins, self.v_k, self.v_embed_ld, 1, stream_ptr()))
         x = ops.gemm(col, self.v_embed_w, bias=self.v_embed_b)                  # (B*T4, 512)
         x = self._ln(x, self.v_norm_w, self.v_norm_b, eps=1e-6)
         t = torch.empty_like(x)
@@ -437,11 +537,122 @@ class XY_Tokenizer:
             syn = [torch.zeros(0, device=device) for _ in range(batch_size)]
         return {"syn_wav_list": syn}
 
+    # ------------------------------------------------------------------ encode side
+    def _conv_gelu(self, x, w, b, B, T, cin, k, stride):
+        """Conv1d(k, pad=(k-1)/2, stride) + exact GELU on token-major x (B*T, cin) as im2col + GEMM."""
+        Tout = (T + 2 * ((k - 1) // 2) - k) // stride + 1
+        col = torch.empty((B * Tout, w.shape[1]), dtype=torch.float32, device=x.device)
+        if w.shape[1] != k * cin:
+            col.zero_()
+        check(self.L.mtts_im2col(ptr(x), ptr(col), B, T, cin, k, w.shape[1], stride, stream_ptr()))
+        return ops.gemm(col, w, bias=b, gelu=True), Tout
+
+    def _encoder(self, mel, mel_len, B, T, e):
+        h, T1 = self._conv_gelu(mel, e["c1_w"], e["c1_b"], B, T, mel.shape[1], e["k"], 1)
+        h, T2 = self._conv_gelu(h, e["c2_w"], e["c2_b"], B, T1, h.shape[1], e["k"], e["stride"])
+        lens = (mel_len // e["stride"]).to(torch.int32).contiguous()
+        check(self.L.mtts_add_rows_mod(ptr(h), ptr(e["pos"]), B * T2, h.shape[1], T2, stream_ptr()))
+        return self._stack(h, e["stack"], e["heads"], lens, B, T2), lens, T2
+
+    def _adapter(self, x, lens, B, T, a):
+        h = ops.gemm(x, a["proj_w"], bias=a["proj_b"]) if a["proj_w"] is not None else x.clone()
+        check(self.L.mtts_add_rows_mod(ptr(h), ptr(a["pos"]), B * T, h.shape[1], T, stream_ptr()))
+        h = self._stack(h, a["stack"], a["heads"], lens, B, T)
+        return ops.gemm(h, a["out_w"], bias=a["out_b"]) if a["out_w"] is not None else h
+
+    @torch.no_grad()
+    def log_mel(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav (B, n_samples) fp32 on device (zero-padded to the 30 s chunk) -> log-mel (B*T, n_mels) token-major."""
+        B, Ls = wav.shape
+        T = Ls // self.fe_hop
+        L = self.L
+        frames = torch.empty((B * T, self.fe_nfft), dtype=torch.float32, device=wav.device)
+        check(L.mtts_stft_frames(ptr(wav), wav.stride(0), ptr(self.fe_window), ptr(frames), B, T, Ls, self.fe_nfft, self.fe_hop,
+                                 stream_ptr()))
+        spec = ops.gemm_simt(frames, self.fe_dft)                       # exact fp32 DFT: (B*T, 2F)
+        F = self.fe_nfft // 2 + 1
+        power = torch.empty((B * T, self.fe_pld), dtype=torch.float32, device=wav.device)
+        check(L.mtts_power_spectrum(ptr(spec), spec.stride(0), ptr(power), self.fe_pld, B * T, F, stream_ptr()))
+        mel = ops.gemm_simt(power, self.fe_melw)                        # (B*T, n_mels)
+        check(L.mtts_logmel_finish(ptr(mel), B, T * self.fe_mels, stream_ptr()))
+        return mel
+
+    @torch.no_grad()
+    def tokenize_tokens(self, x: torch.Tensor, input_lengths: torch.Tensor):
+        """x (B, 1, T<=30 s) on device, lengths (B,) -> (codes (nq, B, T_code) int64, code lengths (B,))."""
+        if not getattr(self, "_enc_ready", False):
+            raise RuntimeError("XY_Tokenizer.encode: encoder-side weights are not loaded")
+        dev = self.device
+        B = x.shape[0]
+        wav = torch.zeros((B, self.fe_nsamples), dtype=torch.float32, device=dev)
+        Tn = min(x.shape[-1], self.fe_nsamples)
+        wav[:, :Tn] = x[:, 0, :Tn]
+        lens = torch.clamp(input_lengths.to(dev), max=self.fe_nsamples)
+        # samples beyond each item's length are padding for the extractor (it is handed xi[:, :x_len], model.py:66)
+        wav *= (torch.arange(self.fe_nsamples, device=dev)[None, :] < lens[:, None])
+        mel = self.log_mel(wav)
+        T = self.fe_nsamples // self.fe_hop
+        mel_len = (lens + self.fe_hop - 1) // self.fe_hop                 # attention_mask[:, ::hop].sum()
+        sem, l2, T2 = self._encoder(mel, mel_len, B, T, self.enc["semantic_encoder"])
+        sem = self._adapter(sem, l2, B, T2, self.enc["semantic_encoder_adapter"])
+        aco, _, _ = self._encoder(mel, mel_len, B, T, self.enc["acoustic_encoder"])
+        cat = torch.cat([sem, aco], dim=1).contiguous()                   # channel concat, token-major
+        h = self._adapter(cat, l2, B, T2, self.enc["pre_rvq_adapter"])
+        # ResidualDownConv (modules.py:426-477): 4 frames -> 1; gate/up convs (k = stride = 4) are one interleaved GEMM
+        # with the SwiGLU epilogue; down_proj + residual; LayerNorm
+        pool = self.ds_pool
+        T3 = T2 // pool
+        x4 = h.view(B * T3, pool * h.shape[1])
+        gu = ops.gemm(x4, self.ds_gu_w, swiglu=True)
+        c = ops.gemm(gu, self.ds_down_w, residual=x4)
+        z = self._ln(c, self.ds_ln_w, self.ds_ln_b)
+        l3 = (l2 // pool).to(torch.int64)
+        valid = (torch.arange(T3, device=dev)[None, :] < l3[:, None]).reshape(-1)
+        codes = self.quantizer.encode_tokens(z, valid)
+        return codes.view(self.nq, B, T3), l3
+
+    @torch.inference_mode()
+    def inference_tokenize(self, x, input_lengths):
+        codes, l3 = self.tokenize_tokens(x.to(self.device), input_lengths)
+        return {"zq": None, "codes": codes, "codes_lengths": l3}
+
     @torch.inference_mode()
     def encode(self, wav_list, overlap_seconds=10, device=None):
-        raise NotImplementedError(
-            "XY_Tokenizer.encode: the mel / encoder front-end (SURVEY.md §8f #1) is the next tier; the ResidualVQ part "
-            "of encode is available as `self.quantizer(z, lengths)` on the down-sampled features")
-
-    def inference_tokenize(self, x, input_lengths):
-        raise NotImplementedError("see XY_Tokenizer.encode")
+        """B x (T,) waveforms at 16 kHz -> {"codes_list": B x (nq, T // 1280) int64}; 30 s windows with
+        (30 - overlap) s hop (model.py:130-192). Chunk bookkeeping is host arithmetic on the known lengths."""
+        device = torch.device(device) if device is not None else self.device
+        if device.type != "cuda":
+            raise RuntimeError("XY_Tokenizer.encode runs on CUDA only (no CPU path)")
+        duration_seconds = 30 - overlap_seconds
+        chunk_size = int(30 * self.input_sample_rate)
+        duration_size = int(duration_seconds * self.input_sample_rate)
+        code_duration_length = duration_size // self.encoder_downsample_rate
+        lens = [int(len(w)) for w in wav_list]
+        batch_size = len(wav_list)
+        max_length = max(lens) if lens else 0
+        wav_tensor = torch.zeros(batch_size, 1, max_length, device=device)
+        for i, w in enumerate(wav_list):
+            wav_tensor[i, 0, :lens[i]] = w.to(device)
+        max_chunks = (max_length + duration_size - 1) // duration_size if duration_size > 0 else 0
+        chunks = []
+        for chunk_idx in range(max_chunks):
+            start = chunk_idx * duration_size
+            end = min(start + chunk_size, max_length)
+            chunk_lens = [min(max(l - start, 0), end - start) for l in lens]
+            if max(chunk_lens) == 0:
+                continue
+            codes, code_lens = self.tokenize_tokens(wav_tensor[:, :, start:end],
+                                                    torch.tensor(chunk_lens, dtype=torch.int64, device=device))
+            code_lens = code_lens.cpu().tolist()
+            valid = torch.zeros(self.nq, batch_size, code_duration_length, device=device, dtype=torch.long)
+            for b in range(batch_size):
+                n = min(code_lens[b], code_duration_length)
+                if n > 0:
+                    valid[:, b, :n] = codes[:, b, :n]
+            chunks.append(valid)
+        if chunks:
+            codes_tensor = torch.cat(chunks, dim=-1)
+            codes_list = [codes_tensor[:, i, :lens[i] // self.encoder_downsample_rate] for i in range(batch_size)]
+        else:
+            codes_list = [torch.zeros(self.nq, 0, device=device, dtype=torch.long) for _ in range(batch_size)]
+        return {"codes_list": codes_list}

@@ -147,3 +147,98 @@ class CodecOracle:
             chunks.append(valid)
         full = torch.cat(chunks, -1)
         return [full[i, :int(lens[i]) * up] for i in range(B)]
+
+
+    # -------------------------------------------------------------- encode side (model.py:54-101,130-192)
+    def log_mel(self, wav_list):
+        """MelFeatureExtractor (nn/feature_extractor.py:78-104,128-237, torch path): pad to 30 s, torch.stft(400, 160, hann),
+        power, Slaney mel, log10, per-item max-8 clamp, (x+4)/4. -> (B, 80, 3000), frame counts."""
+        from transformers.audio_utils import mel_filter_bank
+        fk = self.gp["feature_extractor_kwargs"]
+        n_fft, hop, n_samples = fk["n_fft"], fk["hop_length"], fk["chunk_length"] * fk["sampling_rate"]
+        B = len(wav_list)
+        wav = torch.zeros(B, n_samples)
+        lens = []
+        for i, w in enumerate(wav_list):
+            n = min(len(w), n_samples)
+            wav[i, :n] = w[:n]
+            lens.append(n)
+        stft = torch.stft(wav, n_fft, hop, window=torch.hann_window(n_fft), return_complex=True)
+        mag = stft[..., :-1].abs() ** 2
+        filt = torch.from_numpy(mel_filter_bank(num_frequency_bins=1 + n_fft // 2, num_mel_filters=fk["feature_size"],
+                                                min_frequency=0.0, max_frequency=fk["sampling_rate"] / 2,
+                                                sampling_rate=fk["sampling_rate"], norm="slaney", mel_scale="slaney")).float()
+        log_spec = torch.clamp(filt.T @ mag, min=1e-10).log10()
+        mx = log_spec.max(dim=2, keepdim=True)[0].max(dim=1, keepdim=True)[0]
+        log_spec = (torch.maximum(log_spec, mx - 8.0) + 4.0) / 4.0
+        frames = torch.tensor([(n + hop - 1) // hop for n in lens])
+        return log_spec, frames
+
+    def _audio_encoder(self, mel, mel_len, name):
+        sd, kw = self.sd, self.gp[f"{name}_kwargs"]
+        x = F.gelu(F.conv1d(mel, sd[f"{name}.conv1.weight"], sd[f"{name}.conv1.bias"], padding=1))
+        x = F.gelu(F.conv1d(x, sd[f"{name}.conv2.weight"], sd[f"{name}.conv2.bias"], stride=kw["stride_size"], padding=1))
+        out_len = (mel_len // kw["stride_size"]).long()
+        max_pos = (kw["max_audio_seconds"] * kw["sampling_rate"] // kw["hop_length"]) // kw["stride_size"]
+        h = self._stack(x.permute(0, 2, 1), f"{name}.", kw["encoder_layers"], kw["encoder_attention_heads"], out_len,
+                        sinusoids(max_pos, kw["d_model"]))
+        return h, out_len          # (B, T, D) token-major
+
+    def _transformer(self, x, lens, name):
+        sd, kw = self.sd, self.gp[f"{name}_kwargs"]
+        if kw["input_dim"] != kw["d_model"]:
+            x = F.linear(x, sd[f"{name}.proj.weight"], sd[f"{name}.proj.bias"])
+        h = self._stack(x, f"{name}.", kw["encoder_layers"], kw["encoder_attention_heads"], lens,
+                        sinusoids(kw["max_source_positions"], kw["d_model"]))
+        if kw["output_dim"] != kw["d_model"]:
+            h = F.linear(h, sd[f"{name}.out_proj.weight"], sd[f"{name}.out_proj.bias"])
+        return h
+
+    def tokenize(self, wav_list):
+        """inference_tokenize (model.py:54-101) on one chunk -> pre-RVQ features (B, T/4.., 3072), codes (nq, B, T), lengths."""
+        from oracle import rvq_np
+        sd = self.sd
+        mel, frames = self.log_mel(wav_list)
+        sem, l2 = self._audio_encoder(mel, frames, "semantic_encoder")
+        sem = self._transformer(sem, l2, "semantic_encoder_adapter")
+        aco, _ = self._audio_encoder(mel, frames, "acoustic_encoder")
+        h = self._transformer(torch.cat([sem, aco], dim=-1), l2, "pre_rvq_adapter")
+        p = self.gp["downsample_kwargs"]["avg_pooler"]
+        B, T, D = h.shape
+        xt = h.permute(0, 2, 1)
+        g = F.conv1d(xt, sd["downsample.gate_proj.weight"], stride=p).permute(0, 2, 1)
+        u = F.conv1d(xt, sd["downsample.up_proj.weight"], stride=p).permute(0, 2, 1)
+        xr = h.reshape(B, -1, D * p)
+        c = F.linear(F.silu(g) * u, sd["downsample.down_proj.weight"])
+        z = F.layer_norm(c + xr, (D * p,), sd["downsample.layer_norm.weight"], sd["downsample.layer_norm.bias"])
+        l3 = l2 // p
+        w_in = torch.from_numpy(weight_norm_weight(sd["quantizer.input_proj.weight_v"].numpy(), sd["quantizer.input_proj.weight_g"].numpy()))
+        zt = F.linear(z, w_in[:, :, 0], sd["quantizer.input_proj.bias"])
+        T3 = z.shape[1]
+        valid = (torch.arange(T3)[None, :] < l3[:, None]).reshape(-1).numpy()
+        cbs = np.stack([sd[f"quantizer.quantizers.{i}.codebook"].numpy() for i in range(self.nq)])
+        codes, _, _, _ = rvq_np.rvq_forward(zt.reshape(B * T3, -1).numpy(), cbs, valid)
+        return z, torch.from_numpy(codes).view(self.nq, B, T3), l3
+
+    def encode(self, wav_list, overlap_seconds=10):
+        sr, down = self.gp["input_sample_rate"], 1280
+        chunk, dur = int(30 * sr), int((30 - overlap_seconds) * sr)
+        code_dur = dur // down
+        lens = [len(w) for w in wav_list]
+        Lm = max(lens)
+        B = len(wav_list)
+        chunks = []
+        for ci in range((Lm + dur - 1) // dur):
+            start, end = ci * dur, min(ci * dur + chunk, Lm)
+            cl = [min(max(l - start, 0), end - start) for l in lens]
+            if max(cl) == 0:
+                continue
+            _, codes, l3 = self.tokenize([w[start:start + n] for w, n in zip(wav_list, cl)])
+            valid = torch.zeros(self.nq, B, code_dur, dtype=torch.long)
+            for b in range(B):
+                n = min(int(l3[b]), code_dur)
+                if n > 0:
+                    valid[:, b, :n] = codes[:, b, :n]
+            chunks.append(valid)
+        full = torch.cat(chunks, -1)
+        return [full[:, i, :lens[i] // down] for i in range(B)]

@@ -165,3 +165,52 @@ def full_codec_params():
         vocos_kwargs=dict(input_channels=80, dim=512, intermediate_dim=4096, num_layers=30, n_fft=960, hop_size=240,
                           padding="same"),
     )
+
+
+# ------------------------------------------------------------------------------------------------ encode side
+def encoder_param_specs(gp):
+    """(name, shape, kind) of the encode-side parameters (semantic / acoustic OmniAudioEncoder, the two adapter
+    Transformers, ResidualDownConv) under the reference's state-dict names (model.py:26-38, nn/modules.py:208-326,
+    426-477, 519-640)."""
+    specs = []
+    for name in ("semantic_encoder", "acoustic_encoder"):
+        kw = gp[f"{name}_kwargs"]
+        d, k = kw["d_model"], kw["kernel_size"]
+        specs += [(f"{name}.conv1.weight", (d, kw["num_mel_bins"], k), "conv_out"), (f"{name}.conv1.bias", (d,), "bias"),
+                  (f"{name}.conv2.weight", (d, d, k), "conv_out"), (f"{name}.conv2.bias", (d,), "bias")]
+        for l in range(kw["encoder_layers"]):
+            specs += _transformer_layer_specs(f"{name}.layers.{l}.", d, kw["encoder_ffn_dim"])
+        specs += [(f"{name}.layer_norm.weight", (d,), "ln_w"), (f"{name}.layer_norm.bias", (d,), "bias")]
+    for name in ("semantic_encoder_adapter", "pre_rvq_adapter"):
+        kw = gp[f"{name}_kwargs"]
+        d = kw["d_model"]
+        if kw["input_dim"] != d:
+            specs += [(f"{name}.proj.weight", (d, kw["input_dim"]), "lin"), (f"{name}.proj.bias", (d,), "bias")]
+        for l in range(kw["encoder_layers"]):
+            specs += _transformer_layer_specs(f"{name}.layers.{l}.", d, kw["encoder_ffn_dim"])
+        specs += [(f"{name}.layer_norm.weight", (d,), "ln_w"), (f"{name}.layer_norm.bias", (d,), "bias")]
+        if kw["output_dim"] != d:
+            specs += [(f"{name}.out_proj.weight", (kw["output_dim"], d), "lin"), (f"{name}.out_proj.bias", (kw["output_dim"],), "bias")]
+    dk = gp["downsample_kwargs"]
+    d, p = dk["d_model"], dk["avg_pooler"]
+    specs += [("downsample.gate_proj.weight", (d * p, d, p), "conv_out"), ("downsample.up_proj.weight", (d * p, d, p), "conv_out"),
+              ("downsample.down_proj.weight", (d * p, d * p), "lin"),
+              ("downsample.layer_norm.weight", (d * p,), "ln_w"), ("downsample.layer_norm.bias", (d * p,), "bias")]
+    return specs
+
+
+def make_encoder_weights(gp, seed):
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    sd = {}
+    for name, shape, kind in encoder_param_specs(gp):
+        if kind == "lin":
+            w = rng.standard_normal(shape, dtype=f) * f(1.0 / np.sqrt(shape[1]))
+        elif kind == "conv_out":
+            w = rng.standard_normal(shape, dtype=f) * f(1.0 / np.sqrt(shape[1] * shape[2]))
+        elif kind == "ln_w":
+            w = (1.0 + 0.1 * rng.standard_normal(shape)).astype(f)
+        else:
+            w = (0.02 * rng.standard_normal(shape)).astype(f)
+        sd[name] = w.astype(f)
+    return sd

@@ -27,7 +27,52 @@ def build_ref_codec(gp, seed):
     return model
 
 
+def gen_encode():
+    """Reference XY_Tokenizer.encode on CPU (tiny config): codes, and the pre-RVQ features / mel of one chunk."""
+    from oracle.codec_weights import make_encoder_weights
+    XY, _, _ = ref_shims.import_codec()
+    gp, seed = TINY_CODEC, 33
+    torch.manual_seed(0)
+    model = XY(gp).eval()
+    sd = make_codec_weights(gp, seed)
+    sd.update(make_encoder_weights(gp, seed + 7))
+    missing, unexpected = model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not unexpected, unexpected
+    bad = [m for m in missing if not any(s in m for s in ("positional_embedding", "inited", "cluster_size", "embed_avg", "istft.window"))]
+    assert not bad, bad
+    for q in model.quantizer.quantizers:
+        q.inited.fill_(True)
+    rng = np.random.default_rng(9)
+    out = {"seed": np.int64(seed)}
+    # a smooth-ish signal so that the log-mel has structure: filtered noise + tones; 35 s and 3 s (SURVEY §4 sizes)
+    def sig(n):
+        t = np.arange(n) / 16000.0
+        x = 0.3 * np.sin(2 * np.pi * 220 * t) + 0.2 * np.sin(2 * np.pi * 1330 * t + 1.0) + 0.05 * rng.standard_normal(n)
+        return (x * (0.5 + 0.5 * np.sin(2 * np.pi * 0.7 * t))).astype(np.float32)
+    wavs = [sig(35 * 16000), sig(3 * 16000)]
+    with torch.no_grad():
+        codes = model.encode([torch.from_numpy(w) for w in wavs], overlap_seconds=10, device=torch.device("cpu"))["codes_list"]
+        # one-chunk internals for the oracle pin
+        x = torch.zeros(2, 1, 480000)
+        x[0, 0] = torch.from_numpy(wavs[0][:480000])
+        x[1, 0, :48000] = torch.from_numpy(wavs[1])
+        lens = torch.tensor([480000, 48000])
+        feats = model.feature_extractor([x[0, 0].numpy(), x[1, 0, :48000].numpy()], sampling_rate=16000, return_tensors="pt",
+                                        return_attention_mask=True)
+        tok = model.inference_tokenize(x, lens)
+    for i, (w, c) in enumerate(zip(wavs, codes)):
+        out[f"len{i}"] = np.int64(len(w))
+        out[f"codes{i}"] = c.numpy().astype(np.int16)
+        print("encode", i, len(w), c.shape)
+    out["mel_sub"] = feats["input_features"].numpy()[:, :, ::25].astype(np.float32)   # decimated in time
+    out["mel_frames"] = feats["attention_mask"].sum(-1).numpy()
+    out["chunk_codes"] = tok["codes"].numpy().astype(np.int16)
+    out["chunk_code_lens"] = tok["codes_lengths"].numpy()
+    np.savez_compressed(os.path.join(GOLD, "codec_encode.npz"), **out)
+
+
 def main():
+    gen_encode()
     out = {}
     cases = {
         "tiny": (TINY_CODEC, 21, [30, 11]),           # one window, ragged batch

@@ -180,3 +180,51 @@ def test_codec_kernels_against_torch_functional():
     env = F.fold(win.square().expand(1, Ti, -1).transpose(1, 2), output_size=(1, size), kernel_size=(1, 960), stride=(1, 240)).squeeze()[360:-360]
     ref = yy / env
     assert (wav - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+def _spt_with_encoder(gp, seed):
+    from moss_ttsd_b200.xy_tokenizer.model import XY_Tokenizer
+    from oracle.codec_weights import make_codec_weights, make_encoder_weights
+    sd = make_codec_weights(gp, seed)
+    sd.update(make_encoder_weights(gp, seed + 7))
+    spt = XY_Tokenizer(gp)
+    spt.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return spt.to("cuda")
+
+
+def test_encode_matches_reference_golden():
+    """XY_Tokenizer.encode (log-mel, two encoders, adapters, gated down-conv, RVQ) vs the reference's encode.
+    The front end runs its GEMMs in TF32, so the pre-RVQ features carry ~1e-3 relative noise and a code whose two best
+    candidates are closer than that may flip; the gate is therefore an agreement RATE per codebook layer (first layer
+    >= 95 %), with exact shapes / lengths / chunking. The RVQ search itself is bit-exact (tests above)."""
+    from oracle.codec_weights import TINY_CODEC
+    from tests.test_codec_encode_common import make_signals
+    g = gold("codec_encode.npz")
+    spt = _spt_with_encoder(TINY_CODEC, int(g["seed"]))
+    wavs = [torch.from_numpy(w).cuda() for w in make_signals()]
+    mel = spt.log_mel(torch.stack([wavs[0][:480000], torch.nn.functional.pad(wavs[1], (0, 480000 - 48000))]))
+    mel = mel.view(2, 3000, 80).permute(0, 2, 1).cpu().numpy()
+    assert np.abs(mel[:, :, ::25] - g["mel_sub"]).max() <= 2e-3
+    out = spt.encode(wavs, overlap_seconds=10)["codes_list"]
+    rates = []
+    for i, c in enumerate(out):
+        want = g[f"codes{i}"].astype(np.int64)
+        assert tuple(c.shape) == want.shape and c.dtype == torch.int64
+        rates.append((c.cpu().numpy() == want).mean(1))
+    rates = np.mean(rates, 0)
+    print("encode code agreement per RVQ layer:", np.round(rates, 3))
+    assert rates[0] >= 0.95 and rates.mean() >= 0.80
+    tok = spt.inference_tokenize(torch.stack([wavs[0][:480000], torch.nn.functional.pad(wavs[1], (0, 480000 - 48000))])[:, None],
+                                 torch.tensor([480000, 48000]))
+    assert tok["codes"].shape == (8, 2, 375) and tok["codes_lengths"].tolist() == g["chunk_code_lens"].tolist()
+
+
+def test_encode_then_decode_round_trip_shapes():
+    from oracle.codec_weights import TINY_CODEC
+    spt = _spt_with_encoder(TINY_CODEC, 33)
+    wav = torch.randn(16000 * 4, device="cuda") * 0.1
+    codes = spt.encode([wav])["codes_list"]
+    assert codes[0].shape == (8, 50)
+    rec = spt.decode(codes)["syn_wav_list"][0]
+    assert rec.shape == (50 * 1920,) and torch.isfinite(rec).all()
+    assert spt.encode([])["codes_list"] == []

@@ -141,3 +141,26 @@ def test_cached_oracle_equals_reference_greedy(lm_gold, sd):
     ids, mask = torch.from_numpy(lm_gold["ids"]), torch.from_numpy(lm_gold["mask"])
     seq = m.generate(ids, mask, max_length=ids.shape[1] + 24, speech_range=TINY["speech_token_range"])
     np.testing.assert_array_equal(seq.numpy(), lm_gold["greedy_f32"])
+
+
+def test_codec_oracle_encode_matches_reference():
+    """Oracle restatement of XY_Tokenizer.encode vs the reference's own encode on CPU (35 s + 3 s, two windows)."""
+    from oracle.codec_oracle import CodecOracle
+    from oracle.codec_weights import TINY_CODEC, make_codec_weights, make_encoder_weights
+    from tests.test_codec_encode_common import make_signals
+    g = gold("codec_encode.npz")
+    seed = int(g["seed"])
+    sd = make_codec_weights(TINY_CODEC, seed)
+    sd.update(make_encoder_weights(TINY_CODEC, seed + 7))
+    orc = CodecOracle(TINY_CODEC, sd)
+    wavs = [torch.from_numpy(w) for w in make_signals()]
+    with torch.no_grad():
+        mel, frames = orc.log_mel([wavs[0][:480000], wavs[1]])
+        codes = orc.encode(wavs)
+    assert frames.tolist() == g["mel_frames"].tolist()
+    assert np.abs(mel.numpy()[:, :, ::25] - g["mel_sub"]).max() <= 1e-4
+    for i, c in enumerate(codes):
+        want = g[f"codes{i}"].astype(np.int64)
+        assert tuple(c.shape) == want.shape == (8, int(g[f"len{i}"]) // 1280)
+        agree = (c.numpy() == want).all(0).mean()
+        assert agree >= 0.98, agree   # identical torch ops; the few flips are fp32 near-ties of numpy-BLAS vs torch-MKL
