@@ -1,0 +1,79 @@
+"""process_batch end to end on the GPU with tiny random-init models and a stand-in tokenizer (no tokenizer/weights are
+available offline): return layout, text-only and prompt-audio items, and agreement with the staged
+pipeline run by hand."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from tests.common import TINY, tiny_model
+
+pytestmark = pytest.mark.gpu
+
+
+class Tok:
+    pad_token_id = 151643
+
+    def encode(self, s):
+        return [(ord(c) * 7 + i) % 151000 for i, c in enumerate(s)]
+
+
+def _codec():
+    from moss_ttsd_b200.xy_tokenizer.model import XY_Tokenizer
+    from oracle.codec_weights import TINY_CODEC, make_codec_weights, make_encoder_weights
+    gp = copy.deepcopy(TINY_CODEC)
+    gp["quantizer_kwargs"]["codebook_size"] = 1024   # LM speech channels emit ids in [0, 1024)
+    sd = make_codec_weights(gp, 3)
+    sd.update(make_encoder_weights(gp, 4))
+    spt = XY_Tokenizer(gp)
+    spt.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return spt.to("cuda")
+
+
+def test_process_batch_text_and_prompt_audio():
+    from moss_ttsd_b200 import generation_utils as gu
+    model, _ = tiny_model()
+    model.generation_config.eos_token_id = 152694
+    model.generation_config.max_new_tokens = 12
+    spt = _codec()
+    rng = np.random.default_rng(0)
+    wav = torch.from_numpy((0.1 * rng.standard_normal(16000 * 2)).astype(np.float32))[None]
+    items = [
+        {"text": "[S1]Hello there.[S2]Hi!"},
+        {"text": "[S1]Second item, a bit longer than the first one.", "prompt_audio": (wav, 16000), "prompt_text": "[S1]ref"},
+        {"text": "[S1]a", "prompt_audio_speaker1": (wav, 16000), "prompt_text_speaker1": "one",
+         "prompt_audio_speaker2": (wav[:, :16000], 16000), "prompt_text_speaker2": "two"},
+    ]
+    texts, audios = gu.process_batch(items, Tok(), model, spt, "cuda", "You are a speech synthesizer.", start_idx=5,
+                                     use_normalize=True)
+    assert [t["index"] for t in texts] == [5, 6, 7]
+    assert texts[0]["final_text"].startswith("<speaker1>") and texts[0]["use_normalize"] is True
+    assert texts[2]["original_text"] == "[S1]one[S2]two[S1]a"
+    assert len(audios) == 3
+    for i, a in enumerate(audios):
+        assert a is not None and a["sample_rate"] == 24000 and a["index"] == 5 + i
+        w = a["audio_data"]
+        assert w.device.type == "cpu" and w.dim() == 2 and w.shape[0] == 1 and w.dtype == torch.float32
+        assert w.shape[1] % 1920 == 0 and 0 < w.shape[1] <= 12 * 1920 and torch.isfinite(w).all()
+    # the same thing staged by hand gives the same waveform for item 0
+    g0 = gu.shifting_inputs(gu.process_inputs(Tok(), spt, "You are a speech synthesizer.", texts[0]["final_text"], "cuda"), Tok())
+    g1 = gu.shifting_inputs(gu.process_inputs(Tok(), spt, "You are a speech synthesizer.", texts[1]["final_text"], "cuda",
+                                              gu.load_audio_data((wav, 16000))), Tok())
+    g2 = gu.shifting_inputs(gu.process_inputs(Tok(), spt, "You are a speech synthesizer.", texts[2]["final_text"], "cuda",
+                                              gu.load_audio_data({"speaker1": (wav, 16000), "speaker2": (wav[:, :16000], 16000)})), Tok())
+    assert g1.shape[0] - (len(Tok().encode("x")) - 1) > g0.shape[0] - 100  # prompt audio rows were appended
+    ids, mask = gu.rpadding([g0, g1, g2], 8, Tok())
+    out = model.generate(input_ids=ids.cuda(), attention_mask=mask.cuda())
+    speech = gu.undelay(out[:, ids.shape[1] - 7:])
+    end = int(gu.find_max_valid_positions(speech)[0]) + 1
+    w0 = spt.decode([speech[0, :end].permute(1, 0)])["syn_wav_list"][0].cpu()
+    assert torch.equal(w0, audios[0]["audio_data"][0])
+
+
+def test_process_batch_sample_without_audio_returns_none():
+    """A row whose channel 1 never leaves the pad value has no audio: None, like the reference (generation_utils.py:437-440)."""
+    from moss_ttsd_b200 import generation_utils as gu
+    speech = torch.full((2, 6, 8), 1024)
+    speech[1, :3, 1] = 7
+    assert gu.find_max_valid_positions(speech).tolist() == [-1, 2]
