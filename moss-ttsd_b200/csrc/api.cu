@@ -23,6 +23,15 @@ bool mtts_pdl_enabled() {
   return v == 1;
 }
 
+bool mtts_pdl_small_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTTS_PDL_SMALL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1 && mtts_pdl_enabled();
+}
+
 static int g_num_sms[64] = {0};
 
 int mtts_num_sms() {

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(kThreads) gqa_attn_kernel(const AttnParams p) 
   constexpr int NQ = QT * G;  // query vectors handled per CTA
   constexpr int kUnroll = (QT > 1) ? 4 : 8;  // keys in flight per half-warp (decode: 16 x 16 B loads per lane)
   pdl_launch_dependents();    // the o_proj GEMM may start streaming its weights while attention runs
+  pdl_wait();
   extern __shared__ float sm[];
   float* sm_m = sm;                       // [kGroups][NQ]
   float* sm_l = sm_m + kGroups * NQ;      // [kGroups][NQ]
@@ -259,6 +260,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 template <int G>
 __global__ void __launch_bounds__(kThreads) gqa_decode_kernel(const AttnParams p) {
   pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* sm_m = sm;                        // [kDecRows][G]
   float* sm_l = sm_m + kDecRows * G;       // [kDecRows][G]
@@ -444,7 +446,7 @@ template <int G>
 int launch_decode(const AttnParams& p, int rows, cudaStream_t stream) {
   const size_t smem = sizeof(float) * (size_t)kDecRows * G * (kD + 2);
   dim3 grid(rows, p.Hkv, p.nsplit);
-  gqa_decode_kernel<G><<<grid, kThreads, smem, stream>>>(p);
+  MTTS_CUDA_CHECK(mtts_launch(gqa_decode_kernel<G>, grid, dim3(kThreads), smem, stream, p));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }
@@ -454,7 +456,7 @@ int launch_attn(const AttnParams& p, int tiles, cudaStream_t stream) {
   constexpr int NQ = QT * G;
   const size_t smem = sizeof(float) * (size_t)kGroups * NQ * (kD + 2);
   dim3 grid(tiles, p.Hkv, p.nsplit);
-  gqa_attn_kernel<QT, G><<<grid, kThreads, smem, stream>>>(p);
+  MTTS_CUDA_CHECK(mtts_launch(gqa_attn_kernel<QT, G>, grid, dim3(kThreads), smem, stream, p));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }

@@ -55,7 +55,8 @@ void mtts_count_launch();  // bumps the process-wide launch counter (bench.py re
 // top so that its own successor can do the same. Kernels must not touch predecessor-dependent memory (reads or
 // writes) before pdl_wait().
 // ---------------------------------------------------------------------------------------------
-bool mtts_pdl_enabled();  // false when MTTS_NO_PDL=1
+bool mtts_pdl_enabled();        // false when MTTS_NO_PDL=1
+bool mtts_pdl_small_enabled();  // PDL attribute on the small (non-GEMM) kernels; MTTS_PDL_SMALL=0 turns it off
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -91,6 +92,15 @@ static inline cudaError_t mtts_launch_cluster(void (*kernel)(KArgs...), dim3 gri
 template <typename... KArgs, typename... Args>
 static inline cudaError_t mtts_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                       Args... args) {
+  if (!mtts_pdl_small_enabled()) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  }
   return mtts_launch_cluster(kernel, grid, block, smem, stream, 1, args...);
 }
 #endif

@@ -21,6 +21,7 @@ struct EmbedParams {
 
 __global__ void embed_sum_kernel(const EmbedParams p) {
   pdl_launch_dependents();  // the GEMM that follows may start streaming its weights now
+  pdl_wait();               // launched with the PDL attribute: our own inputs come from the predecessor
   const int vec_per_row = p.hidden >> 3;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long row = gid / vec_per_row;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x
                                                       const bf16* __restrict__ w, bf16* __restrict__ out,
                                                       long long ldo, int hidden, float eps) {
   pdl_launch_dependents();  // the GEMM that follows may start streaming its weights now
+  pdl_wait();
   __shared__ float red[33];
   const long long row = blockIdx.x;
   const bf16* xr = x + row * ldx;
@@ -126,6 +128,7 @@ struct RopeParams {
 
 __global__ void __launch_bounds__(256) qknorm_rope_kv_kernel(const RopeParams p) {
   pdl_launch_dependents();
+  pdl_wait();
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int heads = p.Hq + 2 * p.Hkv;
@@ -208,7 +211,7 @@ extern "C" int mtts_embed_sum8(const long long* ids, int rows, int channels, con
   p.out = reinterpret_cast<bf16*>(out);
   p.err_flag = err_flag;
   const long long total = (long long)rows * (hidden / 8);
-  embed_sum_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(p);
+  MTTS_CUDA_CHECK(mtts_launch(embed_sum_kernel, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, stream, p));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }
@@ -220,8 +223,8 @@ extern "C" int mtts_rmsnorm(const void* x, long long ldx, const void* w, void* o
                "mtts_rmsnorm: hidden and strides must be multiples of 8");
   if (rows <= 0) return MTTS_OK;
   MTTS_REQUIRE(x && w && out, "mtts_rmsnorm: null pointer");
-  rmsnorm_kernel<<<rows, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(w),
-                                          reinterpret_cast<bf16*>(out), ldo, hidden, eps);
+  MTTS_CUDA_CHECK(mtts_launch(rmsnorm_kernel, dim3(rows), dim3(256), 0, stream, reinterpret_cast<const bf16*>(x), ldx,
+                              reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(out), ldo, hidden, eps));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }
@@ -248,7 +251,7 @@ extern "C" int mtts_qknorm_rope_kvappend(const void* qkv, long long ld_qkv, cons
   p.page_shift = shift; p.num_pages = num_pages; p.rows = rows; p.Hq = num_q_heads; p.Hkv = num_kv_heads; p.eps = eps;
   p.err_flag = err_flag;
   const long long warps = (long long)rows * (num_q_heads + 2 * num_kv_heads);
-  qknorm_rope_kv_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, stream>>>(p);
+  MTTS_CUDA_CHECK(mtts_launch(qknorm_rope_kv_kernel, dim3((unsigned)ceil_div_ll(warps, 8)), dim3(256), 0, stream, p));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }

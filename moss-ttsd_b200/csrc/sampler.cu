@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(kThreads) sample_scan_kernel(const SampleParam
   __shared__ int s_idx[kMaxSlices * kReport];
   __shared__ int s_last;
   pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, c = p.slice_channel[blockIdx.y], slice = p.slice_index[blockIdx.y];
   const mtts_sampler_config& cfg = p.cfg;
   const int V = cfg.vocab[c], S = p.slices_of[c];
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
   __shared__ int s_idx[kCap];
   __shared__ int s_last;
   pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, c = p.slice_channel[blockIdx.y], slice = p.slice_index[blockIdx.y];
   const mtts_sampler_config& cfg = p.cfg;
   if (!cfg.do_sample[c]) return;
@@ -404,6 +406,8 @@ struct StepParams {
 };
 
 __global__ void delay_step_kernel(const StepParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ int s_count;
   const int b = threadIdx.x;
   const int s = *p.step_ptr;
@@ -567,10 +571,10 @@ extern "C" int mtts_sample8(const void* logits, long long ld, int B, const mtts_
     any_sample |= cfg->do_sample[c] != 0;
   }
   p.total_slices = total;
-  sample_scan_kernel<<<dim3(B, total), kThreads, 0, stream>>>(p);
+  MTTS_CUDA_CHECK(mtts_launch(sample_scan_kernel, dim3(B, total), dim3(kThreads), 0, stream, p));
   MTTS_LAUNCH_CHECK();
   if (any_sample) {
-    sample_finish_kernel<<<dim3(B, total), kThreads, 0, stream>>>(p);
+    MTTS_CUDA_CHECK(mtts_launch(sample_finish_kernel, dim3(B, total), dim3(kThreads), 0, stream, p));
     MTTS_LAUNCH_CHECK();
   }
   return MTTS_OK;
@@ -595,7 +599,7 @@ extern "C" int mtts_delay_step(long long* tokens, const long long* tf_tail, long
   p.max_length = max_length; p.speech_lo = speech_lo; p.speech_hi = speech_hi; p.eos_token = eos_token;
   p.pad_token = cfg->pad_token; p.has_eos_criteria = has_eos_criteria; p.cfg = *cfg;
   const int threads = ((B + 31) / 32) * 32;
-  delay_step_kernel<<<1, threads, 0, stream>>>(p);
+  MTTS_CUDA_CHECK(mtts_launch(delay_step_kernel, dim3(1), dim3(threads), 0, stream, p));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }

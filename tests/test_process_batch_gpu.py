@@ -68,7 +68,11 @@ def test_process_batch_text_and_prompt_audio():
     speech = gu.undelay(out[:, ids.shape[1] - 7:])
     end = int(gu.find_max_valid_positions(speech)[0]) + 1
     w0 = spt.decode([speech[0, :end].permute(1, 0)])["syn_wav_list"][0].cpu()
-    assert torch.equal(w0, audios[0]["audio_data"][0])
+    # decoded alone vs decoded inside the equal-length group: same arithmetic up to the TF32 GEMMs' tile / split-K
+    # configuration, which depends on the row count
+    ref = audios[0]["audio_data"][0].double()
+    snr = 10 * torch.log10((ref ** 2).sum() / ((ref - w0.double()) ** 2).sum().clamp_min(1e-30))
+    assert w0.shape == ref.shape and snr >= 40.0, snr
 
 
 def test_process_batch_sample_without_audio_returns_none():
