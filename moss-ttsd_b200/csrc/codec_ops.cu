@@ -4,6 +4,7 @@
 // XY_Tokenizer/xy_tokenizer/nn/modules.py:1144-1153,1399-1409).
 #include "common.cuh"
 #include "mtts_internal.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -189,6 +190,152 @@ __global__ void __launch_bounds__(256) mha_varlen_kernel(const float* __restrict
       *reinterpret_cast<float4*>(out + ((long long)b * T + q) * E + h * kHD + ki * 4) =
           make_float4(acc[i][0] * inv, acc[i][1] * inv, acc[i][2] * inv, acc[i][3] * inv);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core version of the same attention (TF32 mma.sync m16n8k8, fp32 accumulate, flash-style online softmax).
+// CTA = 64 queries x one head, 4 warps x 16 query rows; K/V tiles of 64 keys staged in shared memory as TF32.
+// S = Q K^T uses Q (A, row-major) and K (B, "col-major" = key-major rows) fragments read straight from the padded
+// tiles (pitch 68 words -> conflict-free). For O += P V the probabilities stay in the accumulator layout: thread
+// (g, t) holds P[g][8j+2t] and P[g][8j+2t+1]; feeding them as A-fragment elements k = t and k = t+4 simply permutes
+// the keys of the block, and the V fragment is read with the same permutation (rows 8j+2t and 8j+2t+1), so no
+// register shuffles are needed.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) mha_varlen_tc_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                            const int* __restrict__ lengths, int T, int H,
+                                                            float scale_log2) {
+  extern __shared__ __align__(16) uint32_t smu[];
+  uint32_t* sk = smu;                   // [64][68] tf32
+  uint32_t* sv = sk + kKT * kPitch;     // [64][68] tf32
+  const int E = H * kHD;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kQT;
+  const int len = lengths ? min(lengths[b], T) : T;
+  const int kv_len = len > 0 ? len : T;  // all-masked item: uniform over every key, as in the reference
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const float* base = qkv + (long long)b * T * 3 * E;
+
+  // Q fragments for this warp's 16 rows, pre-scaled by head_dim^-0.5 * log2(e): 8 k-blocks x 4 regs
+  uint32_t qa[8][4];
+  {
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+    const float* p0 = base + (long long)min(r0, T - 1) * 3 * E + h * kHD;
+    const float* p1 = base + (long long)min(r1, T - 1) * 3 * E + h * kHD;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      qa[kk][0] = to_tf32(p0[kk * 8 + t] * scale_log2);
+      qa[kk][1] = to_tf32(p1[kk * 8 + t] * scale_log2);
+      qa[kk][2] = to_tf32(p0[kk * 8 + t + 4] * scale_log2);
+      qa[kk][3] = to_tf32(p1[kk * 8 + t + 4] * scale_log2);
+    }
+  }
+  float o[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[nb][i] = 0.f;
+  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;  // rows g and g+8
+
+  for (int k0 = 0; k0 < kv_len; k0 += kKT) {
+    __syncthreads();
+    for (int i = tid; i < kKT * (kHD / 4); i += 128) {
+      const int r = i >> 4, c4 = (i & 15) * 4;
+      float4 kv4 = make_float4(0.f, 0.f, 0.f, 0.f), vv4 = kv4;
+      if (k0 + r < kv_len) {
+        const float* p = base + (long long)(k0 + r) * 3 * E + h * kHD + c4;
+        kv4 = *reinterpret_cast<const float4*>(p + E);
+        vv4 = *reinterpret_cast<const float4*>(p + 2 * E);
+      }
+      *reinterpret_cast<uint4*>(sk + r * kPitch + c4) = make_uint4(to_tf32(kv4.x), to_tf32(kv4.y), to_tf32(kv4.z), to_tf32(kv4.w));
+      *reinterpret_cast<uint4*>(sv + r * kPitch + c4) = make_uint4(to_tf32(vv4.x), to_tf32(vv4.y), to_tf32(vv4.z), to_tf32(vv4.w));
+    }
+    __syncthreads();
+    // ---- S = Q K^T : 8 key blocks of 8
+    float sc[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[nb][i] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t b0 = sk[(nb * 8 + g) * kPitch + kk * 8 + t];
+        const uint32_t b1 = sk[(nb * 8 + g) * kPitch + kk * 8 + t + 4];
+        mma_tf32_16x8x8(sc[nb], qa[kk], b0, b1);
+      }
+    }
+    // ---- mask keys beyond the item's length, online softmax for rows g (c0,c1) and g+8 (c2,c3)
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int key = k0 + nb * 8 + 2 * t;
+      if (key >= kv_len) { sc[nb][0] = -INFINITY; sc[nb][2] = -INFINITY; }
+      if (key + 1 >= kv_len) { sc[nb][1] = -INFINITY; sc[nb][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(sc[nb][0], sc[nb][1]));
+      mx1 = fmaxf(mx1, fmaxf(sc[nb][2], sc[nb][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = exp2f(m0 - mx0), c1 = exp2f(m1 - mx1);
+    m0 = mx0;
+    m1 = mx1;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      sc[nb][0] = exp2f(sc[nb][0] - mx0);
+      sc[nb][1] = exp2f(sc[nb][1] - mx0);
+      sc[nb][2] = exp2f(sc[nb][2] - mx1);
+      sc[nb][3] = exp2f(sc[nb][3] - mx1);
+      ps0 += sc[nb][0] + sc[nb][1];
+      ps1 += sc[nb][2] + sc[nb][3];
+    }
+    l0 = l0 * c0 + ps0;  // per-thread partial row sums; the quad is reduced once at the end
+    l1 = l1 * c1 + ps1;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1;
+    }
+    // ---- O += P V : key blocks j of 8 (k of the MMA), d blocks nb of 8 (n of the MMA)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t pa[4];
+      pa[0] = to_tf32(sc[j][0]);  // row g,   key 8j+2t   -> k = t
+      pa[1] = to_tf32(sc[j][2]);  // row g+8, key 8j+2t   -> k = t
+      pa[2] = to_tf32(sc[j][1]);  // row g,   key 8j+2t+1 -> k = t+4
+      pa[3] = to_tf32(sc[j][3]);  // row g+8, key 8j+2t+1 -> k = t+4
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        const uint32_t b0 = sv[(j * 8 + 2 * t) * kPitch + nb * 8 + g];
+        const uint32_t b1 = sv[(j * 8 + 2 * t + 1) * kPitch + nb * 8 + g];
+        mma_tf32_16x8x8(o[nb], pa, b0, b1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    if (r0 < T)
+      *reinterpret_cast<float2*>(out + ((long long)b * T + r0) * E + h * kHD + nb * 8 + 2 * t) = make_float2(o[nb][0] * i0, o[nb][1] * i0);
+    if (r1 < T)
+      *reinterpret_cast<float2*>(out + ((long long)b * T + r1) * E + h * kHD + nb * 8 + 2 * t) = make_float2(o[nb][2] * i1, o[nb][3] * i1);
   }
 }
 
@@ -410,8 +557,17 @@ extern "C" int mtts_mha_varlen(const float* qkv, float* out, const int* lengths,
   if (B <= 0 || T <= 0) return MTTS_OK;
   MTTS_REQUIRE(qkv && out, "mtts_mha_varlen: null pointer");
   dim3 grid(ceil_div(T, kQT), num_heads, B);
-  mha_varlen_kernel<<<grid, 256, 4 * kQT * kPitch * sizeof(float), stream>>>(qkv, out, lengths, T, num_heads,
-                                                                            1.0f / sqrtf((float)head_dim));
+  static int use_tc = -1;
+  if (use_tc < 0) {
+    const char* e = getenv("MTTS_MHA_SIMT");
+    use_tc = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (use_tc)
+    mha_varlen_tc_kernel<<<grid, 128, 2 * kKT * kPitch * sizeof(uint32_t), stream>>>(
+        qkv, out, lengths, T, num_heads, 1.4426950408889634f / sqrtf((float)head_dim));
+  else
+    mha_varlen_kernel<<<grid, 256, 4 * kQT * kPitch * sizeof(float), stream>>>(qkv, out, lengths, T, num_heads,
+                                                                              1.0f / sqrtf((float)head_dim));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }

@@ -148,8 +148,9 @@ def test_codec_kernels_against_torch_functional():
     s = s.masked_fill(~km[:, None, None, :], float("-inf"))
     ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, T, H * 64)
     got = ao.view(B, T, H * 64).double()
-    assert (got[0] - ref[0]).abs().max().item() <= 1e-4
-    assert (got[1, :77] - ref[1, :77]).abs().max().item() <= 1e-4
+    # TF32 tensor-core attention (10-bit mantissa operands, fp32 accumulate / softmax)
+    assert (got[0] - ref[0]).abs().max().item() <= 4e-3 * ref.abs().max().item()
+    assert (got[1, :77] - ref[1, :77]).abs().max().item() <= 4e-3 * ref.abs().max().item()
     # dwconv7 + LN
     Bc, Tc, C = 2, 40, 512
     x = torch.randn(Bc, Tc, C, device="cuda", generator=g)
