@@ -124,7 +124,8 @@ int mtts_qknorm_rope_kvappend(const void* qkv, long long ld_qkv, const void* q_n
                               int* err_flag, void* stream);
 
 /* Causal GQA attention over the paged/contiguous cache; decode (rows_per_tile = 1, tile arrays NULL) and prefill
- * (rows_per_tile = 4: tile t covers query rows tile_row0[t] .. +tile_nrows[t] of ONE sequence, consecutive positions).
+ * (rows_per_tile = 64: bf16 tensor-core tiles, or 4: CUDA-core tiles; tile t covers query rows tile_row0[t] .. +tile_nrows[t]
+ * of ONE sequence, consecutive positions).
  * Row r attends keys 0..positions[r] of sequence row_seq[r]. out [rows, Hq*128] bf16. nsplit > 1 splits the keys
  * across CTAs (small batches); workspace from mtts_gqa_attention_workspace_bytes, first 64 KiB zero before first use. */
 size_t mtts_gqa_attention_workspace_bytes(int tiles, int num_kv_heads, int group, int rows_per_tile, int nsplit);
@@ -158,23 +159,24 @@ int mtts_sampler_init_history(const long long* ids, int B, int rows, long long r
                               const mtts_sampler_config* cfg, uint32_t* seen, void* stream);
 
 /* One draw per (row, channel) from the bf16 fused-head logits [B, ld]: masks -> repetition penalty -> temperature ->
- * top-k -> top-p -> multinomial (Philox, stream = (seed, step, row, channel)) or argmax. out_tokens [B, channels] int64.
+ * top-k -> top-p -> multinomial (Philox, stream = (*seed_ptr, step, row, channel); the seed lives in device memory so
+ * that a captured CUDA graph can be replayed with a new seed) or argmax. out_tokens [B, channels] int64.
  * *step_ptr is the device-resident step counter s (0 = first generated row). `workspace`: mtts_sample8_workspace_bytes()
  * bytes, zero-filled once by the caller (the kernels leave it clean); logits rows and per-channel offsets 16-byte aligned. */
 size_t mtts_sample8_workspace_bytes(int B, int channels);
 int mtts_sample8(const void* logits, long long ld, int B, const mtts_sampler_config* cfg, const uint32_t* seen,
-                 const int* step_ptr, unsigned long long seed, long long* out_tokens, int* err_flag, void* workspace,
-                 size_t workspace_bytes, void* stream);
+                 const int* step_ptr, const unsigned long long* seed_ptr, long long* out_tokens, int* err_flag,
+                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* The per-row state machine after the draw: wind-down trigger, teacher forcing (tf_tail [B, channels-1, channels] =
  * prompt[:, P:P+channels-1, :]), wind-down fill, finished fill, append to sequences [B, max_len_rows, channels] at row
- * P + s, history bitmap update, counters/stopping, positions[b] += 1, unfinished_hist[s] = #unfinished rows,
+ * P + s (P = dyn_params[0], max_length = dyn_params[1]; device ints, so a captured graph survives a new prompt), history bitmap update, counters/stopping, positions[b] += 1, unfinished_hist[s] = #unfinished rows,
  * finish_len[b] = length at which row b finished, and finally *step_ptr += 1. tokens [B, channels] is updated in place
  * and is the next step's input_ids. B <= 1024. */
 int mtts_delay_step(long long* tokens, const long long* tf_tail, long long* sequences, long long max_len_rows,
                     int* unfinished, int* needs_steps, int* positions, uint32_t* seen, int* step_ptr,
-                    int* unfinished_hist, int* finish_len, int B, int prompt_rows, int max_length, int speech_lo,
-                    int speech_hi, int eos_token, int has_eos_criteria, const mtts_sampler_config* cfg, void* stream);
+                    int* unfinished_hist, int* finish_len, int B, const int* dyn_params, int speech_lo, int speech_hi,
+                    int eos_token, int has_eos_criteria, const mtts_sampler_config* cfg, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * XY_Tokenizer decode path, fp32, token-major activations [batch*frames, channels]

@@ -65,7 +65,7 @@ SIGNATURES = {
                                    c_void_p]),
     "mtts_sampler_init_history": (c_int, [c_void_p, c_int, c_int, c_ll, _cfg_p, c_void_p, c_void_p]),
     "mtts_sample8_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "mtts_sample8": (c_int, [c_void_p, c_ll, c_int, _cfg_p, c_void_p, c_void_p, c_u64, c_void_p, c_void_p, c_void_p, c_size_t,
+    "mtts_sample8": (c_int, [c_void_p, c_ll, c_int, _cfg_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                              c_void_p]),
     "mtts_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p, c_int, c_void_p]),
     "mtts_mha_varlen": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -80,7 +80,7 @@ SIGNATURES = {
     "mtts_istft_ola": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mtts_add_rows_mod": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
     "mtts_delay_step": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _cfg_p, c_void_p]),
+                                c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, _cfg_p, c_void_p]),
 }
 
 

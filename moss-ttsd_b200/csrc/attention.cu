@@ -451,6 +451,167 @@ int launch_decode(const AttnParams& p, int rows, cudaStream_t stream) {
   return MTTS_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Prefill on tensor cores: bf16 mma.sync m16n8k16 with fp32 accumulation, flash-style online softmax.
+// CTA = up to 64 consecutive query rows of ONE sequence x one q head (4 warps x 16 rows); K tiles of 64 keys are
+// staged row-major ([key][d], pitch 136) and V tiles TRANSPOSED ([d][key], pitch 72) so that every B fragment is one
+// conflict-free 32-bit shared load. P keeps the accumulator layout, which for k16 is exactly the A-fragment layout
+// of two adjacent 8-key blocks. Causal: row (pos0 + r) sees keys <= its own position.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPQ = 64, kPK = 64, kKPitch = 136, kVPitch = 72;
+
+__device__ __forceinline__ void mma_bf16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) gqa_prefill_tc_kernel(const AttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* sk = reinterpret_cast<bf16*>(smraw);        // [64 keys][136]
+  bf16* svt = sk + kPK * kKPitch;                   // [128 d][72]
+  const int tile = blockIdx.x, hq = blockIdx.y;
+  const int G = p.Hq / p.Hkv;
+  const int hk = hq / G;
+  const int row0 = p.tile_row0[tile];
+  const int nrows = p.tile_nrows[tile];
+  const int seq = p.row_seq ? p.row_seq[row0] : row0;
+  const int pos0 = p.positions[row0];
+  const int kv_len = pos0 + nrows;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const float scale_log2 = p.scale_log2;
+
+  // Q fragments: rows (warp*16 + g) and (+8), 8 k-blocks of 16 dims
+  uint32_t qa[8][4];
+  {
+    const int r0 = min(warp * 16 + g, nrows - 1), r1 = min(warp * 16 + g + 8, nrows - 1);
+    const bf16* q0p = p.q + ((long long)(row0 + r0) * p.Hq + hq) * kD;
+    const bf16* q1p = p.q + ((long long)(row0 + r1) * p.Hq + hq) * kD;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      qa[kk][0] = *reinterpret_cast<const uint32_t*>(q0p + kk * 16 + 2 * t);
+      qa[kk][1] = *reinterpret_cast<const uint32_t*>(q1p + kk * 16 + 2 * t);
+      qa[kk][2] = *reinterpret_cast<const uint32_t*>(q0p + kk * 16 + 2 * t + 8);
+      qa[kk][3] = *reinterpret_cast<const uint32_t*>(q1p + kk * 16 + 2 * t + 8);
+    }
+  }
+  float o[16][4];
+#pragma unroll
+  for (int nb = 0; nb < 16; ++nb)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[nb][i] = 0.f;
+  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
+  const int qpos0 = pos0 + warp * 16 + g, qpos1 = qpos0 + 8;  // positions of this thread's two rows
+
+  const int page_mask = (1 << p.page_shift) - 1;
+  const long long head_off = ((long long)hk << p.page_shift) * kD;
+  const long long page_stride = ((long long)p.Hkv << p.page_shift) * kD;
+
+  for (int k0 = 0; k0 < kv_len; k0 += kPK) {
+    __syncthreads();
+    // stage K [key][d] and V^T [d][key]: 64 keys x 16 chunks of 8 dims
+    for (int i = tid; i < kPK * 16; i += 128) {
+      const int r = i >> 4, c8 = (i & 15) * 8;
+      const int key = k0 + r;
+      uint4 kq = make_uint4(0, 0, 0, 0), vq = kq;
+      if (key < kv_len) {
+        const int lp = key >> p.page_shift;
+        const int page = p.block_table ? __ldg(p.block_table + (long long)seq * p.max_pages + lp) : seq * p.max_pages + lp;
+        const long long off = (long long)page * page_stride + head_off + (long long)(key & page_mask) * kD + c8;
+        kq = *reinterpret_cast<const uint4*>(p.k_pool + off);
+        vq = *reinterpret_cast<const uint4*>(p.v_pool + off);
+      }
+      *reinterpret_cast<uint4*>(sk + r * kKPitch + c8) = kq;
+      const bf16* ve = reinterpret_cast<const bf16*>(&vq);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) svt[(c8 + e) * kVPitch + r] = ve[e];
+    }
+    __syncthreads();
+    if (k0 > pos0 + warp * 16 + 15) continue;  // this warp's rows see none of these keys (warp-uniform)
+    // ---- S = Q K^T
+    float sc[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[nb][i] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(sk + (nb * 8 + g) * kKPitch + kk * 16 + 2 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(sk + (nb * 8 + g) * kKPitch + kk * 16 + 2 * t + 8);
+        mma_bf16_16x8x16(sc[nb], qa[kk], b0, b1);
+      }
+    }
+    // ---- scale, causal mask, online softmax
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int key = k0 + nb * 8 + 2 * t;
+      sc[nb][0] = (key <= qpos0) ? sc[nb][0] * scale_log2 : -INFINITY;
+      sc[nb][1] = (key + 1 <= qpos0) ? sc[nb][1] * scale_log2 : -INFINITY;
+      sc[nb][2] = (key <= qpos1) ? sc[nb][2] * scale_log2 : -INFINITY;
+      sc[nb][3] = (key + 1 <= qpos1) ? sc[nb][3] * scale_log2 : -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(sc[nb][0], sc[nb][1]));
+      mx1 = fmaxf(mx1, fmaxf(sc[nb][2], sc[nb][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = fast_exp2(m0 - mx0), c1 = fast_exp2(m1 - mx1);
+    m0 = mx0;
+    m1 = mx1;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      sc[nb][0] = fast_exp2(sc[nb][0] - mx0);
+      sc[nb][1] = fast_exp2(sc[nb][1] - mx0);
+      sc[nb][2] = fast_exp2(sc[nb][2] - mx1);
+      sc[nb][3] = fast_exp2(sc[nb][3] - mx1);
+      ps0 += sc[nb][0] + sc[nb][1];
+      ps1 += sc[nb][2] + sc[nb][3];
+    }
+    l0 = l0 * c0 + ps0;
+    l1 = l1 * c1 + ps1;
+#pragma unroll
+    for (int nb = 0; nb < 16; ++nb) {
+      o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1;
+    }
+    // ---- O += P V : 4 key blocks of 16, 16 d blocks of 8
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16(sc[2 * j][0], sc[2 * j][1]);
+      pa[1] = pack_bf16(sc[2 * j][2], sc[2 * j][3]);
+      pa[2] = pack_bf16(sc[2 * j + 1][0], sc[2 * j + 1][1]);
+      pa[3] = pack_bf16(sc[2 * j + 1][2], sc[2 * j + 1][3]);
+#pragma unroll
+      for (int nb = 0; nb < 16; ++nb) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(svt + (nb * 8 + g) * kVPitch + j * 16 + 2 * t);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(svt + (nb * 8 + g) * kVPitch + j * 16 + 2 * t + 8);
+        mma_bf16_16x8x16(o[nb], pa, b0, b1);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int r0 = warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int nb = 0; nb < 16; ++nb) {
+    if (r0 < nrows)
+      *reinterpret_cast<uint32_t*>(p.out + ((long long)(row0 + r0) * p.Hq + hq) * kD + nb * 8 + 2 * t) =
+          pack_bf16(o[nb][0] * i0, o[nb][1] * i0);
+    if (r1 < nrows)
+      *reinterpret_cast<uint32_t*>(p.out + ((long long)(row0 + r1) * p.Hq + hq) * kD + nb * 8 + 2 * t) =
+          pack_bf16(o[nb][2] * i1, o[nb][3] * i1);
+  }
+}
+
 template <int QT, int G>
 int launch_attn(const AttnParams& p, int tiles, cudaStream_t stream) {
   constexpr int NQ = QT * G;
@@ -500,7 +661,8 @@ extern "C" int mtts_gqa_attention(const void* q, const void* k_pool, const void*
   MTTS_REQUIRE(num_kv_heads > 0 && num_q_heads % num_kv_heads == 0, "mtts_gqa_attention: bad head counts");
   const int G = num_q_heads / num_kv_heads;
   MTTS_REQUIRE(G == 1 || G == 2 || G == 4, "mtts_gqa_attention: GQA group must be 1, 2 or 4 (got %d)", G);
-  MTTS_REQUIRE(rows_per_tile == 1 || rows_per_tile == 4, "mtts_gqa_attention: rows_per_tile must be 1 or 4");
+  MTTS_REQUIRE(rows_per_tile == 1 || rows_per_tile == 4 || rows_per_tile == 64,
+               "mtts_gqa_attention: rows_per_tile must be 1, 4 or 64");
   MTTS_REQUIRE(page_size > 0 && (page_size & (page_size - 1)) == 0, "mtts_gqa_attention: page_size must be a power of two");
   MTTS_REQUIRE(nsplit >= 1 && nsplit <= 64, "mtts_gqa_attention: nsplit out of range");
   if (tiles <= 0) return MTTS_OK;
@@ -522,6 +684,14 @@ extern "C" int mtts_gqa_attention(const void* q, const void* k_pool, const void*
                  "mtts_gqa_attention: too many tiles for split-KV");
     p.counters = reinterpret_cast<int*>(workspace);
     p.ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kAttnCounterBytes);
+  }
+  if (rows_per_tile == 64) {
+    MTTS_REQUIRE(tile_row0 && tile_nrows, "mtts_gqa_attention: 64-row tiles need tile_row0 / tile_nrows");
+    MTTS_REQUIRE(nsplit == 1, "mtts_gqa_attention: prefill tiles do not split the keys");
+    const size_t smem = sizeof(bf16) * (kPK * kKPitch + kD * kVPitch);
+    MTTS_CUDA_CHECK(mtts_launch(gqa_prefill_tc_kernel, dim3(tiles, num_q_heads), dim3(128), smem, stream, p));
+    MTTS_LAUNCH_CHECK();
+    return MTTS_OK;
   }
   if (rows_per_tile == 1 && tile_row0 == nullptr) {
     if (G == 1) return launch_decode<1>(p, tiles, stream);

@@ -111,7 +111,7 @@ struct SampleParams2 {
   mtts_sampler_config cfg;
   const uint32_t* seen;
   const int* step_ptr;
-  unsigned long long seed;
+  const unsigned long long* seed_ptr;  // device-resident so that a captured graph can be re-used with a new seed
   long long* out_tokens;
   int* err_flag;
   SampleWs ws;
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
       if (lane >= o) kincl += up;
     }
     const float Zk = __shfl_sync(0xffffffffu, kincl, 31);
-    const float u = philox_uniform(p.seed, (uint32_t)step, (uint32_t)(b * 8 + c));
+    const float u = philox_uniform(*p.seed_ptr, (uint32_t)step, (uint32_t)(b * 8 + c));
     const float target = u * Zk;
     const float lo = kincl - kpart;
     int choice = -1;
@@ -400,7 +400,8 @@ struct StepParams {
   int* step_ptr;
   int* unfinished_hist;      // [max_steps] number of unfinished rows after each step
   int* finish_len;           // [B] sequence length (rows) at which the row finished (0 = not yet)
-  int B, C, P, max_length;
+  int B, C;
+  const int* dyn;  // device: [0] = prompt rows P, [1] = max_length (so a captured graph survives new prompts)
   int speech_lo, speech_hi, eos_token, pad_token, has_eos_criteria;
   mtts_sampler_config cfg;
 };
@@ -415,7 +416,7 @@ __global__ void delay_step_kernel(const StepParams p) {
   __syncthreads();
   if (b < p.B) {
     const int C = p.C;
-    const int L = p.P + s;  // rows before this append
+    const int L = p.dyn[0] + s;  // rows before this append
     long long tok[8];
     for (int c = 0; c < C; ++c) tok[c] = p.raw_tokens[(long long)b * C + c];
     int n = p.needs_steps[b];
@@ -448,7 +449,7 @@ __global__ void delay_step_kernel(const StepParams p) {
     }
     // counters and stopping (:165-169)
     if (n > 0) n -= 1;
-    const int stop = (L + 1 >= p.max_length) || (p.has_eos_criteria && tok[0] == p.eos_token) || (n == 0);
+    const int stop = (L + 1 >= p.dyn[1]) || (p.has_eos_criteria && tok[0] == p.eos_token) || (n == 0);
     int un = (u && !stop) || (n > 0);
     if (u && !un && p.finish_len[b] == 0) p.finish_len[b] = L + 1;
     p.needs_steps[b] = n;
@@ -540,13 +541,13 @@ extern "C" size_t mtts_sample8_workspace_bytes(int B, int channels) {
 }
 
 extern "C" int mtts_sample8(const void* logits, long long ld, int B, const mtts_sampler_config* cfg,
-                            const uint32_t* seen, const int* step_ptr, unsigned long long seed, long long* out_tokens,
-                            int* err_flag, void* workspace, size_t workspace_bytes, void* stream_) {
+                            const uint32_t* seen, const int* step_ptr, const unsigned long long* seed_ptr,
+                            long long* out_tokens, int* err_flag, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   int rc = validate_cfg(cfg);
   if (rc) return rc;
   if (B <= 0) return MTTS_OK;
-  MTTS_REQUIRE(logits && seen && step_ptr && out_tokens, "mtts_sample8: null pointer");
+  MTTS_REQUIRE(logits && seen && step_ptr && seed_ptr && out_tokens, "mtts_sample8: null pointer");
   MTTS_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0, "mtts_sample8: logits rows must be 16-byte aligned");
   MTTS_REQUIRE(workspace && workspace_bytes >= mtts_sample8_workspace_bytes(B, cfg->channels),
                "mtts_sample8: workspace too small (need %zu bytes, first 4 KiB-aligned integer area zeroed once)",
@@ -554,7 +555,7 @@ extern "C" int mtts_sample8(const void* logits, long long ld, int B, const mtts_
   SampleParams2 p;
   memset(&p, 0, sizeof(p));
   p.logits = reinterpret_cast<const bf16*>(logits); p.ld = ld; p.cfg = *cfg; p.seen = seen; p.step_ptr = step_ptr;
-  p.seed = seed; p.out_tokens = out_tokens; p.err_flag = err_flag;
+  p.seed_ptr = seed_ptr; p.out_tokens = out_tokens; p.err_flag = err_flag;
   sample_ws_layout(B, cfg->channels, &p.ws, reinterpret_cast<uint8_t*>(workspace));
   int total = 0;
   bool any_sample = false;
@@ -582,7 +583,7 @@ extern "C" int mtts_sample8(const void* logits, long long ld, int B, const mtts_
 
 extern "C" int mtts_delay_step(long long* tokens, const long long* tf_tail, long long* sequences, long long max_len_rows,
                                int* unfinished, int* needs_steps, int* positions, uint32_t* seen, int* step_ptr,
-                               int* unfinished_hist, int* finish_len, int B, int prompt_rows, int max_length,
+                               int* unfinished_hist, int* finish_len, int B, const int* dyn_params,
                                int speech_lo, int speech_hi, int eos_token, int has_eos_criteria,
                                const mtts_sampler_config* cfg, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -590,13 +591,13 @@ extern "C" int mtts_delay_step(long long* tokens, const long long* tf_tail, long
   if (rc) return rc;
   MTTS_REQUIRE(B >= 1 && B <= 1024, "mtts_delay_step: batch must be in [1,1024] (got %d)", B);
   MTTS_REQUIRE(tokens && tf_tail && sequences && unfinished && needs_steps && positions && seen && step_ptr &&
-                   unfinished_hist && finish_len,
+                   unfinished_hist && finish_len && dyn_params,
                "mtts_delay_step: null pointer");
   StepParams p;
   p.raw_tokens = tokens; p.tf_tail = tf_tail; p.sequences = sequences; p.max_len_rows = max_len_rows;
   p.unfinished = unfinished; p.needs_steps = needs_steps; p.positions = positions; p.seen = seen; p.step_ptr = step_ptr;
-  p.unfinished_hist = unfinished_hist; p.finish_len = finish_len; p.B = B; p.C = cfg->channels; p.P = prompt_rows;
-  p.max_length = max_length; p.speech_lo = speech_lo; p.speech_hi = speech_hi; p.eos_token = eos_token;
+  p.unfinished_hist = unfinished_hist; p.finish_len = finish_len; p.B = B; p.C = cfg->channels; p.dyn = dyn_params;
+  p.speech_lo = speech_lo; p.speech_hi = speech_hi; p.eos_token = eos_token;
   p.pad_token = cfg->pad_token; p.has_eos_criteria = has_eos_criteria; p.cfg = *cfg;
   const int threads = ((B + 31) / 32) * 32;
   MTTS_CUDA_CHECK(mtts_launch(delay_step_kernel, dim3(1), dim3(threads), 0, stream, p));

@@ -261,6 +261,7 @@ class DecoderEngine:
         self._vocabs = (ctypes.c_int * 8)(*s.vocabs, *([0] * (8 - s.channels)))
         self.err = torch.zeros(4, dtype=torch.int32, device=self.dev)
         self.use_graph = os.environ.get("MTTS_NO_GRAPH", "0") != "1"
+        self.prefill_tile_rows = int(os.environ.get("MTTS_PREFILL_TILE", "64"))  # 64: tensor-core tiles, 4: CUDA cores
         self.graph_replayed_launches = 0  # kernels executed through graph replays (not seen by mtts_launch_count)
 
     # ------------------------------------------------------------------ primitive launches
@@ -348,10 +349,11 @@ class DecoderEngine:
         pos_h = np.concatenate([np.arange(n, dtype=np.int32) for n in lens_h]) if R else np.zeros(0, np.int32)
         seq_h = np.repeat(np.arange(B, dtype=np.int32), lens_h)
         row0_h, nrows_h = [], []
+        tile_rows = self.prefill_tile_rows
         for b in range(B):
-            for t in range(0, int(lens_h[b]), 4):
+            for t in range(0, int(lens_h[b]), tile_rows):
                 row0_h.append(cu[b] + t)
-                nrows_h.append(min(4, int(lens_h[b]) - t))
+                nrows_h.append(min(tile_rows, int(lens_h[b]) - t))
         positions = torch.from_numpy(pos_h).to(self.dev)
         row_seq = torch.from_numpy(seq_h).to(self.dev)
         tile_row0 = torch.tensor(row0_h, dtype=torch.int32, device=self.dev)
@@ -359,7 +361,7 @@ class DecoderEngine:
         a = self._alloc_acts(R)
         gws = self._gemm_ws(R)
         self._embed(ids, a["x"])
-        attn_kw = dict(tiles=len(row0_h), rows_per_tile=4, tile_row0=tile_row0, tile_nrows=tile_nrows, nsplit=1, ws=None)
+        attn_kw = dict(tiles=len(row0_h), rows_per_tile=tile_rows, tile_row0=tile_row0, tile_nrows=tile_nrows, nsplit=1, ws=None)
         xn = self._layers(a, cache, positions, row_seq, attn_kw, gws)
         if all_logits:
             logits = torch.empty((R, self.s.vpad), dtype=torch.bfloat16, device=self.dev)
@@ -372,20 +374,27 @@ class DecoderEngine:
         return logits, lens
 
     # ------------------------------------------------------------------ decode
-    def make_decode_state(self, B: int, cache: KVCache, sampler: SamplerSetup, seed: int, prompt_rows: int,
-                          max_length: int, max_len_rows: int, speech_range, eos_token: int, has_eos_criteria: bool):
-        st = dict(B=B, cache=cache, sampler=sampler, seed=seed, P=prompt_rows, max_length=max_length,
-                  max_len_rows=max_len_rows, speech=speech_range, eos=eos_token, has_eos=has_eos_criteria)
+    def make_decode_state(self, B: int, cache: KVCache, sampler: SamplerSetup, max_len_rows: int, speech_range,
+                          eos_token: int, has_eos_criteria: bool):
+        """Buffers (and, after the first step, the captured CUDA graph) of one decode session. Everything that
+        changes between generate() calls — seed, prompt rows, max_length, the prompt tail, the per-row state — lives
+        in device memory and is refreshed by `reset_decode_state`, so the session (incl. its graph) is reusable."""
+        st = dict(B=B, cache=cache, sampler=sampler, max_len_rows=max_len_rows, speech=speech_range, eos=eos_token,
+                  has_eos=has_eos_criteria)
         i32 = dict(dtype=torch.int32, device=self.dev)
-        st["tokens"] = torch.zeros((B, self.s.channels), dtype=torch.int64, device=self.dev)
+        C = self.s.channels
+        st["tokens"] = torch.zeros((B, C), dtype=torch.int64, device=self.dev)
+        st["tf_tail"] = torch.zeros((B, C - 1, C), dtype=torch.int64, device=self.dev)
         st["positions"] = torch.zeros(B, **i32)
         st["unfinished"] = torch.ones(B, **i32)
         st["needs"] = torch.full((B,), -1, **i32)
         st["finish_len"] = torch.zeros(B, **i32)
         st["step"] = torch.zeros(1, **i32)
+        st["dyn"] = torch.zeros(4, **i32)                       # [prompt rows P, max_length, -, -]
+        st["seed_dev"] = torch.zeros(1, dtype=torch.int64, device=self.dev)
         st["hist"] = torch.full((max(max_len_rows, 8) + 16,), -1, **i32)
         st["seen"] = torch.zeros((B, sampler.words_per_row), dtype=torch.int32, device=self.dev)
-        st["sequences"] = torch.zeros((B, max_len_rows, self.s.channels), dtype=torch.int64, device=self.dev)
+        st["sequences"] = torch.zeros((B, max_len_rows, C), dtype=torch.int64, device=self.dev)
         st["logits"] = torch.empty((B, self.s.vpad), dtype=torch.bfloat16, device=self.dev)
         st["acts"] = self._alloc_acts(B)
         st["gws"] = self._gemm_ws(B)
@@ -398,16 +407,28 @@ class DecoderEngine:
         st["graph"] = None
         return st
 
+    def reset_decode_state(self, st, seed: int, prompt_rows: int, max_length: int):
+        st["unfinished"].fill_(1)
+        st["needs"].fill_(-1)
+        st["finish_len"].zero_()
+        st["step"].zero_()
+        st["hist"].fill_(-1)
+        st["seen"].zero_()
+        st["dyn"].copy_(torch.tensor([prompt_rows, max_length, 0, 0], dtype=torch.int32))
+        st["seed_dev"].copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64))
+        st["P"] = prompt_rows
+        st["max_length"] = max_length
+
     def sample_and_advance(self, st, logits):
         """Draw 8 tokens per row from `logits` and run the delay-pattern state machine (one step)."""
         sm = st["sampler"]
         check(self.L.mtts_sample8(ptr(logits), logits.stride(0), st["B"], ctypes.byref(sm.cfg), ptr(st["seen"]),
-                                  ptr(st["step"]), st["seed"], ptr(st["tokens"]), ptr(self.err), ptr(st["sample_ws"]),
+                                  ptr(st["step"]), ptr(st["seed_dev"]), ptr(st["tokens"]), ptr(self.err), ptr(st["sample_ws"]),
                                   st["sample_ws"].numel(), stream_ptr()))
         check(self.L.mtts_delay_step(ptr(st["tokens"]), ptr(st["tf_tail"]), ptr(st["sequences"]), st["max_len_rows"],
                                      ptr(st["unfinished"]), ptr(st["needs"]), ptr(st["positions"]), ptr(st["seen"]),
-                                     ptr(st["step"]), ptr(st["hist"]), ptr(st["finish_len"]), st["B"], st["P"],
-                                     st["max_length"], st["speech"][0], st["speech"][1], st["eos"],
+                                     ptr(st["step"]), ptr(st["hist"]), ptr(st["finish_len"]), st["B"], ptr(st["dyn"]),
+                                     st["speech"][0], st["speech"][1], st["eos"],
                                      1 if st["has_eos"] else 0, ctypes.byref(sm.cfg), stream_ptr()))
 
     def _decode_body(self, st):

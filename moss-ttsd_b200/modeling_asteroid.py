@@ -130,7 +130,7 @@ class AsteroidTTSInstruct:
         # knobs of the B200 engine (not in the reference)
         self.kv_paged = False
         self.kv_page_size = 64
-        self.sync_every = 8
+        self.sync_every = 16
         if self.device is not None and self.device.type == "cuda":
             self._materialize()
 
@@ -323,43 +323,98 @@ class AsteroidTTSInstruct:
         if isinstance(eos_fill, (list, tuple)):
             eos_fill = eos_fill[0]
         # A row in wind-down ignores max_length for up to C-2 extra rows; allocate for it.
-        max_rows = max(max_length, P + 1) + C + self.sync_every
+        max_rows = max(max_length, P + 1) + C + 2 * self.sync_every
         sampler = self._sampler_setup(gc)
         if seed is None:
             seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)  # follows torch.manual_seed / accelerate set_seed
-        cache = KVCache(self.shape, B, max_rows + 1, dev, paged=self.kv_paged, page_size=self.kv_page_size)
-        st = eng.make_decode_state(B, cache, sampler, seed, P, max_length, max_rows,
-                                   tuple(self.config.speech_token_range), int(eos_fill), has_eos)
+        # One decode session (KV pool, state buffers, captured graph) is kept and re-used while the batch size, the
+        # sampler configuration and the KV geometry allow it: repeated generate() calls (serving, bench steps) then
+        # neither re-allocate ~10 GB nor re-capture the 230-kernel graph.
+        cfg_key = bytes(sampler.cfg)
+        key = (B, self.kv_paged, self.kv_page_size, cfg_key, tuple(self.config.speech_token_range), int(eos_fill), has_eos,
+               eng.use_graph)
+        sess = getattr(self, "_session", None)
+        if sess is None or sess["key"] != key or sess["rows"] < max_rows:
+            self._session = None
+            sess = None
+            rows_cap = max_rows if not getattr(self, "session_headroom", True) else max(max_rows, 1024)
+            cache = KVCache(self.shape, B, rows_cap + 1, dev, paged=self.kv_paged, page_size=self.kv_page_size,
+                            shuffle_pages=self.kv_paged)
+            st = eng.make_decode_state(B, cache, sampler, rows_cap, tuple(self.config.speech_token_range), int(eos_fill),
+                                       has_eos)
+            sess = dict(key=key, rows=rows_cap, st=st, cache=cache)
+            self._session = sess
+        st, cache = sess["st"], sess["cache"]
+        max_rows = sess["rows"]
+        eng.reset_decode_state(st, seed, P, max_length)
         st["sequences"][:, :P].copy_(input_ids[:, :P])
-        st["tf_tail"] = input_ids[:, P:].contiguous()
+        st["tf_tail"].copy_(input_ids[:, P:])
         from . import _lib
         import ctypes
         _lib.check(eng.L.mtts_sampler_init_history(input_ids.data_ptr(), B, P, input_ids.stride(0), ctypes.byref(sampler.cfg),
                                                    st["seen"].data_ptr(), _lib.stream_ptr()))
         # ---- step 0: prefill the prompt, sample from its last position
+        ev_t = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev_t[0].record()
         logits, lens = eng.prefill(input_ids[:, :P], attention_mask[:, :P], cache)
         st["positions"].copy_((lens - 1).to(torch.int32))
         eng.sample_and_advance(st, logits)
+        ev_t[1].record()
         if streamer is not None:
             streamer.put(st["tokens"][:, 0].cpu())
-        # ---- steps 1..: one graph replay per frame; the host looks at the stop flag every `sync_every` steps
+        # ---- steps 1..: one graph replay per frame. The host never waits for the GPU inside the loop: after every
+        # block of `sync_every` replays it enqueues an async copy of the per-step "unfinished rows" counters into pinned
+        # memory and inspects only copies that have already landed, so the stop is noticed at most two blocks late
+        # (the surplus rows are dropped below; the reference syncs twice per step, modeling_asteroid.py:149,169).
         steps_done = 1
         final_len = None
-        hist_host = None
-        while True:
-            if steps_done % self.sync_every == 0 or streamer is not None or steps_done == 1:
-                hist_host = st["hist"][:steps_done].cpu()
-                zero = (hist_host == 0).nonzero()
-                if zero.numel():
-                    final_len = P + int(zero[0]) + 1
+        max_steps = max_rows - P - 1
+        hard_stop = max(1, max_length - P)  # rows that are not winding down all stop here: check synchronously
+        block = 1 if streamer is not None else max(1, int(self.sync_every))
+        pinned = torch.empty(st["hist"].numel(), dtype=torch.int32).pin_memory()
+        pending = []
+
+        def scan(upto):
+            zero = (pinned[:upto] == 0).nonzero()
+            return P + int(zero[0]) + 1 if zero.numel() else None
+
+        def post_check():
+            pinned[:steps_done].copy_(st["hist"][:steps_done], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((ev, steps_done))
+
+        post_check()
+        if streamer is not None:
+            pending[-1][0].synchronize()
+        while final_len is None:
+            if len(pending) >= 2:
+                pending[0][0].synchronize()  # back-pressure: at most two blocks of replays are queued ahead of the GPU
+            while pending and pending[0][0].query():
+                _, upto = pending.pop(0)
+                final_len = scan(upto)
+                if final_len is not None:
                     break
-            if P + steps_done >= max_rows:  # cannot happen unless the stop logic is broken
-                final_len = max_rows
+            if final_len is not None or steps_done >= max_steps:
                 break
-            eng.decode_step(st)
-            steps_done += 1
-            if streamer is not None:
-                streamer.put(st["tokens"][:, 0].cpu())
+            n = min(block, max_steps - steps_done)
+            if steps_done < hard_stop:
+                n = min(n, hard_stop - steps_done)
+            else:
+                n = 1
+            for _ in range(n):
+                eng.decode_step(st)
+                steps_done += 1
+                if streamer is not None:
+                    streamer.put(st["tokens"][:, 0].cpu())
+            post_check()
+            if streamer is not None or steps_done >= hard_stop:
+                pending[-1][0].synchronize()
+        if final_len is None:
+            torch.cuda.synchronize()
+            final_len = scan(steps_done) or (P + steps_done)
+        ev_t[2].record()
+        self._last_timing = (ev_t, steps_done)
         self._check_err()
         if streamer is not None:
             streamer.end()

@@ -148,9 +148,10 @@ def test_delay_state_machine_matches_reference_trace(model):
     sm = SamplerSetup(shape, [False] * 8, None)
     max_length = int(g["max_length"])
     cache = KVCache(shape, B, 8, "cuda")
-    st = eng.make_decode_state(B, cache, sm, 0, P, max_length, max_length + 16, tuple(TINY["speech_token_range"]), 152694, True)
+    st = eng.make_decode_state(B, cache, sm, max_length + 16, tuple(TINY["speech_token_range"]), 152694, True)
+    eng.reset_decode_state(st, 0, P, max_length)
     st["sequences"][:, :P].copy_(ids[:, :P])
-    st["tf_tail"] = ids[:, P:].contiguous()
+    st["tf_tail"].copy_(ids[:, P:])
     offs, vocabs = shape.head_offsets, shape.vocabs
     n = 0
     while True:
@@ -207,12 +208,14 @@ def test_sampler_support_and_distribution_vs_oracle(model, cfg):
         step = torch.full((1,), 9, dtype=torch.int32, device="cuda")  # step 9: pad masked on every ch>=1, EOS allowed
         toks = torch.zeros((B, C), dtype=torch.int64, device="cuda")
         sws = torch.zeros(eng.L.mtts_sample8_workspace_bytes(B, C), dtype=torch.uint8, device="cuda")
+        seed_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
         draws = []
         n_draws = 1 if not do_sample else 400
         for i in range(n_draws):
+            seed_dev.fill_(1000 + i)
             _lib.check(eng.L.mtts_sample8(logits.data_ptr(), logits.stride(0), B, ctypes.byref(sm.cfg), seen.data_ptr(),
-                                          step.data_ptr(), 1000 + i, toks.data_ptr(), eng.err.data_ptr(), sws.data_ptr(),
-                                          sws.numel(), _lib.stream_ptr()))
+                                          step.data_ptr(), seed_dev.data_ptr(), toks.data_ptr(), eng.err.data_ptr(),
+                                          sws.data_ptr(), sws.numel(), _lib.stream_ptr()))
             draws.append(toks.cpu().clone())
         draws = torch.stack(draws)  # (n, B, C)
         assert eng.err.cpu().sum().item() == 0
