@@ -293,14 +293,20 @@ def main():
         nl = 4 * len(w.layers)
         algo = sum(lw[k].numel() * 2 for lw in w.layers for k in ("wqkv", "wo", "wgu", "wd"))
         algo += len(w.layers) * BATCH * 2 * (2 * x.shape[1] + hq.shape[1] + hi.shape[1] + o_qkv.shape[1] + 2 * o_h.shape[1] + o_i.shape[1])
-        for _ in range(3):
+        gemm_sweep()
+        torch.cuda.synchronize()
+        # replayed from a CUDA graph, exactly as the decode step issues these launches (PDL edges included)
+        sweep_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(sweep_graph):
             gemm_sweep()
+        for _ in range(3):
+            sweep_graph.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
+        reps = 10
         e0.record()
         for _ in range(reps):
-            gemm_sweep()  # 3.1 GB of weights per sweep >> 126 MB L2: every launch streams from HBM
+            sweep_graph.replay()  # 3.1 GB of weights per sweep >> 126 MB L2: every launch streams from HBM
         e1.record()
         torch.cuda.synchronize()
         per_launch_ms = e0.elapsed_time(e1) / (reps * nl)

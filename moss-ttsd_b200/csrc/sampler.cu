@@ -98,7 +98,7 @@ struct SampleWs {
   float* slice_val;   // [B][C][kMaxSlices]
   int* slice_idx;     // [B][C][kMaxSlices]
   float* reported;    // [B][C][kMaxSlices * kReport]
-  float* thr;         // [B][C]
+  float* thr;         // [B][C][4]: threshold, global max, global sum of exp(score - max), unused
   int* tickets;       // [B][C][2]  (scan, finish) zero between launches
   int* cand_count;    // [B][C]     zero between launches
   float* cand_val;    // [B][C][kCap]
@@ -216,6 +216,18 @@ __global__ void __launch_bounds__(kThreads) sample_scan_kernel(const SampleParam
     __syncthreads();
     bitonic_sort_desc(s_val, s_idx, kThreads);
     if (tid < kReport) p.ws.reported[(bc * kMaxSlices + slice) * kReport + tid] = s_val[tid];
+    // slice softmax statistics (needed for top-p over the full vocabulary when no top-k precedes it)
+    const float smax = s_val[0];
+    float se = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (j0 + e < V && sv[e] > -INFINITY) se += expf(sv[e] - smax);
+    __shared__ float s_red[33];
+    se = block_sum(se, s_red);
+    if (tid == 0) {
+      p.ws.slice_val[bc * kMaxSlices + slice] = smax;
+      p.ws.slice_idx[bc * kMaxSlices + slice] = __float_as_int(se);
+    }
   }
   // ---- ticket: the last slice of this (row, channel) finishes the phase
   __threadfence();
@@ -240,9 +252,20 @@ __global__ void __launch_bounds__(kThreads) sample_scan_kernel(const SampleParam
     if (tid == 0) p.out_tokens[bc] = bi == 0x7fffffff ? 0 : bi;  // torch.argmax: lowest index on ties
     return;
   }
-  // sampled channel: threshold = k-th largest reported maximum (a lower bound of the k-th largest score)
+  // sampled channel: threshold = k-th largest reported maximum (a lower bound of the k-th largest score). Without
+  // top-k (top-p over the whole vocabulary) the candidate list is the ~1500 largest scores; the nucleus is cut inside
+  // it using the GLOBAL softmax mass (flagged if the nucleus does not fit).
   float thr = -INFINITY;
-  const int k = cfg.top_k[c] > 0 ? min(cfg.top_k[c], V) : V;
+  int k = cfg.top_k[c] > 0 ? min(cfg.top_k[c], V) : V;
+  if (S > 1) {
+    float gm = -INFINITY;
+    for (int t = 0; t < S; ++t) gm = fmaxf(gm, __ldcg(p.ws.slice_val + bc * kMaxSlices + t));
+    float gz = 0.f;
+    for (int t = 0; t < S; ++t)
+      gz += __int_as_float(__ldcg(p.ws.slice_idx + bc * kMaxSlices + t)) * expf(__ldcg(p.ws.slice_val + bc * kMaxSlices + t) - gm);
+    if (tid == 0) { p.ws.thr[bc * 4 + 1] = gm; p.ws.thr[bc * 4 + 2] = gz; }
+    if (cfg.top_k[c] <= 0) k = min(S * kReport, (kCap * 3) / 4);
+  }
   if (S > 1 && k <= S * kReport) {
     const int n = S * kReport;
     int npad = 1;
@@ -255,7 +278,7 @@ __global__ void __launch_bounds__(kThreads) sample_scan_kernel(const SampleParam
     bitonic_sort_desc(s_val, s_idx, npad);
     thr = s_val[k - 1];
   }
-  if (tid == 0) p.ws.thr[bc] = thr;
+  if (tid == 0) p.ws.thr[bc * 4] = thr;
 }
 
 __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SampleParams2 p) {
@@ -272,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
   const int step = *p.step_ptr;
   const ScoreCtx sc = make_ctx(p, b, c, step);
   const long long bc = (long long)b * cfg.channels + c;
-  const float thr = __ldcg(p.ws.thr + bc);
+  const float thr = __ldcg(p.ws.thr + bc * 4);
   const int j0 = slice * kSlice + tid * 8;
   float sv[8];
   scores8(sc, j0, V, sv);
@@ -345,7 +368,9 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
       const float up = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += up;
     }
-    const float Z = __shfl_sync(0xffffffffu, incl, 31);
+    float Z = __shfl_sync(0xffffffffu, incl, 31);
+    const bool global_mass = (cfg.top_k[c] <= 0 && S > 1);
+    if (global_mass) Z = __ldcg(p.ws.thr + bc * 4 + 2);  // softmax mass of the WHOLE row (relative to the same maximum)
     int keep = nk;
     if (cfg.has_top_p[c]) {
       // HF: sort ascending, cum = cumsum(softmax); remove cum <= 1 - top_p; always keep the largest.
@@ -360,6 +385,8 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
       }
       for (int o = 16; o > 0; o >>= 1) my_keep = max(my_keep, __shfl_xor_sync(0xffffffffu, my_keep, o));
       keep = max(my_keep, 1);
+      // full-vocabulary nucleus larger than the candidate list: cannot be represented -> flag (truncated to the list)
+      if (global_mass && keep >= nk && n >= (kCap * 3) / 4 && lane == 0 && p.err_flag) *p.err_flag = 4;
     }
     float kpart = 0.f;
     for (int t = t0; t < min(t1, keep); ++t) kpart += s_val[t];
@@ -484,10 +511,11 @@ int validate_cfg(const mtts_sampler_config* cfg) {
     MTTS_REQUIRE(cfg->vocab[c] > 0, "sampler: vocab[%d] must be positive", c);
     if (cfg->do_sample[c]) {
       const int k = cfg->top_k[c] > 0 ? (cfg->top_k[c] < cfg->vocab[c] ? cfg->top_k[c] : cfg->vocab[c]) : cfg->vocab[c];
-      if (cfg->vocab[c] > kCap && k > kThreads)
+      const bool nucleus_only = cfg->top_k[c] <= 0 && cfg->has_top_p[c] && cfg->top_p[c] < 1.0f;
+      if (cfg->vocab[c] > kCap && k > kThreads && !nucleus_only)
         return mtts_set_error(MTTS_ERR_UNSUPPORTED,
-                              "sampler: channel %d samples over %d tokens with top_k=%d; this build needs top_k <= %d "
-                              "(or vocab <= %d) for sampled channels",
+                              "sampler: channel %d samples over %d tokens with top_k=%d and no top_p < 1; this build needs "
+                              "top_k <= %d, a nucleus (top_p < 1), or vocab <= %d for sampled channels",
                               c, cfg->vocab[c], cfg->top_k[c], kThreads, kCap);
       if (cfg->has_temp[c]) MTTS_REQUIRE(cfg->temperature[c] > 0.f, "sampler: temperature must be > 0");
       if (cfg->has_top_p[c]) MTTS_REQUIRE(cfg->top_p[c] >= 0.f && cfg->top_p[c] <= 1.f, "sampler: top_p must be in [0,1]");
@@ -526,7 +554,7 @@ static size_t sample_ws_layout(int B, int C, SampleWs* ws, uint8_t* base) {
   float* slice_val = reinterpret_cast<float*>(take(bc * kMaxSlices * sizeof(float)));
   int* slice_idx = reinterpret_cast<int*>(take(bc * kMaxSlices * sizeof(int)));
   float* reported = reinterpret_cast<float*>(take(bc * kMaxSlices * kReport * sizeof(float)));
-  float* thr = reinterpret_cast<float*>(take(bc * sizeof(float)));
+  float* thr = reinterpret_cast<float*>(take(bc * 4 * sizeof(float)));
   float* cand_val = reinterpret_cast<float*>(take(bc * kCap * sizeof(float)));
   int* cand_idx = reinterpret_cast<int*>(take(bc * kCap * sizeof(int)));
   if (ws) {

@@ -266,7 +266,7 @@ class AsteroidTTSInstruct:
         if any(e):
             self.engine.err.zero_()
             raise RuntimeError(f"libmtts device-side error flags {e} (1: token id out of range, 2: KV page out of range, "
-                               f"3: sampler candidate overflow)")
+                               f"3: sampler candidate overflow, 4: full-vocabulary nucleus larger than the candidate list)")
 
     # ------------------------------------------------------------------ generate
     def _sampler_setup(self, gc: GenerationConfig) -> SamplerSetup:

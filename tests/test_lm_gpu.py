@@ -199,8 +199,8 @@ def test_sampler_support_and_distribution_vs_oracle(model, cfg):
     hist[0][:, :20] = torch.randint(151665, 152689, (B, 20))
     grid = torch.stack(hist, -1).cuda()  # (B, hist_len, C)
     for do_sample in (False, True):
-        if do_sample and "top_k" not in cfg:
-            continue  # sampling the 152697-way channel without top_k is rejected by this build (see test below)
+        if do_sample and "top_k" not in cfg and "top_p" not in cfg:
+            continue  # sampling the 152697-way channel with neither top_k nor a nucleus is rejected (see test below)
         sm = SamplerSetup(shape, [do_sample] * C, [dict(cfg) for _ in range(C)])
         seen = torch.zeros((B, sm.words_per_row), dtype=torch.int32, device="cuda")
         _lib.check(eng.L.mtts_sampler_init_history(grid.data_ptr(), B, hist_len, grid.stride(0), ctypes.byref(sm.cfg),
@@ -251,9 +251,106 @@ def test_sampler_support_and_distribution_vs_oracle(model, cfg):
 def test_sampling_without_topk_on_text_channel_is_rejected_loudly(model):
     from moss_ttsd_b200 import _lib
     from moss_ttsd_b200.lm_engine import SamplerSetup
-    sm = SamplerSetup(model.shape, [True] * 8, [dict(top_p=0.9) for _ in range(8)])
+    sm = SamplerSetup(model.shape, [True] * 8, [dict(temperature=0.9) for _ in range(8)])  # neither top-k nor a nucleus
     seen = torch.zeros((1, sm.words_per_row), dtype=torch.int32, device="cuda")
     ids = torch.zeros((1, 1, 8), dtype=torch.int64, device="cuda")
     with pytest.raises(_lib.MttsError):
         _lib.check(model.engine.L.mtts_sampler_init_history(ids.data_ptr(), 1, 1, 8, ctypes.byref(sm.cfg), seen.data_ptr(),
                                                             _lib.stream_ptr()))
+
+
+@pytest.mark.parametrize("cfg", [dict(top_p=0.9), dict(repetition_penalty=1.1, temperature=0.8, top_p=0.95)])
+def test_full_vocabulary_nucleus_sampling(model, cfg):
+    """top-p WITHOUT top-k on the 152,697-way channel: the nucleus is cut with the global softmax mass."""
+    from moss_ttsd_b200 import _lib
+    from moss_ttsd_b200.lm_engine import SamplerSetup
+    shape, eng = model.shape, model.engine
+    B, C = 3, 8
+    g = torch.Generator(device="cuda").manual_seed(11)
+    logits = torch.randn((B, shape.vpad), device="cuda", generator=g)
+    for c in range(C):  # a few hundred tokens carry the mass, as in a trained model
+        o, v = shape.head_offsets[c], shape.vocabs[c]
+        idx = torch.randint(0, min(v, 1024) if c else v, (B, 300), device="cuda", generator=g)
+        logits[torch.arange(B, device="cuda")[:, None], o + idx] += 8 + 6 * torch.rand((B, 300), device="cuda", generator=g)
+    logits = logits.to(torch.bfloat16)
+    hist = [torch.randint(0, shape.vocabs[c], (B, 20)) for c in range(C)]
+    grid = torch.stack(hist, -1).cuda()
+    sm = SamplerSetup(shape, [True] * C, [dict(cfg) for _ in range(C)])
+    seen = torch.zeros((B, sm.words_per_row), dtype=torch.int32, device="cuda")
+    _lib.check(eng.L.mtts_sampler_init_history(grid.data_ptr(), B, 20, grid.stride(0), ctypes.byref(sm.cfg), seen.data_ptr(),
+                                               _lib.stream_ptr()))
+    step = torch.full((1,), 9, dtype=torch.int32, device="cuda")
+    toks = torch.zeros((B, C), dtype=torch.int64, device="cuda")
+    sws = torch.zeros(eng.L.mtts_sample8_workspace_bytes(B, C), dtype=torch.uint8, device="cuda")
+    seed_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
+    draws = []
+    for i in range(300):
+        seed_dev.fill_(77 + i)
+        _lib.check(eng.L.mtts_sample8(logits.data_ptr(), logits.stride(0), B, ctypes.byref(sm.cfg), seen.data_ptr(),
+                                      step.data_ptr(), seed_dev.data_ptr(), toks.data_ptr(), eng.err.data_ptr(), sws.data_ptr(),
+                                      sws.numel(), _lib.stream_ptr()))
+        draws.append(toks.cpu().clone())
+    draws = torch.stack(draws)
+    assert eng.err.cpu().sum().item() == 0
+    for c in (0, 3):
+        o, v = shape.head_offsets[c], shape.vocabs[c]
+        loose = dict(cfg, top_p=min(1.0, cfg["top_p"] + 1e-3))
+        kept = _processed_scores_oracle(logits[:, o:o + v].cpu(), hist[c], loose, 1024 if c > 0 else None)
+        base = _processed_scores_oracle(logits[:, o:o + v].cpu(), hist[c], {k_: v_ for k_, v_ in cfg.items() if k_ != "top_p"},
+                                        1024 if c > 0 else None)
+        probs = torch.softmax(_processed_scores_oracle(logits[:, o:o + v].cpu(), hist[c], cfg, 1024 if c > 0 else None), -1)
+        for b in range(B):
+            d = draws[:, b, c]
+            vmin = kept[b][kept[b] > -float("inf")].min()
+            assert (base[b, d] >= vmin).all()
+            top = probs[b].topk(3)
+            for pv, pi in zip(top.values.tolist(), top.indices.tolist()):
+                freq = (d == pi).float().mean().item()
+                assert abs(freq - pv) <= 5 * (pv * (1 - pv) / 300) ** 0.5 + 0.015, (c, b, freq, pv)
+
+
+def test_generate_early_stop_tied_weights_streamer_and_dict():
+    """Without the speech-only trick a random-init model emits a non-speech channel-0 token at once: every row winds down
+    (7 more rows, EOS/pad staircase) and generation stops long before max_length. Checks the stop length and the fill
+    pattern against the oracle's `_sample` restatement on the same (tied) weights, plus streamer / dict outputs."""
+    from oracle import lm_oracle
+    from moss_ttsd_b200.modeling_asteroid import AsteroidTTSConfig, AsteroidTTSInstruct, GenerateDecoderOnlyOutput
+    g = gold("lm_tiny.npz")
+    sd = lm_oracle.make_weights(TINY, 77, speech_only_head0=False, tied=True)
+    cfg = AsteroidTTSConfig(**TINY, eos_token_id=152694, pad_token_id=151643, tie_word_embeddings=True)
+    m = AsteroidTTSInstruct(cfg, device="cuda")
+    m.load_state_dict(sd, tie_word_embeddings=True)
+    assert m._w.embeds is None  # tables are views of the head buffer
+    m.generation_config.eos_token_id = 152694
+    ids, mask = torch.from_numpy(g["ids"]), torch.from_numpy(g["mask"])
+    T = ids.shape[1]
+    P = T - 7
+
+    class Streamer:
+        def __init__(self):
+            self.chunks, self.ended = [], False
+
+        def put(self, x):
+            self.chunks.append(x.clone())
+
+        def end(self):
+            self.ended = True
+
+    st = Streamer()
+    out = m.generate(input_ids=ids.cuda(), attention_mask=mask.cuda(), max_new_tokens=40, streamer=st,
+                     return_dict_in_generate=True)
+    assert isinstance(out, GenerateDecoderOnlyOutput)
+    seq = out.sequences.cpu()
+    ref = lm_oracle.OracleCachedLM(TINY, sd, torch.float32).generate(ids, mask, max_length=T + 40,
+                                                                   speech_range=TINY["speech_token_range"])
+    assert seq.shape == ref.shape and seq.shape[1] < T + 40       # stopped early, at the same length
+    lo, hi = TINY["speech_token_range"]
+    # fill pattern: where the reference wrote EOS (ch0) / pad (ch>0) during wind-down, so do we
+    gen, rgen = seq[:, P:], ref[:, P:]
+    assert torch.equal(gen[..., 0] == 152694, rgen[..., 0] == 152694)
+    assert torch.equal(gen[:, -1], torch.tensor([[152694] + [1024] * 7] * seq.shape[0]))
+    assert st.ended and torch.equal(torch.stack(st.chunks, 1), gen[..., 0])
+    plain = m.generate(input_ids=ids.cuda(), attention_mask=mask.cuda(), max_new_tokens=40)
+    assert torch.equal(plain.cpu(), seq)
+    with pytest.raises(ValueError):
+        m.generate(input_ids=ids[:, :5].cuda(), attention_mask=mask[:, :5].cuda())
