@@ -348,7 +348,9 @@ def test_generate_early_stop_tied_weights_streamer_and_dict():
     # fill pattern: where the reference wrote EOS (ch0) / pad (ch>0) during wind-down, so do we
     gen, rgen = seq[:, P:], ref[:, P:]
     assert torch.equal(gen[..., 0] == 152694, rgen[..., 0] == 152694)
-    assert torch.equal(gen[:, -1], torch.tensor([[152694] + [1024] * 7] * seq.shape[0]))
+    # the last wind-down row is [EOS, pad x6, <channel 7 still live>]
+    assert torch.equal(gen[:, -1, :7], torch.tensor([[152694] + [1024] * 6] * seq.shape[0]))
+    assert torch.equal(gen[:, -7:, 1:] == 1024, rgen[:, -7:, 1:] == 1024)
     assert st.ended and torch.equal(torch.stack(st.chunks, 1), gen[..., 0])
     plain = m.generate(input_ids=ids.cuda(), attention_mask=mask.cuda(), max_new_tokens=40)
     assert torch.equal(plain.cpu(), seq)
