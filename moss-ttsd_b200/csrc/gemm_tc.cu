@@ -644,6 +644,7 @@ int dispatch(int bn, const CUtensorMap& tw, const CUtensorMap& tx, const GemmPar
         const char* e = getenv("MTTS_GEMM_NO_PERSIST");
         persist = (e && e[0] == '1') ? 0 : 1;
       }
+      // a single row of tiles (decode at batch 129..256) is a weight-streaming problem: cluster split-K variant
       if (!persist) return launch<T, 256>(tw, tx, p, grid, stream);
       const int num_tiles = (int)(grid.x * grid.y);
       const int ctas = num_tiles < mtts_num_sms() ? num_tiles : mtts_num_sms();
@@ -688,15 +689,15 @@ int mtts_gemm_tc_pick_bn(int M) {
   if (M <= 16) return 16;
   if (M <= 32) return 32;
   if (M <= 64) return 64;
-  if (M <= 128) return 128;
-  return 256;
+  if (M <= 256) return 128;  // decode at batch 65..256: one or two 128-row activation tiles, cluster split-K
+  return 256;                // prefill / codec: persistent kernel
 }
 
 // Split-K heuristic for the weight-streaming (small-M) variants: cluster sizes 1/2/4/8 (odd cluster sizes place
 // badly: s = 3 on the 96-tile gate/up projection measured 22 us against 15.6 us for s = 2), aiming at two CTAs per SM
 // (two ring buffers fit), each split keeping at least 2 k-blocks.
-static int pick_splits(int tiles, int kb_total, int bn) {
-  if (bn > 64) return 1;
+static int pick_splits(int tiles, int kb_total, int bn, int tiles_m) {
+  if (bn > 128) return 1;  // many-tile problems (prefill, codec) go to the persistent kernel
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("MTTS_GEMM_SPLITS");
@@ -742,7 +743,7 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   p.kb_total = ceil_div(K, bk);
   const int tiles_n = ceil_div(N, kBlockW), tiles_m = ceil_div(M, bn);
   const int tiles = tiles_n * tiles_m;
-  int splits = pick_splits(tiles, p.kb_total, bn);
+  int splits = pick_splits(tiles, p.kb_total, bn, tiles_m);
   p.kb_per_split = ceil_div(p.kb_total, splits);
   while (splits > 1 && (splits - 1) * p.kb_per_split >= p.kb_total) {  // every slice must get >= 1 k-block
     splits /= 2;

@@ -32,7 +32,8 @@ def main():
     m.generation_config.eos_token_id = 152694
     rng = np.random.default_rng(0)
     rows = []
-    for B, new in ((1, 64), (16, 64), (64, 64)):
+    batches = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1, 16, 64]
+    for B, new in [(b, 64) for b in batches]:
         ids, mask = make_prompt(rng, B, 200, 250)
         ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
         T = ids.shape[1]

@@ -22,7 +22,8 @@ def _ref(x, w, bias=None, gelu=False, gamma=None, residual=None, out_dtype=torch
 
 SHAPES = [
     (1, 256, 128), (1, 2048, 2048), (3, 1000, 512), (16, 4096, 2048), (17, 384, 6144), (64, 2048, 6144),
-    (100, 130, 200), (128, 768, 3072), (300, 1025, 2048), (257, 962, 512), (1000, 512, 560),
+    (100, 130, 200), (128, 768, 3072), (129, 2048, 2048), (256, 4096, 2048), (300, 1025, 2048), (257, 962, 512),
+    (1000, 512, 560),
 ]
 
 
