@@ -202,6 +202,47 @@ int mtts_dwconv7_ln(const float* x, const float* conv_w, const float* conv_b, co
 int mtts_convt_gather(const float* y, const float* bias, float* out, int B, int Tin, int Cout, int K, int stride,
                       int Tout, int gelu, void* stream);
 
+/* ---- Small-batch decode step as one persistent kernel (batch 1..4; hidden 2048, intermediate 6144, 16/8 heads x 128).
+ * Runs, for ONE new row per sequence, everything between the embedding sum and the sampler: the Qwen3 layer stack that
+ * AsteroidTTSInstruct.forward drives (modeling_asteroid.py:252-285: RMSNorm, q/k/v projection, per-head q/k RMSNorm +
+ * RoPE, KV-cache append, causal GQA attention, o_proj + residual, RMSNorm, SwiGLU MLP + residual), the final norm and
+ * the 8 lm_heads (:287-288). Same rounding points as the kernel chain (mtts_rmsnorm / mtts_gemm /
+ * mtts_qknorm_rope_kvappend / mtts_gqa_attention), which it replaces launch for launch.
+ * `layers` is a DEVICE array of num_layers descriptors; every matrix is row-major [out, in] bf16, wgu has gate/up rows
+ * interleaved (2j = gate_j, 2j+1 = up_j), heads is [vpad, hidden]. x [B, hidden] bf16 holds the embedding sum (read
+ * only); logits [B, ld_logits] bf16. workspace: mtts_decode_mega_workspace_bytes() bytes, 256-byte aligned, zeroed ONCE
+ * at allocation and owned by this entry point afterwards (it carries the inter-CTA activation words and their tags).
+ * The launch is cooperative (one CTA per SM); it fails with an error instead of hanging when the grid cannot be
+ * co-resident. */
+typedef struct mtts_lm_layer {
+  const void* wqkv; const void* wo; const void* wgu; const void* wd;
+  const void* ln1;  const void* ln2; const void* q_norm; const void* k_norm;
+  void* k_pool;     void* v_pool;   /* [num_pages, num_kv_heads, page_size, head_dim] bf16 of this layer */
+} mtts_lm_layer;
+
+typedef struct mtts_decode_mega_args {
+  const mtts_lm_layer* layers; int num_layers;
+  int hidden, intermediate, num_q_heads, num_kv_heads, head_dim;
+  const void* heads; int vpad;
+  const void* final_norm;
+  const float* inv_freq;          /* [head_dim/2] */
+  const int* positions;           /* [B] position of the new row of each sequence */
+  const int* block_table;         /* [B, max_pages] or NULL (contiguous cache) */
+  int max_pages, page_size, num_pages;
+  const void* x;
+  void* logits; long long ld_logits;
+  int B; int nsplit;              /* split-KV factor, 1..4; B * num_kv_heads * nsplit <= SM count */
+  float eps;
+  void* workspace; long long workspace_bytes;
+  int* err_flag;                  /* set to 2 when a position falls outside the page table */
+  long long* profile_cycles;      /* NULL, or [32 + 16*SMs] device int64 (profiling builds of the host only):
+                                     SM cycles CTA 0 spent in each phase, then per-CTA globaltimer stamps of layer 5 */
+} mtts_decode_mega_args;
+
+int mtts_decode_mega_supported(int hidden, int intermediate, int num_q_heads, int num_kv_heads, int head_dim, int B);
+long long mtts_decode_mega_workspace_bytes(int B, int nsplit);
+int mtts_decode_mega(const mtts_decode_mega_args* args, void* stream);
+
 /* im2col for Conv1d(K odd, pad=(K-1)/2, stride) on token-major x [B,T,Cin]: col[b,t',j*Cin+ci] = x[b,t'*stride+j-pad,ci]
  * (VocosBackbone.embed modules.py:1372; OmniAudioEncoder conv1/conv2 modules.py:238-240). */
 int mtts_im2col(const float* x, float* col, int B, int T, int Cin, int K, int ld_col, int stride, void* stream);

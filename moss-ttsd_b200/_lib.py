@@ -37,6 +37,27 @@ class SamplerConfig(ctypes.Structure):
 
 _cfg_p = ctypes.POINTER(SamplerConfig)
 
+
+class LMLayer(ctypes.Structure):
+    """Mirror of `mtts_lm_layer`: ten device pointers per decoder layer."""
+    _fields_ = [(n, c_void_p) for n in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2", "q_norm", "k_norm", "k_pool", "v_pool")]
+
+
+class DecodeMegaArgs(ctypes.Structure):
+    """Mirror of `mtts_decode_mega_args` (include/mtts.h)."""
+    _fields_ = [
+        ("layers", c_void_p), ("num_layers", c_int),
+        ("hidden", c_int), ("intermediate", c_int), ("num_q_heads", c_int), ("num_kv_heads", c_int), ("head_dim", c_int),
+        ("heads", c_void_p), ("vpad", c_int),
+        ("final_norm", c_void_p), ("inv_freq", c_void_p), ("positions", c_void_p), ("block_table", c_void_p),
+        ("max_pages", c_int), ("page_size", c_int), ("num_pages", c_int),
+        ("x", c_void_p),
+        ("logits", c_void_p), ("ld_logits", c_ll),
+        ("B", c_int), ("nsplit", c_int), ("eps", c_float),
+        ("workspace", c_void_p), ("workspace_bytes", c_ll),
+        ("err_flag", c_void_p), ("profile_cycles", c_void_p),
+    ]
+
 # name -> (restype, argtypes). Kept in the same order as include/mtts.h; tests/test_abi.py checks that every
 # symbol the header declares is listed here and exported by the .so.
 SIGNATURES = {
@@ -79,6 +100,9 @@ SIGNATURES = {
     "mtts_istft_spec": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p]),
     "mtts_istft_ola": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mtts_add_rows_mod": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
+    "mtts_decode_mega_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mtts_decode_mega_workspace_bytes": (c_ll, [c_int, c_int]),
+    "mtts_decode_mega": (c_int, [ctypes.POINTER(DecodeMegaArgs), c_void_p]),
     "mtts_delay_step": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, _cfg_p, c_void_p]),
 }

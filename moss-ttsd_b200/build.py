@@ -43,7 +43,7 @@ def _compile_one(src: str, verbose: bool) -> str:
     srcp = os.path.join(CSRC, src)
     if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(srcp), _headers_mtime()):
         return obj
-    cmd = [NVCC, *NVCC_FLAGS, "-c", srcp, "-o", obj]
+    cmd = [NVCC, *NVCC_FLAGS, *os.environ.get("MTTS_NVCC_FLAGS", "").split(), "-c", srcp, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(OBJDIR, src[:-3] + ".ptxas.log")
     with open(log, "w") as f:

@@ -70,6 +70,7 @@ extern "C" int mtts_init(void) {
     if ((rc = mtts_configure_attention())) return rc;
     if ((rc = mtts_configure_rvq())) return rc;
     if ((rc = mtts_configure_codec())) return rc;
+    if ((rc = mtts_configure_decode_mega())) return rc;
     configured[dev] = true;
   }
   return MTTS_OK;

@@ -1,0 +1,934 @@
+// Small-batch decode step as ONE persistent kernel (batch <= 4 rows, MOSS-TTSD-v0.5 / Qwen3-1.7B widths).
+//
+// At batch 1..4 a decode step is a pure weight stream: 3.47 GB of bf16 matrices are read once and every other
+// tensor is a few KB. A chain of ~230 kernels (even PDL-chained inside a CUDA graph) leaves the HBM idle at
+// every kernel boundary, so here the whole layer stack + LM heads run in one cooperative grid of one CTA per SM:
+//
+//   * every weight matrix [N, K] is split by OUTPUT ROWS over the CTAs (full K per CTA -> no cross-CTA reduction);
+//     a CTA's share of a matrix is one contiguous byte range of the row-major matrix;
+//   * one producer warp per CTA walks the CTA's shares of ALL matrices of the step, in order, and streams them
+//     with 1-D bulk async copies (TMA engine, mbarrier complete_tx) into a 5-stage shared-memory ring of
+//     [16 rows x 1024 k] chunks; it depends on nothing but ring space, so HBM keeps streaming while the consumer
+//     warps wait for activations, normalise, or run attention;
+//   * 16 consumer warps split a chunk along K (64 k each); weights are the A operand of bf16 mma.sync m16n8k16
+//     (ldmatrix from the padded ring rows, conflict-free), the activation rows (n = batch row) are the B operand,
+//     read from a shared-memory copy of the phase input; a 16-warp shared-memory reduction finishes a 16-row tile
+//     and the epilogue (bf16 rounding / residual / SwiGLU) writes it;
+//   * the code is kept SMALL on purpose (one generic projection routine, one staging routine, no per-phase
+//     template copies): the consumer path runs once per layer, so a body that overflows the 32 KB instruction cache
+//     pays an L2 instruction fetch for every line of every layer (measured: 181 KB of SASS -> 2.5x slower);
+//   * there is NO grid barrier: activations travel between phases (q/k/v projection, attention, o_proj, gate/up,
+//     down) as 8-byte {payload, tag} words written with one store and polled by their readers (the "LL" protocol
+//     of collective libraries): one L2 round trip from producer to consumer, no fences, and a reader only ever
+//     waits for the words it needs. The tag encodes (launch, layer, phase), so stale words never match. Every phase
+//     consumes the outputs of ALL CTAs of the previous phase, which makes single buffers safe (a writer two phases
+//     ahead implies every reader has moved on); the cooperative launch guarantees co-residency of the pollers;
+//   * attention at these sizes is latency-, not bandwidth-bound: the first B x Hkv x nsplit CTAs each also own a key
+//     range of one (row, kv head) and issue their K/V loads before they start waiting for q.
+//
+// Rounding points follow the same bf16 eager reference as the kernel-chain path (lm_ops.cu, gemm_tc.cu epilogue,
+// attention.cu); see SURVEY.md Appendix B. Replaces, for one decode row per sequence, the Qwen3 layer stack that
+// AsteroidTTSInstruct.forward drives (modeling_asteroid.py:252-285) and the 8 lm_heads (:287-288).
+#include "common.cuh"
+#include "mtts_internal.h"
+#include "sm100.cuh"
+
+namespace {
+
+using namespace sm100;
+
+constexpr int kH = 2048, kI = 6144, kD = 128, kHq = 16, kHkv = 8, kG = 2;
+constexpr int kNQKV = (kHq + 2 * kHkv) * kD;  // 4096
+constexpr int kCW = 16;                       // consumer warps
+constexpr int kConsumers = kCW * 32;          // 512
+constexpr int kThreads = kConsumers + 32;     // + 1 producer warp
+constexpr int kChunkK = 1024;                 // k elements of one ring chunk
+constexpr int kRowBytes = kChunkK * 2;
+constexpr int kRowPitch = kRowBytes + 16;     // 16-byte skew per row: ldmatrix phases hit 32 distinct banks
+constexpr int kTileRows = 16;
+constexpr int kStageBytes = kTileRows * kRowPitch;
+constexpr int kStages = 5;
+constexpr int kMaxB = 4;
+constexpr int kActPitch = kI + 8;             // bf16 elements; rows 12304 B apart -> conflict-free B-fragment loads
+constexpr int kWsStride = kD + 4;             // attention partial: [M, L, -, -, O[128]] (one LL word per float)
+constexpr int kTagsPerLayer = 8;
+constexpr int kRedTile = kTileRows * kMaxB;   // floats one warp contributes to the tile reduction
+constexpr int kMaxCtas = 160;
+
+constexpr int kSmemRing = kStages * kStageBytes;
+constexpr int kSmemAct = kMaxB * kActPitch * 2 + 256;  // 49472 B (+256 zero bytes); also the attention scratch
+constexpr int kSmemRed = 2 * kCW * kRedTile * 4;     // double-buffered 16-warp tile reduction
+constexpr int kSmemMisc = 4096;                      // barriers, block-reduce scratch, residual rows, RoPE + sentinel tables
+constexpr int kSmemTotal = kSmemRing + kSmemAct + kSmemRed + kSmemMisc;
+static_assert(kSmemTotal <= 227 * 1024, "shared memory budget");
+
+struct MegaParams {
+  const mtts_lm_layer* layers;
+  int num_layers;
+  const bf16* heads;
+  int vpad;
+  const bf16* final_norm;
+  const float* inv_freq;
+  const int* positions;
+  const int* block_table;
+  int max_pages, page_shift, num_pages;
+  const bf16* x_in;   // [B, H] embedding sum (plain bf16, written by the previous kernel)
+  uint2* x_ll[2];     // [B][H/2] words: [0] = layer input / output of down, [1] = output of o_proj
+  uint2* qkv_ll;      // [B][NQKV/2]
+  uint2* h_ll;        // [B][I/2]
+  uint2* ws_ll;       // [B*Hkv*nsplit*G][kWsStride] attention partials, one fp32 per word
+  bf16* logits;
+  long long ld_logits;
+  int nsplit;
+  float eps, scale_log2;
+  unsigned int* tag_base;  // [1] device word: tags used by earlier launches
+  int* err_flag;
+  long long* prof;  // optional: cycles CTA 0 spent per phase, summed over layers (+ per-CTA stamps in trace builds)
+};
+
+// ------------------------------------------------------------------ small PTX helpers
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&a)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+}
+
+// ---- LL words: {payload, tag} in one aligned 8-byte store; a reader polls until the tag is the one it expects.
+// (64-bit SCALAR accesses: single-copy atomic in the PTX memory model, unlike the elements of a vector access.)
+__device__ __forceinline__ void ll_store(uint2* p, uint32_t data, uint32_t tag) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)tag << 32) | data) : "memory");
+}
+__device__ __noinline__ void ll_timeout(uint32_t tag) {
+  printf("mtts: decode_mega wait for tag %u timed out (block %d thread %d)\n", tag, blockIdx.x, threadIdx.x);
+  __trap();  // a protocol bug must surface as a launch error, never as a hung GPU box
+}
+// Pollers issue ALL their loads first and compare the tags afterwards (one L2 round trip per attempt, however many
+// words a thread needs); on a mismatch the whole batch is re-issued.
+__device__ __forceinline__ void ll_issue(const uint2* p, uint32_t& d, uint32_t& t) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  d = (uint32_t)v;
+  t = (uint32_t)(v >> 32);
+}
+__device__ __forceinline__ void ll_issue2(const uint2* p, uint32_t& d0, uint32_t& t0, uint32_t& d1, uint32_t& t1) {
+  unsigned long long v0, v1;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v0), "=l"(v1) : "l"(p) : "memory");
+  d0 = (uint32_t)v0; t0 = (uint32_t)(v0 >> 32);
+  d1 = (uint32_t)v1; t1 = (uint32_t)(v1 >> 32);
+}
+struct LLSpin {
+  uint32_t spins = 0;
+  __device__ __forceinline__ void miss(uint32_t tag) {
+    if (++spins > (1u << 22)) ll_timeout(tag);
+  }
+};
+
+// Rows [r0, r1) of an N-row matrix owned by CTA `cta`: units of `unit` rows dealt out evenly, the remainder rotated
+// by `rot` so that the longer shares of the four per-layer matrices land on different CTAs.
+struct Slice { int r0, r1; };
+__device__ __forceinline__ Slice slice_rows(int n_rows, int unit, int rot, int cta, int G) {
+  const int units = n_rows / unit;
+  const int c = (int)(((unsigned)cta + (unsigned)rot) % (unsigned)G);
+  const int base = units / G, rem = units % G;
+  const int u0 = c * base + min(c, rem);
+  const int nu = base + (c < rem ? 1 : 0);
+  return Slice{u0 * unit, (u0 + nu) * unit};
+}
+// first row of the last 16-row tile of a share (its words are the last a producer publishes in a phase)
+__device__ __forceinline__ int last_tile_row(Slice s) { return s.r0 + ((s.r1 - s.r0 - 1) / kTileRows) * kTileRows; }
+
+// The matrices of the step in consumption order: m = 0 q/k/v, 1 o_proj, 2 gate/up, 3 down (per layer), 4 LM heads.
+// Shares are the same in every layer (rotation depends on m only), so they and the sentinel addresses derived from
+// them are computed once per launch.
+__host__ __device__ constexpr int mat_rows(int m) { return m == 0 ? kNQKV : (m == 2 ? 2 * kI : kH); }
+__host__ __device__ constexpr int mat_unit(int m) { return m == 2 ? 4 : 2; }
+__host__ __device__ constexpr int mat_rot(int m) { return m * 37; }
+
+// Polling by all 512 consumer threads of all CTAs would swamp the L2 request queues that the weight stream also
+// needs, so before a CTA-wide verified load ONE warp watches a sentinel word per producer CTA (the first word of the
+// producer's last tile, batch row B-1); the other warps sleep in the hardware barrier that follows. The sentinel is
+// only a hint: the load after it still checks every tag and retries.
+// `offs`: shared-memory table of the sentinel word offsets (one per producer CTA), built once per launch.
+__device__ __noinline__ void sentinel_wait(const uint2* base, const int* offs, int n, uint32_t tag) {
+  const int lane = threadIdx.x & 31;
+  LLSpin sp;
+  while (true) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int c = lane + 32 * i;
+      uint32_t d, t = tag;
+      if (c < n) ll_issue(base + offs[c], d, t);
+      ok = ok && (t == tag);
+    }
+    if (__all_sync(0xffffffffu, ok)) break;
+    sp.miss(tag);
+  }
+}
+
+struct Ring {
+  uint8_t* stages;
+  uint64_t* full;
+  uint64_t* empty;
+  uint32_t it;
+};
+
+// ------------------------------------------------------------------ consumer: one matrix share
+enum { EPI_QKV = 0, EPI_WO = 1, EPI_GU = 2, EPI_WD = 3, EPI_HEADS = 4 };
+
+// Profiling counters live in shared memory while the kernel runs (a global read-modify-write per tick would itself
+// cost ~0.3 us on the critical path of CTA 0) and are flushed once at the end.
+__shared__ long long s_prof[32];
+
+// act: [kMaxB][kActPitch] bf16 phase input; `out`: LL destination (qkv / x / h words, `out_wpr` words per batch row) or
+// unused for the heads; `res`: [kMaxB][16] raw residual values of the rows of this share (o_proj / down only);
+// `tag`: tag of the words this phase publishes.
+// Bounded wait with the bookkeeping out of line: the fast path is one try_wait and one branch.
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+
+// act: [kMaxB][kActPitch] bf16 phase input, followed by 256 zero bytes (the B operand of the unused batch columns);
+// `out`: LL destination (qkv / x / h words, `out_wpr` words per batch row) or unused for the heads; `res`: [kMaxB][16]
+// raw residual values of the rows of this share (o_proj / down only); `tag`: tag of the words this phase publishes.
+// The loop is issue-bound if it is not kept lean (4 warps per scheduler, 64 KB of weights per trip): no modulo, no
+// select, no bookkeeping inside.
+template <int kB>
+__device__ __noinline__ void consume_matrix(Ring& rg, const MegaParams& p, Slice s, int kch, int epi, const bf16* act,
+                                            float* red, int& red_buf, uint2* out, int out_wpr, const float* res,
+                                            uint32_t tag) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t a_off = (uint32_t)((lane & 15) * kRowPitch + (warp * 64 + (lane >> 4) * 8) * 2);
+  const bf16* b_src = g < kB ? act + g * kActPitch + warp * 64 + 2 * t : act + kMaxB * kActPitch + 2 * t;
+  const int kmul = g < kB ? kChunkK : 0;
+  uint32_t st = rg.it % kStages, par = (rg.it / kStages) & 1;
+  uint32_t n_done = 0;
+  // B fragments (k16 x n8, "col") of this warp's 64-wide k slice of two chunks: batch row g, k = 2t,2t+1 and +8
+  uint32_t bq[8][2];
+  auto load_bq = [&](int kg) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      bq[i][0] = *reinterpret_cast<const uint32_t*>(b_src + (kg + (i >> 2)) * kmul + (i & 3) * 16);
+      bq[i][1] = *reinterpret_cast<const uint32_t*>(b_src + (kg + (i >> 2)) * kmul + (i & 3) * 16 + 8);
+    }
+  };
+  if (kch == 2) load_bq(0);
+#pragma unroll 1
+  for (int r = s.r0; r < s.r1; r += kTileRows) {
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int kg = 0; kg < kch; kg += 2) {  // two chunks per trip (kch is 2 or 6)
+      if (kch != 2) load_bq(kg);
+#pragma unroll
+      for (int kc = 0; kc < 2; ++kc) {
+        mbar_wait_lean(&rg.full[st], par);
+        const uint32_t a_base = smem_u32(rg.stages + st * kStageBytes) + a_off;
+        uint32_t a[4][4];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) ldmatrix_x4(a[ks], a_base + ks * 32);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) mma_16x8x16(c, a[ks], bq[kc * 4 + ks][0], bq[kc * 4 + ks][1]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rg.empty[st]);
+        if (++st == kStages) { st = 0; par ^= 1; }
+        ++n_done;
+      }
+    }
+    // 16-warp reduction of the [16 rows x 4 batch] tile (accumulator columns 2t, 2t+1; only t < 2 are real rows)
+    float* rb = red + red_buf * (kCW * kRedTile) + warp * kRedTile;
+    if (t < 2) {
+      *reinterpret_cast<float2*>(rb + g * kMaxB + 2 * t) = make_float2(c[0], c[1]);
+      *reinterpret_cast<float2*>(rb + (g + 8) * kMaxB + 2 * t) = make_float2(c[2], c[3]);
+    }
+    consumer_sync();
+    if (tid < kRedTile) {  // two warps: lane + 4 holds the next row of the same batch column
+      const float* rr = red + red_buf * (kCW * kRedTile) + tid;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCW; ++w) v += rr[w * kRedTile];
+      const int row = r + (tid >> 2), n = tid & 3;
+      const bool ok = row < s.r1 && n < kB;
+      if (epi == EPI_HEADS) {
+        if (ok) p.logits[(size_t)n * p.ld_logits + row] = __float2bfloat16_rn(v);
+      } else if (epi == EPI_GU) {
+        // rows 2j = gate_j, 2j+1 = up_j: bf16(gate), bf16(silu), bf16(up), bf16(product)
+        const float up = __shfl_down_sync(0xffffffffu, v, 4);
+        const float hv = bf16_round(silu_f(bf16_round(v))) * bf16_round(up);
+        const float hn = __shfl_down_sync(0xffffffffu, hv, 8);
+        if (ok && !(row & 3)) ll_store(out + (size_t)n * out_wpr + (row >> 2), pack_bf16(hv, hn), tag);
+      } else {
+        float xv = v;  // q/k/v: bf16(linear);   o_proj / down: hidden = residual + bf16(linear), both bf16 tensors
+        if (epi != EPI_QKV && ok) xv = bf16_round(res[n * 16 + (row - s.r0)] + bf16_round(v));
+        const float nx = __shfl_down_sync(0xffffffffu, xv, 4);
+        if (ok && !(row & 1)) ll_store(out + (size_t)n * out_wpr + (row >> 1), pack_bf16(xv, nx), tag);
+      }
+    }
+    red_buf ^= 1;
+  }
+  rg.it += n_done;
+}
+
+// Stage B rows of 2048 elements (LL words, or the plain embedding sum) into act with RMSNorm on the way (every CTA
+// does it redundantly: 8 KB per row from L2):
+//   v = mean(x^2); y = bf16(x * rsqrt(v + eps)); out = bf16(w * y)        (lm_ops.cu rmsnorm_kernel)
+// The raw values of rows [keep.r0, keep.r1) are kept in `res` for the residual add of the following projection.
+template <int kB>
+__device__ __noinline__ void stage_norm(const MegaParams& p, const uint2* src_ll, uint32_t tag, const int* sent, int n_gemv,
+                                        const bf16* x_plain, const bf16* __restrict__ w, bf16* act, float* scratch,
+                                        Slice keep, float* res) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint2 xv[kB];
+  const uint2 wv = *reinterpret_cast<const uint2*>(w + tid * 4);
+  if (x_plain) {
+#pragma unroll
+    for (int b = 0; b < kB; ++b) xv[b] = *reinterpret_cast<const uint2*>(x_plain + (size_t)b * kH + tid * 4);
+  } else {
+    if (warp == 0) sentinel_wait(src_ll + (size_t)(kB - 1) * (kH / 2), sent, n_gemv, tag);
+    consumer_sync();
+    LLSpin sp;
+    while (true) {
+      bool ok = true;
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        uint32_t t0, t1;
+        ll_issue2(src_ll + (size_t)b * (kH / 2) + tid * 2, xv[b].x, t0, xv[b].y, t1);
+        ok = ok && t0 == tag && t1 == tag;
+      }
+      if (ok) break;
+      sp.miss(tag);
+    }
+  }
+  const int e = tid * 4;
+  const bool keeps = e + 3 >= keep.r0 && e < keep.r1;
+#pragma unroll
+  for (int b = 0; b < kB; ++b) {
+    const float a[4] = {bf16lo(xv[b].x), bf16hi(xv[b].x), bf16lo(xv[b].y), bf16hi(xv[b].y)};
+    const float ss = warp_sum(fmaf(a[0], a[0], fmaf(a[1], a[1], fmaf(a[2], a[2], a[3] * a[3]))));
+    if (lane == 0) scratch[warp * kMaxB + b] = ss;
+    if (keeps) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (e + j >= keep.r0 && e + j < keep.r1) res[b * 16 + (e + j - keep.r0)] = a[j];
+    }
+  }
+  consumer_sync();
+#pragma unroll
+  for (int b = 0; b < kB; ++b) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kCW; ++i) tot += scratch[i * kMaxB + b];
+    const float inv = rsqrtf(tot * (1.0f / kH) + p.eps);
+    const float o0 = bf16_round(bf16lo(xv[b].x) * inv) * bf16lo(wv.x);
+    const float o1 = bf16_round(bf16hi(xv[b].x) * inv) * bf16hi(wv.x);
+    const float o2 = bf16_round(bf16lo(xv[b].y) * inv) * bf16lo(wv.y);
+    const float o3 = bf16_round(bf16hi(xv[b].y) * inv) * bf16hi(wv.y);
+    *reinterpret_cast<uint2*>(act + b * kActPitch + tid * 4) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
+  }
+  consumer_sync();
+}
+
+// Stage the B rows of the SwiGLU output (6144 elements each) into act, unchanged.
+template <int kB>
+__device__ __noinline__ void stage_h(const MegaParams& p, uint32_t tag, const int* sent, int n_gemv, bf16* act) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) sentinel_wait(p.h_ll + (size_t)(kB - 1) * (kI / 2), sent, n_gemv, tag);
+  consumer_sync();
+  uint2 xv[3][kB];
+  LLSpin sp;
+  while (true) {
+    bool ok = true;
+#pragma unroll
+    for (int pc = 0; pc < 3; ++pc)
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        uint32_t t0, t1;
+        ll_issue2(p.h_ll + (size_t)b * (kI / 2) + pc * (kH / 2) + tid * 2, xv[pc][b].x, t0, xv[pc][b].y, t1);
+        ok = ok && t0 == tag && t1 == tag;
+      }
+    if (ok) break;
+    sp.miss(tag);
+  }
+#pragma unroll
+  for (int pc = 0; pc < 3; ++pc)
+#pragma unroll
+    for (int b = 0; b < kB; ++b) *reinterpret_cast<uint2*>(act + b * kActPitch + pc * kH + tid * 4) = xv[pc][b];
+  consumer_sync();
+}
+
+// Merge the split-KV partials of the attention phase into act[b][head*128 + d] (bf16, as the o_proj input).
+template <int kB>
+__device__ __noinline__ void stage_attn_out(const MegaParams& p, bf16* act, uint32_t tag) {
+  const int units = kB * kHkv * p.nsplit;
+  if ((threadIdx.x >> 5) == 0) {  // sentinel: the last O word of head g = 1 of every unit
+    const int lane = threadIdx.x & 31;
+    LLSpin sp;
+    while (true) {
+      bool ok = true;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int u = lane + 32 * i;
+        uint32_t d, t = tag;
+        if (u < units) ll_issue(p.ws_ll + ((size_t)u * kG + 1) * kWsStride + 4 + 127, d, t);
+        ok = ok && (t == tag);
+      }
+      if (__all_sync(0xffffffffu, ok)) break;
+      sp.miss(tag);
+    }
+  }
+  consumer_sync();
+#pragma unroll 1
+  for (int idx = threadIdx.x; idx < kB * (kH / 4); idx += kConsumers) {
+    const int b = idx / (kH / 4), rem = idx % (kH / 4);
+    const int head = rem >> 5, d4 = (rem & 31) * 4;
+    const int hk = head / kG, g = head % kG;
+    const uint2* base = p.ws_ll + ((size_t)((b * kHkv + hk) * p.nsplit) * kG + g) * kWsStride;
+    float ms[4], ls[4];
+    float4 ov[4];
+    LLSpin sp;
+    while (true) {
+      bool ok = true;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        uint32_t d[6] = {0xff800000u, 0u, 0u, 0u, 0u, 0u}, t[6] = {tag, tag, tag, tag, tag, tag};  // absent split: M = -inf
+        if (s < p.nsplit) {
+          const uint2* w0 = base + (size_t)s * kG * kWsStride;
+          ll_issue2(w0, d[0], t[0], d[1], t[1]);
+          ll_issue2(w0 + 4 + d4, d[2], t[2], d[3], t[3]);
+          ll_issue2(w0 + 6 + d4, d[4], t[4], d[5], t[5]);
+        }
+        ms[s] = __uint_as_float(d[0]); ls[s] = __uint_as_float(d[1]);
+        ov[s] = make_float4(__uint_as_float(d[2]), __uint_as_float(d[3]), __uint_as_float(d[4]), __uint_as_float(d[5]));
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ok = ok && (t[i] == tag);
+      }
+      if (ok) break;
+      sp.miss(tag);
+    }
+    float M = -1e30f;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) M = fmaxf(M, ms[s]);
+    float L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const float w = ex2(ms[s] - M);
+      L = fmaf(ls[s], w, L);
+      o[0] = fmaf(ov[s].x, w, o[0]); o[1] = fmaf(ov[s].y, w, o[1]); o[2] = fmaf(ov[s].z, w, o[2]); o[3] = fmaf(ov[s].w, w, o[3]);
+    }
+    const float inv = 1.0f / L;
+    *reinterpret_cast<uint2*>(act + b * kActPitch + head * kD + d4) =
+        make_uint2(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv));
+  }
+  consumer_sync();
+}
+
+// ------------------------------------------------------------------ attention CTAs
+// Unit = (batch row, kv head, split), one per attention CTA for the whole step. Per layer: all 32 half-warps issue the
+// K/V loads of their first cached key (they do not depend on this step), warps 0..3 wait for q (2 heads), k and v of
+// the new token and finish them (per-head RMSNorm + RoPE, lm_ops.cu qknorm_rope_kv_kernel; the owner split appends
+// k/v to the cache), the cached keys are walked with an fp32 online softmax (attention.cu; 16 lanes per key row,
+// 32 rows per pass, next pass in flight), the owner folds in the new key from shared memory, and the CTA publishes
+// one (M, L, O[128]) partial per q head. The loops are deliberately rolled: this code must stay small.
+// `rope`: [cos[64] | sin[64]] of this unit's position, bf16-rounded, computed once per step.
+struct AttnUnit {
+  int b, hk, pos, k_begin, k_end, owner;  // k_end excludes the new key
+};
+struct AttnLayer { const bf16 *k_pool, *v_pool, *q_norm, *k_norm; };
+
+// one key row (this lane's 8 dims of K and V) folded into the online-softmax state of both q heads
+__device__ __forceinline__ void attn_fold(const float (&qf)[kG][8], uint4 kq, uint4 vq, bool valid, unsigned mask,
+                                       float (&m)[kG], float (&l)[kG], float (&acc)[kG][8]) {
+  float kf[8], vf[8];
+  unpack8(kq, kf);
+  unpack8(vq, vf);
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) s = fmaf(qf[g][d], kf[d], s);
+    s += __shfl_xor_sync(mask, s, 8);
+    s += __shfl_xor_sync(mask, s, 4);
+    s += __shfl_xor_sync(mask, s, 2);
+    s += __shfl_xor_sync(mask, s, 1);
+    if (!valid) s = -INFINITY;
+    const float mx = fmaxf(m[g], s);
+    const float corr = ex2(m[g] - mx), pw = ex2(s - mx);
+    m[g] = mx;
+    l[g] = fmaf(l[g], corr, pw);
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[g][d] = fmaf(pw, vf[d], acc[g][d] * corr);
+  }
+}
+
+__device__ __noinline__ void attention_layer(const MegaParams& p, const AttnLayer& L, const AttnUnit& un, int unit,
+                                                float* scr, const float* rope, uint32_t tag_in, uint32_t tag_out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* s_q = scr;                 // [2][128] normed + roped q (bf16-rounded values)
+  float* s_k = scr + 2 * kD;        // [128]
+  float* s_v = scr + 3 * kD;        // [128]
+  float* s_part = scr + 4 * kD;     // [16 warps][2][kWsStride]
+  const int page_mask = (1 << p.page_shift) - 1;
+  const int b = un.b, hk = un.hk, pos = un.pos, k_end = un.k_end;
+  const long long head_off = ((long long)hk << p.page_shift) * kD;
+  const long long page_stride = ((long long)kHkv << p.page_shift) * kD;
+  const int l16 = lane & 15, rgp = warp * 2 + (lane >> 4);
+
+  auto kv_offset = [&](int key) {
+    key = min(key, k_end - 1);  // clamp: the load is always legal, the score is masked
+    const int lp = key >> p.page_shift;
+    const int page = p.block_table ? __ldg(p.block_table + (long long)b * p.max_pages + lp) : b * p.max_pages + lp;
+    return (long long)page * page_stride + head_off + (long long)(key & page_mask) * kD + l16 * 8;
+  };
+  uint4 kq = make_uint4(0, 0, 0, 0), vq = kq;
+  if (un.k_begin < k_end) {  // in flight while q/k/v of the new token arrive
+    const long long off = kv_offset(un.k_begin + rgp);
+    kq = ld_nc_v4(L.k_pool + off);
+    vq = ld_nc_v4(L.v_pool + off);
+  }
+
+  if (warp < 4) {
+    const int col = warp < 2 ? (hk * kG + warp) * kD : (warp == 2 ? kHq * kD + hk * kD : (kHq + kHkv) * kD + hk * kD);
+    bf16* dst = nullptr;
+    if (warp >= 2 && un.owner) {
+      const int lp = pos >> p.page_shift;
+      int page = -1;
+      if (lp < p.max_pages) page = p.block_table ? p.block_table[(long long)b * p.max_pages + lp] : b * p.max_pages + lp;
+      if (page < 0 || page >= p.num_pages) {
+        if (lane == 0 && p.err_flag) *p.err_flag = 2;
+      } else {
+        dst = const_cast<bf16*>(warp == 2 ? L.k_pool : L.v_pool) + (long long)page * page_stride + head_off +
+              (long long)(pos & page_mask) * kD;
+      }
+    }
+    const bf16* nw = warp < 2 ? L.q_norm : L.k_norm;
+    const uint32_t wa = *reinterpret_cast<const uint32_t*>(nw + 2 * lane);
+    const uint32_t wb = *reinterpret_cast<const uint32_t*>(nw + 64 + 2 * lane);
+    const uint2* src = p.qkv_ll + (size_t)b * (kNQKV / 2) + col / 2;
+    uint32_t a, c;  // elements (2l, 2l+1) and (64+2l, 65+2l)
+    {
+      LLSpin sp;
+      while (true) {
+        uint32_t ta, tc;
+        ll_issue(src + lane, a, ta);
+        ll_issue(src + 32 + lane, c, tc);
+        if (ta == tag_in && tc == tag_in) break;
+        sp.miss(tag_in);
+      }
+    }
+    float x0 = bf16lo(a), x1 = bf16hi(a), x2 = bf16lo(c), x3 = bf16hi(c);
+    float* so = warp < 2 ? s_q + warp * kD : (warp == 2 ? s_k : s_v);
+    if (warp != 3) {
+      float ss = x0 * x0;
+      ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+      ss = warp_sum(ss);
+      const float inv = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
+      x0 = bf16_round(bf16lo(wa) * bf16_round(x0 * inv));
+      x1 = bf16_round(bf16hi(wa) * bf16_round(x1 * inv));
+      x2 = bf16_round(bf16lo(wb) * bf16_round(x2 * inv));
+      x3 = bf16_round(bf16hi(wb) * bf16_round(x3 * inv));
+      const float c0 = rope[2 * lane], c1 = rope[2 * lane + 1], s0 = rope[64 + 2 * lane], s1 = rope[65 + 2 * lane];
+      const float o0 = bf16_round(bf16_round(x0 * c0) + bf16_round(-x2 * s0));
+      const float o1 = bf16_round(bf16_round(x1 * c1) + bf16_round(-x3 * s1));
+      const float o2 = bf16_round(bf16_round(x2 * c0) + bf16_round(x0 * s0));
+      const float o3 = bf16_round(bf16_round(x3 * c1) + bf16_round(x1 * s1));
+      x0 = o0; x1 = o1; x2 = o2; x3 = o3;
+    }
+    so[2 * lane] = x0; so[2 * lane + 1] = x1; so[64 + 2 * lane] = x2; so[65 + 2 * lane] = x3;
+    if (dst) {
+      *reinterpret_cast<uint32_t*>(dst + 2 * lane) = pack_bf16(x0, x1);
+      *reinterpret_cast<uint32_t*>(dst + 64 + 2 * lane) = pack_bf16(x2, x3);
+    }
+  }
+  consumer_sync();
+
+  float qf[kG][8];
+#pragma unroll
+  for (int g = 0; g < kG; ++g)
+#pragma unroll
+    for (int d = 0; d < 8; ++d) qf[g][d] = s_q[g * kD + l16 * 8 + d] * p.scale_log2;
+  float m[kG], l[kG], acc[kG][8];
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    m[g] = -1e30f; l[g] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) acc[g][d] = 0.f;
+  }
+#pragma unroll 1
+  for (int key = un.k_begin + rgp; key - rgp < k_end; key += 32) {
+    uint4 kn = kq, vn = vq;
+    if (key - rgp + 32 < k_end) {  // next pass in flight
+      const long long off = kv_offset(key + 32);
+      kn = ld_nc_v4(L.k_pool + off);
+      vn = ld_nc_v4(L.v_pool + off);
+    }
+    attn_fold(qf, kq, vq, key < k_end, 0xffffffffu, m, l, acc);
+    kq = kn;
+    vq = vn;
+  }
+  if (un.owner && rgp == 0) {  // the new token's key/value (never read back from global memory)
+    const uint4 kn = make_uint4(pack_bf16(s_k[l16 * 8], s_k[l16 * 8 + 1]), pack_bf16(s_k[l16 * 8 + 2], s_k[l16 * 8 + 3]),
+                                pack_bf16(s_k[l16 * 8 + 4], s_k[l16 * 8 + 5]), pack_bf16(s_k[l16 * 8 + 6], s_k[l16 * 8 + 7]));
+    const uint4 vn = make_uint4(pack_bf16(s_v[l16 * 8], s_v[l16 * 8 + 1]), pack_bf16(s_v[l16 * 8 + 2], s_v[l16 * 8 + 3]),
+                                pack_bf16(s_v[l16 * 8 + 4], s_v[l16 * 8 + 5]), pack_bf16(s_v[l16 * 8 + 6], s_v[l16 * 8 + 7]));
+    attn_fold(qf, kn, vn, true, 0x0000ffffu, m, l, acc);  // s_k / s_v hold bf16-rounded values: the packing is exact
+  }
+  __syncwarp();
+  // merge the two half-warps, then the 16 warps
+#pragma unroll
+  for (int g = 0; g < kG; ++g) {
+    const float mo = __shfl_xor_sync(0xffffffffu, m[g], 16);
+    const float lo = __shfl_xor_sync(0xffffffffu, l[g], 16);
+    const float M = fmaxf(m[g], mo);
+    const float wa = ex2(m[g] - M), wb = ex2(mo - M);
+    l[g] = l[g] * wa + lo * wb;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      const float ao = __shfl_xor_sync(0xffffffffu, acc[g][d], 16);
+      acc[g][d] = acc[g][d] * wa + ao * wb;
+    }
+    m[g] = M;
+    if (lane < 16) {
+      float* o = s_part + (warp * kG + g) * kWsStride;
+      if (lane == 0) { o[0] = m[g]; o[1] = l[g]; }
+#pragma unroll
+      for (int d = 0; d < 8; ++d) o[4 + l16 * 8 + d] = acc[g][d];
+    }
+  }
+  consumer_sync();
+  if (tid < kG * kD) {
+    const int g = tid / kD, d = tid % kD;
+    float M = -1e30f;
+#pragma unroll 4
+    for (int w = 0; w < kCW; ++w) M = fmaxf(M, s_part[(w * kG + g) * kWsStride]);
+    float Ls = 0.f, O = 0.f;
+#pragma unroll 2
+    for (int w = 0; w < kCW; ++w) {
+      const float* o = s_part + (w * kG + g) * kWsStride;
+      const float wt = ex2(o[0] - M);
+      Ls = fmaf(o[1], wt, Ls);
+      O = fmaf(o[4 + d], wt, O);
+    }
+    uint2* w0 = p.ws_ll + ((size_t)(unit * kG + g)) * kWsStride;
+    ll_store(w0 + 4 + d, __float_as_uint(O), tag_out);
+    if (d == 0) {
+      ll_store(w0, __float_as_uint(M), tag_out);
+      ll_store(w0 + 1, __float_as_uint(Ls), tag_out);
+    }
+  }
+  consumer_sync();
+}
+
+__device__ __noinline__ void rope_table(float pos, const float* inv_freq, float* rope) {
+  // cos/sin are evaluated in fp32 from pos * inv_freq and rounded to bf16 before use (lm_ops.cu)
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int i = lane; i < 64; i += 32) {
+    float sn, cs;
+    sincosf(pos * inv_freq[i], &sn, &cs);
+    rope[i] = bf16_round(cs);
+    rope[64 + i] = bf16_round(sn);
+  }
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int kB>
+__global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* ring = smem;
+  bf16* act = reinterpret_cast<bf16*>(smem + kSmemRing);
+  float* red = reinterpret_cast<float*>(smem + kSmemRing + kSmemAct);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemRing + kSmemAct + kSmemRed);
+  uint64_t* empty = full + kStages;
+  float* scratch = reinterpret_cast<float*>(empty + kStages + 2);  // [16][kMaxB]
+  float* res_wo = scratch + kCW * kMaxB;   // [kMaxB][16] raw residual values of this CTA's o_proj rows ...
+  float* res_wd = res_wo + kMaxB * 16;     // ... and of its down-projection rows
+  float* rope = res_wd + kMaxB * 16;       // [128]
+  int* sent_wo = reinterpret_cast<int*>(rope + 128);  // sentinel word offsets per producer CTA: o_proj output,
+  int* sent_wd = sent_wo + kMaxCtas;                   // down output,
+  int* sent_gu = sent_wd + kMaxCtas;                   // SwiGLU output
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x;
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], kCW);
+    }
+    fence_barrier_init();
+  }
+  if (tid < 32) s_prof[tid] = 0;
+  if (tid < 64) reinterpret_cast<uint32_t*>(act + kMaxB * kActPitch)[tid] = 0u;
+  const int NL = p.num_layers;
+  const int n_attn = kB * kHkv * p.nsplit;   // CTAs 0 .. n_attn-1 also own one attention unit each
+  const int n_gemv = (int)gridDim.x;         // every CTA streams its share of the projections (an SM sustains ~50 GB/s
+                                             // of bulk copies, so HBM is only saturated with all of them streaming)
+  const uint32_t tag0 = *p.tag_base;         // written by the previous launch (stream order)
+
+  for (int c = tid; c < n_gemv; c += kThreads) {
+    sent_wo[c] = last_tile_row(slice_rows(mat_rows(1), mat_unit(1), mat_rot(1), c, n_gemv)) >> 1;
+    sent_wd[c] = last_tile_row(slice_rows(mat_rows(3), mat_unit(3), mat_rot(3), c, n_gemv)) >> 1;
+    sent_gu[c] = last_tile_row(slice_rows(mat_rows(2), mat_unit(2), mat_rot(2), c, n_gemv)) >> 2;
+  }
+  __syncthreads();
+
+  Ring rg{ring, full, empty, 0u};
+  Slice sl[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) sl[m] = slice_rows(mat_rows(m), mat_unit(m), mat_rot(m), cta, n_gemv);
+  const Slice s_heads = slice_rows(p.vpad, 2, 0, cta, n_gemv);
+
+  if (warp == kCW) {
+    // ---------------- producer warp: the CTA's share of every matrix of the step, in consumption order
+    const int total = NL * 4 + 1;
+#pragma unroll 1
+    for (int mi = 0; mi < total; ++mi) {
+      const int m = mi & 3;
+      const bf16* w;
+      Slice s;
+      int K = kH;
+      if (mi == total - 1) {
+        w = p.heads;
+        s = s_heads;
+      } else {
+        const mtts_lm_layer& L = p.layers[mi >> 2];
+        w = reinterpret_cast<const bf16*>(m == 0 ? L.wqkv : (m == 1 ? L.wo : (m == 2 ? L.wgu : L.wd)));
+        s = sl[m];
+        if (m == 3) K = kI;
+      }
+      const int kch = K / kChunkK;
+#pragma unroll 1
+      for (int r = s.r0; r < s.r1; r += kTileRows) {
+        const int nrows = min(kTileRows, s.r1 - r);
+#pragma unroll 1
+        for (int kc = 0; kc < kch; ++kc) {
+          const uint32_t st = rg.it % kStages, round = rg.it / kStages;
+          if (round > 0) mbar_wait(&rg.empty[st], (round - 1) & 1);
+          if (lane == 0) mbar_arrive_expect_tx(&rg.full[st], (uint32_t)nrows * kRowBytes);
+          __syncwarp();
+          if (lane < nrows)
+            bulk_g2s(rg.stages + st * kStageBytes + lane * kRowPitch, w + (size_t)(r + lane) * K + (size_t)kc * kChunkK,
+                     kRowBytes, &rg.full[st], kEvictFirst);
+          ++rg.it;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps
+  const bool has_unit = cta < n_attn;
+  AttnUnit un;
+  if (has_unit) {
+    const int split = cta % p.nsplit;
+    un.hk = (cta / p.nsplit) % kHkv;
+    un.b = cta / (p.nsplit * kHkv);
+    un.pos = p.positions[un.b];
+    const int kv_len = un.pos + 1;
+    const int per = ((kv_len + p.nsplit - 1) / p.nsplit + 31) / 32 * 32;
+    un.k_begin = min(kv_len, split * per);
+    const int k_end = min(kv_len, un.k_begin + per);
+    un.owner = (un.pos >= un.k_begin && un.pos < k_end) ? 1 : 0;
+    un.k_end = min(k_end, un.pos);
+    if (warp == 0) rope_table((float)un.pos, p.inv_freq, rope);
+  }
+  int red_buf = 0;
+#ifdef MTTS_MEGA_PROFILE
+  const bool prof = p.prof != nullptr && cta == 0 && tid == 0;
+  long long tprev = prof ? clock64() : 0;
+#endif
+#ifdef MTTS_MEGA_TRACE
+#define MEGA_TRACE(slot)                                                            \
+  if (p.prof != nullptr && tid == 0 && l == 5) {                                    \
+    unsigned long long gt;                                                          \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));                          \
+    p.prof[32 + cta * 16 + slot] = (long long)gt;                                   \
+  }
+#else
+#define MEGA_TRACE(slot)
+#endif
+#ifdef MTTS_MEGA_PROFILE
+#define MEGA_TICK(slot)                       \
+  if (prof) {                                 \
+    const long long tn = clock64();           \
+    s_prof[slot] += tn - tprev;               \
+    tprev = tn;                               \
+  }                                           \
+  MEGA_TRACE(slot)
+#else
+#define MEGA_TICK(slot)
+#endif
+#pragma unroll 1
+  for (int l = 0; l <= NL; ++l) {
+    // tags of layer l's words: +1 qkv, +2 attention partials, +3 x after o_proj, +4 h, +5 x after down
+    const uint32_t tg = tag0 + (uint32_t)l * kTagsPerLayer;
+    MEGA_TICK(13)
+    if (l == NL) {  // final norm + LM heads
+      stage_norm<kB>(p, p.x_ll[0], tg - kTagsPerLayer + 5, sent_wd, n_gemv, nullptr, p.final_norm, act, scratch, Slice{0, 0},
+                     res_wo);
+      MEGA_TICK(14)
+      consume_matrix<kB>(rg, p, s_heads, 2, EPI_HEADS, act, red, red_buf, nullptr, 0, nullptr, 0u);
+      MEGA_TICK(15)
+      break;
+    }
+    const mtts_lm_layer& L = p.layers[l];
+    stage_norm<kB>(p, p.x_ll[0], tg - kTagsPerLayer + 5, sent_wd, n_gemv, l == 0 ? p.x_in : nullptr,
+                   reinterpret_cast<const bf16*>(L.ln1), act, scratch, sl[1], res_wo);
+    MEGA_TICK(0)
+    consume_matrix<kB>(rg, p, sl[0], 2, EPI_QKV, act, red, red_buf, p.qkv_ll, kNQKV / 2, nullptr, tg + 1);
+    MEGA_TICK(1)
+    if (has_unit) {
+      const AttnLayer al{reinterpret_cast<const bf16*>(L.k_pool), reinterpret_cast<const bf16*>(L.v_pool),
+                         reinterpret_cast<const bf16*>(L.q_norm), reinterpret_cast<const bf16*>(L.k_norm)};
+      attention_layer(p, al, un, cta, reinterpret_cast<float*>(act), rope, tg + 1, tg + 2);
+    }
+    MEGA_TICK(3)
+    stage_attn_out<kB>(p, act, tg + 2);
+    MEGA_TICK(5)
+    consume_matrix<kB>(rg, p, sl[1], 2, EPI_WO, act, red, red_buf, p.x_ll[1], kH / 2, res_wo, tg + 3);
+    MEGA_TICK(6)
+    stage_norm<kB>(p, p.x_ll[1], tg + 3, sent_wo, n_gemv, nullptr, reinterpret_cast<const bf16*>(L.ln2), act, scratch, sl[3],
+                   res_wd);
+    MEGA_TICK(8)
+    consume_matrix<kB>(rg, p, sl[2], 2, EPI_GU, act, red, red_buf, p.h_ll, kI / 2, nullptr, tg + 4);
+    MEGA_TICK(9)
+    stage_h<kB>(p, tg + 4, sent_gu, n_gemv, act);
+    MEGA_TICK(11)
+    consume_matrix<kB>(rg, p, sl[3], 6, EPI_WD, act, red, red_buf, p.x_ll[0], kH / 2, res_wd, tg + 5);
+    MEGA_TICK(12)
+  }
+#undef MEGA_TICK
+#undef MEGA_TRACE
+  // CTA 0 can only be here after it consumed words of every CTA, i.e. after every CTA has read tag_base
+  if (cta == 0 && tid == 0) {
+    *p.tag_base = tag0 + (uint32_t)(NL + 1) * kTagsPerLayer;
+#ifdef MTTS_MEGA_PROFILE
+    if (p.prof)
+      for (int i = 0; i < 32; ++i) p.prof[i] += s_prof[i];
+#endif
+  }
+}
+
+typedef void (*MegaKernel)(const MegaParams);
+MegaKernel mega_kernel_for(int B) {
+  switch (B) {
+    case 1: return decode_mega_kernel<1>;
+    case 2: return decode_mega_kernel<2>;
+    case 3: return decode_mega_kernel<3>;
+    default: return decode_mega_kernel<4>;
+  }
+}
+
+struct MegaLayout { size_t x0, x1, qkv, h, ws, tag, total; };
+MegaLayout mega_layout(int B, int nsplit) {
+  MegaLayout m;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+  m.tag = take(256);
+  m.x0 = take((size_t)B * (kH / 2) * 8);
+  m.x1 = take((size_t)B * (kH / 2) * 8);
+  m.qkv = take((size_t)B * (kNQKV / 2) * 8);
+  m.h = take((size_t)B * (kI / 2) * 8);
+  m.ws = take((size_t)B * kHkv * nsplit * kG * kWsStride * 8);
+  m.total = o;
+  return m;
+}
+
+}  // namespace
+
+int mtts_configure_decode_mega() {
+  for (int B = 1; B <= kMaxB; ++B) {
+    cudaError_t e = cudaFuncSetAttribute(mega_kernel_for(B), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    if (e != cudaSuccess) return mtts_set_error(MTTS_ERR_CUDA, "decode_mega: smem attribute: %s", cudaGetErrorString(e));
+  }
+  return MTTS_OK;
+}
+
+extern "C" long long mtts_decode_mega_workspace_bytes(int B, int nsplit) {
+  if (B <= 0 || nsplit <= 0) return 0;
+  return (long long)mega_layout(B, nsplit).total;
+}
+
+extern "C" int mtts_decode_mega_supported(int hidden, int intermediate, int q_heads, int kv_heads, int head_dim, int B) {
+  return hidden == kH && intermediate == kI && q_heads == kHq && kv_heads == kHkv && head_dim == kD && B >= 1 && B <= kMaxB;
+}
+
+extern "C" int mtts_decode_mega(const mtts_decode_mega_args* a, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(a != nullptr, "mtts_decode_mega: null args");
+  MTTS_REQUIRE(mtts_decode_mega_supported(a->hidden, a->intermediate, a->num_q_heads, a->num_kv_heads, a->head_dim, a->B),
+               "mtts_decode_mega: unsupported shape (hidden %d, intermediate %d, heads %d/%d x %d, batch %d); "
+               "supported: 2048/6144, 16/8 x 128, batch 1..4",
+               a->hidden, a->intermediate, a->num_q_heads, a->num_kv_heads, a->head_dim, a->B);
+  MTTS_REQUIRE(a->layers && a->heads && a->final_norm && a->inv_freq && a->positions && a->x && a->logits && a->workspace,
+               "mtts_decode_mega: null pointer");
+  MTTS_REQUIRE(a->num_layers >= 1 && a->vpad > 0 && a->vpad % 2 == 0, "mtts_decode_mega: bad num_layers / vpad");
+  MTTS_REQUIRE(a->page_size > 0 && (a->page_size & (a->page_size - 1)) == 0, "mtts_decode_mega: page_size must be a power of two");
+  MTTS_REQUIRE(a->nsplit >= 1 && a->nsplit <= 4, "mtts_decode_mega: nsplit must be in [1,4]");
+  MTTS_REQUIRE(a->B * a->num_kv_heads * a->nsplit <= mtts_num_sms() / 2,
+               "mtts_decode_mega: B * kv_heads * nsplit attention CTAs must leave at least half of the SMs to the projections");
+  MTTS_REQUIRE(a->workspace_bytes >= mtts_decode_mega_workspace_bytes(a->B, a->nsplit), "mtts_decode_mega: workspace too small");
+  MTTS_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "mtts_decode_mega: workspace must be 256-byte aligned");
+  MTTS_REQUIRE(a->ld_logits >= a->vpad, "mtts_decode_mega: ld_logits < vpad");
+  const MegaLayout lay = mega_layout(a->B, a->nsplit);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(a->workspace);
+  MegaParams p;
+  p.layers = a->layers; p.num_layers = a->num_layers;
+  p.heads = reinterpret_cast<const bf16*>(a->heads); p.vpad = a->vpad;
+  p.final_norm = reinterpret_cast<const bf16*>(a->final_norm);
+  p.inv_freq = a->inv_freq; p.positions = a->positions; p.block_table = a->block_table;
+  p.max_pages = a->max_pages; p.num_pages = a->num_pages;
+  int shift = 0;
+  while ((1 << shift) < a->page_size) ++shift;
+  p.page_shift = shift;
+  p.x_in = reinterpret_cast<const bf16*>(a->x);
+  p.x_ll[0] = reinterpret_cast<uint2*>(ws + lay.x0);
+  p.x_ll[1] = reinterpret_cast<uint2*>(ws + lay.x1);
+  p.qkv_ll = reinterpret_cast<uint2*>(ws + lay.qkv);
+  p.h_ll = reinterpret_cast<uint2*>(ws + lay.h);
+  p.ws_ll = reinterpret_cast<uint2*>(ws + lay.ws);
+  p.tag_base = reinterpret_cast<unsigned int*>(ws + lay.tag);
+  p.logits = reinterpret_cast<bf16*>(a->logits); p.ld_logits = a->ld_logits;
+  p.nsplit = a->nsplit; p.eps = a->eps;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)kD);
+  p.err_flag = a->err_flag;
+  p.prof = a->profile_cycles;
+
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)mtts_num_sms());
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident, or the launch fails (never a hung poll loop)
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MTTS_REQUIRE(mtts_num_sms() <= kMaxCtas, "mtts_decode_mega: more SMs than the sentinel tables hold");
+  MTTS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mega_kernel_for(a->B), p));
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}

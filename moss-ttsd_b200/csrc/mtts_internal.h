@@ -9,3 +9,4 @@ int mtts_configure_gemm_tc();
 int mtts_configure_attention();
 int mtts_configure_rvq();
 int mtts_configure_codec();
+int mtts_configure_decode_mega();

@@ -261,6 +261,10 @@ class DecoderEngine:
         self._vocabs = (ctypes.c_int * 8)(*s.vocabs, *([0] * (8 - s.channels)))
         self.err = torch.zeros(4, dtype=torch.int32, device=self.dev)
         self.use_graph = os.environ.get("MTTS_NO_GRAPH", "0") != "1"
+        # batch <= mega_max_b: the whole step (layer stack + LM heads) is ONE persistent kernel. Measured on B200
+        # (ms/step, ctx 460): batch 1: 1.06 vs 1.44 for the kernel chain, batch 2: 1.19 vs 1.46, batch 4: 1.63 vs 1.50.
+        self.use_mega = os.environ.get("MTTS_NO_MEGA", "0") != "1"
+        self.mega_max_b = int(os.environ.get("MTTS_MEGA_MAX_B", "2"))
         self.prefill_tile_rows = int(os.environ.get("MTTS_PREFILL_TILE", "64"))  # 64: tensor-core tiles, 4: CUDA cores
         self.graph_replayed_launches = 0  # kernels executed through graph replays (not seen by mtts_launch_count)
 
@@ -406,8 +410,44 @@ class DecoderEngine:
         st["attn_ws"] = self._attn_workspace(B, 1, nsplit)
         st["sample_ws"] = torch.zeros(self.L.mtts_sample8_workspace_bytes(B, self.s.channels), dtype=torch.uint8,
                                       device=self.dev)
+        st["mega"] = self._make_mega(st) if self.mega_supported(B) else None
         st["graph"] = None
         return st
+
+    # ------------------------------------------------------------------ small-batch persistent decode kernel
+    def mega_supported(self, B: int) -> bool:
+        s = self.s
+        return self.use_mega and B <= self.mega_max_b and bool(self.L.mtts_decode_mega_supported(
+            s.hidden_size, s.intermediate_size, s.num_attention_heads, s.num_key_value_heads, s.head_dim, B))
+
+    def _make_mega(self, st):
+        """Argument block of mtts_decode_mega for this session: a device table of per-layer pointers (weights + this
+        cache's K/V pools), the barrier words and the split-KV workspace."""
+        s, cache, B = self.s, st["cache"], st["B"]
+        tab = np.zeros((s.num_hidden_layers, 10), dtype=np.int64)
+        for l, lw in enumerate(self.w.layers):
+            tab[l] = [lw[k].data_ptr() for k in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2", "q_norm", "k_norm")] + \
+                     [cache.k[l].data_ptr(), cache.v[l].data_ptr()]
+        layers = torch.from_numpy(tab).to(self.dev)
+        # few CTAs per (row, kv head): the o_proj phase of EVERY CTA re-reads all partials
+        nsplit = max(1, min(4, 32 // (B * s.num_key_value_heads)))
+        ws = torch.zeros(self.L.mtts_decode_mega_workspace_bytes(B, nsplit) + 256, dtype=torch.uint8, device=self.dev)
+        off = (-ws.data_ptr()) % 256
+        a = st["acts"]
+        args = _lib.DecodeMegaArgs(
+            layers=layers.data_ptr(), num_layers=s.num_hidden_layers, hidden=s.hidden_size,
+            intermediate=s.intermediate_size, num_q_heads=s.num_attention_heads, num_kv_heads=s.num_key_value_heads,
+            head_dim=s.head_dim, heads=self.w.heads.data_ptr(), vpad=s.vpad, final_norm=self.w.final_norm.data_ptr(),
+            inv_freq=self.w.inv_freq.data_ptr(), positions=st["positions"].data_ptr(),
+            block_table=ptr(cache.block_table), max_pages=cache.max_pages, page_size=cache.page_size,
+            num_pages=cache.num_pages, x=a["x"].data_ptr(),
+            logits=st["logits"].data_ptr(), ld_logits=st["logits"].stride(0), B=B, nsplit=nsplit, eps=s.rms_norm_eps,
+            workspace=ws.data_ptr() + off, workspace_bytes=ws.numel() - 256, err_flag=self.err.data_ptr())
+        prof = None
+        if os.environ.get("MTTS_MEGA_PROFILE", "0") == "1":   # per-phase cycle counters of CTA 0 (scripts/profile_mega.py)
+            prof = torch.zeros(32 + 16 * 160, dtype=torch.int64, device=self.dev)
+            args.profile_cycles = prof.data_ptr()
+        return dict(args=args, keep=(layers, ws), prof=prof, nsplit=nsplit)
 
     def reset_decode_state(self, st, seed: int, prompt_rows: int, max_length: int):
         st["unfinished"].fill_(1)
@@ -436,6 +476,10 @@ class DecoderEngine:
     def _decode_body(self, st):
         a = st["acts"]
         self._embed(st["tokens"], a["x"])
+        if st.get("mega") is not None:
+            check(self.L.mtts_decode_mega(ctypes.byref(st["mega"]["args"]), stream_ptr()))
+            self.sample_and_advance(st, st["logits"])
+            return
         attn_kw = dict(tiles=st["B"], rows_per_tile=1, tile_row0=None, tile_nrows=None, nsplit=st["nsplit"],
                        ws=st["attn_ws"] if st["nsplit"] > 1 else None)
         xn = self._layers(a, st["cache"], st["positions"], None, attn_kw, st["gws"])

