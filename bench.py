@@ -336,6 +336,34 @@ def main():
         a, t, _ = one()
         cpu = {"value": a / t, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
 
+    # ---- p50 decode-step latency at batch 1 (the second half of BASELINE.json's metric): one graph replay = one frame
+    lat = None
+    if rank == 0:
+        t_dec = model._last_timing
+        b64_ms = t_dec[0][1].elapsed_time(t_dec[0][2]) / max(1, t_dec[1] - 1)
+        model.generate(input_ids=ids_dev[:1].contiguous(), attention_mask=mask_dev[:1].contiguous(), max_new_tokens=32,
+                       do_sample=False)
+        st = model._last_state
+        n_rep = 128
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_rep + 1)]
+        for _ in range(8):
+            st["graph"].replay()
+        evs[0].record()
+        for i in range(n_rep):
+            st["graph"].replay()
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        t = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(n_rep))
+        w = model._w
+        ctx = T + 32 + 8 + n_rep // 2
+        streamed = w.heads.numel() * 2 + sum(lw[k].numel() * 2 for lw in w.layers for k in ("wqkv", "wo", "wgu", "wd")) + \
+            ctx * 2 * len(w.layers) * SHAPE["num_key_value_heads"] * SHAPE["head_dim"] * 2
+        peak = float((roof or {}).get("peak", 6650.0))
+        lat = {"batch1_p50_ms": t[n_rep // 2], "batch1_p90_ms": t[int(n_rep * 0.9)], "batch1_context_rows": ctx,
+               "batch1_bytes_per_step": streamed, "batch1_hbm_frac": streamed / (t[n_rep // 2] * 1e-3) / 1e9 / peak,
+               "batch1_path": "persistent single-kernel step (mtts_decode_mega)" if st.get("mega") else "kernel chain",
+               f"batch{BATCH}_avg_ms": b64_ms}
+
     if rank == 0:
         h2d = ids_host.numel() * 8 + mask_host.numel() * 8
         d2h = BATCH * NEW_FRAMES * 1920 * 4
@@ -349,6 +377,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e / args.steps},
             "phases_ms_per_step": {"lm_generate": gen_ms, "codec_decode": codec_ms},
+            "decode_step_latency": lat,
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }))
     if world > 1:

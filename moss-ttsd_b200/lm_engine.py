@@ -431,6 +431,8 @@ class DecoderEngine:
         layers = torch.from_numpy(tab).to(self.dev)
         # few CTAs per (row, kv head): the o_proj phase of EVERY CTA re-reads all partials
         nsplit = max(1, min(4, 32 // (B * s.num_key_value_heads)))
+        if os.environ.get("MTTS_MEGA_NSPLIT"):
+            nsplit = int(os.environ["MTTS_MEGA_NSPLIT"])
         ws = torch.zeros(self.L.mtts_decode_mega_workspace_bytes(B, nsplit) + 256, dtype=torch.uint8, device=self.dev)
         off = (-ws.data_ptr()) % 256
         a = st["acts"]
