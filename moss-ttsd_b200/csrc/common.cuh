@@ -185,5 +185,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// erf-GELU for the epilogue of the TF32 tensor-core GEMMs (nn.GELU() of the codec, modules.py ConvNeXt / transformer
+// MLPs): erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, three orders below the TF32 product error it is applied
+// to), evaluated as q = x/2 * erfc(|x|/sqrt2) so that the negative tail keeps its relative accuracy:
+//   gelu(x) = x - q (x >= 0),  q (x < 0).        ~14 instructions instead of ~45 for erff().
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float q = 0.5f * x * poly * e;
+  return x >= 0.f ? x - q : q;
+}
 
 #endif  // __CUDACC__

@@ -132,7 +132,7 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int 
     if (n + j >= p.N) break;
     float x = v[j];
     if (p.flags & MTTS_EPI_BIAS) x += __ldg(p.bias + n + j);
-    if (p.flags & MTTS_EPI_GELU) x = gelu_erf(x);
+    if (p.flags & MTTS_EPI_GELU) x = p.out_bf16 ? gelu_erf(x) : gelu_fast(x);
     if (p.out_bf16) x = bf16_round(x);  // the reference materialises the bf16 linear output first
     if (p.flags & MTTS_EPI_GAMMA) x *= __ldg(p.gamma + n + j);
     if (p.flags & MTTS_EPI_RESIDUAL) x = r[j] + x;
@@ -352,7 +352,7 @@ constexpr int kPThreads = 320;  // warp0 TMA, warp1 MMA/TMEM, warps 2..9 epilogu
 
 __device__ __forceinline__ float epilogue_scalar(const GemmParams& p, float v, int m, int n, float bias_n, float gamma_n) {
   if (p.flags & MTTS_EPI_BIAS) v += bias_n;
-  if (p.flags & MTTS_EPI_GELU) v = gelu_erf(v);
+  if (p.flags & MTTS_EPI_GELU) v = p.out_bf16 ? gelu_erf(v) : gelu_fast(v);
   if (p.out_bf16) v = bf16_round(v);
   if (p.flags & MTTS_EPI_GAMMA) v *= gamma_n;
   if (p.flags & MTTS_EPI_RESIDUAL) {
@@ -501,6 +501,60 @@ __global__ void __launch_bounds__(kPThreads, 1) gemm_tc_persist_kernel(const __g
                 reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(h);
               else
                 reinterpret_cast<float*>(p.out)[o] = h;
+            }
+          }
+        } else if (p.flags == (MTTS_EPI_BIAS | MTTS_EPI_GELU) && !p.out_bf16) {
+          // the codec's MLP up-projections: the flag tests are hoisted, nothing but bias + GELU + one store per element
+          float* op = reinterpret_cast<float*>(p.out) + (long long)(m0 + c) * p.ldo + n;
+          if (n_ok) {
+            if (m0 + c + 32 <= p.M) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) op[(long long)j * p.ldo] = gelu_fast(__uint_as_float(r[j]) + bias_n);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (m0 + c + j < p.M) op[(long long)j * p.ldo] = gelu_fast(__uint_as_float(r[j]) + bias_n);
+            }
+          }
+        } else if (!p.out_bf16 && !(p.flags & MTTS_EPI_GELU)) {
+          // fp32 bias / layer-scale / residual (the codec's down-projections and attention outputs). The residual may
+          // alias the output (x += ...), so its 32 loads are issued explicitly BEFORE the first store: left to the
+          // compiler every load waits behind the previous element's store (one L2 round trip per element).
+          if (n_ok) {
+            float* op = reinterpret_cast<float*>(p.out) + (long long)(m0 + c) * p.ldo + n;
+            const int lim = min(32, p.M - (m0 + c));
+            float res[32];
+            if (p.flags & MTTS_EPI_RESIDUAL) {
+              const float* rp = reinterpret_cast<const float*>(p.residual) + (long long)(m0 + c) * p.ldr + n;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) res[j] = j < lim ? __ldcg(rp + (long long)j * p.ldr) : 0.f;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) res[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < lim) op[(long long)j * p.ldo] = fmaf(__uint_as_float(r[j]) + bias_n, gamma_n, res[j]);
+          }
+        } else if (p.out_bf16 && !(p.flags & MTTS_EPI_GELU)) {
+          // bf16 linear (+ residual): prefill projections. Same hoisting of the (possibly aliasing) residual loads.
+          if (n_ok) {
+            bf16* op = reinterpret_cast<bf16*>(p.out) + (long long)(m0 + c) * p.ldo + n;
+            const int lim = min(32, p.M - (m0 + c));
+            float res[32];
+            const bool has_res = (p.flags & MTTS_EPI_RESIDUAL) != 0;
+            if (has_res) {
+              const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + (long long)(m0 + c) * p.ldr + n;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) res[j] = j < lim ? __bfloat162float(__ldcg(rp + (long long)j * p.ldr)) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < lim) {
+                float v = bf16_round(__uint_as_float(r[j]) + bias_n) * gamma_n;  // the bf16 linear output comes first
+                if (has_res) v += res[j];
+                op[(long long)j * p.ldo] = __float2bfloat16_rn(v);
+              }
             }
           }
         } else {
