@@ -342,39 +342,67 @@ __global__ void __launch_bounds__(128) mha_varlen_tc_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------
 // ConvNeXt front half: depthwise Conv1d(k=7, pad=3, groups=C) + LayerNorm(C, eps) fused
 // (ConvNeXtBlock.forward modules.py:1142-1150). x/out: [B, T, C]; w: [C, 7]; zero padding at each item's ends.
-// One CTA (C/4 threads) per token.
+// One CTA (C/4 threads, 4 channels each) walks kDwTokens consecutive tokens of one item with a 7-row sliding window in
+// registers: every input row is read once per CTA instead of seven times, the 28 filter taps of a thread stay in
+// registers, and each of the two LayerNorm reductions costs one barrier (warp shuffle + per-warp partials).
 // ------------------------------------------------------------------------------------------------
+constexpr int kDwTokens = 16;
+
 __global__ void dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ cb,
                                   const float* __restrict__ lw, const float* __restrict__ lb, float* __restrict__ out,
                                   int T, int C, float eps) {
-  __shared__ float red[33];
-  const long long tok = blockIdx.x;
-  const int t = (int)(tok % T);
-  const int c = threadIdx.x * 4;
-  float4 a = *reinterpret_cast<const float4*>(cb + c);
+  __shared__ float red[2][2][32];  // [mean | var][parity][warp]
+  const int tiles = (T + kDwTokens - 1) / kDwTokens;
+  const int b = blockIdx.x / tiles, t0 = (blockIdx.x % tiles) * kDwTokens;
+  const int c = threadIdx.x * 4, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const float4 bias = *reinterpret_cast<const float4*>(cb + c);
+  const float4 g = *reinterpret_cast<const float4*>(lw + c);
+  const float4 bb = *reinterpret_cast<const float4*>(lb + c);
   float wk[4][7];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 7; ++j) wk[i][j] = __ldg(w + (c + i) * 7 + j);
+  const float* xb = x + (long long)b * T * C + c;
+  auto row = [&](int tt) {
+    return (tt >= 0 && tt < T) ? *reinterpret_cast<const float4*>(xb + (long long)tt * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 win[7];  // rows t-3 .. t+3 of the current token
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const int tt = t + j - 3;
-    if (tt < 0 || tt >= T) continue;
-    const float4 v = *reinterpret_cast<const float4*>(x + (tok + (j - 3)) * C + c);
-    a.x = fmaf(wk[0][j], v.x, a.x);
-    a.y = fmaf(wk[1][j], v.y, a.y);
-    a.z = fmaf(wk[2][j], v.z, a.z);
-    a.w = fmaf(wk[3][j], v.w, a.w);
+  for (int j = 0; j < 6; ++j) win[j + 1] = row(t0 - 3 + j);
+  const float invC = 1.0f / (float)C;
+#pragma unroll 1
+  for (int i = 0; i < kDwTokens; ++i) {
+    const int t = t0 + i;
+    if (t >= T) break;  // uniform
+#pragma unroll
+    for (int j = 0; j < 6; ++j) win[j] = win[j + 1];
+    win[6] = row(t + 3);
+    float4 a = bias;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      a.x = fmaf(wk[0][j], win[j].x, a.x);
+      a.y = fmaf(wk[1][j], win[j].y, a.y);
+      a.z = fmaf(wk[2][j], win[j].z, a.z);
+      a.w = fmaf(wk[3][j], win[j].w, a.w);
+    }
+    const int par = i & 1;
+    float s = warp_sum((a.x + a.y) + (a.z + a.w));
+    if (lane == 0) red[0][par][warp] = s;
+    __syncthreads();
+    float tot = 0.f;
+    for (int k = 0; k < nw; ++k) tot += red[0][par][k];
+    const float mean = tot * invC;
+    const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+    s = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+    if (lane == 0) red[1][par][warp] = s;
+    __syncthreads();
+    tot = 0.f;
+    for (int k = 0; k < nw; ++k) tot += red[1][par][k];
+    const float inv = rsqrtf(tot * invC + eps);
+    *reinterpret_cast<float4*>(out + ((long long)b * T + t) * C + c) =
+        make_float4(d0 * inv * g.x + bb.x, d1 * inv * g.y + bb.y, d2 * inv * g.z + bb.z, d3 * inv * g.w + bb.w);
   }
-  const float mean = block_sum((a.x + a.y) + (a.z + a.w), red) / (float)C;
-  const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
-  const float var = block_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3), red) / (float)C;
-  const float inv = rsqrtf(var + eps);
-  const float4 g = *reinterpret_cast<const float4*>(lw + c);
-  const float4 bb = *reinterpret_cast<const float4*>(lb + c);
-  *reinterpret_cast<float4*>(out + tok * C + c) =
-      make_float4(d0 * inv * g.x + bb.x, d1 * inv * g.y + bb.y, d2 * inv * g.z + bb.z, d3 * inv * g.w + bb.w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -578,7 +606,8 @@ extern "C" int mtts_dwconv7_ln(const float* x, const float* conv_w, const float*
   MTTS_REQUIRE(C % 128 == 0 && C <= 4096, "mtts_dwconv7_ln: C must be a multiple of 128 and <= 4096");
   if (B <= 0 || T <= 0) return MTTS_OK;
   MTTS_REQUIRE(x && conv_w && conv_b && ln_w && ln_b && out, "mtts_dwconv7_ln: null pointer");
-  dwconv7_ln_kernel<<<(unsigned)((long long)B * T), C / 4, 0, stream>>>(x, conv_w, conv_b, ln_w, ln_b, out, T, C, eps);
+  const int tiles = ceil_div(T, kDwTokens);
+  dwconv7_ln_kernel<<<(unsigned)((long long)B * tiles), C / 4, 0, stream>>>(x, conv_w, conv_b, ln_w, ln_b, out, T, C, eps);
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }
