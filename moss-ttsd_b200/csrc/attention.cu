@@ -13,6 +13,7 @@
 // warps walk different keys, so one CTA consumes 8 keys per step.
 #include "common.cuh"
 #include "mtts_internal.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -452,6 +453,245 @@ int launch_decode(const AttnParams& p, int rows, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Decode on tensor cores. The CUDA-core kernel above needs 2 FMA + an unpack per K/V byte, which is ~13 us of issue
+// time per layer at batch 64 (120 MB of K/V) against the 18 us the bytes take to arrive: it is half issue-bound.
+// Here the G query heads of a kv head are rows of an m16n8k16 A operand (the other rows are zero), K tiles of 64 keys
+// are the B operand of S = Q K^T straight from their row-major shared-memory image (ldmatrix), the probabilities are
+// re-packed to bf16 in registers (as the reference's eager path does before P @ V) and V is the B operand of O += P V
+// through ldmatrix.trans. K/V tiles arrive by cp.async (16 B per thread, XOR-swizzled 16-byte chunks so that both
+// ldmatrix flavours are conflict-free). One CTA = (row, kv head, split), 4 warps x 16 keys per tile; STAGES = 1 when
+// enough CTAs share an SM to overlap each other's loads, 2 otherwise.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTcKeys = 64;
+constexpr int kTcTileBytes = kTcKeys * kD * 2;  // 16 KB per K or V tile
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int G, int STAGES>
+__global__ void __launch_bounds__(128, STAGES == 1 ? 4 : 3) gqa_decode_tc_kernel(const AttnParams p) {
+  static_assert(G <= 8, "the q heads of one kv head are rows 0..G-1 of the 16-row MMA tile");
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(128) uint8_t smraw[];
+  __shared__ int s_is_last;
+  const int row = blockIdx.x, hk = blockIdx.y, split = blockIdx.z;
+  const int seq = p.row_seq ? p.row_seq[row] : row;
+  const int kv_len = p.positions[row] + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+
+  int k_begin = 0, k_end = kv_len;
+  if (p.nsplit > 1) {
+    const int per = ((kv_len + p.nsplit - 1) / p.nsplit + kTcKeys - 1) / kTcKeys * kTcKeys;
+    k_begin = min(kv_len, split * per);
+    k_end = min(kv_len, k_begin + per);
+  }
+  const int ntiles = (k_end - k_begin + kTcKeys - 1) / kTcKeys;
+
+  // Q as A fragments: row g = head g (zero for g >= G), 8 k-steps of 16 dims; rows 8..15 of the tile are all zero
+  uint32_t qa[8][2];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    qa[ks][0] = qa[ks][1] = 0u;
+    if (g < G) {
+      const bf16* qp = p.q + ((long long)row * p.Hq + hk * G + g) * kD + ks * 16 + 2 * t;
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(qp);
+      qa[ks][1] = *reinterpret_cast<const uint32_t*>(qp + 8);
+    }
+  }
+  const int page_mask = (1 << p.page_shift) - 1;
+  const long long head_off = ((long long)hk << p.page_shift) * kD;
+  const long long page_stride = ((long long)p.Hkv << p.page_shift) * kD;
+  const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(smraw));
+
+  auto issue = [&](int tile, int stage) {
+    const int key0 = k_begin + tile * kTcKeys;
+    const uint32_t kdst = smem0 + stage * 2 * kTcTileBytes, vdst = kdst + kTcTileBytes;
+    const int c = tid & 15;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kr = (tid >> 4) + 8 * j;                       // key row inside the tile
+      const int key = min(key0 + kr, k_end - 1);               // clamp: the copy is always legal, the score is masked
+      const int lp = key >> p.page_shift;
+      const int page = p.block_table ? __ldg(p.block_table + (long long)seq * p.max_pages + lp) : seq * p.max_pages + lp;
+      const long long off = (long long)page * page_stride + head_off + (long long)(key & page_mask) * kD + c * 8;
+      const uint32_t so = kr * 256 + ((c ^ (kr & 7)) << 4);    // 16-byte chunks XOR-swizzled by the row
+      cp_async16(kdst + so, p.k_pool + off);
+      cp_async16(vdst + so, p.v_pool + off);
+    }
+    cp_async_commit();
+  };
+
+  float o[16][4];
+#pragma unroll
+  for (int d = 0; d < 16; ++d)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[d][i] = 0.f;
+  float m = -1e30f, l = 0.f;  // online-softmax state of row g (replicated over the 4 lanes of a quad)
+
+  // STAGES == 1 relies on the other CTAs of the SM (4 resident) to keep loads in flight while this one computes.
+  if (ntiles > 0) issue(0, 0);
+  if (STAGES == 2 && ntiles > 1) issue(1, 1);
+#pragma unroll 1
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int stage = STAGES == 2 ? (tile & 1) : 0;
+    if (STAGES == 2 && tile + 1 < ntiles) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    const uint32_t kbase = smem0 + stage * 2 * kTcTileBytes, vbase = kbase + kTcTileBytes;
+    // ---- S = Q K^T for this warp's 16 keys (two 8-key column tiles)
+    float s[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[j][i] = 0.f;
+    {
+      const int kr = 16 * warp + (lane & 7) + ((lane >> 4) & 1) * 8;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const int ch = 2 * ks + ((lane >> 3) & 1);
+        uint32_t b[4];
+        ldsm_x4(b, kbase + kr * 256 + ((ch ^ (kr & 7)) << 4));
+        mma_bf16(s[0], qa[ks][0], 0u, qa[ks][1], 0u, b[0], b[1]);
+        mma_bf16(s[1], qa[ks][0], 0u, qa[ks][1], 0u, b[2], b[3]);
+      }
+    }
+    // ---- online softmax of row g over these 16 keys (this lane holds keys 2t, 2t+1 of both column tiles)
+    const int kcol = k_begin + tile * kTcKeys + 16 * warp + 2 * t;
+    float sc[4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) sc[2 * j + e] = (kcol + 8 * j + e < k_end) ? s[j][e] * p.scale_log2 : -INFINITY;
+    float mx = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float mn = fmaxf(m, mx);
+    const float corr = fast_exp2(m - mn);
+    m = mn;
+    float ps = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      sc[i] = fast_exp2(sc[i] - mn);
+      ps += sc[i];
+    }
+    ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+    ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+    l = fmaf(l, corr, ps);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) { o[d][0] *= corr; o[d][1] *= corr; }
+    // ---- O += P V : P (bf16, as the reference casts the probabilities) is the A operand, rows 8..15 zero
+    const uint32_t pa0 = pack_bf16(sc[0], sc[1]), pa2 = pack_bf16(sc[2], sc[3]);
+    {
+      const int kr = 16 * warp + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+      for (int dp = 0; dp < 8; ++dp) {
+        const int ch = 2 * dp + ((lane >> 4) & 1);
+        uint32_t b[4];
+        ldsm_x4_trans(b, vbase + kr * 256 + ((ch ^ (kr & 7)) << 4));
+        mma_bf16(o[2 * dp], pa0, 0u, pa2, 0u, b[0], b[1]);
+        mma_bf16(o[2 * dp + 1], pa0, 0u, pa2, 0u, b[2], b[3]);
+      }
+    }
+    if (tile + STAGES < ntiles) {
+      __syncthreads();  // every warp is done with this stage
+      issue(tile + STAGES, stage);
+    }
+  }
+
+  // ---- combine the 4 warps (rows g < G live in lanes 0 .. 4G-1), then the splits
+  __syncthreads();
+  float* sm_m = reinterpret_cast<float*>(smraw);      // [4][G]
+  float* sm_l = sm_m + 4 * G;                          // [4][G]
+  float* sm_o = sm_l + 4 * G;                          // [4][G][128]
+  if (g < G) {
+    if (t == 0) { sm_m[warp * G + g] = m; sm_l[warp * G + g] = l; }
+#pragma unroll
+    for (int d = 0; d < 16; ++d)
+      *reinterpret_cast<float2*>(sm_o + (warp * G + g) * kD + 8 * d + 2 * t) = make_float2(o[d][0], o[d][1]);
+  }
+  __syncthreads();
+  const int unit = row * p.Hkv + hk;
+  float* wsb = p.ws ? p.ws + ((long long)unit * p.nsplit) * G * (kD + 2) : nullptr;
+  for (int oi = tid; oi < G * kD; oi += 128) {
+    const int gg = oi / kD, d = oi % kD;
+    float M = -1e30f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, sm_m[w * G + gg]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float wt = fast_exp2(sm_m[w * G + gg] - M);
+      L = fmaf(sm_l[w * G + gg], wt, L);
+      O = fmaf(sm_o[(w * G + gg) * kD + d], wt, O);
+    }
+    if (p.nsplit == 1) {
+      p.out[((long long)row * p.Hq + hk * G + gg) * kD + d] = __float2bfloat16_rn(O / L);
+    } else {
+      float* w0 = wsb + (long long)split * G * (kD + 2) + gg * (kD + 2);
+      __stcg(w0 + 2 + d, O);
+      if (d == 0) {
+        __stcg(w0, M);
+        __stcg(w0 + 1, L);
+      }
+    }
+  }
+  if (p.nsplit == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(p.counters + unit, 1);
+    const int last = prev == p.nsplit - 1;
+    if (last) p.counters[unit] = 0;
+    s_is_last = last;
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  for (int oi = tid; oi < G * kD; oi += 128) {
+    const int gg = oi / kD, d = oi % kD;
+    float M = -1e30f;
+    for (int sidx = 0; sidx < p.nsplit; ++sidx) M = fmaxf(M, __ldcg(wsb + ((long long)sidx * G + gg) * (kD + 2)));
+    float L = 0.f, O = 0.f;
+    for (int sidx = 0; sidx < p.nsplit; ++sidx) {
+      const float* w0 = wsb + ((long long)sidx * G + gg) * (kD + 2);
+      const float wt = fast_exp2(__ldcg(w0) - M);
+      L = fmaf(__ldcg(w0 + 1), wt, L);
+      O = fmaf(__ldcg(w0 + 2 + d), wt, O);
+    }
+    p.out[((long long)row * p.Hq + hk * G + gg) * kD + d] = __float2bfloat16_rn(O / L);
+  }
+}
+
+template <int G>
+int launch_decode_tc(const AttnParams& p, int rows, cudaStream_t stream) {
+  dim3 grid(rows, p.Hkv, p.nsplit);
+  const long long ctas = (long long)rows * p.Hkv * p.nsplit;
+  if (ctas >= 3LL * mtts_num_sms()) {
+    MTTS_CUDA_CHECK(mtts_launch(gqa_decode_tc_kernel<G, 1>, grid, dim3(128), (size_t)2 * kTcTileBytes, stream, p));
+  } else {
+    MTTS_CUDA_CHECK(mtts_launch(gqa_decode_tc_kernel<G, 2>, grid, dim3(128), (size_t)4 * kTcTileBytes, stream, p));
+  }
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Prefill on tensor cores: bf16 mma.sync m16n8k16 with fp32 accumulation, flash-style online softmax.
 // CTA = up to 64 consecutive query rows of ONE sequence x one q head (4 warps x 16 rows); K tiles of 64 keys are
 // staged row-major ([key][d], pitch 136) and V tiles TRANSPOSED ([d][key], pitch 72) so that every B fragment is one
@@ -640,6 +880,10 @@ int mtts_configure_attention() {
   if ((rc = configure_attn<4, 1>())) return rc;
   if ((rc = configure_attn<4, 2>())) return rc;
   if ((rc = configure_attn<4, 4>())) return rc;
+  cudaError_t e = cudaFuncSetAttribute(gqa_decode_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kTcTileBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gqa_decode_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kTcTileBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gqa_decode_tc_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kTcTileBytes);
+  if (e != cudaSuccess) return mtts_set_error(MTTS_ERR_CUDA, "attention: smem attribute: %s", cudaGetErrorString(e));
   return MTTS_OK;
 }
 
@@ -694,6 +938,16 @@ extern "C" int mtts_gqa_attention(const void* q, const void* k_pool, const void*
     return MTTS_OK;
   }
   if (rows_per_tile == 1 && tile_row0 == nullptr) {
+    static int use_tc = -1;
+    if (use_tc < 0) {
+      const char* e = getenv("MTTS_ATTN_SIMT");
+      use_tc = (e && e[0] == '1') ? 0 : 1;
+    }
+    if (use_tc) {
+      if (G == 1) return launch_decode_tc<1>(p, tiles, stream);
+      if (G == 2) return launch_decode_tc<2>(p, tiles, stream);
+      if (G == 4) return launch_decode_tc<4>(p, tiles, stream);
+    }
     if (G == 1) return launch_decode<1>(p, tiles, stream);
     if (G == 2) return launch_decode<2>(p, tiles, stream);
     return launch_decode<4>(p, tiles, stream);

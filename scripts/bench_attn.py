@@ -9,7 +9,7 @@ L = _lib.load()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 ctxs = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["460", "800"])]
 shape = LMShape()
-cache = KVCache(shape, B, 1024, "cuda")
+cache = KVCache(shape, B, max(1024, max(ctxs) + 8), "cuda")
 cache.k.normal_(); cache.v.normal_()
 q = torch.randn(B, 16 * 128, device="cuda").to(torch.bfloat16)
 out = torch.empty_like(q)
