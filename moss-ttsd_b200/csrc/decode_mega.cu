@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include "mtts_internal.h"
 #include "sm100.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -80,6 +81,7 @@ struct MegaParams {
   bf16* logits;
   long long ld_logits;
   int nsplit;
+  int sentinel;  // 1: one warp watches sentinel words before the CTA-wide verified load
   float eps, scale_log2;
   unsigned int* tag_base;  // [1] device word: tags used by earlier launches
   int* err_flag;
@@ -307,8 +309,10 @@ __device__ __noinline__ void stage_norm(const MegaParams& p, const uint2* src_ll
 #pragma unroll
     for (int b = 0; b < kB; ++b) xv[b] = *reinterpret_cast<const uint2*>(x_plain + (size_t)b * kH + tid * 4);
   } else {
-    if (warp == 0) sentinel_wait(src_ll + (size_t)(kB - 1) * (kH / 2), sent, n_gemv, tag);
-    consumer_sync();
+    if (p.sentinel) {
+      if (warp == 0) sentinel_wait(src_ll + (size_t)(kB - 1) * (kH / 2), sent, n_gemv, tag);
+      consumer_sync();
+    }
     LLSpin sp;
     while (true) {
       bool ok = true;
@@ -355,8 +359,10 @@ __device__ __noinline__ void stage_norm(const MegaParams& p, const uint2* src_ll
 template <int kB>
 __device__ __noinline__ void stage_h(const MegaParams& p, uint32_t tag, const int* sent, int n_gemv, bf16* act) {
   const int tid = threadIdx.x, warp = tid >> 5;
-  if (warp == 0) sentinel_wait(p.h_ll + (size_t)(kB - 1) * (kI / 2), sent, n_gemv, tag);
-  consumer_sync();
+  if (p.sentinel) {
+    if (warp == 0) sentinel_wait(p.h_ll + (size_t)(kB - 1) * (kI / 2), sent, n_gemv, tag);
+    consumer_sync();
+  }
   uint2 xv[3][kB];
   LLSpin sp;
   while (true) {
@@ -383,7 +389,7 @@ __device__ __noinline__ void stage_h(const MegaParams& p, uint32_t tag, const in
 template <int kB>
 __device__ __noinline__ void stage_attn_out(const MegaParams& p, bf16* act, uint32_t tag) {
   const int units = kB * kHkv * p.nsplit;
-  if ((threadIdx.x >> 5) == 0) {  // sentinel: the last O word of head g = 1 of every unit
+  if (p.sentinel && (threadIdx.x >> 5) == 0) {  // sentinel: the last O word of head g = 1 of every unit
     const int lane = threadIdx.x & 31;
     LLSpin sp;
     while (true) {
@@ -915,6 +921,16 @@ extern "C" int mtts_decode_mega(const mtts_decode_mega_args* a, void* stream_) {
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)kD);
   p.err_flag = a->err_flag;
   p.prof = a->profile_cycles;
+  {
+    // batch 1: every thread polls the words it needs directly (2.6 % faster: one round trip less per exchange);
+    // batch >= 2: a sentinel warp first, the poll traffic of 148 x 512 threads grows with the batch
+    static int sen = -1;
+    if (sen < 0) {
+      const char* e = getenv("MTTS_MEGA_SENTINEL");
+      sen = e ? (e[0] == '0' ? 0 : 1) : 2;
+    }
+    p.sentinel = sen == 2 ? (a->B > 1 ? 1 : 0) : sen;
+  }
 
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
