@@ -538,12 +538,15 @@ __global__ void __launch_bounds__(128, STAGES == 1 ? 4 : 3) gqa_decode_tc_kernel
     cp_async_commit();
   };
 
-  float o[16][4];
+  // O is accumulated TRANSPOSED (O^T = V^T P^T: 16 dims x 8 heads per MMA tile, 8 tiles): 32 accumulator registers
+  // instead of the 64 of O = P V, of which half would belong to the zero rows; this is what lets 5 CTAs share an SM.
+  // ot[dt][0..1] = dims 16 dt + g, heads 2t, 2t+1 ; ot[dt][2..3] = dims 16 dt + g + 8.
+  float ot[8][4];
 #pragma unroll
-  for (int d = 0; d < 16; ++d)
+  for (int d = 0; d < 8; ++d)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o[d][i] = 0.f;
-  float m = -1e30f, l = 0.f;  // online-softmax state of row g (replicated over the 4 lanes of a quad)
+    for (int i = 0; i < 4; ++i) ot[d][i] = 0.f;
+  float m = -1e30f, l = 0.f;  // online-softmax state of head g (replicated over the 4 lanes of a quad)
 
   // STAGES == 1 relies on the other CTAs of the SM (4 resident) to keep loads in flight while this one computes.
   if (ntiles > 0) issue(0, 0);
@@ -593,19 +596,24 @@ __global__ void __launch_bounds__(128, STAGES == 1 ? 4 : 3) gqa_decode_tc_kernel
     ps += __shfl_xor_sync(0xffffffffu, ps, 1);
     ps += __shfl_xor_sync(0xffffffffu, ps, 2);
     l = fmaf(l, corr, ps);
-#pragma unroll
-    for (int d = 0; d < 16; ++d) { o[d][0] *= corr; o[d][1] *= corr; }
-    // ---- O += P V : P (bf16, as the reference casts the probabilities) is the A operand, rows 8..15 zero
-    const uint32_t pa0 = pack_bf16(sc[0], sc[1]), pa2 = pack_bf16(sc[2], sc[3]);
     {
-      const int kr = 16 * warp + (lane & 7) + ((lane >> 3) & 1) * 8;
+      // this lane's accumulator columns are heads 2t and 2t+1: their rescale factors live in lanes 8t and 8t+4
+      const float c0 = __shfl_sync(0xffffffffu, corr, 8 * t), c1 = __shfl_sync(0xffffffffu, corr, 8 * t + 4);
 #pragma unroll
-      for (int dp = 0; dp < 8; ++dp) {
-        const int ch = 2 * dp + ((lane >> 4) & 1);
-        uint32_t b[4];
-        ldsm_x4_trans(b, vbase + kr * 256 + ((ch ^ (kr & 7)) << 4));
-        mma_bf16(o[2 * dp], pa0, 0u, pa2, 0u, b[0], b[1]);
-        mma_bf16(o[2 * dp + 1], pa0, 0u, pa2, 0u, b[2], b[3]);
+      for (int d = 0; d < 8; ++d) { ot[d][0] *= c0; ot[d][1] *= c1; ot[d][2] *= c0; ot[d][3] *= c1; }
+    }
+    // ---- O^T += V^T P^T : V^T tiles (16 dims x 16 keys) are the A operand through ldmatrix.trans; P^T (bf16, as the
+    // reference casts the probabilities) is the B operand, and the score accumulators already have its layout
+    // (k = keys 2t, 2t+1 (+8), n = head g)
+    const uint32_t pb0 = pack_bf16(sc[0], sc[1]), pb1 = pack_bf16(sc[2], sc[3]);
+    {
+      const int kr = 16 * warp + (lane & 7) + ((lane >> 4) & 1) * 8;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        const int ch = 2 * dt + ((lane >> 3) & 1);
+        uint32_t a[4];
+        ldsm_x4_trans(a, vbase + kr * 256 + ((ch ^ (kr & 7)) << 4));
+        mma_bf16(ot[dt], a[0], a[1], a[2], a[3], pb0, pb1);
       }
     }
     if (tile + STAGES < ntiles) {
@@ -619,11 +627,17 @@ __global__ void __launch_bounds__(128, STAGES == 1 ? 4 : 3) gqa_decode_tc_kernel
   float* sm_m = reinterpret_cast<float*>(smraw);      // [4][G]
   float* sm_l = sm_m + 4 * G;                          // [4][G]
   float* sm_o = sm_l + 4 * G;                          // [4][G][128]
-  if (g < G) {
-    if (t == 0) { sm_m[warp * G + g] = m; sm_l[warp * G + g] = l; }
+  if (g < G && t == 0) { sm_m[warp * G + g] = m; sm_l[warp * G + g] = l; }
 #pragma unroll
-    for (int d = 0; d < 16; ++d)
-      *reinterpret_cast<float2*>(sm_o + (warp * G + g) * kD + 8 * d + 2 * t) = make_float2(o[d][0], o[d][1]);
+  for (int e = 0; e < 2; ++e) {
+    const int head = 2 * t + e;
+    if (head < G) {
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        sm_o[(warp * G + head) * kD + 16 * d + g] = ot[d][e];
+        sm_o[(warp * G + head) * kD + 16 * d + g + 8] = ot[d][2 + e];
+      }
+    }
   }
   __syncthreads();
   const int unit = row * p.Hkv + hk;
@@ -682,7 +696,12 @@ template <int G>
 int launch_decode_tc(const AttnParams& p, int rows, cudaStream_t stream) {
   dim3 grid(rows, p.Hkv, p.nsplit);
   const long long ctas = (long long)rows * p.Hkv * p.nsplit;
-  if (ctas >= 3LL * mtts_num_sms()) {
+  static int force_stages = -1;
+  if (force_stages < 0) {
+    const char* e = getenv("MTTS_ATTN_STAGES");
+    force_stages = e ? atoi(e) : 0;
+  }
+  if (force_stages == 1 || (force_stages == 0 && ctas >= 3LL * mtts_num_sms())) {
     MTTS_CUDA_CHECK(mtts_launch(gqa_decode_tc_kernel<G, 1>, grid, dim3(128), (size_t)2 * kTcTileBytes, stream, p));
   } else {
     MTTS_CUDA_CHECK(mtts_launch(gqa_decode_tc_kernel<G, 2>, grid, dim3(128), (size_t)4 * kTcTileBytes, stream, p));
