@@ -202,6 +202,18 @@ int mtts_dwconv7_ln(const float* x, const float* conv_w, const float* conv_b, co
 int mtts_convt_gather(const float* y, const float* bias, float* out, int B, int Tin, int Cout, int K, int stride,
                       int Tout, int gelu, void* stream);
 
+/* Decode attention fused with its prologue: for ONE new row per sequence it does what mtts_qknorm_rope_kvappend +
+ * mtts_gqa_attention do (HF Qwen3Attention.forward, installed modeling_qwen3.py:236-288: q/k RMSNorm, RoPE, cache
+ * update, attention), bit-identically, in one launch: q and the new K/V row never travel through global memory and the
+ * first K/V tile is requested before the kernel waits for the q/k/v projection (programmatic dependent launch).
+ * qkv [rows, (Hq + 2 Hkv) * 128] bf16 is the projection output; out [rows, Hq * 128] bf16; the new key/value is
+ * appended at positions[row]; workspace as for mtts_gqa_attention (tiles = rows, rows_per_tile = 1). */
+int mtts_gqa_decode_fused(const void* qkv, long long ld_qkv, const void* q_norm_w, const void* k_norm_w,
+                          const float* inv_freq, float eps, void* k_pool, void* v_pool, const int* block_table,
+                          int max_pages, int page_size, int num_pages, const int* positions, void* out, int rows,
+                          int num_q_heads, int num_kv_heads, int head_dim, int nsplit, void* workspace,
+                          size_t workspace_bytes, int* err_flag, void* stream);
+
 /* ---- Small-batch decode step as one persistent kernel (batch 1..4; hidden 2048, intermediate 6144, 16/8 heads x 128).
  * Runs, for ONE new row per sequence, everything between the embedding sum and the sampler: the Qwen3 layer stack that
  * AsteroidTTSInstruct.forward drives (modeling_asteroid.py:252-285: RMSNorm, q/k/v projection, per-head q/k RMSNorm +

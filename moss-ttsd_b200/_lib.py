@@ -100,6 +100,9 @@ SIGNATURES = {
     "mtts_istft_spec": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p]),
     "mtts_istft_ola": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mtts_add_rows_mod": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
+    "mtts_gqa_decode_fused": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                      c_size_t, c_void_p, c_void_p]),
     "mtts_decode_mega_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "mtts_decode_mega_workspace_bytes": (c_ll, [c_int, c_int]),
     "mtts_decode_mega": (c_int, [ctypes.POINTER(DecodeMegaArgs), c_void_p]),

@@ -38,6 +38,15 @@ struct AttnParams {
   int nsplit;
   float* ws;       // split partials
   int* counters;   // [tiles * Hkv]
+  // fused decode (mtts_gqa_decode_fused): q/k/v of the new row come straight from the projection output
+  const bf16* qkv;        // [rows, (Hq + 2 Hkv) * 128]
+  long long ld_qkv;
+  const bf16* q_norm_w;
+  const bf16* k_norm_w;
+  const float* inv_freq;
+  float eps;
+  int num_pages;
+  int* err_flag;
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
@@ -464,6 +473,7 @@ int launch_decode(const AttnParams& p, int rows, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kTcKeys = 64;
 constexpr int kTcTileBytes = kTcKeys * kD * 2;  // 16 KB per K or V tile
+constexpr int kTcNewBytes = (8 + 2) * kD * 2;    // fused variant: q heads, k, v of the new row
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -483,11 +493,16 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int G, int STAGES>
+// FUSED: the kernel also does what mtts_qknorm_rope_kvappend does for its (row, kv head): per-head RMSNorm + RoPE of the
+// G query heads and of the new key straight from the q/k/v projection output, append of the new key/value to the cache
+// (by the split that owns position pos) and their insertion into the shared-memory tile, so that neither q nor the new
+// K/V row makes a round trip through global memory and the first K/V tile is requested BEFORE the wait on the
+// projection kernel (programmatic dependent launch): the cached keys do not depend on it.
+template <int G, int STAGES, bool FUSED>
 __global__ void __launch_bounds__(128, STAGES == 1 ? 4 : 3) gqa_decode_tc_kernel(const AttnParams p) {
   static_assert(G <= 8, "the q heads of one kv head are rows 0..G-1 of the 16-row MMA tile");
   pdl_launch_dependents();
-  pdl_wait();
+  if (!FUSED) pdl_wait();
   extern __shared__ __align__(128) uint8_t smraw[];
   __shared__ int s_is_last;
   const int row = blockIdx.x, hk = blockIdx.y, split = blockIdx.z;
@@ -504,17 +519,6 @@ __global__ void __launch_bounds__(128, STAGES == 1 ? 4 : 3) gqa_decode_tc_kernel
   }
   const int ntiles = (k_end - k_begin + kTcKeys - 1) / kTcKeys;
 
-  // Q as A fragments: row g = head g (zero for g >= G), 8 k-steps of 16 dims; rows 8..15 of the tile are all zero
-  uint32_t qa[8][2];
-#pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
-    qa[ks][0] = qa[ks][1] = 0u;
-    if (g < G) {
-      const bf16* qp = p.q + ((long long)row * p.Hq + hk * G + g) * kD + ks * 16 + 2 * t;
-      qa[ks][0] = *reinterpret_cast<const uint32_t*>(qp);
-      qa[ks][1] = *reinterpret_cast<const uint32_t*>(qp + 8);
-    }
-  }
   const int page_mask = (1 << p.page_shift) - 1;
   const long long head_off = ((long long)hk << p.page_shift) * kD;
   const long long page_stride = ((long long)p.Hkv << p.page_shift) * kD;
@@ -551,12 +555,88 @@ __global__ void __launch_bounds__(128, STAGES == 1 ? 4 : 3) gqa_decode_tc_kernel
   // STAGES == 1 relies on the other CTAs of the SM (4 resident) to keep loads in flight while this one computes.
   if (ntiles > 0) issue(0, 0);
   if (STAGES == 2 && ntiles > 1) issue(1, 1);
+
+  // Q as A fragments: row g = head g (zero for g >= G), 8 k-steps of 16 dims; rows 8..15 of the tile are all zero
+  uint32_t qa[8][2];
+  bf16* s_new = reinterpret_cast<bf16*>(smraw + STAGES * 2 * kTcTileBytes);  // FUSED: [G q heads | k | v] x 128 bf16
+  const int pos = kv_len - 1;
+  if (FUSED) {
+    pdl_wait();  // the projection output is needed from here on
+    const bool owner = pos >= k_begin && pos < k_end;
+    for (int item = warp; item < G + 2; item += 4) {  // G query heads, then k, then v of this kv head
+      const int col = item < G ? (hk * G + item) * kD : (item == G ? p.Hq * kD + hk * kD : (p.Hq + p.Hkv) * kD + hk * kD);
+      const bf16* src = p.qkv + (long long)row * p.ld_qkv + col;
+      const uint32_t a = *reinterpret_cast<const uint32_t*>(src + 2 * lane);       // elements 2l, 2l+1
+      const uint32_t b = *reinterpret_cast<const uint32_t*>(src + 64 + 2 * lane);  // elements 64+2l, 65+2l
+      float x0 = bf16lo(a), x1 = bf16hi(a), x2 = bf16lo(b), x3 = bf16hi(b);
+      if (item <= G) {  // same arithmetic, in the same order, as qknorm_rope_kv_kernel (lm_ops.cu)
+        const bf16* nw = item < G ? p.q_norm_w : p.k_norm_w;
+        float ss = x0 * x0;
+        ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+        ss = warp_sum(ss);
+        const float inv = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
+        const uint32_t wa = *reinterpret_cast<const uint32_t*>(nw + 2 * lane);
+        const uint32_t wb = *reinterpret_cast<const uint32_t*>(nw + 64 + 2 * lane);
+        x0 = bf16_round(bf16lo(wa) * bf16_round(x0 * inv));
+        x1 = bf16_round(bf16hi(wa) * bf16_round(x1 * inv));
+        x2 = bf16_round(bf16lo(wb) * bf16_round(x2 * inv));
+        x3 = bf16_round(bf16hi(wb) * bf16_round(x3 * inv));
+        const float f0 = (float)pos * p.inv_freq[2 * lane];
+        const float f1 = (float)pos * p.inv_freq[2 * lane + 1];
+        const float c0 = bf16_round(cosf(f0)), s0 = bf16_round(sinf(f0));
+        const float c1 = bf16_round(cosf(f1)), s1 = bf16_round(sinf(f1));
+        const float o0 = bf16_round(x0 * c0) + bf16_round(-x2 * s0);
+        const float o1 = bf16_round(x1 * c1) + bf16_round(-x3 * s1);
+        const float o2 = bf16_round(x2 * c0) + bf16_round(x0 * s0);
+        const float o3 = bf16_round(x3 * c1) + bf16_round(x1 * s1);
+        x0 = o0; x1 = o1; x2 = o2; x3 = o3;
+      }
+      const uint32_t lo = pack_bf16(x0, x1), hi = pack_bf16(x2, x3);
+      *reinterpret_cast<uint32_t*>(s_new + item * kD + 2 * lane) = lo;
+      *reinterpret_cast<uint32_t*>(s_new + item * kD + 64 + 2 * lane) = hi;
+      if (item >= G && owner) {  // append the new key / value row to the cache
+        const int lp = pos >> p.page_shift;
+        int page = -1;
+        if (pos >= 0 && lp < p.max_pages) page = p.block_table ? p.block_table[(long long)seq * p.max_pages + lp] : seq * p.max_pages + lp;
+        if (page < 0 || page >= p.num_pages) {
+          if (p.err_flag && lane == 0) *p.err_flag = 2;
+        } else {
+          bf16* dst = const_cast<bf16*>(item == G ? p.k_pool : p.v_pool) + (long long)page * page_stride + head_off +
+                      (long long)(pos & page_mask) * kD;
+          *reinterpret_cast<uint32_t*>(dst + 2 * lane) = lo;
+          *reinterpret_cast<uint32_t*>(dst + 64 + 2 * lane) = hi;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    qa[ks][0] = qa[ks][1] = 0u;
+    if (g < G) {
+      const bf16* qp = FUSED ? s_new + g * kD + ks * 16 + 2 * t : p.q + ((long long)row * p.Hq + hk * G + g) * kD + ks * 16 + 2 * t;
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(qp);
+      qa[ks][1] = *reinterpret_cast<const uint32_t*>(qp + 8);
+    }
+  }
 #pragma unroll 1
   for (int tile = 0; tile < ntiles; ++tile) {
     const int stage = STAGES == 2 ? (tile & 1) : 0;
     if (STAGES == 2 && tile + 1 < ntiles) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
     const uint32_t kbase = smem0 + stage * 2 * kTcTileBytes, vbase = kbase + kTcTileBytes;
+    if (FUSED) {  // the new row is not in the cache image that was copied: put it into the tile (uniform branch)
+      const int r = pos - (k_begin + tile * kTcKeys);
+      if (r >= 0 && r < kTcKeys) {
+        if (tid < 32) {
+          const int c = tid & 15;
+          const uint4 v = *reinterpret_cast<const uint4*>(s_new + (G + (tid >> 4)) * kD + c * 8);
+          uint8_t* dst = smraw + stage * 2 * kTcTileBytes + (tid >> 4) * kTcTileBytes + r * 256 + ((c ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = v;
+        }
+        __syncthreads();
+      }
+    }
     // ---- S = Q K^T for this warp's 16 keys (two 8-key column tiles)
     float s[2][4];
 #pragma unroll
@@ -692,7 +772,7 @@ __global__ void __launch_bounds__(128, STAGES == 1 ? 4 : 3) gqa_decode_tc_kernel
   }
 }
 
-template <int G>
+template <int G, bool FUSED>
 int launch_decode_tc(const AttnParams& p, int rows, cudaStream_t stream) {
   dim3 grid(rows, p.Hkv, p.nsplit);
   const long long ctas = (long long)rows * p.Hkv * p.nsplit;
@@ -702,9 +782,9 @@ int launch_decode_tc(const AttnParams& p, int rows, cudaStream_t stream) {
     force_stages = e ? atoi(e) : 0;
   }
   if (force_stages == 1 || (force_stages == 0 && ctas >= 3LL * mtts_num_sms())) {
-    MTTS_CUDA_CHECK(mtts_launch(gqa_decode_tc_kernel<G, 1>, grid, dim3(128), (size_t)2 * kTcTileBytes, stream, p));
+    MTTS_CUDA_CHECK(mtts_launch(gqa_decode_tc_kernel<G, 1, FUSED>, grid, dim3(128), (size_t)2 * kTcTileBytes + kTcNewBytes, stream, p));
   } else {
-    MTTS_CUDA_CHECK(mtts_launch(gqa_decode_tc_kernel<G, 2>, grid, dim3(128), (size_t)4 * kTcTileBytes, stream, p));
+    MTTS_CUDA_CHECK(mtts_launch(gqa_decode_tc_kernel<G, 2, FUSED>, grid, dim3(128), (size_t)4 * kTcTileBytes + kTcNewBytes, stream, p));
   }
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
@@ -899,9 +979,13 @@ int mtts_configure_attention() {
   if ((rc = configure_attn<4, 1>())) return rc;
   if ((rc = configure_attn<4, 2>())) return rc;
   if ((rc = configure_attn<4, 4>())) return rc;
-  cudaError_t e = cudaFuncSetAttribute(gqa_decode_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kTcTileBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(gqa_decode_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kTcTileBytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(gqa_decode_tc_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kTcTileBytes);
+  const int big = 4 * kTcTileBytes + kTcNewBytes;
+  cudaError_t e = cudaFuncSetAttribute(gqa_decode_tc_kernel<1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gqa_decode_tc_kernel<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gqa_decode_tc_kernel<4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gqa_decode_tc_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gqa_decode_tc_kernel<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gqa_decode_tc_kernel<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e != cudaSuccess) return mtts_set_error(MTTS_ERR_CUDA, "attention: smem attribute: %s", cudaGetErrorString(e));
   return MTTS_OK;
 }
@@ -963,9 +1047,9 @@ extern "C" int mtts_gqa_attention(const void* q, const void* k_pool, const void*
       use_tc = (e && e[0] == '1') ? 0 : 1;
     }
     if (use_tc) {
-      if (G == 1) return launch_decode_tc<1>(p, tiles, stream);
-      if (G == 2) return launch_decode_tc<2>(p, tiles, stream);
-      if (G == 4) return launch_decode_tc<4>(p, tiles, stream);
+      if (G == 1) return launch_decode_tc<1, false>(p, tiles, stream);
+      if (G == 2) return launch_decode_tc<2, false>(p, tiles, stream);
+      if (G == 4) return launch_decode_tc<4, false>(p, tiles, stream);
     }
     if (G == 1) return launch_decode<1>(p, tiles, stream);
     if (G == 2) return launch_decode<2>(p, tiles, stream);
@@ -981,4 +1065,45 @@ extern "C" int mtts_gqa_attention(const void* q, const void* k_pool, const void*
   MTTS_ATTN_CASE(4, 4)
 #undef MTTS_ATTN_CASE
   return mtts_set_error(MTTS_ERR_UNSUPPORTED, "mtts_gqa_attention: unsupported configuration");
+}
+
+extern "C" int mtts_gqa_decode_fused(const void* qkv, long long ld_qkv, const void* q_norm_w, const void* k_norm_w,
+                                     const float* inv_freq, float eps, void* k_pool, void* v_pool, const int* block_table,
+                                     int max_pages, int page_size, int num_pages, const int* positions, void* out, int rows,
+                                     int num_q_heads, int num_kv_heads, int head_dim, int nsplit, void* workspace,
+                                     size_t workspace_bytes, int* err_flag, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(head_dim == kD, "mtts_gqa_decode_fused: head_dim must be 128 (got %d)", head_dim);
+  MTTS_REQUIRE(page_size > 0 && (page_size & (page_size - 1)) == 0, "mtts_gqa_decode_fused: page_size must be a power of two");
+  MTTS_REQUIRE(num_kv_heads > 0 && num_q_heads % num_kv_heads == 0, "mtts_gqa_decode_fused: bad head counts");
+  const int G = num_q_heads / num_kv_heads;
+  MTTS_REQUIRE(G == 1 || G == 2 || G == 4, "mtts_gqa_decode_fused: q heads per kv head must be 1, 2 or 4 (got %d)", G);
+  MTTS_REQUIRE(nsplit >= 1 && nsplit <= 64, "mtts_gqa_decode_fused: nsplit out of range");
+  if (rows <= 0) return MTTS_OK;
+  MTTS_REQUIRE(qkv && q_norm_w && k_norm_w && inv_freq && k_pool && v_pool && positions && out,
+               "mtts_gqa_decode_fused: null pointer");
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = nullptr;
+  p.k_pool = reinterpret_cast<const bf16*>(k_pool); p.v_pool = reinterpret_cast<const bf16*>(v_pool);
+  p.block_table = block_table; p.max_pages = max_pages;
+  int shift = 0;
+  while ((1 << shift) < page_size) ++shift;
+  p.page_shift = shift;
+  p.positions = positions; p.out = reinterpret_cast<bf16*>(out);
+  p.Hq = num_q_heads; p.Hkv = num_kv_heads;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
+  p.nsplit = nsplit;
+  if (nsplit > 1) {
+    const size_t need = mtts_gqa_attention_workspace_bytes(rows, num_kv_heads, G, 1, nsplit);
+    MTTS_REQUIRE(workspace && workspace_bytes >= need, "mtts_gqa_decode_fused: workspace too small (%zu < %zu)", workspace_bytes, need);
+    p.counters = reinterpret_cast<int*>(workspace);
+    p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kAttnCounterBytes);
+  }
+  p.qkv = reinterpret_cast<const bf16*>(qkv); p.ld_qkv = ld_qkv;
+  p.q_norm_w = reinterpret_cast<const bf16*>(q_norm_w); p.k_norm_w = reinterpret_cast<const bf16*>(k_norm_w);
+  p.inv_freq = inv_freq; p.eps = eps; p.num_pages = num_pages; p.err_flag = err_flag;
+  if (G == 1) return launch_decode_tc<1, true>(p, rows, stream);
+  if (G == 2) return launch_decode_tc<2, true>(p, rows, stream);
+  return launch_decode_tc<4, true>(p, rows, stream);
 }

@@ -264,6 +264,9 @@ class DecoderEngine:
         # batch <= mega_max_b: the whole step (layer stack + LM heads) is ONE persistent kernel. Measured on B200
         # (ms/step, ctx 460): batch 1: 1.06 vs 1.44 for the kernel chain, batch 2: 1.19 vs 1.46, batch 4: 1.63 vs 1.50.
         self.use_mega = os.environ.get("MTTS_NO_MEGA", "0") != "1"
+        # decode steps of the kernel chain: q/k norm + RoPE + cache append run inside the attention kernel
+        self.fused_decode_attn = (os.environ.get("MTTS_ATTN_FUSED", "1") != "0" and os.environ.get("MTTS_ATTN_SIMT", "0") != "1"
+                                  and s.head_dim == 128 and s.num_attention_heads // s.num_key_value_heads in (1, 2, 4))
         self.mega_max_b = int(os.environ.get("MTTS_MEGA_MAX_B", "2"))
         self.prefill_tile_rows = int(os.environ.get("MTTS_PREFILL_TILE", "64"))  # 64: tensor-core tiles, 4: CUDA cores
         self.graph_replayed_launches = 0  # kernels executed through graph replays (not seen by mtts_launch_count)
@@ -327,8 +330,17 @@ class DecoderEngine:
         for l, lw in enumerate(self.w.layers):
             self._rmsnorm(x, lw["ln1"], xn)
             ops.gemm(xn, lw["wqkv"], out=qkv, workspace=gws)
-            self._rope_kv(qkv, lw, positions, row_seq, q, cache, l)
-            self._attention(q, cache, l, positions, row_seq, ao, **attn_kw)
+            if self.fused_decode_attn and attn_kw["rows_per_tile"] == 1 and row_seq is None:
+                ws = attn_kw["ws"]
+                check(self.L.mtts_gqa_decode_fused(
+                    ptr(qkv), qkv.stride(0), ptr(lw["q_norm"]), ptr(lw["k_norm"]), ptr(self.w.inv_freq), self.s.rms_norm_eps,
+                    ptr(cache.k[l]), ptr(cache.v[l]), ptr(cache.block_table), cache.max_pages, cache.page_size,
+                    cache.num_pages, ptr(positions), ptr(ao), qkv.shape[0], self.s.num_attention_heads,
+                    self.s.num_key_value_heads, self.s.head_dim, attn_kw["nsplit"], ptr(ws),
+                    ws.numel() if ws is not None else 0, ptr(self.err), stream_ptr()))
+            else:
+                self._rope_kv(qkv, lw, positions, row_seq, q, cache, l)
+                self._attention(q, cache, l, positions, row_seq, ao, **attn_kw)
             ops.gemm(ao, lw["wo"], out=x, residual=x, workspace=gws)
             self._rmsnorm(x, lw["ln2"], xn)
             ops.gemm(xn, lw["wgu"], out=h, swiglu=True, workspace=gws)

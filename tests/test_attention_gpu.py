@@ -63,3 +63,59 @@ def test_decode_attention_matches_fp32_reference(B, Hq, Hkv, max_ctx, nsplit, pa
     # bf16 probabilities and bf16 output rounding: |O| <= ~3, one bf16 ulp there is 0.016
     assert err <= 0.03, err
     assert torch.isfinite(got).all()
+
+
+@pytest.mark.parametrize("B,Hq,Hkv,max_ctx,nsplit,paged", [(3, 16, 8, 200, 1, False), (9, 16, 8, 333, 3, True),
+                                                           (70, 16, 8, 130, 1, False), (5, 16, 4, 257, 2, True)])
+def test_fused_decode_attention_is_bit_identical_to_the_two_kernel_path(B, Hq, Hkv, max_ctx, nsplit, paged):
+    """mtts_gqa_decode_fused == mtts_qknorm_rope_kvappend + mtts_gqa_attention: same output bits, same cache rows."""
+    from moss_ttsd_b200 import _lib, ops
+    ops.ensure_init()
+    L = _lib.load()
+    D, page = 128, 64
+    g = torch.Generator(device="cuda").manual_seed(7 * B + max_ctx)
+    rng = np.random.default_rng(3 * B + max_ctx)
+    lens = rng.integers(1, max_ctx + 1, B)
+    lens[0] = max_ctx
+    lens[-1] = 1
+    if B > 2:
+        lens[1] = 64 * 2 + 1  # the new row opens a page / a key tile
+    max_pages = (max_ctx + page - 1) // page
+    num_pages = B * max_pages
+    ids = np.arange(num_pages, dtype=np.int32)
+    if paged:
+        rng.shuffle(ids)
+    table = torch.from_numpy(ids.reshape(B, max_pages)).cuda()
+    pos = torch.from_numpy((lens - 1).astype(np.int32)).cuda()
+    qkv = torch.randn((B, (Hq + 2 * Hkv) * D), device="cuda", generator=g).to(torch.bfloat16)
+    qn = (1 + 0.2 * torch.randn(D, device="cuda", generator=g)).to(torch.bfloat16)
+    kn = (1 + 0.2 * torch.randn(D, device="cuda", generator=g)).to(torch.bfloat16)
+    inv_freq = (1.0 / (1e6 ** (torch.arange(0, D, 2).float() / D))).cuda()
+    pools = [torch.randn((num_pages, Hkv, page, D), device="cuda", generator=g).to(torch.bfloat16) for _ in range(2)]
+    err = torch.zeros(4, dtype=torch.int32, device="cuda")
+    tb = table.data_ptr() if paged else None
+    outs, caches = [], []
+    for fused in (False, True):
+        k_pool, v_pool = pools[0].clone(), pools[1].clone()
+        out = torch.empty((B, Hq * D), dtype=torch.bfloat16, device="cuda")
+        ws = torch.zeros(L.mtts_gqa_attention_workspace_bytes(B, Hkv, Hq // Hkv, 1, nsplit), dtype=torch.uint8, device="cuda")
+        if fused:
+            _lib.check(L.mtts_gqa_decode_fused(qkv.data_ptr(), qkv.stride(0), qn.data_ptr(), kn.data_ptr(), inv_freq.data_ptr(), 1e-6,
+                                               k_pool.data_ptr(), v_pool.data_ptr(), tb, max_pages, page, num_pages, pos.data_ptr(),
+                                               out.data_ptr(), B, Hq, Hkv, D, nsplit, ws.data_ptr(), ws.numel(), err.data_ptr(),
+                                               _lib.stream_ptr()))
+        else:
+            q = torch.empty((B, Hq * D), dtype=torch.bfloat16, device="cuda")
+            _lib.check(L.mtts_qknorm_rope_kvappend(qkv.data_ptr(), qkv.stride(0), qn.data_ptr(), kn.data_ptr(), inv_freq.data_ptr(),
+                                                   pos.data_ptr(), None, q.data_ptr(), k_pool.data_ptr(), v_pool.data_ptr(), tb,
+                                                   max_pages, page, num_pages, B, Hq, Hkv, D, 1e-6, err.data_ptr(),
+                                                   _lib.stream_ptr()))
+            _lib.check(L.mtts_gqa_attention(q.data_ptr(), k_pool.data_ptr(), v_pool.data_ptr(), tb, max_pages, page, None, None,
+                                            None, pos.data_ptr(), out.data_ptr(), B, 1, Hq, Hkv, D, nsplit, ws.data_ptr(),
+                                            ws.numel(), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        outs.append(out)
+        caches.append((k_pool, v_pool))
+    assert int(err.abs().sum()) == 0
+    assert torch.equal(caches[0][0], caches[1][0]) and torch.equal(caches[0][1], caches[1][1])
+    assert torch.equal(outs[0], outs[1])
