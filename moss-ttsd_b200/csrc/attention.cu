@@ -475,8 +475,9 @@ constexpr int kTcKeys = 64;
 constexpr int kTcTileBytes = kTcKeys * kD * 2;  // 16 KB per K or V tile
 constexpr int kTcNewBytes = (8 + 2) * kD * 2;    // fused variant: q heads, k, v of the new row
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+// 16-byte async copy; `valid == false` writes 16 zero bytes instead (src-size 0), the address is not dereferenced
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -531,13 +532,16 @@ __global__ void __launch_bounds__(128, STAGES == 1 ? 4 : 3) gqa_decode_tc_kernel
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int kr = (tid >> 4) + 8 * j;                       // key row inside the tile
-      const int key = min(key0 + kr, k_end - 1);               // clamp: the copy is always legal, the score is masked
+      // rows past the range are ZERO-filled (their scores are masked, but 0 x stale NaN bits in V would still poison
+      // O); in the fused variant so is the row of the new token, which is patched in from shared memory later
+      const bool live = key0 + kr < (FUSED ? min(k_end, kv_len - 1) : k_end);
+      const int key = min(key0 + kr, k_end - 1);
       const int lp = key >> p.page_shift;
       const int page = p.block_table ? __ldg(p.block_table + (long long)seq * p.max_pages + lp) : seq * p.max_pages + lp;
       const long long off = (long long)page * page_stride + head_off + (long long)(key & page_mask) * kD + c * 8;
       const uint32_t so = kr * 256 + ((c ^ (kr & 7)) << 4);    // 16-byte chunks XOR-swizzled by the row
-      cp_async16(kdst + so, p.k_pool + off);
-      cp_async16(vdst + so, p.v_pool + off);
+      cp_async16(kdst + so, p.k_pool + off, live);
+      cp_async16(vdst + so, p.v_pool + off, live);
     }
     cp_async_commit();
   };
