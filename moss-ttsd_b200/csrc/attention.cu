@@ -809,6 +809,165 @@ __device__ __forceinline__ void mma_bf16_16x8x16(float (&c)[4], const uint32_t (
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Prefill, flash style on the same machinery as the decode kernel above: CTA = up to 64 consecutive query rows of one
+// sequence x one q head (4 warps x 16 rows, every MMA row is a real query), K/V tiles of 64 keys double-buffered by
+// cp.async with XOR-swizzled 16-byte chunks, K as the B operand of S = Q K^T through ldmatrix, V as the B operand of
+// O += P V through ldmatrix.trans, P re-packed to bf16 in registers. Causal: row (pos0 + r) sees keys <= pos0 + r.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 3) gqa_prefill_fa_kernel(const AttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(128) uint8_t smraw[];
+  const int tile = blockIdx.x, hq = blockIdx.y;
+  const int G = p.Hq / p.Hkv, hk = hq / G;
+  const int row0 = p.tile_row0[tile], nrows = p.tile_nrows[tile];
+  const int seq = p.row_seq ? p.row_seq[row0] : row0;
+  const int pos0 = p.positions[row0];
+  const int kv_len = pos0 + nrows;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int ntiles = (kv_len + kTcKeys - 1) / kTcKeys;
+  const int page_mask = (1 << p.page_shift) - 1;
+  const long long head_off = ((long long)hk << p.page_shift) * kD;
+  const long long page_stride = ((long long)p.Hkv << p.page_shift) * kD;
+  const uint32_t smem0 = static_cast<uint32_t>(__cvta_generic_to_shared(smraw));
+
+  auto issue = [&](int kt, int stage) {
+    const int key0 = kt * kTcKeys;
+    const uint32_t kdst = smem0 + stage * 2 * kTcTileBytes, vdst = kdst + kTcTileBytes;
+    const int c = tid & 15;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kr = (tid >> 4) + 8 * j;
+      const bool live = key0 + kr < kv_len;  // rows past the sequence are zero-filled
+      const int key = min(key0 + kr, kv_len - 1);
+      const int lp = key >> p.page_shift;
+      const int page = p.block_table ? __ldg(p.block_table + (long long)seq * p.max_pages + lp) : seq * p.max_pages + lp;
+      const long long off = (long long)page * page_stride + head_off + (long long)(key & page_mask) * kD + c * 8;
+      const uint32_t so = kr * 256 + ((c ^ (kr & 7)) << 4);
+      cp_async16(kdst + so, p.k_pool + off, live);
+      cp_async16(vdst + so, p.v_pool + off, live);
+    }
+    cp_async_commit();
+  };
+  issue(0, 0);
+  if (ntiles > 1) issue(1, 1);
+
+  // Q fragments: rows r0 = 16 warp + g and r0 + 8 (clamped for the load, masked at the store), 8 k-steps of 16 dims
+  uint32_t qa[8][4];
+  {
+    const int ra = min(warp * 16 + g, nrows - 1), rb = min(warp * 16 + g + 8, nrows - 1);
+    const bf16* qpa = p.q + ((long long)(row0 + ra) * p.Hq + hq) * kD + 2 * t;
+    const bf16* qpb = p.q + ((long long)(row0 + rb) * p.Hq + hq) * kD + 2 * t;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(qpa + ks * 16);
+      qa[ks][1] = *reinterpret_cast<const uint32_t*>(qpb + ks * 16);
+      qa[ks][2] = *reinterpret_cast<const uint32_t*>(qpa + ks * 16 + 8);
+      qa[ks][3] = *reinterpret_cast<const uint32_t*>(qpb + ks * 16 + 8);
+    }
+  }
+  float o[16][4];
+#pragma unroll
+  for (int d = 0; d < 16; ++d)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[d][i] = 0.f;
+  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
+  const int qp0 = pos0 + warp * 16 + g, qp1 = qp0 + 8;  // positions of this lane's two query rows
+
+#pragma unroll 1
+  for (int kt = 0; kt < ntiles; ++kt) {
+    const int stage = kt & 1;
+    if (kt + 1 < ntiles) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    const uint32_t kbase = smem0 + stage * 2 * kTcTileBytes, vbase = kbase + kTcTileBytes;
+    const int key0 = kt * kTcKeys;
+    if (key0 <= pos0 + warp * 16 + 15) {  // warp-uniform: some key of this tile is visible to some row of this warp
+      float s[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[j][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          const int kr = 16 * jp + (lane & 7) + ((lane >> 4) & 1) * 8;
+          const int ch = 2 * ks + ((lane >> 3) & 1);
+          uint32_t b[4];
+          ldsm_x4(b, kbase + kr * 256 + ((ch ^ (kr & 7)) << 4));
+          mma_bf16(s[2 * jp], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b[0], b[1]);
+          mma_bf16(s[2 * jp + 1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b[2], b[3]);
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = key0 + 8 * j + 2 * t + e;
+          s[j][e] = (key <= qp0 && key < kv_len) ? s[j][e] * p.scale_log2 : -INFINITY;
+          s[j][2 + e] = (key <= qp1 && key < kv_len) ? s[j][2 + e] * p.scale_log2 : -INFINITY;
+          mx0 = fmaxf(mx0, s[j][e]);
+          mx1 = fmaxf(mx1, s[j][2 + e]);
+        }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+      const float c0 = fast_exp2(m0 - mn0), c1 = fast_exp2(m1 - mn1);
+      m0 = mn0; m1 = mn1;
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          s[j][e] = fast_exp2(s[j][e] - mn0);
+          s[j][2 + e] = fast_exp2(s[j][2 + e] - mn1);
+          ps0 += s[j][e];
+          ps1 += s[j][2 + e];
+        }
+      ps0 += __shfl_xor_sync(0xffffffffu, ps0, 1);
+      ps0 += __shfl_xor_sync(0xffffffffu, ps0, 2);
+      ps1 += __shfl_xor_sync(0xffffffffu, ps1, 1);
+      ps1 += __shfl_xor_sync(0xffffffffu, ps1, 2);
+      l0 = fmaf(l0, c0, ps0);
+      l1 = fmaf(l1, c1, ps1);
+#pragma unroll
+      for (int d = 0; d < 16; ++d) { o[d][0] *= c0; o[d][1] *= c0; o[d][2] *= c1; o[d][3] *= c1; }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {  // 16 keys per k-step: score column tiles 2kk, 2kk+1 are the A fragment
+        const uint32_t pa0 = pack_bf16(s[2 * kk][0], s[2 * kk][1]), pa1 = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+        const uint32_t pa2 = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), pa3 = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+        const int kr = 16 * kk + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int dp = 0; dp < 8; ++dp) {
+          const int ch = 2 * dp + ((lane >> 4) & 1);
+          uint32_t b[4];
+          ldsm_x4_trans(b, vbase + kr * 256 + ((ch ^ (kr & 7)) << 4));
+          mma_bf16(o[2 * dp], pa0, pa1, pa2, pa3, b[0], b[1]);
+          mma_bf16(o[2 * dp + 1], pa0, pa1, pa2, pa3, b[2], b[3]);
+        }
+      }
+    }
+    if (kt + 2 < ntiles) {
+      __syncthreads();  // every warp is done with this stage
+      issue(kt + 2, stage);
+    }
+  }
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int ra = warp * 16 + g, rb = ra + 8;
+#pragma unroll
+  for (int d = 0; d < 16; ++d) {
+    if (ra < nrows)
+      *reinterpret_cast<uint32_t*>(p.out + ((long long)(row0 + ra) * p.Hq + hq) * kD + 8 * d + 2 * t) = pack_bf16(o[d][0] * i0, o[d][1] * i0);
+    if (rb < nrows)
+      *reinterpret_cast<uint32_t*>(p.out + ((long long)(row0 + rb) * p.Hq + hq) * kD + 8 * d + 2 * t) = pack_bf16(o[d][2] * i1, o[d][3] * i1);
+  }
+}
+
 __global__ void __launch_bounds__(128) gqa_prefill_tc_kernel(const AttnParams p) {
   pdl_launch_dependents();
   pdl_wait();
@@ -984,6 +1143,8 @@ int mtts_configure_attention() {
   if ((rc = configure_attn<4, 2>())) return rc;
   if ((rc = configure_attn<4, 4>())) return rc;
   const int big = 4 * kTcTileBytes + kTcNewBytes;
+  if (cudaFuncSetAttribute(gqa_prefill_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kTcTileBytes) != cudaSuccess)
+    return mtts_set_error(MTTS_ERR_CUDA, "attention: smem attribute (prefill)");
   cudaError_t e = cudaFuncSetAttribute(gqa_decode_tc_kernel<1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gqa_decode_tc_kernel<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(gqa_decode_tc_kernel<4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -1039,6 +1200,16 @@ extern "C" int mtts_gqa_attention(const void* q, const void* k_pool, const void*
   if (rows_per_tile == 64) {
     MTTS_REQUIRE(tile_row0 && tile_nrows, "mtts_gqa_attention: 64-row tiles need tile_row0 / tile_nrows");
     MTTS_REQUIRE(nsplit == 1, "mtts_gqa_attention: prefill tiles do not split the keys");
+    static int use_fa = -1;
+    if (use_fa < 0) {
+      const char* e = getenv("MTTS_PREFILL_OLD");
+      use_fa = (e && e[0] == '1') ? 0 : 1;
+    }
+    if (use_fa) {
+      MTTS_CUDA_CHECK(mtts_launch(gqa_prefill_fa_kernel, dim3(tiles, num_q_heads), dim3(128), (size_t)4 * kTcTileBytes, stream, p));
+      MTTS_LAUNCH_CHECK();
+      return MTTS_OK;
+    }
     const size_t smem = sizeof(bf16) * (kPK * kKPitch + kD * kVPitch);
     MTTS_CUDA_CHECK(mtts_launch(gqa_prefill_tc_kernel, dim3(tiles, num_q_heads), dim3(128), smem, stream, p));
     MTTS_LAUNCH_CHECK();

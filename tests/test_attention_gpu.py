@@ -127,3 +127,53 @@ def test_fused_decode_attention_is_bit_identical_to_the_two_kernel_path(B, Hq, H
     for a, b_ in zip(caches[0], caches[1]):
         assert torch.equal(torch.nan_to_num(a.float(), nan=123.0), torch.nan_to_num(b_.float(), nan=123.0))
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("lens,Hq,Hkv,paged", [([70, 1, 64, 65, 130], 16, 8, False), ([457, 300], 16, 8, True),
+                                                ([33, 200, 17], 8, 8, True), ([129, 64], 16, 4, False)])
+def test_prefill_attention_matches_fp32_reference(lens, Hq, Hkv, paged):
+    """64-row causal tiles (flash-style tensor-core kernel) against fp32 eager attention, packed ragged sequences."""
+    from moss_ttsd_b200 import _lib, ops
+    ops.ensure_init()
+    L = _lib.load()
+    D, page = 128, 64
+    B = len(lens)
+    g = torch.Generator(device="cuda").manual_seed(sum(lens))
+    rng = np.random.default_rng(sum(lens))
+    max_ctx = max(lens)
+    max_pages = (max_ctx + page - 1) // page
+    num_pages = B * max_pages
+    ids = np.arange(num_pages, dtype=np.int32)
+    if paged:
+        rng.shuffle(ids)
+    table = torch.from_numpy(ids.reshape(B, max_pages)).cuda()
+    k_pool = torch.randn((num_pages, Hkv, page, D), device="cuda", generator=g).to(torch.bfloat16)
+    v_pool = torch.randn((num_pages, Hkv, page, D), device="cuda", generator=g).to(torch.bfloat16)
+    R = sum(lens)
+    q = torch.randn((R, Hq, D), device="cuda", generator=g).to(torch.bfloat16)
+    pos_h = np.concatenate([np.arange(n, dtype=np.int32) for n in lens])
+    seq_h = np.repeat(np.arange(B, dtype=np.int32), lens)
+    cu = np.concatenate([[0], np.cumsum(lens)])
+    row0_h, nrows_h = [], []
+    for b in range(B):
+        for t0 in range(0, lens[b], 64):
+            row0_h.append(cu[b] + t0)
+            nrows_h.append(min(64, lens[b] - t0))
+    dev = lambda a: torch.from_numpy(np.asarray(a, dtype=np.int32)).cuda()
+    positions, row_seq, tile_row0, tile_nrows = dev(pos_h), dev(seq_h), dev(row0_h), dev(nrows_h)
+    out = torch.empty((R, Hq * D), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.mtts_gqa_attention(q.data_ptr(), k_pool.data_ptr(), v_pool.data_ptr(), table.data_ptr() if paged else None,
+                                    max_pages, page, tile_row0.data_ptr(), tile_nrows.data_ptr(), row_seq.data_ptr(),
+                                    positions.data_ptr(), out.data_ptr(), len(row0_h), 64, Hq, Hkv, D, 1, None, 0,
+                                    _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    kl = k_pool[table.long()].permute(0, 1, 3, 2, 4).reshape(B, max_pages * page, Hkv, D).float()
+    vl = v_pool[table.long()].permute(0, 1, 3, 2, 4).reshape(B, max_pages * page, Hkv, D).float()
+    got = out.float().view(R, Hq, D)
+    worst = 0.0
+    for b in range(B):
+        for r in range(lens[b]):
+            ref = _reference(q[cu[b] + r:cu[b] + r + 1].float(), kl[b:b + 1], vl[b:b + 1], [r + 1], Hq, Hkv)[0]
+            worst = max(worst, (got[cu[b] + r] - ref).abs().max().item())
+    assert worst <= 0.03, worst
+    assert torch.isfinite(got).all()
