@@ -250,12 +250,54 @@ class XY_Tokenizer:
                     ("enhanced_vocos.head.out.weight", (vk["n_fft"] + 2, dim), dim), ("enhanced_vocos.head.out.bias", (vk["n_fft"] + 2,), -1)])
         return out
 
-    def init_random_weights(self, seed=0, device="cuda"):
-        """Seeded random decode-side weights generated on the device (bench / smoke; no parity role)."""
+    def encoder_param_shapes(self):
+        """(name, shape, fan_in) of every encode-side tensor under the reference's state-dict names (model.py:26-38:
+        semantic / acoustic OmniAudioEncoder, the two adapter Transformers, ResidualDownConv)."""
+        gp = self.params
+        out = []
+
+        def layer(p, d, ffn):
+            for nm in ("self_attn_layer_norm", "final_layer_norm"):
+                out.extend([(p + nm + ".weight", (d,), 0), (p + nm + ".bias", (d,), -1)])
+            for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+                out.append((p + f"self_attn.{nm}.weight", (d, d), d))
+                if nm != "k_proj":
+                    out.append((p + f"self_attn.{nm}.bias", (d,), -1))
+            out.extend([(p + "fc1.weight", (ffn, d), d), (p + "fc1.bias", (ffn,), -1),
+                        (p + "fc2.weight", (d, ffn), ffn), (p + "fc2.bias", (d,), -1)])
+
+        for name in ("semantic_encoder", "acoustic_encoder"):
+            kw = gp[f"{name}_kwargs"]
+            d, k = kw["d_model"], kw["kernel_size"]
+            out.extend([(f"{name}.conv1.weight", (d, kw["num_mel_bins"], k), kw["num_mel_bins"] * k), (f"{name}.conv1.bias", (d,), -1),
+                        (f"{name}.conv2.weight", (d, d, k), d * k), (f"{name}.conv2.bias", (d,), -1)])
+            for l in range(kw["encoder_layers"]):
+                layer(f"{name}.layers.{l}.", d, kw["encoder_ffn_dim"])
+            out.extend([(f"{name}.layer_norm.weight", (d,), 0), (f"{name}.layer_norm.bias", (d,), -1)])
+        for name in ("semantic_encoder_adapter", "pre_rvq_adapter"):
+            kw = gp[f"{name}_kwargs"]
+            d = kw["d_model"]
+            if kw["input_dim"] != d:
+                out.extend([(f"{name}.proj.weight", (d, kw["input_dim"]), kw["input_dim"]), (f"{name}.proj.bias", (d,), -1)])
+            for l in range(kw["encoder_layers"]):
+                layer(f"{name}.layers.{l}.", d, kw["encoder_ffn_dim"])
+            out.extend([(f"{name}.layer_norm.weight", (d,), 0), (f"{name}.layer_norm.bias", (d,), -1)])
+            if kw["output_dim"] != d:
+                out.extend([(f"{name}.out_proj.weight", (kw["output_dim"], d), d), (f"{name}.out_proj.bias", (kw["output_dim"],), -1)])
+        dk = gp["downsample_kwargs"]
+        d, pl = dk["d_model"], dk["avg_pooler"]
+        out.extend([("downsample.gate_proj.weight", (d * pl, d, pl), d * pl), ("downsample.up_proj.weight", (d * pl, d, pl), d * pl),
+                    ("downsample.down_proj.weight", (d * pl, d * pl), d * pl),
+                    ("downsample.layer_norm.weight", (d * pl,), 0), ("downsample.layer_norm.bias", (d * pl,), -1)])
+        return out
+
+    def init_random_weights(self, seed=0, device="cuda", encoder=False):
+        """Seeded random weights generated on the device (bench / smoke; no parity role): the decode side, plus the
+        encode side with `encoder=True`."""
         dev = torch.device(device)
         g = torch.Generator(device=dev).manual_seed(seed)
         sd = {}
-        for name, shape, fan in self.param_shapes():
+        for name, shape, fan in self.param_shapes() + (self.encoder_param_shapes() if encoder else []):
             t = torch.empty(shape, dtype=torch.float32, device=dev).normal_(0.0, 1.0, generator=g)
             if fan > 0:
                 t *= fan ** -0.5
