@@ -3,11 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Workload (BASELINE.json configs[2], widened by the codec so that the unit really is generated audio):
-  v0.5-shaped LM (Qwen3-1.7B dims, 8 codebooks), random init, bf16; batch 64 per GPU; prompts of 200 text rows +
-  250 audio rows (two 10 s speaker prompts) delay-shifted; greedy; 375 new frames (30 s) per script; then
-  XY_Tokenizer.decode (shipped config, random init) to 24 kHz waveforms. One "step" = one such batch end to end.
-  metric = audio-seconds generated per wall-second, whole job (all ranks).
+Workload (BASELINE.json configs[4], "C5": the end-to-end LM + codec throughput configuration, batch 256 per GPU):
+  v0.5-shaped LM (Qwen3-1.7B dims, 8 codebooks), random init, bf16; 256 dialogue scripts per GPU per step; prompts of
+  a ragged text part (uniform 64..512 rows) + 250 audio rows (two 10 s speaker prompts), delay-shifted and
+  left-padded as process_inputs does; greedy; 375 new frames (30 s) per script; then XY_Tokenizer.decode (shipped
+  config, random init) to 24 kHz waveforms. One "step" = one such batch end to end (2048 scripts = 8 steps on one GPU,
+  one step each on 8). metric = audio-seconds generated per wall-second, whole job (all ranks).
 
 One rank per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); requests are sharded, no data-path collective; the
 timed region is bracketed by barrier + synchronize and the MAX over ranks is reported.
@@ -32,13 +33,15 @@ import torch
 SHAPE = dict(hidden_size=2048, intermediate_size=6144, num_hidden_layers=28, num_attention_heads=16,
              num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-6, rope_theta=1e6, vocab_size=152697,
              speech_vocab_size=1025, channels=8, speech_token_range=[151665, 152689])
-BATCH = int(os.environ.get("MTTS_BENCH_BATCH", 64))
+BATCH = int(os.environ.get("MTTS_BENCH_BATCH", 256))
 TEXT_ROWS, AUDIO_ROWS, NEW_FRAMES = 200, 250, int(os.environ.get("MTTS_BENCH_FRAMES", 375))
 FRAME_S = 0.08
 METRIC = "audio-sec generated/sec (RTF), LM decode + codec decode, whole job"
 UNIT = "audio_s/s"
-WORKLOAD = (f"C3+codec: v0.5-shaped LM bf16 greedy decode, batch {BATCH}/GPU, prompt {TEXT_ROWS} text + {AUDIO_ROWS} audio rows "
-            f"(2x10 s), {NEW_FRAMES} new frames ({NEW_FRAMES * FRAME_S:.0f} s) per script, then XY_Tokenizer.decode to 24 kHz")
+TEXT_MIN, TEXT_MAX = 64, 512
+WORKLOAD = (f"C5: end-to-end LM + codec, v0.5-shaped LM bf16 greedy decode, batch {BATCH} scripts/GPU, prompts of "
+            f"{TEXT_MIN}..{TEXT_MAX} text rows (ragged, left-padded) + {AUDIO_ROWS} audio rows (2x10 s), {NEW_FRAMES} new frames "
+            f"({NEW_FRAMES * FRAME_S:.0f} s) per script, then XY_Tokenizer.decode to 24 kHz")
 
 
 def make_prompt(rng, B, text_rows, audio_rows):
@@ -53,6 +56,23 @@ def make_prompt(rng, B, text_rows, audio_rows):
     for i in range(C):
         sh[:, i:n + i, i] = g[:, :, i]
     return sh, np.ones((B, n + C - 1), dtype=np.float64)
+
+
+def make_ragged_prompts(rng, B, audio_rows):
+    """C5 prompts: per script a text part of TEXT_MIN..TEXT_MAX rows + `audio_rows` prompt-audio rows, delay-shifted
+    (+7 rows) and LEFT-padded to the longest script with mask 0 (generation_utils.process_inputs / rpadding)."""
+    lo, hi, C = 151665, 152689, 8
+    lens = rng.integers(TEXT_MIN, TEXT_MAX + 1, B)
+    T = int(lens.max()) + audio_rows + C - 1
+    ids = np.full((B, T, C), 1024, dtype=np.int64)
+    ids[:, :, 0] = 151643
+    mask = np.zeros((B, T), dtype=np.float64)
+    for b in range(B):
+        one, _ = make_prompt(rng, 1, int(lens[b]), audio_rows)
+        n = one.shape[1]
+        ids[b, T - n:] = one[0]
+        mask[b, T - n:] = 1.0
+    return ids, mask, lens
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -191,7 +211,7 @@ def main():
         spt = XY_Tokenizer(yaml.safe_load(f)["generator_params"])
     spt.init_random_weights(seed=5, device=dev)
     rng = np.random.default_rng(1000 + rank)
-    ids_np, mask_np = make_prompt(rng, BATCH, TEXT_ROWS, AUDIO_ROWS)
+    ids_np, mask_np, text_lens = make_ragged_prompts(rng, BATCH, AUDIO_ROWS)
     ids_host = torch.from_numpy(ids_np).pin_memory()
     mask_host = torch.from_numpy(mask_np).pin_memory()
     ids_dev, mask_dev = ids_host.to(dev), mask_host.to(dev)
@@ -271,7 +291,7 @@ def main():
     e2e = frames_e * FRAME_S / (ms_e / 1e3)
 
     # ---- roofline leg: the dominant kernel of the step (dense-projection GEMM of the decode step, M = batch)
-    roof = None
+    roof = roof_other = None
     if rank == 0:
         from moss_ttsd_b200 import ops
         w = model._w
@@ -324,10 +344,50 @@ def main():
                 traffic = json.load(f).get("dram_bytes_per_launch")
         except Exception:
             pass
-        roof = {"kernel": "gemm_tc_kernel<bf16, BN=64> (decode-step dense projections, M=batch)", "bound": "hbm",
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": algo / nl, "avg_launch_us": per_launch_ms * 1e3, "traffic": traffic}
+        gemm_roof = {"kernel": f"gemm_tc_kernel<bf16> (decode-step dense projections, M = {BATCH} rows, cluster split-K)", "bound": "hbm",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                     "algorithmic_bytes_per_launch": algo / nl, "avg_launch_us": per_launch_ms * 1e3, "traffic": traffic,
+                     "launches_per_decode_step": nl + 1, "us_per_decode_step": per_launch_ms * 1e3 * nl}
+        # ---- decode attention over the KV cache the timed batches left behind (K+V of every cached token of every row)
+        sess = model._session
+        cache = sess["cache"]
+        ctx_rows = torch.from_numpy((text_lens + AUDIO_ROWS + 7 + NEW_FRAMES // 2).astype(np.int32)).to(dev)
+        q = torch.randn(BATCH, SHAPE["num_attention_heads"] * SHAPE["head_dim"], device=dev).to(torch.bfloat16)
+        ao = torch.empty_like(q)
+
+        def attn_sweep():
+            for l in range(len(w.layers)):
+                _lib.check(L.mtts_gqa_attention(q.data_ptr(), cache.k[l].data_ptr(), cache.v[l].data_ptr(), _lib.ptr(cache.block_table),
+                                                cache.max_pages, cache.page_size, None, None, None, ctx_rows.data_ptr(), ao.data_ptr(),
+                                                BATCH, 1, SHAPE["num_attention_heads"], SHAPE["num_key_value_heads"],
+                                                SHAPE["head_dim"], 1, None, 0, _lib.stream_ptr()))
+
+        attn_sweep()
+        torch.cuda.synchronize()
+        ag = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ag):
+            attn_sweep()
+        for _ in range(3):
+            ag.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            ag.replay()  # 28 layers x (K + V of ~700 rows x 256 sequences) = 21 GB per sweep >> L2
+        e1.record()
+        torch.cuda.synchronize()
+        a_ms = e0.elapsed_time(e1) / (reps * len(w.layers))
+        a_bytes = float((ctx_rows.sum().item() + BATCH)) * 2 * SHAPE["num_key_value_heads"] * SHAPE["head_dim"] * 2 + 2 * q.numel() * 2
+        a_ach = a_bytes / (a_ms * 1e-3) / 1e9
+        attn_roof = {"kernel": "gqa_decode_tc_kernel<G=2> (decode attention over the KV cache, one query row per sequence)",
+                     "bound": "hbm", "achieved": a_ach, "peak": peak, "unit": "GB/s", "frac": a_ach / peak,
+                     "peak_source": gemm_roof["peak_source"], "algorithmic_bytes_per_launch": a_bytes,
+                     "avg_launch_us": a_ms * 1e3, "traffic": None, "launches_per_decode_step": len(w.layers),
+                     "us_per_decode_step": a_ms * 1e3 * len(w.layers), "mean_context_rows": float(ctx_rows.float().mean().item()),
+                     "note": "peak is the measured COPY bandwidth (read + write); a read-only stream can exceed it "
+                             "(the weight stream of mtts_decode_mega reads at 7.1-7.7 TB/s)"}
+        # the dominant kernel of the step is the one with the larger share of a decode step
+        roof, roof_other = (attn_roof, gemm_roof) if attn_roof["us_per_decode_step"] >= gemm_roof["us_per_decode_step"] else (gemm_roof, attn_roof)
 
     cpu = None
     if rank == 0 and world == 1 and os.environ.get("MTTS_BENCH_SKIP_CPU", "0") != "1":
@@ -371,14 +431,15 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (random-init weights, random prompt grids)",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "prompt_rows": T, "new_frames": NEW_FRAMES,
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "prompt_rows_padded": T,
+                       "prompt_rows_mean": float(text_lens.mean()) + AUDIO_ROWS + 7, "new_frames": NEW_FRAMES,
                        "kv_cache": "contiguous", "sampling": "greedy", "codec": "fp32 storage, TF32 tensor-core GEMMs",
-                       "l2": "no flush needed: 3.5 GB weights + >4 GB KV per step exceed the 126 MB L2"},
+                       "l2": "no flush needed: 3.5 GB weights + ~20 GB KV per decode step exceed the 126 MB L2"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e / args.steps},
             "phases_ms_per_step": {"lm_generate": gen_ms, "codec_decode": codec_ms},
             "decode_step_latency": lat,
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_other": roof_other, "cpu_baseline": cpu,
         }))
     if world > 1:
         dist.destroy_process_group()
