@@ -116,3 +116,50 @@ def test_mega_rejects_unsupported_shapes():
     import ctypes
     rc = L.mtts_decode_mega(ctypes.byref(args), None)
     assert rc != 0 and b"unsupported shape" in L.mtts_last_error()
+
+
+def test_full_width_decode_logits_match_the_fp32_oracle():
+    """Teacher-forced decode-step logits of BOTH decode paths (kernel chain, persistent kernel) at the real model width
+    (2 layers, tied 152697-row heads) against the fp32 oracle restatement of the reference (oracle/lm_oracle.py)."""
+    from moss_ttsd_b200.lm_engine import DecoderEngine, KVCache, LMShape, LMWeights, SamplerSetup
+    from oracle import lm_oracle
+    shape_d = dict(hidden_size=2048, intermediate_size=6144, num_hidden_layers=2, num_attention_heads=16,
+                   num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-6, rope_theta=1e6, vocab_size=152697,
+                   speech_vocab_size=1025, channels=8, speech_token_range=[151665, 152689])
+    sd = lm_oracle.make_weights(shape_d, 77, tied=True)
+    shape = LMShape(num_hidden_layers=2)
+    w = LMWeights(shape, "cuda").load_state_dict(sd, tie_word_embeddings=True)
+    rng = np.random.default_rng(5)
+    B, P, n = 2, 24, 6
+    full = np.zeros((B, P + n, 8), dtype=np.int64)
+    full[:, :, 0] = rng.integers(151665, 152689, (B, P + n))
+    full[:, :, 1:] = rng.integers(0, 1024, (B, P + n, 7))
+    mask = np.ones((B, P + n), dtype=np.int64)
+    mask[1, :3] = 0
+    ref = lm_oracle.OracleLM(shape_d, sd, torch.float32).logits_all(torch.from_numpy(full), torch.from_numpy(mask))
+    ref = torch.cat([r for r in ref], dim=-1)  # (B, P+n, sum vocab), unpadded heads
+    offs, vocabs = shape.head_offsets, shape.vocabs
+    ids, m = torch.from_numpy(full).cuda(), torch.from_numpy(mask).cuda()
+    worst = {}
+    for name, use_mega in (("chain", False), ("mega", True)):
+        eng = DecoderEngine(w)
+        eng.use_mega, eng.use_graph, eng.mega_max_b = use_mega, False, 4
+        cache = KVCache(shape, B, 128, "cuda")
+        st = eng.make_decode_state(B, cache, SamplerSetup(shape, [False] * 8, None), 128, (151665, 152689), 152694, False)
+        eng.reset_decode_state(st, 0, P, 100)
+        lg, lens = eng.prefill(ids[:, :P], m[:, :P], cache)
+        st["positions"].copy_((lens - 1).to(torch.int32))
+        eng.sample_and_advance(st, lg)
+        assert (st["mega"] is not None) == use_mega
+        err = 0.0
+        for k in range(n):
+            st["tokens"].copy_(ids[:, P + k])
+            eng.decode_step(st)
+            got = st["logits"].float().cpu()
+            got = torch.cat([got[:, offs[c]:offs[c] + vocabs[c]] for c in range(8)], dim=-1)
+            err = max(err, (got - ref[:, P + k]).abs().max().item())
+        worst[name] = err
+    scale = ref.abs().max().item()
+    # bf16 activations / weights against an fp32 reference: a few bf16 ulps of the largest logit
+    assert worst["chain"] <= 0.03 * max(1.0, scale), (worst, scale)
+    assert worst["mega"] <= 0.03 * max(1.0, scale), (worst, scale)
