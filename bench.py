@@ -379,10 +379,16 @@ def main():
         a_ms = e0.elapsed_time(e1) / (reps * len(w.layers))
         a_bytes = float((ctx_rows.sum().item() + BATCH)) * 2 * SHAPE["num_key_value_heads"] * SHAPE["head_dim"] * 2 + 2 * q.numel() * 2
         a_ach = a_bytes / (a_ms * 1e-3) / 1e9
+        a_traffic = None
+        try:  # dram__bytes_read + dram__bytes_write of one launch at batch 256 / context 720 (uniform), ncu --set full
+            with open(os.path.join(ROOT, "profiles", "attn_traffic.json")) as f:
+                a_traffic = json.load(f).get("dram_bytes_per_launch") if BATCH == 256 else None
+        except Exception:
+            pass
         attn_roof = {"kernel": "gqa_decode_tc_kernel<G=2> (decode attention over the KV cache, one query row per sequence)",
                      "bound": "hbm", "achieved": a_ach, "peak": peak, "unit": "GB/s", "frac": a_ach / peak,
                      "peak_source": gemm_roof["peak_source"], "algorithmic_bytes_per_launch": a_bytes,
-                     "avg_launch_us": a_ms * 1e3, "traffic": None, "launches_per_decode_step": len(w.layers),
+                     "avg_launch_us": a_ms * 1e3, "traffic": a_traffic, "launches_per_decode_step": len(w.layers),
                      "us_per_decode_step": a_ms * 1e3 * len(w.layers), "mean_context_rows": float(ctx_rows.float().mean().item()),
                      "note": "peak is the measured COPY bandwidth (read + write); a read-only stream can exceed it "
                              "(the weight stream of mtts_decode_mega reads at 7.1-7.7 TB/s)"}
