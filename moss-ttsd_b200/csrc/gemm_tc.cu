@@ -795,12 +795,10 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   if (flags & MTTS_EPI_SWIGLU)
     MTTS_REQUIRE((N % 4) == 0 && !(flags & ~MTTS_EPI_SWIGLU), "mtts_gemm: SWIGLU needs N % 4 == 0 and no other flags");
 
-  int bn = mtts_gemm_tc_pick_bn(M);
-  // batch 129..256 against a wide matrix (gate/up: 96 weight tiles): one 256-row activation tile per CTA in the
-  // persistent kernel reads every activation byte once per weight tile instead of once per (tile, split) and needs
-  // no split-K reduction (measured at M = 256, N = 12288: 21 us against 30 us); narrow matrices keep the cluster
-  // split-K kernel, which is the only way to put all SMs on 16-32 weight tiles
-  if (bn == 128 && M > 128 && ceil_div(N, kBlockW) * 5 >= mtts_num_sms() * 3) bn = 256;
+  const int bn = mtts_gemm_tc_pick_bn(M);
+  // (Routing wide matrices at batch 129..256 to the persistent 256-row-tile kernel wins in isolation — 21 vs 30 us at
+  // N = 12288 — but loses inside a decode step, 5.31 vs 5.23 ms at batch 256: its one-CTA-per-SM footprint keeps the
+  // neighbouring launches from becoming resident early and prefetching their weights.)
   const int bk = kSwizzleBytes / eb;
   GemmParams p;
   memset(&p, 0, sizeof(p));
