@@ -799,9 +799,10 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   // (Routing wide matrices at batch 129..256 to the persistent 256-row-tile kernel wins in isolation — 21 vs 30 us at
   // N = 12288 — but loses inside a decode step, 5.31 vs 5.23 ms at batch 256: its one-CTA-per-SM footprint keeps the
   // neighbouring launches from becoming resident early and prefetching their weights.)
-  // The LM heads at batch 129..256 (1250 weight tiles) are a many-tile problem like prefill: one 256-row activation
-  // tile per CTA in the persistent kernel (145 us against 330 us with two 128-row tiles per weight tile).
-  if (bn == 128 && M > 128 && ceil_div(N, kBlockW) >= 4 * mtts_num_sms()) bn = 256;
+  // The LM heads at batch 65..256 (1250 weight tiles) are a many-tile problem like prefill: one 256-row activation
+  // tile per CTA in the persistent kernel (batch 128: 145 us against 176 us; batch 256: 165 us against 330 us with
+  // two 128-row tiles per weight tile).
+  if (bn == 128 && ceil_div(N, kBlockW) >= 4 * mtts_num_sms()) bn = 256;
   const int bk = kSwizzleBytes / eb;
   GemmParams p;
   memset(&p, 0, sizeof(p));
