@@ -96,6 +96,50 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const bf16* __restrict__ x
   }
 }
 
+// Decode-sized variant (hidden == 2048): one WARP per row, the row stays in registers (8 x 16 B per lane), the
+// statistic is a shuffle reduction — no shared memory, no block barrier, one pass over the data. 3.9 -> ~2 us per
+// launch, and a decode step has 57 of them.
+__global__ void __launch_bounds__(256) rmsnorm_warp_kernel(const bf16* __restrict__ x, long long ldx,
+                                                           const bf16* __restrict__ w, bf16* __restrict__ out,
+                                                           long long ldo, int rows, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const bf16* xr = x + row * ldx;
+  uint4 u[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u[i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t a[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lo = bf16lo(a[j]), hi = bf16hi(a[j]);
+      ss = fmaf(lo, lo, ss);
+      ss = fmaf(hi, hi, ss);
+    }
+  }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(ss * (1.0f / 2048.0f) + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 wv = *reinterpret_cast<const uint4*>(w + (i * 32 + lane) * 8);
+    const uint32_t a[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+    const uint32_t b[4] = {wv.x, wv.y, wv.z, wv.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lo = bf16_round(bf16lo(a[j]) * inv) * bf16lo(b[j]);
+      const float hi = bf16_round(bf16hi(a[j]) * inv) * bf16hi(b[j]);
+      o[j] = pack_bf16(lo, hi);
+    }
+    *reinterpret_cast<uint4*>(out + row * ldo + (i * 32 + lane) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Per-head q/k RMSNorm + RoPE + KV-cache append (HF Qwen3Attention.forward, installed
 // modeling_qwen3.py:236-271; apply_rotary_pos_emb :86-181; DynamicCache.update replaced by an in-place
@@ -241,6 +285,13 @@ extern "C" int mtts_rmsnorm(const void* x, long long ldx, const void* w, void* o
                "mtts_rmsnorm: hidden and strides must be multiples of 8");
   if (rows <= 0) return MTTS_OK;
   MTTS_REQUIRE(x && w && out, "mtts_rmsnorm: null pointer");
+  if (hidden == 2048 && rows <= 1024) {  // decode steps: a warp per row, 2 rows per CTA (spread over the SMs)
+    MTTS_CUDA_CHECK(mtts_launch(rmsnorm_warp_kernel, dim3((rows + 1) / 2), dim3(64), 0, stream,
+                                reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(w),
+                                reinterpret_cast<bf16*>(out), ldo, rows, eps));
+    MTTS_LAUNCH_CHECK();
+    return MTTS_OK;
+  }
   MTTS_CUDA_CHECK(mtts_launch(rmsnorm_kernel, dim3(rows), dim3(256), 0, stream, reinterpret_cast<const bf16*>(x), ldx,
                               reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(out), ldo, hidden, eps));
   MTTS_LAUNCH_CHECK();
