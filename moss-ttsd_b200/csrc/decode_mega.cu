@@ -7,7 +7,7 @@
 //   * every weight matrix [N, K] is split by OUTPUT ROWS over the CTAs (full K per CTA -> no cross-CTA reduction);
 //     a CTA's share of a matrix is one contiguous byte range of the row-major matrix;
 //   * one producer warp per CTA walks the CTA's shares of ALL matrices of the step, in order, and streams them
-//     with 1-D bulk async copies (TMA engine, mbarrier complete_tx) into a 5-stage shared-memory ring of
+//     with 1-D bulk async copies (TMA engine, mbarrier complete_tx) into a 4-stage shared-memory ring of
 //     [16 rows x 1024 k] chunks; it depends on nothing but ring space, so HBM keeps streaming while the consumer
 //     warps wait for activations, normalise, or run attention;
 //   * 16 consumer warps split a chunk along K (64 k each); weights are the A operand of bf16 mma.sync m16n8k16
@@ -48,11 +48,18 @@ constexpr int kRowBytes = kChunkK * 2;
 constexpr int kRowPitch = kRowBytes + 16;     // 16-byte skew per row: ldmatrix phases hit 32 distinct banks
 constexpr int kTileRows = 16;
 constexpr int kStageBytes = kTileRows * kRowPitch;
-constexpr int kStages = 5;
+// Four stages, not five: with five the CTA needs the 228 KB shared-memory carve-out, which leaves 28 KB of L1 for the
+// stack frames of 544 threads and the read-only loads; four stages fit the 196 KB carve-out (60 KB of L1) and the
+// step is 5 % (batch 1) to 9 % (batch 2) faster. Three stages (164 KB) lose again: the ring gets too shallow.
+#ifndef MTTS_MEGA_STAGES
+#define MTTS_MEGA_STAGES 4
+#endif
+constexpr int kStages = MTTS_MEGA_STAGES;
 constexpr int kMaxB = 4;
 constexpr int kActPitch = kI + 8;             // bf16 elements; rows 12304 B apart -> conflict-free B-fragment loads
 constexpr int kWsStride = kD + 4;             // attention partial: [M, L, -, -, O[128]] (one LL word per float)
 constexpr int kTagsPerLayer = 8;
+
 constexpr int kRedTile = kTileRows * kMaxB;   // floats one warp contributes to the tile reduction
 constexpr int kMaxCtas = 160;
 
@@ -661,7 +668,14 @@ __device__ __noinline__ void rope_table(float pos, const float* inv_freq, float*
 
 // ------------------------------------------------------------------ the kernel
 template <int kB>
-__global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaParams p) {
+__global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaParams p_in) {
+  // The parameter block is handed to the (non-inlined) phase routines by reference. A reference to the kernel argument
+  // would make the compiler keep a per-thread copy in LOCAL memory (a 400-byte stack frame per thread, served by
+  // whatever L1 the 227 KB of shared memory leave over); one shared copy per CTA is read with LDS instead.
+  __shared__ MegaParams s_params;
+  if (threadIdx.x == 0) s_params = p_in;
+  __syncthreads();
+  const MegaParams& p = p_in;  // the kernel body itself reads the constant bank
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* ring = smem;
   bf16* act = reinterpret_cast<bf16*>(smem + kSmemRing);
@@ -736,7 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
           __syncwarp();
           if (lane < nrows)
             bulk_g2s(rg.stages + st * kStageBytes + lane * kRowPitch, w + (size_t)(r + lane) * K + (size_t)kc * kChunkK,
-                     kRowBytes, &rg.full[st], kEvictFirst);
+                     kRowBytes, &rg.full[st], kEvictFirst);  // evict-normal instead: 13 % slower
           ++rg.it;
         }
       }
@@ -792,37 +806,37 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
     const uint32_t tg = tag0 + (uint32_t)l * kTagsPerLayer;
     MEGA_TICK(13)
     if (l == NL) {  // final norm + LM heads
-      stage_norm<kB>(p, p.x_ll[0], tg - kTagsPerLayer + 5, sent_wd, n_gemv, nullptr, p.final_norm, act, scratch, Slice{0, 0},
+      stage_norm<kB>(s_params, p.x_ll[0], tg - kTagsPerLayer + 5, sent_wd, n_gemv, nullptr, p.final_norm, act, scratch, Slice{0, 0},
                      res_wo);
       MEGA_TICK(14)
-      consume_matrix<kB>(rg, p, s_heads, 2, EPI_HEADS, act, red, red_buf, nullptr, 0, nullptr, 0u);
+      consume_matrix<kB>(rg, s_params, s_heads, 2, EPI_HEADS, act, red, red_buf, nullptr, 0, nullptr, 0u);
       MEGA_TICK(15)
       break;
     }
     const mtts_lm_layer& L = p.layers[l];
-    stage_norm<kB>(p, p.x_ll[0], tg - kTagsPerLayer + 5, sent_wd, n_gemv, l == 0 ? p.x_in : nullptr,
+    stage_norm<kB>(s_params, p.x_ll[0], tg - kTagsPerLayer + 5, sent_wd, n_gemv, l == 0 ? p.x_in : nullptr,
                    reinterpret_cast<const bf16*>(L.ln1), act, scratch, sl[1], res_wo);
     MEGA_TICK(0)
-    consume_matrix<kB>(rg, p, sl[0], 2, EPI_QKV, act, red, red_buf, p.qkv_ll, kNQKV / 2, nullptr, tg + 1);
+    consume_matrix<kB>(rg, s_params, sl[0], 2, EPI_QKV, act, red, red_buf, p.qkv_ll, kNQKV / 2, nullptr, tg + 1);
     MEGA_TICK(1)
     if (has_unit) {
       const AttnLayer al{reinterpret_cast<const bf16*>(L.k_pool), reinterpret_cast<const bf16*>(L.v_pool),
                          reinterpret_cast<const bf16*>(L.q_norm), reinterpret_cast<const bf16*>(L.k_norm)};
-      attention_layer(p, al, un, cta, reinterpret_cast<float*>(act), rope, tg + 1, tg + 2);
+      attention_layer(s_params, al, un, cta, reinterpret_cast<float*>(act), rope, tg + 1, tg + 2);
     }
     MEGA_TICK(3)
-    stage_attn_out<kB>(p, act, tg + 2);
+    stage_attn_out<kB>(s_params, act, tg + 2);
     MEGA_TICK(5)
-    consume_matrix<kB>(rg, p, sl[1], 2, EPI_WO, act, red, red_buf, p.x_ll[1], kH / 2, res_wo, tg + 3);
+    consume_matrix<kB>(rg, s_params, sl[1], 2, EPI_WO, act, red, red_buf, p.x_ll[1], kH / 2, res_wo, tg + 3);
     MEGA_TICK(6)
-    stage_norm<kB>(p, p.x_ll[1], tg + 3, sent_wo, n_gemv, nullptr, reinterpret_cast<const bf16*>(L.ln2), act, scratch, sl[3],
+    stage_norm<kB>(s_params, p.x_ll[1], tg + 3, sent_wo, n_gemv, nullptr, reinterpret_cast<const bf16*>(L.ln2), act, scratch, sl[3],
                    res_wd);
     MEGA_TICK(8)
-    consume_matrix<kB>(rg, p, sl[2], 2, EPI_GU, act, red, red_buf, p.h_ll, kI / 2, nullptr, tg + 4);
+    consume_matrix<kB>(rg, s_params, sl[2], 2, EPI_GU, act, red, red_buf, p.h_ll, kI / 2, nullptr, tg + 4);
     MEGA_TICK(9)
-    stage_h<kB>(p, tg + 4, sent_gu, n_gemv, act);
+    stage_h<kB>(s_params, tg + 4, sent_gu, n_gemv, act);
     MEGA_TICK(11)
-    consume_matrix<kB>(rg, p, sl[3], 6, EPI_WD, act, red, red_buf, p.x_ll[0], kH / 2, res_wd, tg + 5);
+    consume_matrix<kB>(rg, s_params, sl[3], 6, EPI_WD, act, red, red_buf, p.x_ll[0], kH / 2, res_wd, tg + 5);
     MEGA_TICK(12)
   }
 #undef MEGA_TICK
