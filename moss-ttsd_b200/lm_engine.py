@@ -262,12 +262,12 @@ class DecoderEngine:
         self.err = torch.zeros(4, dtype=torch.int32, device=self.dev)
         self.use_graph = os.environ.get("MTTS_NO_GRAPH", "0") != "1"
         # batch <= mega_max_b: the whole step (layer stack + LM heads) is ONE persistent kernel. Measured on B200
-        # (ms/step, ctx 460): batch 1: 1.06 vs 1.44 for the kernel chain, batch 2: 1.19 vs 1.46, batch 4: 1.63 vs 1.50.
+        # (ms/step, ctx 460): batch 1: 1.00 vs 1.44 for the kernel chain, batch 2: 1.09 vs 1.46, batch 4: 1.35 vs 1.36.
         self.use_mega = os.environ.get("MTTS_NO_MEGA", "0") != "1"
         # decode steps of the kernel chain: q/k norm + RoPE + cache append run inside the attention kernel
         self.fused_decode_attn = (os.environ.get("MTTS_ATTN_FUSED", "1") != "0" and os.environ.get("MTTS_ATTN_SIMT", "0") != "1"
                                   and s.head_dim == 128 and s.num_attention_heads // s.num_key_value_heads in (1, 2, 4))
-        self.mega_max_b = int(os.environ.get("MTTS_MEGA_MAX_B", "2"))
+        self.mega_max_b = int(os.environ.get("MTTS_MEGA_MAX_B", "4"))
         self.prefill_tile_rows = int(os.environ.get("MTTS_PREFILL_TILE", "64"))  # 64: tensor-core tiles, 4: CUDA cores
         self.graph_replayed_launches = 0  # kernels executed through graph replays (not seen by mtts_launch_count)
 
