@@ -936,14 +936,14 @@ extern "C" int mtts_decode_mega(const mtts_decode_mega_args* a, void* stream_) {
   p.err_flag = a->err_flag;
   p.prof = a->profile_cycles;
   {
-    // batch 1: every thread polls the words it needs directly (2.6 % faster: one round trip less per exchange);
-    // batch >= 2: a sentinel warp first, the poll traffic of 148 x 512 threads grows with the batch
+    // one sentinel warp per CTA before the CTA-wide verified load (MTTS_MEGA_SENTINEL=0: every thread polls the words
+    // it needs directly — 3.5 % slower at batch 1 and 4, 1 % at batch 2)
     static int sen = -1;
     if (sen < 0) {
       const char* e = getenv("MTTS_MEGA_SENTINEL");
-      sen = e ? (e[0] == '0' ? 0 : 1) : 2;
+      sen = (e && e[0] == '0') ? 0 : 1;
     }
-    p.sentinel = sen == 2 ? (a->B > 1 ? 1 : 0) : sen;
+    p.sentinel = sen;
   }
 
   cudaLaunchConfig_t cfg;
