@@ -243,7 +243,7 @@ typedef struct mtts_decode_mega_args {
   int max_pages, page_size, num_pages;
   const void* x;
   void* logits; long long ld_logits;
-  int B; int nsplit;              /* split-KV factor, 1..4; B * num_kv_heads * nsplit <= SM count */
+  int B; int nsplit;              /* split-KV factor, 1..16; B * num_kv_heads * nsplit <= SM count */
   float eps;
   void* workspace; long long workspace_bytes;
   int* err_flag;                  /* set to 2 when a position falls outside the page table */

@@ -173,7 +173,10 @@ __device__ __forceinline__ int last_tile_row(Slice s) { return s.r0 + ((s.r1 - s
 // them are computed once per launch.
 __host__ __device__ constexpr int mat_rows(int m) { return m == 0 ? kNQKV : (m == 2 ? 2 * kI : kH); }
 __host__ __device__ constexpr int mat_unit(int m) { return m == 2 ? 4 : 2; }
-__host__ __device__ constexpr int mat_rot(int m) { return m * 37; }
+#ifndef MTTS_MEGA_ROT
+#define MTTS_MEGA_ROT 0
+#endif
+__host__ __device__ constexpr int mat_rot(int m) { return m * MTTS_MEGA_ROT; }
 
 // Polling by all 512 consumer threads of all CTAs would swamp the L2 request queues that the weight stream also
 // needs, so before a CTA-wide verified load ONE warp watches a sentinel word per producer CTA (the first word of the
@@ -402,7 +405,7 @@ __device__ __noinline__ void stage_attn_out(const MegaParams& p, bf16* act, uint
     while (true) {
       bool ok = true;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 5; ++i) {
         const int u = lane + 32 * i;
         uint32_t d, t = tag;
         if (u < units) ll_issue(p.ws_ll + ((size_t)u * kG + 1) * kWsStride + 4 + 127, d, t);
@@ -419,37 +422,45 @@ __device__ __noinline__ void stage_attn_out(const MegaParams& p, bf16* act, uint
     const int head = rem >> 5, d4 = (rem & 31) * 4;
     const int hk = head / kG, g = head % kG;
     const uint2* base = p.ws_ll + ((size_t)((b * kHkv + hk) * p.nsplit) * kG + g) * kWsStride;
-    float ms[4], ls[4];
-    float4 ov[4];
-    LLSpin sp;
-    while (true) {
-      bool ok = true;
+    // splits are merged four at a time (one polling batch each), groups with a running online-softmax state
+    float M = -1e30f, L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int s0 = 0; s0 < p.nsplit; s0 += 4) {
+      float ms[4], ls[4];
+      float4 ov[4];
+      LLSpin sp;
+      while (true) {
+        bool ok = true;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          uint32_t d[6] = {0xff800000u, 0u, 0u, 0u, 0u, 0u}, t[6] = {tag, tag, tag, tag, tag, tag};  // absent split: M = -inf
+          if (s0 + s < p.nsplit) {
+            const uint2* w0 = base + (size_t)(s0 + s) * kG * kWsStride;
+            ll_issue2(w0, d[0], t[0], d[1], t[1]);
+            ll_issue2(w0 + 4 + d4, d[2], t[2], d[3], t[3]);
+            ll_issue2(w0 + 6 + d4, d[4], t[4], d[5], t[5]);
+          }
+          ms[s] = __uint_as_float(d[0]); ls[s] = __uint_as_float(d[1]);
+          ov[s] = make_float4(__uint_as_float(d[2]), __uint_as_float(d[3]), __uint_as_float(d[4]), __uint_as_float(d[5]));
+#pragma unroll
+          for (int i = 0; i < 6; ++i) ok = ok && (t[i] == tag);
+        }
+        if (ok) break;
+        sp.miss(tag);
+      }
+      float Mn = M;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) Mn = fmaxf(Mn, ms[s]);
+      const float c = ex2(M - Mn);
+      M = Mn;
+      L *= c;
+      o[0] *= c; o[1] *= c; o[2] *= c; o[3] *= c;
 #pragma unroll
       for (int s = 0; s < 4; ++s) {
-        uint32_t d[6] = {0xff800000u, 0u, 0u, 0u, 0u, 0u}, t[6] = {tag, tag, tag, tag, tag, tag};  // absent split: M = -inf
-        if (s < p.nsplit) {
-          const uint2* w0 = base + (size_t)s * kG * kWsStride;
-          ll_issue2(w0, d[0], t[0], d[1], t[1]);
-          ll_issue2(w0 + 4 + d4, d[2], t[2], d[3], t[3]);
-          ll_issue2(w0 + 6 + d4, d[4], t[4], d[5], t[5]);
-        }
-        ms[s] = __uint_as_float(d[0]); ls[s] = __uint_as_float(d[1]);
-        ov[s] = make_float4(__uint_as_float(d[2]), __uint_as_float(d[3]), __uint_as_float(d[4]), __uint_as_float(d[5]));
-#pragma unroll
-        for (int i = 0; i < 6; ++i) ok = ok && (t[i] == tag);
+        const float w = ex2(ms[s] - M);
+        L = fmaf(ls[s], w, L);
+        o[0] = fmaf(ov[s].x, w, o[0]); o[1] = fmaf(ov[s].y, w, o[1]); o[2] = fmaf(ov[s].z, w, o[2]); o[3] = fmaf(ov[s].w, w, o[3]);
       }
-      if (ok) break;
-      sp.miss(tag);
-    }
-    float M = -1e30f;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) M = fmaxf(M, ms[s]);
-    float L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      const float w = ex2(ms[s] - M);
-      L = fmaf(ls[s], w, L);
-      o[0] = fmaf(ov[s].x, w, o[0]); o[1] = fmaf(ov[s].y, w, o[1]); o[2] = fmaf(ov[s].z, w, o[2]); o[3] = fmaf(ov[s].w, w, o[3]);
     }
     const float inv = 1.0f / L;
     *reinterpret_cast<uint2*>(act + b * kActPitch + head * kD + d4) =
@@ -759,12 +770,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
   }
 
   // ---------------- consumer warps
-  const bool has_unit = cta < n_attn;
+#ifndef MTTS_MEGA_UNIT_STRIDE
+#define MTTS_MEGA_UNIT_STRIDE 1
+#endif
+  const bool has_unit = (cta % MTTS_MEGA_UNIT_STRIDE) == 0 && cta / MTTS_MEGA_UNIT_STRIDE < n_attn;
+  const int unit_id = cta / MTTS_MEGA_UNIT_STRIDE;
   AttnUnit un;
   if (has_unit) {
-    const int split = cta % p.nsplit;
-    un.hk = (cta / p.nsplit) % kHkv;
-    un.b = cta / (p.nsplit * kHkv);
+    const int split = unit_id % p.nsplit;
+    un.hk = (unit_id / p.nsplit) % kHkv;
+    un.b = unit_id / (p.nsplit * kHkv);
     un.pos = p.positions[un.b];
     const int kv_len = un.pos + 1;
     const int per = ((kv_len + p.nsplit - 1) / p.nsplit + 31) / 32 * 32;
@@ -822,7 +837,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
     if (has_unit) {
       const AttnLayer al{reinterpret_cast<const bf16*>(L.k_pool), reinterpret_cast<const bf16*>(L.v_pool),
                          reinterpret_cast<const bf16*>(L.q_norm), reinterpret_cast<const bf16*>(L.k_norm)};
-      attention_layer(s_params, al, un, cta, reinterpret_cast<float*>(act), rope, tg + 1, tg + 2);
+      attention_layer(s_params, al, un, unit_id, reinterpret_cast<float*>(act), rope, tg + 1, tg + 2);
     }
     MEGA_TICK(3)
     stage_attn_out<kB>(s_params, act, tg + 2);
@@ -906,9 +921,9 @@ extern "C" int mtts_decode_mega(const mtts_decode_mega_args* a, void* stream_) {
                "mtts_decode_mega: null pointer");
   MTTS_REQUIRE(a->num_layers >= 1 && a->vpad > 0 && a->vpad % 2 == 0, "mtts_decode_mega: bad num_layers / vpad");
   MTTS_REQUIRE(a->page_size > 0 && (a->page_size & (a->page_size - 1)) == 0, "mtts_decode_mega: page_size must be a power of two");
-  MTTS_REQUIRE(a->nsplit >= 1 && a->nsplit <= 4, "mtts_decode_mega: nsplit must be in [1,4]");
-  MTTS_REQUIRE(a->B * a->num_kv_heads * a->nsplit <= mtts_num_sms() / 2,
-               "mtts_decode_mega: B * kv_heads * nsplit attention CTAs must leave at least half of the SMs to the projections");
+  MTTS_REQUIRE(a->nsplit >= 1 && a->nsplit <= 16, "mtts_decode_mega: nsplit must be in [1,16]");
+  MTTS_REQUIRE(a->B * a->num_kv_heads * a->nsplit <= mtts_num_sms(),
+               "mtts_decode_mega: B * kv_heads * nsplit attention units exceed the SM count (one unit per CTA)");
   MTTS_REQUIRE(a->workspace_bytes >= mtts_decode_mega_workspace_bytes(a->B, a->nsplit), "mtts_decode_mega: workspace too small");
   MTTS_REQUIRE((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "mtts_decode_mega: workspace must be 256-byte aligned");
   MTTS_REQUIRE(a->ld_logits >= a->vpad, "mtts_decode_mega: ld_logits < vpad");

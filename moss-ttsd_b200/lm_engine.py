@@ -262,7 +262,8 @@ class DecoderEngine:
         self.err = torch.zeros(4, dtype=torch.int32, device=self.dev)
         self.use_graph = os.environ.get("MTTS_NO_GRAPH", "0") != "1"
         # batch <= mega_max_b: the whole step (layer stack + LM heads) is ONE persistent kernel. Measured on B200
-        # (ms/step, ctx 460): batch 1: 1.00 vs 1.44 for the kernel chain, batch 2: 1.09 vs 1.46, batch 4: 1.35 vs 1.36.
+        # (ms/step, ctx 460): batch 1: 0.97 vs 1.44 for the kernel chain, batch 2: 1.06 vs 1.46, batch 3: 1.16 vs 1.33,
+        # batch 4: 1.22 vs 1.36.
         self.use_mega = os.environ.get("MTTS_NO_MEGA", "0") != "1"
         # decode steps of the kernel chain: q/k norm + RoPE + cache append run inside the attention kernel
         self.fused_decode_attn = (os.environ.get("MTTS_ATTN_FUSED", "1") != "0" and os.environ.get("MTTS_ATTN_SIMT", "0") != "1"
@@ -441,8 +442,9 @@ class DecoderEngine:
             tab[l] = [lw[k].data_ptr() for k in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2", "q_norm", "k_norm")] + \
                      [cache.k[l].data_ptr(), cache.v[l].data_ptr()]
         layers = torch.from_numpy(tab).to(self.dev)
-        # few CTAs per (row, kv head): the o_proj phase of EVERY CTA re-reads all partials
-        nsplit = max(1, min(4, 32 // (B * s.num_key_value_heads)))
+        # one attention unit (row, kv head, key range) per CTA; measured best: 4 key ranges up to batch 3, 3 at batch 4
+        # (~115 keys = 4 passes per unit at ctx 460; more ranges cost more partial reads in every CTA's o_proj phase)
+        nsplit = 4 if B <= 3 else 3
         if os.environ.get("MTTS_MEGA_NSPLIT"):
             nsplit = int(os.environ["MTTS_MEGA_NSPLIT"])
         ws = torch.zeros(self.L.mtts_decode_mega_workspace_bytes(B, nsplit) + 256, dtype=torch.uint8, device=self.dev)
