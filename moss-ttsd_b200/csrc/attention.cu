@@ -785,7 +785,14 @@ int launch_decode_tc(const AttnParams& p, int rows, cudaStream_t stream) {
     const char* e = getenv("MTTS_ATTN_STAGES");
     force_stages = e ? atoi(e) : 0;
   }
-  if (force_stages == 1 || (force_stages == 0 && ctas >= 3LL * mtts_num_sms())) {
+  // One K/V stage: 4 CTAs per SM; two stages: 3 per SM but loads overlap inside the CTA. Time goes with the number of
+  // CTA waves, so the variant that fills its last wave better wins (batch 64: 512 CTAs on 592 slots -> one stage,
+  // 25.6 vs 31.4 us; batch 96: 768 CTAs -> two stages, 45.8 vs 51.9 us); comparable fills favour two stages.
+  const long long slots1 = 4LL * mtts_num_sms(), slots2 = 3LL * mtts_num_sms();
+  const double fill1 = (double)ctas / (double)(((ctas + slots1 - 1) / slots1) * slots1);
+  const double fill2 = (double)ctas / (double)(((ctas + slots2 - 1) / slots2) * slots2);
+  const bool one_stage = force_stages ? force_stages == 1 : fill2 < 0.97 * fill1;
+  if (one_stage) {
     MTTS_CUDA_CHECK(mtts_launch(gqa_decode_tc_kernel<G, 1, FUSED>, grid, dim3(128), (size_t)2 * kTcTileBytes + kTcNewBytes, stream, p));
   } else {
     MTTS_CUDA_CHECK(mtts_launch(gqa_decode_tc_kernel<G, 2, FUSED>, grid, dim3(128), (size_t)4 * kTcTileBytes + kTcNewBytes, stream, p));
