@@ -275,6 +275,18 @@ def main():
         torch.cuda.synchronize()
         return BATCH * n
 
+    if os.environ.get("MTTS_BENCH_LAUNCHLIST", "0") == "1":
+        # launch-list mode for `ncu --metrics gpu__time_duration.sum`: the hot path exactly as the timed region runs it
+        # (prefill, every decode step, un-delay, codec decode), --steps times, and nothing else (no sweeps, no CPU leg)
+        for _ in range(args.warmup):
+            step_resident()
+        ms, frames, launches = timed(args.steps, step_resident)
+        if rank == 0:
+            print(json.dumps({"mode": "launch list (not a bench value)", "steps": args.steps, "warmup": args.warmup,
+                              "batch_per_gpu": BATCH, "new_frames": NEW_FRAMES, "gpu_launches": int(launches)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for _ in range(args.warmup):
         step_resident()
     clocks = ClockSampler(local)

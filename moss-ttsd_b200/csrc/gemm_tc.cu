@@ -764,6 +764,9 @@ static int pick_splits(int tiles, int kb_total, int bn, int tiles_m) {
     forced = e ? atoi(e) : 0;
   }
   if (forced > 0) return forced > 8 ? 8 : forced;
+  // (batch 129..256, two activation tiles per weight tile: raising the target to 3, 4 or 6 CTAs per SM, i.e. splitting
+  // the 192-tile gate/up projection 2 or 4 ways and q/k/v 8 ways, loses in the full step: 5.27 / 5.62 / 5.60 ms against
+  // 4.97 ms at batch 256.)
   const int target = 2 * mtts_num_sms();
   int s = 1;
   while (s < 8 && tiles * (s * 2) <= target && kb_total / (s * 2) >= 2) s *= 2;

@@ -116,6 +116,7 @@ struct SampleParams2 {
   int* err_flag;
   SampleWs ws;
   int total_slices;
+  int chunk;  // kSlice-wide pieces one CTA scans (> 1 only when every channel is greedy and the batch is large)
   unsigned char slice_channel[kMaxSlices];
   unsigned char slice_index[kMaxSlices];
   unsigned char slices_of[8];
@@ -194,16 +195,54 @@ __global__ void __launch_bounds__(kThreads) sample_scan_kernel(const SampleParam
   const int tid = threadIdx.x;
   const int step = *p.step_ptr;
   const ScoreCtx sc = make_ctx(p, b, c, step);
-  const int j0 = slice * kSlice + tid * 8;
-  float sv[8];
-  scores8(sc, j0, V, sv);
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-#pragma unroll
-  for (int e = 0; e < 8; ++e)
-    if (j0 + e < V && better(sv[e], j0 + e, bv, bi)) { bv = sv[e]; bi = j0 + e; }
+  const int j0 = slice * p.chunk * kSlice + tid * 8;
   const long long bc = (long long)b * cfg.channels + c;
   const bool greedy = !cfg.do_sample[c];
+  float sv[8];
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  if (!greedy) {
+    scores8(sc, j0, V, sv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (j0 + e < V && better(sv[e], j0 + e, bv, bi)) { bv = sv[e]; bi = j0 + e; }
+  } else {
+    // Greedy: the scan is issue-bound (ncu: 386 instructions per warp for 8 logits per thread), so a group of 8 raw
+    // logits is first reduced with plain max and only searched for its index when it beats the running best; groups
+    // that contain a masked or penalised entry (or any group under a temperature) take the general path. Large
+    // batches walk `chunk` pieces per CTA, four 16-byte loads in flight per thread.
+    for (int it = 0; it < p.chunk; it += 4) {
+      uint4 u[4];
+      bool fast[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int jq = j0 + (it + q) * kSlice;
+        fast[q] = it + q < p.chunk && jq + 8 <= V;
+        if (fast[q]) u[q] = *reinterpret_cast<const uint4*>(sc.lg + jq);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int jq = j0 + (it + q) * kSlice;
+        if (it + q >= p.chunk || jq >= V) continue;
+        bool plain = fast[q] && !sc.has_temp && !(sc.mask_idx >= jq && sc.mask_idx < jq + 8);
+        if (plain && sc.has_rep) plain = ((sc.seen[jq >> 5] >> (jq & 31)) & 0xffu) == 0u;
+        if (plain) {
+          const float v0 = bf16lo(u[q].x), v1 = bf16hi(u[q].x), v2 = bf16lo(u[q].y), v3 = bf16hi(u[q].y);
+          const float v4 = bf16lo(u[q].z), v5 = bf16hi(u[q].z), v6 = bf16lo(u[q].w), v7 = bf16hi(u[q].w);
+          const float m = fmaxf(fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)), fmaxf(fmaxf(v4, v5), fmaxf(v6, v7)));
+          if (m > bv) {  // pieces are visited in ascending index order: an equal maximum further on never wins
+            bv = m;
+            bi = jq + (v0 == m ? 0 : v1 == m ? 1 : v2 == m ? 2 : v3 == m ? 3 : v4 == m ? 4 : v5 == m ? 5 : v6 == m ? 6 : 7);
+          }
+        } else {
+          scores8(sc, jq, V, sv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (jq + e < V && better(sv[e], jq + e, bv, bi)) { bv = sv[e]; bi = jq + e; }
+        }
+      }
+    }
+  }
   if (greedy) {
     block_argmax(bv, bi, s_val, s_idx);
     if (tid == 0) {
@@ -587,9 +626,17 @@ extern "C" int mtts_sample8(const void* logits, long long ld, int B, const mtts_
   sample_ws_layout(B, cfg->channels, &p.ws, reinterpret_cast<uint8_t*>(workspace));
   int total = 0;
   bool any_sample = false;
+  for (int c = 0; c < cfg->channels; ++c) any_sample |= cfg->do_sample[c] != 0;
+  // sampled channels keep one piece per CTA (their threshold search reports per-thread maxima of one piece)
+  // batch 256: 127 us with one piece per CTA, 87 / 68 / 62 / 63 us with 2 / 4 / 8 / 16; batch 64: 34 / 24 / 20 / 19 / 20 us
+  int chunk = any_sample ? 1 : (B >= 128 ? 8 : B >= 32 ? 4 : B >= 16 ? 2 : 1);
+  if (const char* e = getenv("MTTS_SAMPLE_CHUNK")) {  // experiment knob (scripts/bench_sampler.py)
+    if (!any_sample && atoi(e) >= 1 && atoi(e) <= 38) chunk = atoi(e);
+  }
+  p.chunk = chunk;
   for (int c = 0; c < cfg->channels; ++c) {
     MTTS_REQUIRE(cfg->logit_offset[c] % 8 == 0, "mtts_sample8: logit_offset[%d] must be a multiple of 8", c);
-    const int S = (cfg->vocab[c] + kSlice - 1) / kSlice;
+    const int S = (cfg->vocab[c] + kSlice * chunk - 1) / (kSlice * chunk);
     MTTS_REQUIRE(S <= kMaxSlices && total + S <= kMaxSlices, "mtts_sample8: vocabulary too large for %d slices", kMaxSlices);
     p.slices_of[c] = (unsigned char)S;
     for (int s2 = 0; s2 < S; ++s2) {
@@ -597,7 +644,6 @@ extern "C" int mtts_sample8(const void* logits, long long ld, int B, const mtts_
       p.slice_index[total] = (unsigned char)s2;
       ++total;
     }
-    any_sample |= cfg->do_sample[c] != 0;
   }
   p.total_slices = total;
   MTTS_CUDA_CHECK(mtts_launch(sample_scan_kernel, dim3(B, total), dim3(kThreads), 0, stream, p));

@@ -248,6 +248,51 @@ def test_sampler_support_and_distribution_vs_oracle(model, cfg):
                     assert abs(freq - pv) <= 5 * sigma + 0.01, (c, b, pi, freq, pv)
 
 
+@pytest.mark.parametrize("B", [32, 77, 128, 256])
+def test_greedy_scan_large_batches_matches_argmax(model, B):
+    """At batch >= 32 one CTA of the greedy scan walks several 4096-logit pieces of a row; the result must stay
+    torch.argmax of the processed scores (lowest index on ties), wherever the winner sits in the row."""
+    from moss_ttsd_b200 import _lib
+    from moss_ttsd_b200.lm_engine import SamplerSetup
+    torch.manual_seed(B)
+    shape, eng, C = model.shape, model.engine, 8
+    cfg = dict(repetition_penalty=1.3)
+    logits = torch.zeros((B, shape.vpad), dtype=torch.bfloat16, device="cuda")
+    logits.normal_(0, 1.0)
+    V0, o0 = shape.vocabs[0], shape.head_offsets[0]
+    # planted winners on channel 0: first / last logit, either side of every piece boundary, and exact ties
+    spots = [0, V0 - 1, 4095, 4096, 65535, 65536, 131071, 131072, V0 - 2, 77777]
+    for b in range(B):
+        j = spots[b % len(spots)]
+        logits[b, o0 + j] = 30.0
+        if b % 3 == 0 and j + 5000 < V0:
+            logits[b, o0 + j + 5000] = 30.0  # tie: the lower index wins
+    hist_len = 24
+    hist = [torch.randint(0, shape.vocabs[c], (B, hist_len)) for c in range(C)]
+    for b in range(0, B, 4):
+        hist[0][b, 0] = spots[b % len(spots)]  # penalised winner: 30 / 1.3 still wins, but the value path is exercised
+    grid = torch.stack(hist, -1).cuda()
+    sm = SamplerSetup(shape, [False] * C, [dict(cfg) for _ in range(C)])
+    seen = torch.zeros((B, sm.words_per_row), dtype=torch.int32, device="cuda")
+    _lib.check(eng.L.mtts_sampler_init_history(grid.data_ptr(), B, hist_len, grid.stride(0), ctypes.byref(sm.cfg),
+                                               seen.data_ptr(), _lib.stream_ptr()))
+    step = torch.full((1,), 9, dtype=torch.int32, device="cuda")
+    toks = torch.zeros((B, C), dtype=torch.int64, device="cuda")
+    sws = torch.zeros(eng.L.mtts_sample8_workspace_bytes(B, C), dtype=torch.uint8, device="cuda")
+    seed_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for _ in range(2):  # twice: the tickets must be back at zero after a launch
+        toks.zero_()
+        _lib.check(eng.L.mtts_sample8(logits.data_ptr(), logits.stride(0), B, ctypes.byref(sm.cfg), seen.data_ptr(),
+                                      step.data_ptr(), seed_dev.data_ptr(), toks.data_ptr(), eng.err.data_ptr(),
+                                      sws.data_ptr(), sws.numel(), _lib.stream_ptr()))
+        got = toks.cpu()
+        for c in range(C):
+            o, v = shape.head_offsets[c], shape.vocabs[c]
+            sc = _processed_scores_oracle(logits[:, o:o + v].cpu(), hist[c], cfg, 1024 if c > 0 else None)
+            assert torch.equal(got[:, c], sc.argmax(-1)), c
+    assert eng.err.cpu().sum().item() == 0
+
+
 def test_sampling_without_topk_on_text_channel_is_rejected_loudly(model):
     from moss_ttsd_b200 import _lib
     from moss_ttsd_b200.lm_engine import SamplerSetup
