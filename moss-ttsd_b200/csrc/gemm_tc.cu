@@ -57,6 +57,7 @@ struct GemmParams {
   long long ldr;
   int flags;
   int vec_ok;     // output / residual rows allow 4-wide vector access
+  int pair_tiles_n;  // > 0: CTA-pair kernel, number of 256-row weight tiles
 };
 
 template <typename T>
@@ -364,6 +365,105 @@ __device__ __forceinline__ float epilogue_scalar(const GemmParams& p, float v, i
   return v;
 }
 
+// Drains 32 TMEM lanes x 128 accumulator columns (one epilogue warp's share of a tile) through the fused epilogue:
+// lane = output column n, TMEM column = activation row m0 + c.
+__device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t taddr, int m0, int n, bool n_ok, float bias_n,
+                                              float gamma_n, int lane) {
+#pragma unroll 1
+  for (int c = 0; c < 128; c += 32) {
+    if (m0 + c >= p.M) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + c, r);
+    tmem_ld_wait();
+    if (p.flags & MTTS_EPI_SWIGLU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int m = m0 + c + j;
+        float v = __uint_as_float(r[j]);
+        if (p.out_bf16) v = bf16_round(v);
+        const float other = __shfl_xor_sync(0xffffffffu, v, 1);
+        if ((lane & 1) == 0 && n_ok && m < p.M) {
+          float sg = silu_f(v);
+          if (p.out_bf16) sg = bf16_round(sg);
+          const float h = sg * other;
+          const long long o = (long long)m * p.ldo + (n >> 1);
+          if (p.out_bf16)
+            reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(h);
+          else
+            reinterpret_cast<float*>(p.out)[o] = h;
+        }
+      }
+    } else if (p.flags == (MTTS_EPI_BIAS | MTTS_EPI_GELU) && !p.out_bf16) {
+      // the codec's MLP up-projections: the flag tests are hoisted, nothing but bias + GELU + one store per element
+      float* op = reinterpret_cast<float*>(p.out) + (long long)(m0 + c) * p.ldo + n;
+      if (n_ok) {
+        if (m0 + c + 32 <= p.M) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) op[(long long)j * p.ldo] = gelu_fast(__uint_as_float(r[j]) + bias_n);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (m0 + c + j < p.M) op[(long long)j * p.ldo] = gelu_fast(__uint_as_float(r[j]) + bias_n);
+        }
+      }
+    } else if (!p.out_bf16 && !(p.flags & MTTS_EPI_GELU)) {
+      // fp32 bias / layer-scale / residual (the codec's down-projections and attention outputs). The residual may
+      // alias the output (x += ...), so its 32 loads are issued explicitly BEFORE the first store: left to the
+      // compiler every load waits behind the previous element's store (one L2 round trip per element).
+      if (n_ok) {
+        float* op = reinterpret_cast<float*>(p.out) + (long long)(m0 + c) * p.ldo + n;
+        const int lim = min(32, p.M - (m0 + c));
+        float res[32];
+        if (p.flags & MTTS_EPI_RESIDUAL) {
+          const float* rp = reinterpret_cast<const float*>(p.residual) + (long long)(m0 + c) * p.ldr + n;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) res[j] = j < lim ? __ldcg(rp + (long long)j * p.ldr) : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) res[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < lim) op[(long long)j * p.ldo] = fmaf(__uint_as_float(r[j]) + bias_n, gamma_n, res[j]);
+      }
+    } else if (p.out_bf16 && !(p.flags & MTTS_EPI_GELU)) {
+      // bf16 linear (+ residual): prefill projections. Same hoisting of the (possibly aliasing) residual loads.
+      if (n_ok) {
+        bf16* op = reinterpret_cast<bf16*>(p.out) + (long long)(m0 + c) * p.ldo + n;
+        const int lim = min(32, p.M - (m0 + c));
+        float res[32];
+        const bool has_res = (p.flags & MTTS_EPI_RESIDUAL) != 0;
+        if (has_res) {
+          const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + (long long)(m0 + c) * p.ldr + n;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) res[j] = j < lim ? __bfloat162float(__ldcg(rp + (long long)j * p.ldr)) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < lim) {
+            float v = bf16_round(__uint_as_float(r[j]) + bias_n) * gamma_n;  // the bf16 linear output comes first
+            if (has_res) v += res[j];
+            op[(long long)j * p.ldo] = __float2bfloat16_rn(v);
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int m = m0 + c + j;
+        if (n_ok && m < p.M) {
+          const float v = epilogue_scalar(p, __uint_as_float(r[j]), m, n, bias_n, gamma_n);
+          const long long o = (long long)m * p.ldo + n;
+          if (p.out_bf16)
+            reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(v);
+          else
+            reinterpret_cast<float*>(p.out)[o] = v;
+        }
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kPThreads, 1) gemm_tc_persist_kernel(const __grid_constant__ CUtensorMap tmap_w,
                                                                        const __grid_constant__ CUtensorMap tmap_x,
@@ -479,99 +579,7 @@ __global__ void __launch_bounds__(kPThreads, 1) gemm_tc_persist_kernel(const __g
       tc_fence_after();
       const uint32_t taddr = tmem_base + a * kPBN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
       const int m0 = m_tile * kPBN + half * 128;
-#pragma unroll 1
-      for (int c = 0; c < 128; c += 32) {
-        if (m0 + c >= p.M) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c, r);
-        tmem_ld_wait();
-        if (p.flags & MTTS_EPI_SWIGLU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int m = m0 + c + j;
-            float v = __uint_as_float(r[j]);
-            if (p.out_bf16) v = bf16_round(v);
-            const float other = __shfl_xor_sync(0xffffffffu, v, 1);
-            if ((lane & 1) == 0 && n_ok && m < p.M) {
-              float sg = silu_f(v);
-              if (p.out_bf16) sg = bf16_round(sg);
-              const float h = sg * other;
-              const long long o = (long long)m * p.ldo + (n >> 1);
-              if (p.out_bf16)
-                reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(h);
-              else
-                reinterpret_cast<float*>(p.out)[o] = h;
-            }
-          }
-        } else if (p.flags == (MTTS_EPI_BIAS | MTTS_EPI_GELU) && !p.out_bf16) {
-          // the codec's MLP up-projections: the flag tests are hoisted, nothing but bias + GELU + one store per element
-          float* op = reinterpret_cast<float*>(p.out) + (long long)(m0 + c) * p.ldo + n;
-          if (n_ok) {
-            if (m0 + c + 32 <= p.M) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) op[(long long)j * p.ldo] = gelu_fast(__uint_as_float(r[j]) + bias_n);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (m0 + c + j < p.M) op[(long long)j * p.ldo] = gelu_fast(__uint_as_float(r[j]) + bias_n);
-            }
-          }
-        } else if (!p.out_bf16 && !(p.flags & MTTS_EPI_GELU)) {
-          // fp32 bias / layer-scale / residual (the codec's down-projections and attention outputs). The residual may
-          // alias the output (x += ...), so its 32 loads are issued explicitly BEFORE the first store: left to the
-          // compiler every load waits behind the previous element's store (one L2 round trip per element).
-          if (n_ok) {
-            float* op = reinterpret_cast<float*>(p.out) + (long long)(m0 + c) * p.ldo + n;
-            const int lim = min(32, p.M - (m0 + c));
-            float res[32];
-            if (p.flags & MTTS_EPI_RESIDUAL) {
-              const float* rp = reinterpret_cast<const float*>(p.residual) + (long long)(m0 + c) * p.ldr + n;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) res[j] = j < lim ? __ldcg(rp + (long long)j * p.ldr) : 0.f;
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) res[j] = 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < lim) op[(long long)j * p.ldo] = fmaf(__uint_as_float(r[j]) + bias_n, gamma_n, res[j]);
-          }
-        } else if (p.out_bf16 && !(p.flags & MTTS_EPI_GELU)) {
-          // bf16 linear (+ residual): prefill projections. Same hoisting of the (possibly aliasing) residual loads.
-          if (n_ok) {
-            bf16* op = reinterpret_cast<bf16*>(p.out) + (long long)(m0 + c) * p.ldo + n;
-            const int lim = min(32, p.M - (m0 + c));
-            float res[32];
-            const bool has_res = (p.flags & MTTS_EPI_RESIDUAL) != 0;
-            if (has_res) {
-              const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + (long long)(m0 + c) * p.ldr + n;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) res[j] = j < lim ? __bfloat162float(__ldcg(rp + (long long)j * p.ldr)) : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < lim) {
-                float v = bf16_round(__uint_as_float(r[j]) + bias_n) * gamma_n;  // the bf16 linear output comes first
-                if (has_res) v += res[j];
-                op[(long long)j * p.ldo] = __float2bfloat16_rn(v);
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int m = m0 + c + j;
-            if (n_ok && m < p.M) {
-              const float v = epilogue_scalar(p, __uint_as_float(r[j]), m, n, bias_n, gamma_n);
-              const long long o = (long long)m * p.ldo + n;
-              if (p.out_bf16)
-                reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(v);
-              else
-                reinterpret_cast<float*>(p.out)[o] = v;
-            }
-          }
-        }
-      }
+      persist_drain(p, taddr, m0, n, n_ok, bias_n, gamma_n, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[a]);
@@ -583,6 +591,152 @@ __global__ void __launch_bounds__(kPThreads, 1) gemm_tc_persist_kernel(const __g
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant of the persistent kernel (cta_group::2): the two CTAs of a 2-cluster (one TPC) share a
+// 256 (weight rows) x 256 (activation rows) tile. Each CTA stages only ITS 128 weight rows and ITS 128 activation rows
+// per k-block — 32 KB instead of the 48 KB a single-CTA 128 x 256 tile needs for the same 2 x 128 x 256 x BK flops per
+// SM — and the leader's MMA reads both halves of the activation tile, one from each SM. At TF32 the single-CTA kernel
+// is bound by what one SM can pull from L2 (48 KB per 2.1 MFLOP, ~520 TFLOP/s at the ~80 GB/s per SM the crossbar
+// sustains); the pair needs a third less. Accumulators: 128 lanes x 256 columns per CTA, two of them (double buffer).
+// ---------------------------------------------------------------------------------------------
+constexpr int kP2Stages = 6;  // 6 x 32 KB
+constexpr int kP2Bytes = kP2Stages * 2 * kBlockW * kSwizzleBytes + 1024 + 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kPThreads, 1) gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                                                                    const __grid_constant__ CUtensorMap tmap_x,
+                                                                    const GemmParams p, int tiles_n, int num_tiles) {
+  constexpr int BK = Traits<T>::kBlockK;
+  constexpr int UK = Traits<T>::kUmmaK;
+  constexpr uint32_t kHalfBytes = kBlockW * kSwizzleBytes;  // 128 rows x 128 B: one operand half per CTA per stage
+  constexpr uint32_t kIdesc = make_idesc(Traits<T>::kFmt, 2 * kBlockW, kPBN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kP2Stages * kHalfBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kP2Stages * kHalfBytes);  // used in the leader only
+  uint64_t* empty_bar = full_bar + kP2Stages;
+  uint64_t* tmem_full_bar = empty_bar + kP2Stages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2], used in the leader only: 16 epilogue warps arrive
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = p.kb_total;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_x);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kP2Stages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tmem_full_bar[a], 1);
+        mbar_init(&tmem_empty_bar[a], 16);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2sm<512>(tmem_ptr_smem);
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before either one signals the other
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs): own halves, byte counts land on the leader's full barrier =================
+    if (lane == 0) {
+      pdl_wait();
+      const uint32_t leader_full = mapa_u32(smem_u32(full_bar), 0);
+      int it = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int n_tile = t % tiles_n, m_tile = t / tiles_n;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kP2Stages;
+          const uint32_t ph = (it / kP2Stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 4 * kHalfBytes);
+          tma_load_2d_2sm(smem_a + s * kHalfBytes, &tmap_w, leader_full + s * 8, kb * BK,
+                          n_tile * 2 * kBlockW + (int)rank * kBlockW, kEvictLast);
+          tma_load_2d_2sm(smem_b + s * kHalfBytes, &tmap_x, leader_full + s * 8, kb * BK,
+                          m_tile * kPBN + (int)rank * (kPBN / 2), kEvictNormal);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (lane == 0 && rank == 0) {
+      int it = 0, ti = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs, ++ti) {
+        const int a = ti & 1;
+        const uint32_t aph = (ti >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[a], aph ^ 1);  // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + a * kPBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kP2Stages;
+          const uint32_t ph = (it / kP2Stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + s * kHalfBytes);
+          const uint32_t b_addr = smem_u32(smem_b + s * kHalfBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * UK * (int)sizeof(T));
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * UK * (int)sizeof(T));
+            if constexpr (sizeof(T) == 2)
+              umma_bf16_2sm(tacc, da, db, kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else
+              umma_tf32_2sm(tacc, da, db, kIdesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[s], 3);  // frees the stage in both CTAs
+        }
+        umma_commit_2sm(&tmem_full_bar[a], 3);
+      }
+    }
+  } else {
+    // ================= epilogue (both CTAs): own 128 weight rows x all 256 activation rows =================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    pdl_wait();
+    const uint32_t leader_empty = mapa_u32(smem_u32(tmem_empty_bar), 0);
+    int ti = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++ti) {
+      const int n_tile = t % tiles_n, m_tile = t / tiles_n;
+      const int a = ti & 1;
+      const uint32_t aph = (ti >> 1) & 1;
+      const int n = n_tile * 2 * kBlockW + (int)rank * kBlockW + quarter * 32 + lane;
+      const bool n_ok = n < p.N;
+      const float bias_n = (n_ok && (p.flags & MTTS_EPI_BIAS)) ? __ldg(p.bias + n) : 0.f;
+      const float gamma_n = (n_ok && (p.flags & MTTS_EPI_GAMMA)) ? __ldg(p.gamma + n) : 1.f;
+      mbar_wait(&tmem_full_bar[a], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + a * kPBN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int m0 = m_tile * kPBN + half * 128;
+      persist_drain(p, taddr, m0, n, n_ok, bias_n, gamma_n, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_empty + a * 8);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may leave (or free its TMEM) while the pair's MMAs or remote arrivals are in flight
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<512>(tmem_base);
   }
 }
 
@@ -684,6 +838,15 @@ int launch(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, di
   return MTTS_OK;
 }
 
+static bool persist_disabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MTTS_GEMM_NO_PERSIST");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <typename T>
 int dispatch(int bn, const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, dim3 grid,
              cudaStream_t stream) {
@@ -693,13 +856,35 @@ int dispatch(int bn, const CUtensorMap& tw, const CUtensorMap& tx, const GemmPar
     case 64: return launch<T, 64>(tw, tx, p, grid, stream);
     case 128: return launch<T, 128>(tw, tx, p, grid, stream);
     default: {
-      static int persist = -1;
-      if (persist < 0) {
-        const char* e = getenv("MTTS_GEMM_NO_PERSIST");
-        persist = (e && e[0] == '1') ? 0 : 1;
-      }
       // a single row of tiles (decode at batch 129..256) is a weight-streaming problem: cluster split-K variant
-      if (!persist) return launch<T, 256>(tw, tx, p, grid, stream);
+      if (persist_disabled()) return launch<T, 256>(tw, tx, p, grid, stream);
+      if (p.pair_tiles_n > 0) {  // CTA-pair kernel: 256 x 256 tiles, tensor maps with 128-row boxes
+        const int num_tiles = p.pair_tiles_n * (int)grid.y;
+        const int pairs = num_tiles < mtts_num_sms() / 2 ? num_tiles : mtts_num_sms() / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(kPThreads);
+        cfg.dynamicSmemBytes = kP2Bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (mtts_pdl_enabled()) {
+          attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[na].val.programmaticStreamSerializationAllowed = 1;
+          ++na;
+        }
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
+        MTTS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<T>, tw, tx, p, p.pair_tiles_n, num_tiles));
+        MTTS_LAUNCH_CHECK();
+        return MTTS_OK;
+      }
       const int num_tiles = (int)(grid.x * grid.y);
       const int ctas = num_tiles < mtts_num_sms() ? num_tiles : mtts_num_sms();
       MTTS_CUDA_CHECK(mtts_launch(gemm_tc_persist_kernel<T>, dim3(ctas), dim3(kPThreads), smem_bytes<kPBN, kPStages>(), stream,
@@ -736,6 +921,8 @@ int mtts_configure_gemm_tc() {
                                        smem_bytes<kPBN, kPStages>()));
   MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        smem_bytes<kPBN, kPStages>()));
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_pair_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2Bytes));
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_pair_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2Bytes));
   return MTTS_OK;
 }
 
@@ -829,7 +1016,15 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   CUtensorMap tw, tx;
   int rc = get_tmap(w, N, K, ldw, kBlockW, eb, &tw);
   if (rc) return rc;
-  rc = get_tmap(x, M, K, ldx, bn, eb, &tx);
+  // large problems on the persistent route: CTA pairs (cta_group::2) on 256 x 256 tiles
+  static int pair_mode = -1;
+  if (pair_mode < 0) {
+    const char* e = getenv("MTTS_GEMM_2CTA");
+    pair_mode = e ? atoi(e) : 1;  // MTTS_GEMM_2CTA=0: the single-CTA persistent kernel
+  }
+  const bool pair = pair_mode > 0 && bn == 256 && !persist_disabled();
+  if (pair) p.pair_tiles_n = ceil_div(N, 2 * kBlockW);
+  rc = get_tmap(x, M, K, ldx, pair ? kPBN / 2 : bn, eb, &tx);
   if (rc) return rc;
   dim3 grid(tiles_n, tiles_m, splits);
   if (in_dtype == MTTS_DTYPE_BF16) return dispatch<bf16>(bn, tw, tx, p, grid, stream);
