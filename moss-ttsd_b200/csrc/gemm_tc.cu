@@ -157,6 +157,20 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int 
   }
 }
 
+#ifdef MTTS_GEMM_TRACE
+// debug build only (scripts/trace_gemm.py): per-CTA phase timestamps (globaltimer, ns) of the most recent launch
+__device__ unsigned long long g_gemm_trace[4096 * 16];
+__device__ __forceinline__ void gemm_trace(int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (cta < 4096) g_gemm_trace[cta * 16 + slot] = t;
+}
+#define GEMM_TRACE(slot) gemm_trace(slot)
+#else
+#define GEMM_TRACE(slot)
+#endif
+
 template <typename T, int BN, int kStages>
 __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_w,
                                                               const __grid_constant__ CUtensorMap tmap_x,
@@ -185,6 +199,7 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
   const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
   const int num_kb = kb_end - kb_begin;  // host guarantees >= 1
 
+  if (threadIdx.x == 0) GEMM_TRACE(0);
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_x);
@@ -205,6 +220,7 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) GEMM_TRACE(1);
   // Only now (TMEM columns are ours) may the next kernel in the stream start its prologue / weight prefetch: a
   // dependent that grabbed TMEM first and then sat in griddepcontrol.wait would deadlock against our allocation.
   pdl_launch_dependents();
@@ -222,6 +238,7 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
         tma_load_2d(smem_a + it * kABytes, &tmap_w, &full_bar[it], (kb_begin + it) * BK, n_tile * kBlockW, pol_w);
       }
       pdl_wait();
+      GEMM_TRACE(2);
       // (2) activations are the predecessor's output
       for (int it = 0; it < pre; ++it)
         tma_load_2d(smem_b + it * kBBytes, &tmap_x, &full_bar[it], (kb_begin + it) * BK, m_tile * BN, pol_x);
@@ -242,6 +259,7 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&full_bar[s], ph);
+        if (it == 0) GEMM_TRACE(3);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem_a + s * kABytes);
         const uint32_t b_addr = smem_u32(smem_b + s * kBBytes);
@@ -257,6 +275,7 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
         umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
       }
       umma_commit(tmem_full_bar);  // accumulator complete
+      GEMM_TRACE(4);
     }
   } else {
     // ================= epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =================
@@ -266,7 +285,9 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
     const int m_base = m_tile * BN;
     const int mv = min(BN, p.M - m_base);  // valid activation rows in this tile
     pdl_wait();  // residual reads and output writes below depend on / conflict with the predecessor
+    if (epi_tid == 0) GEMM_TRACE(11);
     mbar_wait(tmem_full_bar, 0);
+    if (epi_tid == 0) GEMM_TRACE(5);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     // ---- stage the fp32 accumulator (partial) tile as [m][128 n] in the now idle smem ring
@@ -279,12 +300,14 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
 #pragma unroll
       for (int j = 0; j < 16; ++j) stage[(c + j) * kBlockW + n_local] = __uint_as_float(r[j]);
     }
+    if (epi_tid == 0) GEMM_TRACE(6);
     if (p.splits == 1) asm volatile("bar.sync 1, 128;" ::: "memory");
   }
 
   // ---- split-K: all partial tiles of this cluster are staged
   __syncwarp();  // reconverge the single-lane producer / MMA warps: barrier.cluster is warp-aligned
   if (p.splits > 1) cluster_sync_all();
+  if (threadIdx.x == 64) GEMM_TRACE(7);
 
   if (warp >= 2) {
     const int epi_tid = threadIdx.x - 64;
@@ -329,15 +352,22 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
     }
   }
 
-  // nobody may exit (and have its shared memory reassigned) while a peer is still reading it
+  // nobody may exit (and have its shared memory reassigned) while a peer is still reading it. Execution barrier only:
+  // the peers' DSMEM loads have returned before they arrive, and our output stores need not be visible to anyone here
+  // (pc sampling: the epilogue warps spent ~3 us in the release form of this barrier, waiting for their own stores).
+  if (threadIdx.x == 64) GEMM_TRACE(8);
+  // (arriving per thread right after its last DSMEM load, before the output stores, was slower: the unaligned barrier
+  // forms cost more than the overlap gained)
   __syncwarp();
-  if (p.splits > 1) cluster_sync_all();
+  if (p.splits > 1) cluster_sync_relaxed();
+  if (threadIdx.x == 64) GEMM_TRACE(9);
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kCols>(tmem_base);
+    if (lane == 0) GEMM_TRACE(10);
   }
 }
 
@@ -950,7 +980,11 @@ static int pick_splits(int tiles, int kb_total, int bn, int tiles_m) {
     const char* e = getenv("MTTS_GEMM_SPLITS");
     forced = e ? atoi(e) : 0;
   }
-  if (forced > 0) return forced > 8 ? 8 : forced;
+  if (forced > 0) return forced >= 8 ? 8 : forced >= 4 ? 4 : forced >= 2 ? 2 : 1;  // cluster sizes are powers of two
+  // (A cta_group::2 version of this kernel for batch 129..256 — pairs over two adjacent weight tiles, half the L2->SM
+  // bytes — was bit-exact but slower in the full step, 5.05-5.9 ms against 4.90 ms: its extra cluster barriers and the
+  // two-pass reduction of the 256 x 128 partial tile cost more than the main loop saved. Moving the partial tiles
+  // through an L2 workspace instead of DSMEM, 16 DSMEM loads per round and a non-inlined epilogue were each slower too.)
   // (batch 129..256, two activation tiles per weight tile: raising the target to 3, 4 or 6 CTAs per SM, i.e. splitting
   // the 192-tile gate/up projection 2 or 4 ways and q/k/v 8 ways, loses in the full step: 5.27 / 5.62 / 5.60 ms against
   // 4.97 ms at batch 256.)
@@ -1030,3 +1064,9 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   if (in_dtype == MTTS_DTYPE_BF16) return dispatch<bf16>(bn, tw, tx, p, grid, stream);
   return dispatch<float>(bn, tw, tx, p, grid, stream);
 }
+
+#ifdef MTTS_GEMM_TRACE
+extern "C" int mtts_debug_gemm_trace(unsigned long long* dst_host, int n) {
+  return (int)cudaMemcpyFromSymbol(dst_host, g_gemm_trace, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
