@@ -24,6 +24,8 @@ SHAPES = [
     (1, 256, 128), (1, 2048, 2048), (3, 1000, 512), (16, 4096, 2048), (17, 384, 6144), (64, 2048, 6144),
     (100, 130, 200), (128, 768, 3072), (129, 2048, 2048), (256, 4096, 2048), (300, 1025, 2048), (257, 962, 512),
     (1000, 512, 560),
+    # >= 592 weight tiles at 65..256 rows: the LM-heads route (CTA-pair kernel with one, partly out-of-bounds, row tile)
+    (200, 76032, 128), (77, 75900, 192),
 ]
 
 
