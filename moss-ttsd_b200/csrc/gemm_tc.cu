@@ -632,7 +632,7 @@ __global__ void __launch_bounds__(kPThreads, 1) gemm_tc_persist_kernel(const __g
 // is bound by what one SM can pull from L2 (48 KB per 2.1 MFLOP, ~520 TFLOP/s at the ~80 GB/s per SM the crossbar
 // sustains); the pair needs a third less. Accumulators: 128 lanes x 256 columns per CTA, two of them (double buffer).
 // ---------------------------------------------------------------------------------------------
-constexpr int kP2Stages = 6;  // 6 x 32 KB
+constexpr int kP2Stages = 6;  // 6 x 32 KB (5 and 7 measure the same within run-to-run noise)
 constexpr int kP2Bytes = kP2Stages * 2 * kBlockW * kSwizzleBytes + 1024 + 256;
 
 template <typename T>
