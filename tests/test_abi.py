@@ -43,3 +43,21 @@ def test_product_never_imports_oracle():
 def test_sampler_config_struct_size_matches_header():
     # 1 + 8*11 arrays of 4-byte fields + 3 trailing ints = 92 ints
     assert ctypes.sizeof(_lib.SamplerConfig) == 4 * (1 + 8 * 11 + 1 + 2)
+
+
+def test_bench_launch_list_summary_tool_reads_the_committed_list():
+    """profiles/r01_launches_bench.csv.gz (ncu launch list of the bench command) parses into complete decode steps whose
+    dominant kernels are the ones bench.py reports as roofline / roofline_other."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "scripts"))
+    import summarize_bench_launches as sbl
+    rows = list(sbl.load(os.path.join(root, "profiles", "r01_launches_bench.csv.gz")))
+    dec, nsteps = sbl.decode_steps(rows)
+    assert nsteps >= 40 and len(dec) % nsteps == 0
+    per_step = {}
+    for name, us, _ in dec:
+        per_step[sbl.short(name)] = per_step.get(sbl.short(name), 0.0) + us / nsteps
+    top2 = sorted(per_step, key=per_step.get, reverse=True)[:2]
+    assert any("gqa_decode_tc_kernel" in k for k in top2) and any("gemm_tc_kernel" in k for k in top2)
