@@ -36,6 +36,20 @@ def batches(indices: Sequence[int], batch_size: int) -> List[List[int]]:
     return [list(indices[i:i + batch_size]) for i in range(0, len(indices), batch_size)]
 
 
+def length_bucketed_batches(indices: Sequence[int], lengths: Sequence[int], batch_size: int) -> List[List[int]]:
+    """Batches of at most `batch_size` requests with similar expected lengths (the longest-row tail): a
+    batch decodes until its LONGEST row has finished (modeling_asteroid.py:166-169), so its cost is max(length), not the
+    mean. Sorting by decreasing expected length and cutting consecutive runs minimises the sum of the batch maxima over
+    all partitions into batches of this size; ties are broken by index, so every rank computes the same batches."""
+    order = sorted(indices, key=lambda i: (-int(lengths[i]), i))
+    return batches(order, batch_size)
+
+
+def decode_steps(lengths: Sequence[int], batch_list: Sequence[Sequence[int]]) -> int:
+    """Decode steps a rank spends on `batch_list` when every batch runs until its longest row is done."""
+    return sum(max(int(lengths[i]) for i in b) for b in batch_list if len(b))
+
+
 def gather_results(local: dict, world_size: int) -> dict:
     """Merge {request index: result} dicts from all ranks on every rank (host-side; no GPU collective)."""
     if world_size <= 1:

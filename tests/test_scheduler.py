@@ -25,6 +25,31 @@ def test_shards_partition_the_requests():
     assert scheduler.shard_requests([], 4, 1) == []
 
 
+def test_length_bucketed_batches_minimise_the_longest_row_tail():
+    import random
+    rng = random.Random(3)
+    lengths = [rng.randint(125, 750) for _ in range(37)]  # 10..60 s scripts, in frames
+    idx = list(range(len(lengths)))
+    got = scheduler.length_bucketed_batches(idx, lengths, 8)
+    assert sorted(i for b in got for i in b) == idx and all(1 <= len(b) <= 8 for b in got) and len(got) == 5
+    arrival = scheduler.batches(idx, 8)
+    assert scheduler.decode_steps(lengths, got) <= scheduler.decode_steps(lengths, arrival)
+    # optimal among ALL partitions into batches of <= 2 (brute force over pairings of 6 requests)
+    small = [300, 120, 710, 125, 690, 310]
+
+    def pairings(items):
+        if not items:
+            yield []
+            return
+        a = items[0]
+        for j in range(1, len(items)):
+            for rest in pairings(items[1:j] + items[j + 1:]):
+                yield [[a, items[j]]] + rest
+    best = min(scheduler.decode_steps(small, p) for p in pairings(list(range(6))))
+    assert scheduler.decode_steps(small, scheduler.length_bucketed_batches(range(6), small, 2)) == best
+    assert scheduler.length_bucketed_batches([], [], 4) == []
+
+
 def test_two_rank_gloo_gather(tmp_path):
     script = tmp_path / "w.py"
     script.write_text(textwrap.dedent(f"""
