@@ -102,6 +102,80 @@ def gen_lm():
     np.savez_compressed(os.path.join(GOLD, "lm_tiny.npz"), **out)
 
 
+MARGIN, MARGIN_SEED, MARGIN_GAIN, MARGIN_NEW = (lm_oracle.MARGIN_SHAPE, lm_oracle.MARGIN_SEED, lm_oracle.MARGIN_GAIN,
+                                                 lm_oracle.MARGIN_NEW)
+
+
+def build_ref_lm_sd(shape, sd, dtype):
+    """The reference model loaded with an explicit state dict (same harness care as build_ref_lm)."""
+    ma = ref_shims.import_lm()
+    model = ref_shims.make_lm(ma, ref_cfg_kwargs(shape), torch.float32)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all("embed_tokens" in m for m in missing), missing
+    rot = model.model.language_model.rotary_emb
+    inv32 = rot.inv_freq.clone()
+    model = model.to(dtype).eval()
+    rot.inv_freq = inv32
+    rot.original_inv_freq = inv32.clone()
+    ref_shims.bind_generation_helpers(model)
+    return model
+
+
+def gen_lm_margin():
+    """Free-running greedy horizon with a planted decision margin (lm_oracle.make_planted_weights): the reference's
+    bf16 and fp32 `_sample` runs must agree with each other over all MARGIN_NEW rows, and so must any correct
+    implementation."""
+    shape = MARGIN
+    rng = np.random.default_rng(8)
+    ids, mask = make_prompt(rng, 2, [7, 4], [14, 11], shape)
+    sd = lm_oracle.make_planted_weights(shape, MARGIN_SEED, emb_gain=MARGIN_GAIN)
+    out = dict(ids=ids, mask=mask, seed=np.int64(MARGIN_SEED), gain=np.float64(MARGIN_GAIN))
+    T = ids.shape[1]
+    lo, hi = shape["speech_token_range"]
+    for name, dtype in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        model = build_ref_lm_sd(shape, sd, dtype)
+        seq = ref_shims.run_sample(model, torch.from_numpy(ids), torch.from_numpy(mask), max_length=T + MARGIN_NEW)
+        out[f"greedy_{name}"] = seq.numpy()
+        with torch.no_grad():
+            o = model(input_ids=seq, attention_mask=torch.cat([torch.from_numpy(mask)[:, :T - 7],
+                                                               torch.ones(2, seq.shape[1] - (T - 7), dtype=torch.float64)], 1),
+                      return_dict=True)
+        la = [l.float() for l in o.logits_all]
+        gaps = []
+        for c in range(8):
+            l = la[c][:, T - 7 - 1 + 7:-1]                      # positions that predict rows where every channel is free
+            l = l[..., lo:hi] if c == 0 else l[..., :1024]
+            t2 = l.topk(2, -1).values
+            gaps.append((t2[..., 0] - t2[..., 1]).min().item())
+        out[f"min_gap_{name}"] = np.float64(min(gaps))
+        print("margin", name, seq.shape, "min top-2 gap", min(gaps))
+    assert np.array_equal(out["greedy_f32"], out["greedy_bf16"]), "the reference's own bf16 and fp32 runs disagree"
+    np.savez_compressed(os.path.join(GOLD, "lm_margin.npz"), **out)
+
+
+LONG_ROWS = 12100
+
+
+def gen_lm_longctx():
+    """RoPE / attention range: reference bf16 + fp32 last-position logits of the TINY model on a 12.1 k-row prompt."""
+    shape = TINY
+    rng = np.random.default_rng(21)
+    ids, mask = make_prompt(rng, 1, [100], [LONG_ROWS - 100 - 7], shape)
+    assert ids.shape[1] == LONG_ROWS
+    out = dict(seed=np.int64(21), rows=np.int64(LONG_ROWS))
+    lo, hi = shape["speech_token_range"]
+    for name, dtype in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        model, _ = build_ref_lm(shape, TINY_SEED, dtype)
+        with torch.no_grad():
+            h = model.model(input_ids=torch.from_numpy(ids), attention_mask=torch.from_numpy(mask)).last_hidden_state[:, -4:]
+            la = [head(h).float().numpy() for head in model.lm_heads]
+        out[f"logits0_speech_{name}"] = la[0][..., lo:hi]
+        out[f"logits17_{name}"] = np.stack(la[1:], 0)
+        print("longctx", name, la[1].shape)
+    np.savez_compressed(os.path.join(GOLD, "lm_longctx.npz"), **out)
+
+
 class _Scripted(torch.nn.Module):
     """Stands in for the network inside the reference's `_sample`: returns scripted last-position logits."""
 
@@ -203,6 +277,10 @@ def main(argv):
     what = set(argv) or {"lm", "sampler", "rvq", "codec", "utils"}
     if "lm" in what:
         gen_lm()
+    if "lm_margin" in what:
+        gen_lm_margin()
+    if "lm_longctx" in what:
+        gen_lm_longctx()
     if "sampler" in what:
         gen_sampler()
     if "rvq" in what:

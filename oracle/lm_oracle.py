@@ -68,6 +68,39 @@ def make_weights(shape: dict, seed: int, std: float = 0.02, speech_only_head0: b
     return sd
 
 
+# Shape / seed / gain of the planted-margin model behind tests/golden/lm_margin.npz (oracle/gen_golden.py gen_lm_margin)
+MARGIN_SHAPE = dict(hidden_size=1024, intermediate_size=2048, num_hidden_layers=2, num_attention_heads=8,
+                    num_key_value_heads=4, head_dim=128, rms_norm_eps=1e-6, rope_theta=1e6, vocab_size=152697,
+                    speech_vocab_size=1025, channels=8, speech_token_range=[151665, 152689])
+MARGIN_SEED, MARGIN_GAIN, MARGIN_NEW = 4321, 10.0, 40
+
+
+def make_planted_weights(shape: dict, seed: int, std: float = 0.02, emb_gain: float = 5.0) -> Dict[str, torch.Tensor]:
+    """`make_weights` plus a planted decision margin, for the free-running greedy horizon test.
+
+    A random-init model's top-2 logit gap is below bf16 rounding noise in ~1 decision out of 10, so two correct bf16
+    implementations (and the reference's own bf16 vs fp32 runs) part after a handful of rows. Here every channel's
+    head copies the channel's embedding rows through a seeded permutation of the 1024 codes
+    (lm_heads.c[base + perm_c[j]] = embedding_list.c[base + j]; base = speech_token_range[0] for channel 0), so that
+    the winning logit is ~|E|^2 / rms(x) — about sqrt(hidden/8) standard deviations of the competing logits — while
+    the decoder layers still perturb every logit (embedding rows are scaled by `emb_gain` so that the embedding sum is
+    not drowned by the layers' residual contributions). With hidden >= 1024 the gap is > 5 sigma: the next token of channel c
+    is perm_c[previous token of channel c] for the reference and for any correct implementation, and a wrong token
+    fed back, a wrong position or a corrupted cache row changes the chain immediately."""
+    sd = make_weights(shape, seed, std=std, speech_only_head0=True, tied=False)
+    rng = np.random.default_rng(seed + 99991)
+    lo, _ = shape["speech_token_range"]
+    n_codes = shape["speech_vocab_size"] - 1
+    for c in range(shape["channels"]):
+        base = lo if c == 0 else 0
+        perm = torch.from_numpy(rng.permutation(n_codes))
+        emb = sd[f"model.embedding_list.{c}.weight"]
+        emb *= emb_gain
+        head = sd[f"lm_heads.{c}.weight"]
+        head[base + perm] = emb[base:base + n_codes].clone()
+    return sd
+
+
 def rmsnorm(x, w, eps):
     dt = x.dtype
     h = x.to(torch.float32)

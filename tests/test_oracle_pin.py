@@ -164,3 +164,17 @@ def test_codec_oracle_encode_matches_reference():
         assert tuple(c.shape) == want.shape == (8, int(g[f"len{i}"]) // 1280)
         agree = (c.numpy() == want).all(0).mean()
         assert agree >= 0.98, agree   # identical torch ops; the few flips are fp32 near-ties of numpy-BLAS vs torch-MKL
+
+
+def test_lm_oracle_greedy_matches_reference_on_the_planted_margin_model():
+    """lm_margin.npz: the reference's `_sample` (bf16 and fp32 agree with each other over all 40 generated rows) on the
+    planted-margin model; the KV-cached bf16 oracle must reproduce the grid exactly."""
+    g = gold("lm_margin.npz")
+    assert np.array_equal(g["greedy_bf16"], g["greedy_f32"])
+    assert float(g["min_gap_bf16"]) > 5.0          # top-2 gap of every free decision, in logit units (|logit| ~ 60)
+    sd = lm_oracle.make_planted_weights(lm_oracle.MARGIN_SHAPE, int(g["seed"]), emb_gain=float(g["gain"]))
+    ids, mask = torch.from_numpy(g["ids"]), torch.from_numpy(g["mask"])
+    T = ids.shape[1]
+    seq = lm_oracle.OracleCachedLM(lm_oracle.MARGIN_SHAPE, sd, torch.bfloat16).generate(
+        ids, mask, max_length=T + lm_oracle.MARGIN_NEW, speech_range=lm_oracle.MARGIN_SHAPE["speech_token_range"])
+    np.testing.assert_array_equal(seq.numpy(), g["greedy_bf16"])
