@@ -42,6 +42,7 @@ extern "C" {
 #define MTTS_EPI_GAMMA 4
 #define MTTS_EPI_RESIDUAL 8
 #define MTTS_EPI_SWIGLU 16
+#define MTTS_EPI_EXACT_ACT 32 /* fp32 outputs: erff() GELU instead of the 1.5e-7 polynomial (exact-mode codec encode) */
 
 const char* mtts_last_error(void);
 int mtts_version(void);
@@ -191,6 +192,18 @@ int mtts_layernorm(const float* x, const float* w, const float* b, float* out, l
  * scaled), out [B*T, H*64]; keys >= lengths[b] are masked. */
 int mtts_mha_varlen(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads, int head_dim,
                     void* stream);
+
+/* Same contraction with fp32 CUDA-core products, fp32 softmax and expf(): the exact mode of XY_Tokenizer.encode, whose
+ * integer codes must match the reference's fp32 matmuls (model.py:54-101 -> modules.py:117-160). */
+int mtts_mha_varlen_fp32(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads, int head_dim,
+                         void* stream);
+
+/* 3xTF32 operand split for fp32-accurate products on the tcgen05 TF32 path: x [rows, K] fp32 -> out [rows, 3K] with
+ * hi = rna_tf32(x), lo = x - hi laid out [hi | lo | hi] (weights_order = 0, activations) or [hi | hi | lo]
+ * (weights_order = 1), so that mtts_gemm over K' = 3K computes hi*hi + lo*hi + hi*lo in fp32 accumulators — the
+ * fp32 `aten::linear` of the codec encoder (modules.py:84-87,181-182; `matmul.allow_tf32 = False`). */
+int mtts_split_tf32x3(const float* x, long long ldx, float* out, long long ldo, long long rows, int K, int weights_order,
+                      void* stream);
 
 /* ConvNeXtBlock front half (modules.py:1142-1150): depthwise Conv1d(k=7,pad=3) + LayerNorm(C, eps). x,out [B,T,C];
  * conv_w [C,7]; zero padding at both ends of every item. */

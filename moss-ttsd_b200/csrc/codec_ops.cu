@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------------
 constexpr int kHD = 64, kQT = 64, kKT = 64, kPitch = 68;
 
+template <bool kExactExp>
 __global__ void __launch_bounds__(256) mha_varlen_kernel(const float* __restrict__ qkv, float* __restrict__ out,
                                                          const int* __restrict__ lengths, int T, int H, float scale) {
   extern __shared__ __align__(16) float sm[];
@@ -150,11 +151,11 @@ __global__ void __launch_bounds__(256) mha_varlen_kernel(const float* __restrict
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
       mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
       const float mn = fmaxf(m[i], mx);
-      const float corr = __expf(m[i] - mn);
+      const float corr = kExactExp ? expf(m[i] - mn) : __expf(m[i] - mn);
       float ps = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float pr = __expf(s[i][j] - mn);
+        const float pr = kExactExp ? expf(s[i][j] - mn) : __expf(s[i][j] - mn);
         ps += pr;
         sp[(qi * 4 + i) * kPitch + ki + 16 * j] = pr;
       }
@@ -557,10 +558,32 @@ __global__ void add_rows_mod_kernel(float* __restrict__ x, const float* __restri
   *reinterpret_cast<float4*>(x + r * C + c) = v;
 }
 
+// 3xTF32 split (see mtts_split_tf32x3 in mtts.h): hi = x rounded to TF32 (10-bit mantissa, round to nearest), lo = x - hi
+// (exact in fp32); the tcgen05 TF32 MMA then truncates lo to its top 10 mantissa bits — a 2^-22 relative error on x.
+__global__ void split_tf32x3_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ out, long long ldo,
+                                    long long rows, int K, int weights_order) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int kv = K >> 2;
+  if (gid >= rows * kv) return;
+  const long long r = gid / kv;
+  const int c = (int)(gid % kv) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+  float4 hi, lo;
+  hi.x = __uint_as_float(to_tf32(v.x)); hi.y = __uint_as_float(to_tf32(v.y));
+  hi.z = __uint_as_float(to_tf32(v.z)); hi.w = __uint_as_float(to_tf32(v.w));
+  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+  float* o = out + r * ldo + c;
+  *reinterpret_cast<float4*>(o) = hi;
+  *reinterpret_cast<float4*>(o + K) = weights_order ? hi : lo;
+  *reinterpret_cast<float4*>(o + 2 * K) = weights_order ? lo : hi;
+}
+
 }  // namespace
 
 int mtts_configure_codec() {
-  MTTS_CUDA_CHECK(cudaFuncSetAttribute(mha_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(mha_varlen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(4 * kQT * kPitch * sizeof(float))));
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(mha_varlen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(4 * kQT * kPitch * sizeof(float))));
   return MTTS_OK;
 }
@@ -594,8 +617,34 @@ extern "C" int mtts_mha_varlen(const float* qkv, float* out, const int* lengths,
     mha_varlen_tc_kernel<<<grid, 128, 2 * kKT * kPitch * sizeof(uint32_t), stream>>>(
         qkv, out, lengths, T, num_heads, 1.4426950408889634f / sqrtf((float)head_dim));
   else
-    mha_varlen_kernel<<<grid, 256, 4 * kQT * kPitch * sizeof(float), stream>>>(qkv, out, lengths, T, num_heads,
-                                                                              1.0f / sqrtf((float)head_dim));
+    mha_varlen_kernel<false><<<grid, 256, 4 * kQT * kPitch * sizeof(float), stream>>>(qkv, out, lengths, T, num_heads,
+                                                                                     1.0f / sqrtf((float)head_dim));
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_mha_varlen_fp32(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads,
+                                    int head_dim, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(head_dim == kHD, "mtts_mha_varlen_fp32: head_dim must be 64 (got %d)", head_dim);
+  if (B <= 0 || T <= 0) return MTTS_OK;
+  MTTS_REQUIRE(qkv && out, "mtts_mha_varlen_fp32: null pointer");
+  dim3 grid(ceil_div(T, kQT), num_heads, B);
+  mha_varlen_kernel<true><<<grid, 256, 4 * kQT * kPitch * sizeof(float), stream>>>(qkv, out, lengths, T, num_heads,
+                                                                                    1.0f / sqrtf((float)head_dim));
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_split_tf32x3(const float* x, long long ldx, float* out, long long ldo, long long rows, int K,
+                                 int weights_order, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(K > 0 && K % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && ldo >= 3LL * K,
+               "mtts_split_tf32x3: K, ldx, ldo must be multiples of 4 and ldo >= 3K");
+  if (rows <= 0) return MTTS_OK;
+  MTTS_REQUIRE(x && out, "mtts_split_tf32x3: null pointer");
+  const long long total = rows * (K / 4);
+  split_tf32x3_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(x, ldx, out, ldo, rows, K, weights_order);
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }

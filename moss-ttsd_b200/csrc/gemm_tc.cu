@@ -133,7 +133,7 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int 
     if (n + j >= p.N) break;
     float x = v[j];
     if (p.flags & MTTS_EPI_BIAS) x += __ldg(p.bias + n + j);
-    if (p.flags & MTTS_EPI_GELU) x = p.out_bf16 ? gelu_erf(x) : gelu_fast(x);
+    if (p.flags & MTTS_EPI_GELU) x = (p.out_bf16 || (p.flags & MTTS_EPI_EXACT_ACT)) ? gelu_erf(x) : gelu_fast(x);
     if (p.out_bf16) x = bf16_round(x);  // the reference materialises the bf16 linear output first
     if (p.flags & MTTS_EPI_GAMMA) x *= __ldg(p.gamma + n + j);
     if (p.flags & MTTS_EPI_RESIDUAL) x = r[j] + x;
@@ -383,7 +383,7 @@ constexpr int kPThreads = 320;  // warp0 TMA, warp1 MMA/TMEM, warps 2..9 epilogu
 
 __device__ __forceinline__ float epilogue_scalar(const GemmParams& p, float v, int m, int n, float bias_n, float gamma_n) {
   if (p.flags & MTTS_EPI_BIAS) v += bias_n;
-  if (p.flags & MTTS_EPI_GELU) v = p.out_bf16 ? gelu_erf(v) : gelu_fast(v);
+  if (p.flags & MTTS_EPI_GELU) v = (p.out_bf16 || (p.flags & MTTS_EPI_EXACT_ACT)) ? gelu_erf(v) : gelu_fast(v);
   if (p.out_bf16) v = bf16_round(v);
   if (p.flags & MTTS_EPI_GAMMA) v *= gamma_n;
   if (p.flags & MTTS_EPI_RESIDUAL) {
@@ -1017,7 +1017,8 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   if (flags & MTTS_EPI_GAMMA) MTTS_REQUIRE(gamma != nullptr, "mtts_gemm: EPI_GAMMA without gamma");
   if (flags & MTTS_EPI_RESIDUAL) MTTS_REQUIRE(residual != nullptr, "mtts_gemm: EPI_RESIDUAL without residual");
   if (flags & MTTS_EPI_SWIGLU)
-    MTTS_REQUIRE((N % 4) == 0 && !(flags & ~MTTS_EPI_SWIGLU), "mtts_gemm: SWIGLU needs N % 4 == 0 and no other flags");
+    MTTS_REQUIRE((N % 4) == 0 && !(flags & ~(MTTS_EPI_SWIGLU | MTTS_EPI_EXACT_ACT)),
+                 "mtts_gemm: SWIGLU needs N % 4 == 0 and no other flags");
 
   int bn = mtts_gemm_tc_pick_bn(M);
   // (Routing wide matrices at batch 129..256 to the persistent 256-row-tile kernel wins in isolation — 21 vs 30 us at

@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 BF16, F32 = 0, 1
-EPI_BIAS, EPI_GELU, EPI_GAMMA, EPI_RESIDUAL, EPI_SWIGLU = 1, 2, 4, 8, 16
+EPI_BIAS, EPI_GELU, EPI_GAMMA, EPI_RESIDUAL, EPI_SWIGLU, EPI_EXACT_ACT = 1, 2, 4, 8, 16, 32
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -53,8 +53,34 @@ def gemm_workspace(device, nbytes: int) -> torch.Tensor:
     return ws
 
 
+def split_tf32x3(x: torch.Tensor, weights_order: bool = False) -> torch.Tensor:
+    """fp32 [rows, K] -> [rows, 3K] hi/lo TF32 split (mtts_split_tf32x3): [hi|lo|hi] for activations, [hi|hi|lo] for
+    weights, so that a TF32 tensor-core GEMM over 3K computes the product to fp32 accuracy."""
+    _cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, K = x.shape
+    out = torch.empty((rows, 3 * K), dtype=torch.float32, device=x.device)
+    check(_lib.load().mtts_split_tf32x3(ptr(x), x.stride(0), ptr(out), out.stride(0), rows, K, 1 if weights_order else 0,
+                                        stream_ptr()))
+    return out
+
+
+class ExactWeight:
+    """An fp32 weight [N, K] together with its [hi|hi|lo] split [N, 3K], built once at load time (exact-mode GEMMs)."""
+
+    def __init__(self, w: torch.Tensor):
+        self.w = w
+        self.split = split_tf32x3(w.contiguous(), weights_order=True)
+        self.shape = w.shape
+
+
+def gemm_exact(x, w: ExactWeight, out=None, **kw):
+    """fp32-accurate `x @ w^T` on the tcgen05 TF32 path: 3xTF32 (hi*hi + lo*hi + hi*lo, fp32 accumulate), erff GELU."""
+    return gemm(split_tf32x3(x), w.split, out=out, _exact_act=True, **kw)
+
+
 def gemm(x, w, out=None, *, out_dtype=None, bias=None, gelu=False, gamma=None, residual=None, swiglu=False,
-         workspace=None):
+         workspace=None, _exact_act=False):
     """out[M,N] = epi(x[M,K] @ w[N,K]^T) on the tcgen05 path (mtts_gemm)."""
     _cuda(x, w, out, bias, gamma, residual)
     assert x.dim() == 2 and w.dim() == 2 and x.shape[1] == w.shape[1], (x.shape, w.shape)
@@ -80,6 +106,8 @@ def gemm(x, w, out=None, *, out_dtype=None, bias=None, gelu=False, gamma=None, r
         assert residual.dtype == out.dtype and residual.shape == out.shape and residual.stride(1) == 1
     if swiglu:
         flags |= EPI_SWIGLU
+    if _exact_act:
+        flags |= EPI_EXACT_ACT
     L = _lib.load()
     need = L.mtts_gemm_workspace_bytes(M, N, K, _dt(x))
     ws = workspace if workspace is not None else gemm_workspace(x.device, need)

@@ -138,6 +138,7 @@ class ResidualVQ:
         nq = n_quantizers or self.num_quantizers
         if self.in_w is not None:
             zt = ops.gemm_simt(zt, self.in_w, bias=self.in_b)  # exact fp32: a TF32 product here would move codes
+        self._last_zin = zt                                    # (N, rvq_dim) projected vectors: parity tests read them
         codes, _, _ = ops.rvq_encode(zt.contiguous(), self.codebooks[:nq].contiguous(), self.norms[:nq].contiguous(),
                                      valid=valid.contiguous(), want_zq=False)
         return codes
@@ -180,6 +181,13 @@ class XY_Tokenizer:
         self._sd = None
         self._ready = False
         self.training = False
+        # encode() produces INTEGER codes that must equal the reference's, whose matmuls are true fp32
+        # (`matmul.allow_tf32 = False`): by default the encoder front end runs every GEMM as 3xTF32
+        # (fp32-accurate products, fp32 accumulate), attention on fp32 CUDA cores and the exact erf GELU. Setting
+        # `encode_exact = False` selects plain TF32 tensor-core GEMMs (2-3x faster; ~1e-3 feature noise flips the codes
+        # whose two best candidates are closer than that — the rate is reported by tests/test_codec_gpu.py).
+        self.encode_exact = True
+        self._exact_w = {}
 
     # ------------------------------------------------------------------ loading
     @classmethod
@@ -331,6 +339,7 @@ class XY_Tokenizer:
     def _prepare(self):
         sd, dev, gp = self._sd, self.device, self.params
         f = lambda k: sd[k].to(dev, torch.float32).contiguous()
+        self._exact_w = {}
         self.quantizer.load(sd, "quantizer.", dev)
         # post-RVQ adapter (Transformer, modules.py:519-640)
         pk = gp["post_rvq_adapter_kwargs"]
@@ -463,17 +472,28 @@ class XY_Tokenizer:
                                     rows_per_item, stream_ptr()))
         return out
 
-    def _stack(self, h, st: _TransformerStack, heads, lengths, B, T):
+    def _mm(self, x, w, exact=False, **kw):
+        """Dense layer: TF32 tensor-core GEMM, or (exact) the 3xTF32 product against the weight's cached hi/lo split."""
+        if not exact:
+            return ops.gemm(x, w, **kw)
+        ew = self._exact_w.get(w.data_ptr())
+        if ew is None or ew.w is not w:
+            ew = ops.ExactWeight(w)
+            self._exact_w[w.data_ptr()] = ew
+        return ops.gemm_exact(x, ew, **kw)
+
+    def _stack(self, h, st: _TransformerStack, heads, lengths, B, T, exact=False):
         E = h.shape[1]
+        mha = self.L.mtts_mha_varlen_fp32 if exact else self.L.mtts_mha_varlen
         for lw in st.layers:
             xn = self._ln(h, lw["ln1_w"], lw["ln1_b"])
-            qkv = ops.gemm(xn, lw["wqkv"], bias=lw["bqkv"])
+            qkv = self._mm(xn, lw["wqkv"], exact, bias=lw["bqkv"])
             ao = torch.empty((B * T, E), dtype=torch.float32, device=h.device)
-            check(self.L.mtts_mha_varlen(ptr(qkv), ptr(ao), ptr(lengths), B, T, heads, E // heads, stream_ptr()))
-            ops.gemm(ao, lw["wo"], bias=lw["bo"], residual=h, out=h)
+            check(mha(ptr(qkv), ptr(ao), ptr(lengths), B, T, heads, E // heads, stream_ptr()))
+            self._mm(ao, lw["wo"], exact, bias=lw["bo"], residual=h, out=h)
             xn = self._ln(h, lw["ln2_w"], lw["ln2_b"], out=xn)
-            ff = ops.gemm(xn, lw["fc1_w"], bias=lw["fc1_b"], gelu=True)
-            ops.gemm(ff, lw["fc2_w"], bias=lw["fc2_b"], residual=h, out=h)
+            ff = self._mm(xn, lw["fc1_w"], exact, bias=lw["fc1_b"], gelu=True)
+            self._mm(ff, lw["fc2_w"], exact, bias=lw["fc2_b"], residual=h, out=h)
         return self._ln(h, st.ln_w, st.ln_b, lengths=lengths, rows_per_item=T)  # + zero rows beyond each length
 
     @torch.no_grad()
@@ -580,27 +600,27 @@ class XY_Tokenizer:
         return {"syn_wav_list": syn}
 
     # ------------------------------------------------------------------ encode side
-    def _conv_gelu(self, x, w, b, B, T, cin, k, stride):
+    def _conv_gelu(self, x, w, b, B, T, cin, k, stride, exact=False):
         """Conv1d(k, pad=(k-1)/2, stride) + exact GELU on token-major x (B*T, cin) as im2col + GEMM."""
         Tout = (T + 2 * ((k - 1) // 2) - k) // stride + 1
         col = torch.empty((B * Tout, w.shape[1]), dtype=torch.float32, device=x.device)
         if w.shape[1] != k * cin:
             col.zero_()
         check(self.L.mtts_im2col(ptr(x), ptr(col), B, T, cin, k, w.shape[1], stride, stream_ptr()))
-        return ops.gemm(col, w, bias=b, gelu=True), Tout
+        return self._mm(col, w, exact, bias=b, gelu=True), Tout
 
-    def _encoder(self, mel, mel_len, B, T, e):
-        h, T1 = self._conv_gelu(mel, e["c1_w"], e["c1_b"], B, T, mel.shape[1], e["k"], 1)
-        h, T2 = self._conv_gelu(h, e["c2_w"], e["c2_b"], B, T1, h.shape[1], e["k"], e["stride"])
+    def _encoder(self, mel, mel_len, B, T, e, exact=False):
+        h, T1 = self._conv_gelu(mel, e["c1_w"], e["c1_b"], B, T, mel.shape[1], e["k"], 1, exact)
+        h, T2 = self._conv_gelu(h, e["c2_w"], e["c2_b"], B, T1, h.shape[1], e["k"], e["stride"], exact)
         lens = (mel_len // e["stride"]).to(torch.int32).contiguous()
         check(self.L.mtts_add_rows_mod(ptr(h), ptr(e["pos"]), B * T2, h.shape[1], T2, stream_ptr()))
-        return self._stack(h, e["stack"], e["heads"], lens, B, T2), lens, T2
+        return self._stack(h, e["stack"], e["heads"], lens, B, T2, exact), lens, T2
 
-    def _adapter(self, x, lens, B, T, a):
-        h = ops.gemm(x, a["proj_w"], bias=a["proj_b"]) if a["proj_w"] is not None else x.clone()
+    def _adapter(self, x, lens, B, T, a, exact=False):
+        h = self._mm(x, a["proj_w"], exact, bias=a["proj_b"]) if a["proj_w"] is not None else x.clone()
         check(self.L.mtts_add_rows_mod(ptr(h), ptr(a["pos"]), B * T, h.shape[1], T, stream_ptr()))
-        h = self._stack(h, a["stack"], a["heads"], lens, B, T)
-        return ops.gemm(h, a["out_w"], bias=a["out_b"]) if a["out_w"] is not None else h
+        h = self._stack(h, a["stack"], a["heads"], lens, B, T, exact)
+        return self._mm(h, a["out_w"], exact, bias=a["out_b"]) if a["out_w"] is not None else h
 
     @torch.no_grad()
     def log_mel(self, wav: torch.Tensor) -> torch.Tensor:
@@ -635,21 +655,23 @@ class XY_Tokenizer:
         mel = self.log_mel(wav)
         T = self.fe_nsamples // self.fe_hop
         mel_len = (lens + self.fe_hop - 1) // self.fe_hop                 # attention_mask[:, ::hop].sum()
-        sem, l2, T2 = self._encoder(mel, mel_len, B, T, self.enc["semantic_encoder"])
-        sem = self._adapter(sem, l2, B, T2, self.enc["semantic_encoder_adapter"])
-        aco, _, _ = self._encoder(mel, mel_len, B, T, self.enc["acoustic_encoder"])
+        ex = bool(self.encode_exact)
+        sem, l2, T2 = self._encoder(mel, mel_len, B, T, self.enc["semantic_encoder"], ex)
+        sem = self._adapter(sem, l2, B, T2, self.enc["semantic_encoder_adapter"], ex)
+        aco, _, _ = self._encoder(mel, mel_len, B, T, self.enc["acoustic_encoder"], ex)
         cat = torch.cat([sem, aco], dim=1).contiguous()                   # channel concat, token-major
-        h = self._adapter(cat, l2, B, T2, self.enc["pre_rvq_adapter"])
+        h = self._adapter(cat, l2, B, T2, self.enc["pre_rvq_adapter"], ex)
         # ResidualDownConv (modules.py:426-477): 4 frames -> 1; gate/up convs (k = stride = 4) are one interleaved GEMM
         # with the SwiGLU epilogue; down_proj + residual; LayerNorm
         pool = self.ds_pool
         T3 = T2 // pool
         x4 = h.view(B * T3, pool * h.shape[1])
-        gu = ops.gemm(x4, self.ds_gu_w, swiglu=True)
-        c = ops.gemm(gu, self.ds_down_w, residual=x4)
+        gu = self._mm(x4, self.ds_gu_w, ex, swiglu=True)
+        c = self._mm(gu, self.ds_down_w, ex, residual=x4)
         z = self._ln(c, self.ds_ln_w, self.ds_ln_b)
         l3 = (l2 // pool).to(torch.int64)
         valid = (torch.arange(T3, device=dev)[None, :] < l3[:, None]).reshape(-1)
+        self._last_pre_rvq = z                                            # (B*T3, input_dim): parity tests read it
         codes = self.quantizer.encode_tokens(z, valid)
         return codes.view(self.nq, B, T3), l3
 

@@ -121,3 +121,26 @@ def test_gemm_rejects_cpu_tensors():
     from moss_ttsd_b200 import ops, _lib
     with pytest.raises(_lib.MttsError):
         ops.gemm(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(8, 64, dtype=torch.bfloat16))
+
+
+def test_3xtf32_gemm_is_fp32_accurate():
+    """ops.gemm_exact (hi/lo TF32 split, K' = 3K, fp32 TMEM accumulators) against an fp64 product: error at the level of
+    an fp32 FMA chain (gemm_simt), three orders below the plain TF32 tensor-core product."""
+    from moss_ttsd_b200 import ops
+    torch.manual_seed(1)
+    M, N, K = 300, 520, 768
+    x = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * K ** -0.5
+    b = torch.randn(N, device="cuda") * 0.1
+    ref = (x.double() @ w.double().t() + b.double())
+    scale = ref.abs().max().item()
+    e_exact = (ops.gemm_exact(x, ops.ExactWeight(w), bias=b).double() - ref).abs().max().item() / scale
+    e_simt = (ops.gemm_simt(x, w, bias=b).double() - ref).abs().max().item() / scale
+    e_tf32 = (ops.gemm(x, w, bias=b).double() - ref).abs().max().item() / scale
+    print(f"relative to max |out|: 3xTF32 {e_exact:.2e}, fp32 SIMT {e_simt:.2e}, TF32 {e_tf32:.2e}")
+    assert e_exact <= 2e-6 and e_exact <= 10 * max(e_simt, 1e-7)
+    assert e_tf32 >= 20 * e_exact
+    # erf GELU epilogue of the exact path
+    g_ref = torch.nn.functional.gelu(ref)
+    g = ops.gemm_exact(x, ops.ExactWeight(w), bias=b, gelu=True).double()
+    assert (g - g_ref).abs().max().item() / g_ref.abs().max().item() <= 2e-6
