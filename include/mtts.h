@@ -179,6 +179,21 @@ int mtts_delay_step(long long* tokens, const long long* tf_tail, long long* sequ
                     int* unfinished_hist, int* finish_len, int B, const int* dyn_params, int speech_lo, int speech_hi,
                     int eos_token, int has_eos_criteria, const mtts_sampler_config* cfg, void* stream);
 
+/* Per-row variants (continuous batching): `row_ctl` [B][4] int32 = {step0, P, max_length, eos_at} gives every
+ * row its own step origin (its state machine runs at step - step0), prompt length and max_length, so a finished row's
+ * slot can be refilled with a queued request while the other rows keep decoding (the reference keeps feeding finished
+ * rows [EOS, pad x7] until the longest row is done, modeling_asteroid.py:155-158,166-169). eos_at > 0: channel 0 is
+ * forced to EOS from sequence row eos_at on (per-request length budget; the row winds down as after a sampled EOS).
+ * `unfinished_hist` is a ring of `hist_len` entries here. row_ctl == NULL: identical to the functions above. */
+int mtts_sample8_rows(const void* logits, long long ld, int B, const mtts_sampler_config* cfg, const uint32_t* seen,
+                      const int* step_ptr, const int* row_ctl, const unsigned long long* seed_ptr, long long* out_tokens,
+                      int* err_flag, void* workspace, size_t workspace_bytes, void* stream);
+int mtts_delay_step_rows(long long* tokens, const long long* tf_tail, long long* sequences, long long max_len_rows,
+                         int* unfinished, int* needs_steps, int* positions, uint32_t* seen, int* step_ptr,
+                         int* unfinished_hist, int hist_len, int* finish_len, int B, const int* dyn_params,
+                         const int* row_ctl, int speech_lo, int speech_hi, int eos_token, int has_eos_criteria,
+                         const mtts_sampler_config* cfg, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * XY_Tokenizer decode path, fp32, token-major activations [batch*frames, channels]
  * (XY_Tokenizer/xy_tokenizer/model.py:103-128 -> nn/modules.py). All dense layers go through mtts_gemm (TF32).

@@ -88,6 +88,8 @@ SIGNATURES = {
     "mtts_sample8_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mtts_sample8": (c_int, [c_void_p, c_ll, c_int, _cfg_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                              c_void_p]),
+    "mtts_sample8_rows": (c_int, [c_void_p, c_ll, c_int, _cfg_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_size_t, c_void_p]),
     "mtts_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p, c_int, c_void_p]),
     "mtts_mha_varlen": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mtts_mha_varlen_fp32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -110,6 +112,9 @@ SIGNATURES = {
     "mtts_decode_mega": (c_int, [ctypes.POINTER(DecodeMegaArgs), c_void_p]),
     "mtts_delay_step": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, _cfg_p, c_void_p]),
+    "mtts_delay_step_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, _cfg_p,
+                                     c_void_p]),
 }
 
 

@@ -111,6 +111,7 @@ struct SampleParams2 {
   mtts_sampler_config cfg;
   const uint32_t* seen;
   const int* step_ptr;
+  const int* row_ctl;  // optional [B][4] = {step0, P, max_length, eos_at}: per-row step origin (continuous batching)
   const unsigned long long* seed_ptr;  // device-resident so that a captured graph can be re-used with a new seed
   long long* out_tokens;
   int* err_flag;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(kThreads) sample_scan_kernel(const SampleParam
   const mtts_sampler_config& cfg = p.cfg;
   const int V = cfg.vocab[c], S = p.slices_of[c];
   const int tid = threadIdx.x;
-  const int step = *p.step_ptr;
+  const int step = *p.step_ptr - (p.row_ctl ? p.row_ctl[b * 4] : 0);
   const ScoreCtx sc = make_ctx(p, b, c, step);
   const int j0 = slice * p.chunk * kSlice + tid * 8;
   const long long bc = (long long)b * cfg.channels + c;
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
   if (!cfg.do_sample[c]) return;
   const int V = cfg.vocab[c], S = p.slices_of[c];
   const int tid = threadIdx.x;
-  const int step = *p.step_ptr;
+  const int step = *p.step_ptr - (p.row_ctl ? p.row_ctl[b * 4] : 0);
   const ScoreCtx sc = make_ctx(p, b, c, step);
   const long long bc = (long long)b * cfg.channels + c;
   const float thr = __ldcg(p.ws.thr + bc * 4);
@@ -465,9 +466,15 @@ struct StepParams {
   uint32_t* seen;
   int* step_ptr;
   int* unfinished_hist;      // [max_steps] number of unfinished rows after each step
+  int hist_len;              // per-row mode: ring length of unfinished_hist
   int* finish_len;           // [B] sequence length (rows) at which the row finished (0 = not yet)
   int B, C;
   const int* dyn;  // device: [0] = prompt rows P, [1] = max_length (so a captured graph survives new prompts)
+  // optional [B][4] = {step0, P, max_length, eos_at}: every row runs the state machine from its own step origin with
+  // its own prompt length / length limit (continuous batching: a finished row's slot is refilled while the others go
+  // on), and `eos_at` > 0 replaces channel 0's token by EOS from sequence row `eos_at` on (a per-request length budget:
+  // the row then winds down exactly as if the model had emitted EOS there, modeling_asteroid.py:140-153)
+  const int* row_ctl;
   int speech_lo, speech_hi, eos_token, pad_token, has_eos_criteria;
   mtts_sampler_config cfg;
 };
@@ -477,16 +484,20 @@ __global__ void delay_step_kernel(const StepParams p) {
   pdl_wait();
   __shared__ int s_count;
   const int b = threadIdx.x;
-  const int s = *p.step_ptr;
+  const int gs = *p.step_ptr;
   if (threadIdx.x == 0) s_count = 0;
   __syncthreads();
   if (b < p.B) {
     const int C = p.C;
-    const int L = p.dyn[0] + s;  // rows before this append
+    const int* rc = p.row_ctl ? p.row_ctl + b * 4 : nullptr;
+    const int s = gs - (rc ? rc[0] : 0);
+    const int max_length = rc ? rc[2] : p.dyn[1];
+    const int L = (rc ? rc[1] : p.dyn[0]) + s;  // rows before this append
     long long tok[8];
     for (int c = 0; c < C; ++c) tok[c] = p.raw_tokens[(long long)b * C + c];
     int n = p.needs_steps[b];
     const int u = p.unfinished[b];
+    if (rc && rc[3] > 0 && L >= rc[3] && n < 0) tok[0] = p.eos_token;  // length budget reached: emit EOS on channel 0
     // wind-down trigger (:140-141)
     if (!(tok[0] >= p.speech_lo && tok[0] < p.speech_hi) && n < 0) n = C - 1;
     // teacher forcing of the delayed prompt tail (:143-145)
@@ -515,18 +526,20 @@ __global__ void delay_step_kernel(const StepParams p) {
     }
     // counters and stopping (:165-169)
     if (n > 0) n -= 1;
-    const int stop = (L + 1 >= p.dyn[1]) || (p.has_eos_criteria && tok[0] == p.eos_token) || (n == 0);
+    const int stop = (L + 1 >= max_length) || (p.has_eos_criteria && tok[0] == p.eos_token) || (n == 0);
     int un = (u && !stop) || (n > 0);
     if (u && !un && p.finish_len[b] == 0) p.finish_len[b] = L + 1;
     p.needs_steps[b] = n;
     p.unfinished[b] = un;
-    p.positions[b] += 1;
+    // per-row mode: a finished row's slot waits for its next request; its KV length stays put (it keeps being fed
+    // [EOS, pad x7], which nothing consumes) so that it never outgrows the pages it owns
+    if (!rc || u) p.positions[b] += 1;
     if (un) atomicAdd(&s_count, 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    p.unfinished_hist[s] = s_count;
-    *p.step_ptr = s + 1;
+    p.unfinished_hist[p.row_ctl ? gs % p.hist_len : gs] = s_count;
+    *p.step_ptr = gs + 1;
   }
 }
 
@@ -610,6 +623,14 @@ extern "C" size_t mtts_sample8_workspace_bytes(int B, int channels) {
 extern "C" int mtts_sample8(const void* logits, long long ld, int B, const mtts_sampler_config* cfg,
                             const uint32_t* seen, const int* step_ptr, const unsigned long long* seed_ptr,
                             long long* out_tokens, int* err_flag, void* workspace, size_t workspace_bytes, void* stream_) {
+  return mtts_sample8_rows(logits, ld, B, cfg, seen, step_ptr, nullptr, seed_ptr, out_tokens, err_flag, workspace,
+                           workspace_bytes, stream_);
+}
+
+extern "C" int mtts_sample8_rows(const void* logits, long long ld, int B, const mtts_sampler_config* cfg,
+                                 const uint32_t* seen, const int* step_ptr, const int* row_ctl,
+                                 const unsigned long long* seed_ptr, long long* out_tokens, int* err_flag, void* workspace,
+                                 size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   int rc = validate_cfg(cfg);
   if (rc) return rc;
@@ -622,6 +643,7 @@ extern "C" int mtts_sample8(const void* logits, long long ld, int B, const mtts_
   SampleParams2 p;
   memset(&p, 0, sizeof(p));
   p.logits = reinterpret_cast<const bf16*>(logits); p.ld = ld; p.cfg = *cfg; p.seen = seen; p.step_ptr = step_ptr;
+  p.row_ctl = row_ctl;
   p.seed_ptr = seed_ptr; p.out_tokens = out_tokens; p.err_flag = err_flag;
   sample_ws_layout(B, cfg->channels, &p.ws, reinterpret_cast<uint8_t*>(workspace));
   int total = 0;
@@ -660,17 +682,29 @@ extern "C" int mtts_delay_step(long long* tokens, const long long* tf_tail, long
                                int* unfinished_hist, int* finish_len, int B, const int* dyn_params,
                                int speech_lo, int speech_hi, int eos_token, int has_eos_criteria,
                                const mtts_sampler_config* cfg, void* stream_) {
+  return mtts_delay_step_rows(tokens, tf_tail, sequences, max_len_rows, unfinished, needs_steps, positions, seen, step_ptr,
+                              unfinished_hist, 0, finish_len, B, dyn_params, nullptr, speech_lo, speech_hi, eos_token,
+                              has_eos_criteria, cfg, stream_);
+}
+
+extern "C" int mtts_delay_step_rows(long long* tokens, const long long* tf_tail, long long* sequences,
+                                    long long max_len_rows, int* unfinished, int* needs_steps, int* positions,
+                                    uint32_t* seen, int* step_ptr, int* unfinished_hist, int hist_len, int* finish_len,
+                                    int B, const int* dyn_params, const int* row_ctl, int speech_lo, int speech_hi,
+                                    int eos_token, int has_eos_criteria, const mtts_sampler_config* cfg, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   int rc = validate_cfg(cfg);
   if (rc) return rc;
   MTTS_REQUIRE(B >= 1 && B <= 1024, "mtts_delay_step: batch must be in [1,1024] (got %d)", B);
   MTTS_REQUIRE(tokens && tf_tail && sequences && unfinished && needs_steps && positions && seen && step_ptr &&
-                   unfinished_hist && finish_len && dyn_params,
+                   unfinished_hist && finish_len && (dyn_params || row_ctl),
                "mtts_delay_step: null pointer");
+  MTTS_REQUIRE(row_ctl == nullptr || hist_len > 0, "mtts_delay_step_rows: hist_len must be positive with row_ctl");
   StepParams p;
   p.raw_tokens = tokens; p.tf_tail = tf_tail; p.sequences = sequences; p.max_len_rows = max_len_rows;
   p.unfinished = unfinished; p.needs_steps = needs_steps; p.positions = positions; p.seen = seen; p.step_ptr = step_ptr;
-  p.unfinished_hist = unfinished_hist; p.finish_len = finish_len; p.B = B; p.C = cfg->channels; p.dyn = dyn_params;
+  p.unfinished_hist = unfinished_hist; p.hist_len = hist_len; p.finish_len = finish_len; p.B = B; p.C = cfg->channels;
+  p.dyn = dyn_params; p.row_ctl = row_ctl;
   p.speech_lo = speech_lo; p.speech_hi = speech_hi; p.eos_token = eos_token;
   p.pad_token = cfg->pad_token; p.has_eos_criteria = has_eos_criteria; p.cfg = *cfg;
   const int threads = ((B + 31) / 32) * 32;

@@ -326,11 +326,15 @@ class DecoderEngine:
             need = max(need, self.L.mtts_gemm_workspace_bytes(R, n, k, ops.BF16))
         return torch.zeros(need, dtype=torch.uint8, device=self.dev)
 
-    def _layers(self, a, cache, positions, row_seq, attn_kw, gws):
+    def _layers(self, a, cache, positions, row_seq, attn_kw, gws, want_output=True):
         x, xn, qkv, q, ao, h = a["x"], a["xn"], a["qkv"], a["q"], a["ao"], a["h"]
+        last = len(self.w.layers) - 1
         for l, lw in enumerate(self.w.layers):
             self._rmsnorm(x, lw["ln1"], xn)
             ops.gemm(xn, lw["wqkv"], out=qkv, workspace=gws)
+            if l == last and not want_output:          # only this layer's K/V are still needed
+                self._rope_kv(qkv, lw, positions, row_seq, q, cache, l)
+                return None
             if self.fused_decode_attn and attn_kw["rows_per_tile"] == 1 and row_seq is None:
                 ws = attn_kw["ws"]
                 check(self.L.mtts_gqa_decode_fused(
@@ -358,16 +362,28 @@ class DecoderEngine:
         mask = (attention_mask != 0)
         lens = mask.sum(1).to(torch.int64)
         lens_h = lens.cpu().numpy()
-        R = int(lens_h.sum())
         flat_idx = mask.reshape(-1).nonzero(as_tuple=False).squeeze(1)          # packing is pure index plumbing
         ids = input_ids.reshape(B * P, C).index_select(0, flat_idx).contiguous()
-        cu = np.zeros(B + 1, dtype=np.int64)
+        out = self.prefill_packed(ids, lens_h, np.arange(B, dtype=np.int32), cache, "all" if all_logits else "last")
+        if all_logits:
+            return out, flat_idx, lens
+        return out, lens
+
+    def prefill_packed(self, ids: torch.Tensor, lens_h, slots_h, cache: KVCache, logits: Optional[str] = "last"):
+        """Packed prefill: `ids` (R, C) int64 holds the rows of len(lens_h) sequences back to back; sequence i has
+        lens_h[i] rows at positions 0 .. lens_h[i]-1 and its K/V go to cache slot slots_h[i] (a row of the page table:
+        with continuous batching the slot is wherever a finished request made room). logits: "last" -> [n, Vpad] of each
+        sequence's last row, "all" -> [R, Vpad], None -> only the K/V side effect (admission of a queued request)."""
+        lens_h = np.asarray(lens_h, dtype=np.int64)
+        n = len(lens_h)
+        R = int(lens_h.sum())
+        cu = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(lens_h, out=cu[1:])
-        pos_h = np.concatenate([np.arange(n, dtype=np.int32) for n in lens_h]) if R else np.zeros(0, np.int32)
-        seq_h = np.repeat(np.arange(B, dtype=np.int32), lens_h)
+        pos_h = np.concatenate([np.arange(k, dtype=np.int32) for k in lens_h]) if R else np.zeros(0, np.int32)
+        seq_h = np.repeat(np.asarray(slots_h, dtype=np.int32), lens_h)
         row0_h, nrows_h = [], []
         tile_rows = self.prefill_tile_rows
-        for b in range(B):
+        for b in range(n):
             for t in range(0, int(lens_h[b]), tile_rows):
                 row0_h.append(cu[b] + t)
                 nrows_h.append(min(tile_rows, int(lens_h[b]) - t))
@@ -379,16 +395,18 @@ class DecoderEngine:
         gws = self._gemm_ws(R)
         self._embed(ids, a["x"])
         attn_kw = dict(tiles=len(row0_h), rows_per_tile=tile_rows, tile_row0=tile_row0, tile_nrows=tile_nrows, nsplit=1, ws=None)
-        xn = self._layers(a, cache, positions, row_seq, attn_kw, gws)
-        if all_logits:
-            logits = torch.empty((R, self.s.vpad), dtype=torch.bfloat16, device=self.dev)
-            ops.gemm(xn, self.w.heads, out=logits, workspace=gws)
-            return logits, flat_idx, lens
+        xn = self._layers(a, cache, positions, row_seq, attn_kw, gws, want_output=logits is not None)
+        if logits is None:
+            return None
+        if logits == "all":
+            out = torch.empty((R, self.s.vpad), dtype=torch.bfloat16, device=self.dev)
+            ops.gemm(xn, self.w.heads, out=out, workspace=gws)
+            return out
         last = torch.from_numpy(cu[1:] - 1).to(self.dev)
         hl = xn.index_select(0, last).contiguous()
-        logits = torch.empty((B, self.s.vpad), dtype=torch.bfloat16, device=self.dev)
-        ops.gemm(hl, self.w.heads, out=logits, workspace=self._gemm_ws(B))
-        return logits, lens
+        out = torch.empty((n, self.s.vpad), dtype=torch.bfloat16, device=self.dev)
+        ops.gemm(hl, self.w.heads, out=out, workspace=self._gemm_ws(n))
+        return out
 
     # ------------------------------------------------------------------ decode
     def make_decode_state(self, B: int, cache: KVCache, sampler: SamplerSetup, max_len_rows: int, speech_range,
@@ -480,14 +498,15 @@ class DecoderEngine:
     def sample_and_advance(self, st, logits):
         """Draw 8 tokens per row from `logits` and run the delay-pattern state machine (one step)."""
         sm = st["sampler"]
-        check(self.L.mtts_sample8(ptr(logits), logits.stride(0), st["B"], ctypes.byref(sm.cfg), ptr(st["seen"]),
-                                  ptr(st["step"]), ptr(st["seed_dev"]), ptr(st["tokens"]), ptr(self.err), ptr(st["sample_ws"]),
-                                  st["sample_ws"].numel(), stream_ptr()))
-        check(self.L.mtts_delay_step(ptr(st["tokens"]), ptr(st["tf_tail"]), ptr(st["sequences"]), st["max_len_rows"],
-                                     ptr(st["unfinished"]), ptr(st["needs"]), ptr(st["positions"]), ptr(st["seen"]),
-                                     ptr(st["step"]), ptr(st["hist"]), ptr(st["finish_len"]), st["B"], ptr(st["dyn"]),
-                                     st["speech"][0], st["speech"][1], st["eos"],
-                                     1 if st["has_eos"] else 0, ctypes.byref(sm.cfg), stream_ptr()))
+        rc = st.get("row_ctl")   # per-row step origin / prompt length / limits (continuous batching), else None
+        check(self.L.mtts_sample8_rows(ptr(logits), logits.stride(0), st["B"], ctypes.byref(sm.cfg), ptr(st["seen"]),
+                                       ptr(st["step"]), ptr(rc), ptr(st["seed_dev"]), ptr(st["tokens"]), ptr(self.err),
+                                       ptr(st["sample_ws"]), st["sample_ws"].numel(), stream_ptr()))
+        check(self.L.mtts_delay_step_rows(ptr(st["tokens"]), ptr(st["tf_tail"]), ptr(st["sequences"]), st["max_len_rows"],
+                                          ptr(st["unfinished"]), ptr(st["needs"]), ptr(st["positions"]), ptr(st["seen"]),
+                                          ptr(st["step"]), ptr(st["hist"]), st.get("hist_len", 0), ptr(st["finish_len"]),
+                                          st["B"], ptr(st["dyn"]), ptr(rc), st["speech"][0], st["speech"][1], st["eos"],
+                                          1 if st["has_eos"] else 0, ctypes.byref(sm.cfg), stream_ptr()))
 
     def _decode_body(self, st):
         a = st["acts"]

@@ -268,6 +268,55 @@ class AsteroidTTSInstruct:
             raise RuntimeError(f"libmtts device-side error flags {e} (1: token id out of range, 2: KV page out of range, "
                                f"3: sampler candidate overflow, 4: full-vocabulary nucleus larger than the candidate list)")
 
+    # ------------------------------------------------------------------ continuous batching (not in the reference)
+    @torch.no_grad()
+    def generate_continuous(self, prompts, max_new_tokens=None, max_length=None, max_batch: int = 256, eos_at=None,
+                            generation_config: Optional[GenerationConfig] = None, seed: Optional[int] = None,
+                            pool_pages: Optional[int] = None, sync_every: int = 8, **kwargs):
+        """Decode a QUEUE of scripts through `max_batch` slots, refilling a slot as soon as its row has finished
+        (continuous.ContinuousDecoder) instead of padding every batch to its longest row (modeling_asteroid.py:155-169).
+        prompts: list of (T_i, 8) int64 delay-shifted grids WITHOUT left padding (last 7 rows = teacher-forced tail);
+        max_new_tokens / max_length: scalar or per-prompt list with generate()'s meaning; eos_at: optional per-prompt
+        length budgets (sequence row from which channel 0 is forced to EOS). Returns a list of (L_i, 8) LongTensors: for
+        every prompt the rows a solo generate() call returns."""
+        from .continuous import ContinuousDecoder, Request
+        gc = copy.deepcopy(generation_config if generation_config is not None else self.generation_config)
+        gc.update(**kwargs)
+        n = len(prompts)
+        C = self.config.channels
+        per = lambda v, i: (v[i] if isinstance(v, (list, tuple)) else v)
+        reqs = []
+        for i, g in enumerate(prompts):
+            g = torch.as_tensor(g)
+            if g.dim() != 2 or g.shape[1] != C:
+                raise ValueError(f"Expected (T, {C}) prompt grids, got {tuple(g.shape)}")
+            if g.shape[0] < C:
+                raise ValueError("prompt grid must include the (channels-1) delay rows")
+            mnt = per(max_new_tokens, i) if max_new_tokens is not None else gc.max_new_tokens
+            ml = g.shape[0] + mnt if mnt is not None else (per(max_length, i) if max_length is not None else gc.max_length)
+            reqs.append(Request(i, g.to(self.device).contiguous(), int(ml), int(per(eos_at, i)) if eos_at is not None else 0))
+        if not reqs:
+            return []
+        eos = gc.eos_token_id
+        if isinstance(eos, (list, tuple)):
+            eos = eos[0] if len(eos) else None
+        eos_fill = self.config.eos_token_id if self.config.eos_token_id is not None else (eos if eos is not None else 0)
+        sampler = self._sampler_setup(gc)
+        slots = min(max_batch, n)
+        max_rows = max(r.max_length for r in reqs) + 2 * C
+        key = (slots, bytes(sampler.cfg), pool_pages, sync_every)
+        cd = getattr(self, "_continuous", None)
+        if cd is None or cd[0] != key or cd[1].max_rows < max_rows:
+            self._continuous = None
+            cd = (key, ContinuousDecoder(self.engine, slots, max(max_rows, 1024), sampler, tuple(self.config.speech_token_range),
+                                         int(eos_fill), pool_pages=pool_pages, page_size=self.kv_page_size,
+                                         sync_every=sync_every))
+            self._continuous = cd
+        if seed is None:
+            seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)
+        res = cd[1].run(reqs, seed=seed)
+        return [res[i] for i in range(n)]
+
     # ------------------------------------------------------------------ generate
     def _sampler_setup(self, gc: GenerationConfig) -> SamplerSetup:
         C = self.channels
@@ -294,10 +343,12 @@ class AsteroidTTSInstruct:
     @torch.no_grad()
     def generate(self, input_ids: torch.LongTensor = None, attention_mask: Optional[torch.Tensor] = None,
                  generation_config: Optional[GenerationConfig] = None, streamer=None, seed: Optional[int] = None,
-                 **kwargs):
+                 eos_at=None, **kwargs):
         """input_ids (B, T, 8) int64 — the delay-shifted, left-padded prompt grid whose last 7 rows are the
         teacher-forced tail; attention_mask (B, T). Returns LongTensor (B, T - 7 + G, 8) (or
-        GenerateDecoderOnlyOutput with return_dict_in_generate), exactly the rows CustomMixin._sample returns."""
+        GenerateDecoderOnlyOutput with return_dict_in_generate), exactly the rows CustomMixin._sample returns.
+        `eos_at` (not in the reference): optional per-row length budgets — sequence row (in this padded grid) from which
+        channel 0 of row b is forced to EOS, after which the row winds down as after a sampled EOS; 0 = no budget."""
         gc = copy.deepcopy(generation_config if generation_config is not None else self.generation_config)
         gc.update(**kwargs)
         if gc.output_attentions or gc.output_hidden_states or gc.output_scores or gc.output_logits:
@@ -332,7 +383,7 @@ class AsteroidTTSInstruct:
         # neither re-allocate ~10 GB nor re-capture the 230-kernel graph.
         cfg_key = bytes(sampler.cfg)
         key = (B, self.kv_paged, self.kv_page_size, cfg_key, tuple(self.config.speech_token_range), int(eos_fill), has_eos,
-               eng.use_graph)
+               eng.use_graph, eos_at is not None)
         sess = getattr(self, "_session", None)
         if sess is None or sess["key"] != key or sess["rows"] < max_rows:
             self._session = None
@@ -342,11 +393,20 @@ class AsteroidTTSInstruct:
                             shuffle_pages=self.kv_paged)
             st = eng.make_decode_state(B, cache, sampler, rows_cap, tuple(self.config.speech_token_range), int(eos_fill),
                                        has_eos)
+            if eos_at is not None:
+                st["row_ctl"] = torch.zeros((B, 4), dtype=torch.int32, device=dev)
+                st["hist_len"] = st["hist"].numel()
+                st["mega"] = None
             sess = dict(key=key, rows=rows_cap, st=st, cache=cache)
             self._session = sess
         st, cache = sess["st"], sess["cache"]
         max_rows = sess["rows"]
         eng.reset_decode_state(st, seed, P, max_length)
+        if eos_at is not None:
+            ctl = torch.zeros((B, 4), dtype=torch.int32)
+            ctl[:, 1], ctl[:, 2] = P, max_length
+            ctl[:, 3] = torch.as_tensor(eos_at, dtype=torch.int32)
+            st["row_ctl"].copy_(ctl)
         st["sequences"][:, :P].copy_(input_ids[:, :P])
         st["tf_tail"].copy_(input_ids[:, P:])
         from . import _lib

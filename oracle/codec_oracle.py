@@ -25,14 +25,21 @@ def sinusoids(length, channels, max_timescale=10000):
 
 
 class CodecOracle:
-    def __init__(self, gp: dict, sd_np: dict):
+    def __init__(self, gp: dict, sd_np: dict, device="cpu"):
+        """`device="cuda"`: the same eager torch ops on the GPU (bench.py's `gpu_eager_baseline` leg, decode side only)."""
         self.gp = gp
-        self.sd = {k: torch.from_numpy(np.asarray(v)).float() for k, v in sd_np.items()}
+        self.dev = torch.device(device)
+        cpu = {k: (v.detach().cpu().float() if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v)).float())
+               for k, v in sd_np.items()}
+        if "quantizer.output_proj.weight_v" in cpu:
+            self.w_out = torch.from_numpy(weight_norm_weight(cpu["quantizer.output_proj.weight_v"].numpy(),
+                                                             cpu["quantizer.output_proj.weight_g"].numpy())).to(self.dev)
+        self.sd = {k: v.to(self.dev) for k, v in cpu.items()}
         self.nq = gp["quantizer_kwargs"]["num_quantizers"]
 
     # -------------------------------------------------------------- pieces
     def _attn_mask(self, seq_len, max_len):
-        valid = torch.arange(max_len)[None, :] < seq_len[:, None]
+        valid = torch.arange(max_len, device=self.dev)[None, :] < seq_len[:, None]
         m = (valid[:, None, :, None] & valid[:, None, None, :]).float()
         return m + (1.0 - m) * torch.finfo(torch.float32).min
 
@@ -56,21 +63,20 @@ class CodecOracle:
 
     def _stack(self, h, prefix, n_layers, heads, seq_len, pos):
         B, T, E = h.shape
-        h = h + (pos[:T] if T < pos.shape[0] else pos)
+        h = h + (pos[:T] if T < pos.shape[0] else pos).to(h.device)
         for l in range(n_layers):
             h = self._layer(h, f"{prefix}layers.{l}.", heads, seq_len)
         h = F.layer_norm(h, (E,), self.sd[prefix + "layer_norm.weight"], self.sd[prefix + "layer_norm.bias"])
-        mask = (torch.arange(T)[None, :] < seq_len[:, None])[..., None]
-        return torch.where(mask, h, torch.zeros((), dtype=h.dtype))
+        mask = (torch.arange(T, device=self.dev)[None, :] < seq_len[:, None])[..., None]
+        return torch.where(mask, h, torch.zeros((), dtype=h.dtype, device=self.dev))
 
     def decode_codes(self, codes):
         sd = self.sd
         nq, B, T = codes.shape
-        emb = torch.zeros(B, T, sd["quantizer.quantizers.0.codebook"].shape[1])
+        emb = torch.zeros(B, T, sd["quantizer.quantizers.0.codebook"].shape[1], device=self.dev)
         for i in range(nq):
             emb += F.embedding(codes[i], sd[f"quantizer.quantizers.{i}.codebook"])
-        w = torch.from_numpy(weight_norm_weight(sd["quantizer.output_proj.weight_v"].numpy(), sd["quantizer.output_proj.weight_g"].numpy()))
-        return F.linear(emb, w[:, :, 0], sd["quantizer.output_proj.bias"])  # (B, T, 3072) token-major
+        return F.linear(emb, self.w_out[:, :, 0], sd["quantizer.output_proj.bias"])  # (B, T, 3072) token-major
 
     def detokenize(self, codes, lengths):
         gp, sd = self.gp, self.sd
@@ -110,7 +116,7 @@ class CodecOracle:
         mag, ph = o.chunk(2, dim=1)
         mag = torch.clip(torch.exp(mag), max=1e2)
         S = mag * (torch.cos(ph) + 1j * torch.sin(ph))
-        win = torch.hann_window(n_fft)
+        win = torch.hann_window(n_fft, device=self.dev)
         pad = (n_fft - hop) // 2
         Bn, N, T = S.shape
         ifft = torch.fft.irfft(S, n_fft, dim=1, norm="backward") * win[None, :, None]
@@ -126,11 +132,11 @@ class CodecOracle:
         dur_len = int((30 - overlap_seconds) * in_sr // down)
         dur_wav = dur_len * up
         B = len(codes_list)
-        lens = torch.tensor([c.shape[-1] for c in codes_list])
+        lens = torch.tensor([c.shape[-1] for c in codes_list], device=self.dev)
         Tm = int(lens.max())
-        codes = torch.zeros(self.nq, B, Tm, dtype=torch.long)
+        codes = torch.zeros(self.nq, B, Tm, dtype=torch.long, device=self.dev)
         for i, c in enumerate(codes_list):
-            codes[:, i, :c.shape[-1]] = c
+            codes[:, i, :c.shape[-1]] = c.to(self.dev)
         chunks = []
         for ci in range((Tm + dur_len - 1) // dur_len):
             start = ci * dur_len
@@ -139,9 +145,10 @@ class CodecOracle:
             if cl.max() == 0:
                 continue
             wav = self.detokenize(codes[:, :, start:end], cl)
-            valid = torch.zeros(B, dur_wav)
+            valid = torch.zeros(B, dur_wav, device=self.dev)
+            cl_h = cl.tolist()
             for b in range(B):
-                n = min(int(cl[b]) * up, dur_wav)
+                n = min(int(cl_h[b]) * up, dur_wav)
                 if n > 0:
                     valid[b, :n] = wav[b, :n]
             chunks.append(valid)

@@ -116,18 +116,26 @@ def rotate_half(x):
 
 
 class OracleLM:
-    def __init__(self, shape: dict, sd: Dict[str, torch.Tensor], dtype=torch.float32):
+    def __init__(self, shape: dict, sd: Dict[str, torch.Tensor], dtype=torch.float32, device="cpu"):
+        """`device="cuda"` runs the same eager torch ops on the GPU (bench.py's `gpu_eager_baseline` leg: the reference's
+        own PyTorch-eager path on the same B200); parity tests and the CPU baseline use the default."""
         self.s = shape
         self.dtype = dtype
-        self.sd = {k: v.to(dtype) for k, v in sd.items()}
+        self.dev = torch.device(device)
+        moved = {}
+        self.sd = {}
+        for k, v in sd.items():                                   # tied tables stay one tensor
+            if id(v) not in moved:
+                moved[id(v)] = v.to(self.dev, dtype)
+            self.sd[k] = moved[id(v)]
         D = shape["head_dim"]
-        self.inv_freq = 1.0 / (shape["rope_theta"] ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))
+        self.inv_freq = (1.0 / (shape["rope_theta"] ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))).to(self.dev)
 
     def embed_sum(self, ids):
         B, S, C = ids.shape
         if C != self.s["channels"]:
             raise ValueError(f"Expected {self.s['channels']} channels, got {C}")
-        out = torch.zeros(B, S, self.s["hidden_size"], dtype=self.dtype)
+        out = torch.zeros(B, S, self.s["hidden_size"], dtype=self.dtype, device=self.dev)
         for c in range(C):
             out += F.embedding(ids[..., c], self.sd[f"model.embedding_list.{c}.weight"])
         return out
@@ -137,7 +145,7 @@ class OracleLM:
         s, sd = self.s, self.sd
         B, S, _ = ids.shape
         if attention_mask is None:
-            attention_mask = torch.ones(B, S)
+            attention_mask = torch.ones(B, S, device=self.dev)
         am = attention_mask.long()
         pos = am.cumsum(-1) - 1
         pos = pos.masked_fill(am == 0, 1)
@@ -145,9 +153,9 @@ class OracleLM:
         emb = torch.cat((freqs, freqs), dim=-1)
         cos, sin = emb.cos().to(self.dtype)[:, None], emb.sin().to(self.dtype)[:, None]
         minv = torch.finfo(self.dtype).min
-        causal = torch.tril(torch.ones(S, S, dtype=torch.bool))
+        causal = torch.tril(torch.ones(S, S, dtype=torch.bool, device=self.dev))
         allowed = causal[None, None] & (am[:, None, None, :] != 0)
-        add_mask = torch.zeros(B, 1, S, S, dtype=self.dtype).masked_fill(~allowed, minv)
+        add_mask = torch.zeros(B, 1, S, S, dtype=self.dtype, device=self.dev).masked_fill(~allowed, minv)
         x = self.embed_sum(ids)
         Hq, Hkv, D = s["num_attention_heads"], s["num_key_value_heads"], s["head_dim"]
         eps = s["rms_norm_eps"]
@@ -228,8 +236,9 @@ def sample_loop(logits_fn, input_ids, max_length, speech_range, eos_token_id=152
     """CustomMixin._sample restated (modeling_asteroid.py:83-169). `logits_fn(ids (B,L,8)) -> list of 8 (B,V_c)`
     last-position logits; `draw_fn(step, channel, probs)` replaces torch.multinomial for sampled channels."""
     B, T, C = input_ids.shape
-    unfinished = torch.ones(B, dtype=torch.long)
-    needs = -1 * torch.ones(B, dtype=torch.long)
+    dev = input_ids.device
+    unfinished = torch.ones(B, dtype=torch.long, device=dev)
+    needs = -1 * torch.ones(B, dtype=torch.long, device=dev)
     tf = input_ids
     ids = input_ids[:, :-(C - 1)]
     base = ids.shape[1]
@@ -272,7 +281,7 @@ def sample_loop(logits_fn, input_ids, max_length, speech_range, eos_token_id=152
                 nt[:, i] = nt[:, i] * unfinished + pd * (1 - unfinished)
         ids = torch.cat([ids, nt[:, None, :]], dim=1)
         needs = torch.where(needs > 0, needs - 1, needs)
-        stop = torch.full((B,), ids.shape[1] >= max_length, dtype=torch.bool)
+        stop = torch.full((B,), ids.shape[1] >= max_length, dtype=torch.bool, device=dev)
         if has_eos_criteria:
             stop = stop | (ids[:, -1, 0] == eos_token_id)
         stop = stop | (needs == 0)
@@ -289,8 +298,8 @@ class OracleCachedLM(OracleLM):
     """The same arithmetic with a per-layer K/V cache (what the reference does through HF DynamicCache): used as the
     timed CPU baseline in bench.py and pinned against the full-recompute path in tests/test_oracle_pin.py."""
 
-    def __init__(self, shape, sd, dtype=torch.float32):
-        super().__init__(shape, sd, dtype)
+    def __init__(self, shape, sd, dtype=torch.float32, device="cpu"):
+        super().__init__(shape, sd, dtype, device)
         self.k, self.v, self.mask = None, None, None
 
     def reset(self):
@@ -308,10 +317,10 @@ class OracleCachedLM(OracleLM):
         emb = torch.cat((freqs, freqs), dim=-1)
         cos, sin = emb.cos().to(self.dtype)[:, None], emb.sin().to(self.dtype)[:, None]
         minv = torch.finfo(self.dtype).min
-        qi = torch.arange(past, total)[:, None]
-        ki = torch.arange(total)[None, :]
+        qi = torch.arange(past, total, device=self.dev)[:, None]
+        ki = torch.arange(total, device=self.dev)[None, :]
         allowed = (ki <= qi)[None, None] & (am[:, None, None, :] != 0)
-        add_mask = torch.zeros(B, 1, S, total, dtype=self.dtype).masked_fill(~allowed, minv)
+        add_mask = torch.zeros(B, 1, S, total, dtype=self.dtype, device=self.dev).masked_fill(~allowed, minv)
         x = self.embed_sum(ids)
         Hq, Hkv, D = s["num_attention_heads"], s["num_key_value_heads"], s["head_dim"]
         eps = s["rms_norm_eps"]
@@ -352,7 +361,8 @@ class OracleCachedLM(OracleLM):
         state = dict(fed=0)
 
         def logits_fn(cur):
-            am = torch.cat([attention_mask[:, :P], torch.ones(cur.shape[0], cur.shape[1] - P, dtype=attention_mask.dtype)], 1)
+            am = torch.cat([attention_mask[:, :P], torch.ones(cur.shape[0], cur.shape[1] - P, dtype=attention_mask.dtype,
+                                                              device=attention_mask.device)], 1)
             new = cur[:, state["fed"]:]
             state["fed"] = cur.shape[1]
             with torch.no_grad():
