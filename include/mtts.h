@@ -213,6 +213,11 @@ int mtts_mha_varlen(const float* qkv, float* out, const int* lengths, int B, int
 int mtts_mha_varlen_fp32(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads, int head_dim,
                          void* stream);
 
+/* Window bookkeeping of XY_Tokenizer.encode / decode (model.py:214-216,241-243): dst[b, i] = i < lens[b] ? src[b, i] : 0
+ * for b < B, i < n; elements of 4 (waveform fp32) or 8 bytes (int64 codes); row strides in elements. */
+int mtts_rows_prefix_copy(const void* src, long long lds, void* dst, long long ldd, const int* lens, int B, int n,
+                          int elem_bytes, void* stream);
+
 /* 3xTF32 operand split for fp32-accurate products on the tcgen05 TF32 path: x [rows, K] fp32 -> out [rows, 3K] with
  * hi = rna_tf32(x), lo = x - hi laid out [hi | lo | hi] (weights_order = 0, activations) or [hi | hi | lo]
  * (weights_order = 1), so that mtts_gemm over K' = 3K computes hi*hi + lo*hi + hi*lo in fp32 accumulators — the

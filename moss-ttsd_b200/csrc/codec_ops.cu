@@ -558,6 +558,17 @@ __global__ void add_rows_mod_kernel(float* __restrict__ x, const float* __restri
   *reinterpret_cast<float4*>(x + r * C + c) = v;
 }
 
+// Chunk bookkeeping of XY_Tokenizer.encode / decode (model.py:214-216,241-243: one Python slice copy per item per
+// window): dst[b, i] = i < lens[b] ? src[b, i] : 0 for all items of a window in one launch.
+template <typename T>
+__global__ void rows_prefix_copy_kernel(const T* __restrict__ src, long long lds, T* __restrict__ dst, long long ldd,
+                                        const int* __restrict__ lens, int n) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[(long long)b * ldd + i] = i < lens[b] ? src[(long long)b * lds + i] : T(0);
+}
+
 // 3xTF32 split (see mtts_split_tf32x3 in mtts.h): hi = x rounded to TF32 (10-bit mantissa, round to nearest), lo = x - hi
 // (exact in fp32); the tcgen05 TF32 MMA then truncates lo to its top 10 mantissa bits — a 2^-22 relative error on x.
 __global__ void split_tf32x3_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ out, long long ldo,
@@ -632,6 +643,23 @@ extern "C" int mtts_mha_varlen_fp32(const float* qkv, float* out, const int* len
   dim3 grid(ceil_div(T, kQT), num_heads, B);
   mha_varlen_kernel<true><<<grid, 256, 4 * kQT * kPitch * sizeof(float), stream>>>(qkv, out, lengths, T, num_heads,
                                                                                     1.0f / sqrtf((float)head_dim));
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_rows_prefix_copy(const void* src, long long lds, void* dst, long long ldd, const int* lens, int B, int n,
+                                     int elem_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "mtts_rows_prefix_copy: elem_bytes must be 4 or 8");
+  if (B <= 0 || n <= 0) return MTTS_OK;
+  MTTS_REQUIRE(src && dst && lens, "mtts_rows_prefix_copy: null pointer");
+  dim3 grid(ceil_div(n, 256), B);
+  if (elem_bytes == 4)
+    rows_prefix_copy_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(src), lds,
+                                                            reinterpret_cast<float*>(dst), ldd, lens, n);
+  else
+    rows_prefix_copy_kernel<long long><<<grid, 256, 0, stream>>>(reinterpret_cast<const long long*>(src), lds,
+                                                                reinterpret_cast<long long*>(dst), ldd, lens, n);
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }

@@ -129,9 +129,22 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 __device__ __forceinline__ void ll_store(uint2* p, uint32_t data, uint32_t tag) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)tag << 32) | data) : "memory");
 }
-__device__ __noinline__ void ll_timeout(uint32_t tag) {
-  printf("mtts: decode_mega wait for tag %u timed out (block %d thread %d)\n", tag, blockIdx.x, threadIdx.x);
-  __trap();  // a protocol bug must surface as a launch error, never as a hung GPU box
+// Bounded waits WITHOUT a trap: a wait that exceeds 2^25 polls (>= 20 s at one L2 round trip per poll: a protocol bug,
+// or the GPU taken away from this cooperative grid for that long) raises the abort word; every other wait of the launch
+// notices it within 1024 polls and gives up too, so the kernel runs to its end (with garbage results), device error
+// flag 5 is set and the host raises — the context survives and other streams' work (e.g. an overlapped codec decode)
+// is unaffected.
+__device__ unsigned int g_mega_abort;   // tag0 + 1 of the launch that gave up (0: none)
+__device__ int* g_mega_err;             // the err_flag of the current launch (every CTA writes the same pointer)
+__device__ __noinline__ bool ll_slow_check(uint32_t tag, uint32_t spins, uint32_t launch_key) {
+  if (*reinterpret_cast<volatile unsigned int*>(&g_mega_abort) == launch_key) return true;
+  if (spins < (1u << 25)) return false;
+  printf("mtts: decode_mega wait for tag %u timed out (block %d thread %d): aborting the launch\n", tag, blockIdx.x,
+         threadIdx.x);
+  atomicExch(&g_mega_abort, launch_key);
+  if (g_mega_err) *g_mega_err = 5;
+  __threadfence();
+  return true;
 }
 // Pollers issue ALL their loads first and compare the tags afterwards (one L2 round trip per attempt, however many
 // words a thread needs); on a mismatch the whole batch is re-issued.
@@ -147,10 +160,13 @@ __device__ __forceinline__ void ll_issue2(const uint2* p, uint32_t& d0, uint32_t
   d0 = (uint32_t)v0; t0 = (uint32_t)(v0 >> 32);
   d1 = (uint32_t)v1; t1 = (uint32_t)(v1 >> 32);
 }
+__shared__ uint32_t s_launch_key;  // tag0 + 1 of this launch
 struct LLSpin {
   uint32_t spins = 0;
-  __device__ __forceinline__ void miss(uint32_t tag) {
-    if (++spins > (1u << 22)) ll_timeout(tag);
+  // true: give up (this launch has been aborted)
+  __device__ __forceinline__ bool miss(uint32_t tag) {
+    if ((++spins & 1023u) != 0) return false;
+    return ll_slow_check(tag, spins, s_launch_key);
   }
 };
 
@@ -196,7 +212,7 @@ __device__ __noinline__ void sentinel_wait(const uint2* base, const int* offs, i
       ok = ok && (t == tag);
     }
     if (__all_sync(0xffffffffu, ok)) break;
-    sp.miss(tag);
+    if (sp.miss(tag)) break;
   }
 }
 
@@ -333,7 +349,7 @@ __device__ __noinline__ void stage_norm(const MegaParams& p, const uint2* src_ll
         ok = ok && t0 == tag && t1 == tag;
       }
       if (ok) break;
-      sp.miss(tag);
+      if (sp.miss(tag)) break;
     }
   }
   const int e = tid * 4;
@@ -386,7 +402,7 @@ __device__ __noinline__ void stage_h(const MegaParams& p, uint32_t tag, const in
         ok = ok && t0 == tag && t1 == tag;
       }
     if (ok) break;
-    sp.miss(tag);
+    if (sp.miss(tag)) break;
   }
 #pragma unroll
   for (int pc = 0; pc < 3; ++pc)
@@ -412,7 +428,7 @@ __device__ __noinline__ void stage_attn_out(const MegaParams& p, bf16* act, uint
         ok = ok && (t == tag);
       }
       if (__all_sync(0xffffffffu, ok)) break;
-      sp.miss(tag);
+      if (sp.miss(tag)) break;
     }
   }
   consumer_sync();
@@ -446,7 +462,7 @@ __device__ __noinline__ void stage_attn_out(const MegaParams& p, bf16* act, uint
           for (int i = 0; i < 6; ++i) ok = ok && (t[i] == tag);
         }
         if (ok) break;
-        sp.miss(tag);
+        if (sp.miss(tag)) break;
       }
       float Mn = M;
 #pragma unroll
@@ -559,7 +575,7 @@ __device__ __noinline__ void attention_layer(const MegaParams& p, const AttnLaye
         ll_issue(src + lane, a, ta);
         ll_issue(src + 32 + lane, c, tc);
         if (ta == tag_in && tc == tag_in) break;
-        sp.miss(tag_in);
+        if (sp.miss(tag_in)) break;
       }
     }
     float x0 = bf16lo(a), x1 = bf16hi(a), x2 = bf16lo(c), x3 = bf16hi(c);
@@ -717,6 +733,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
   const int n_gemv = (int)gridDim.x;         // every CTA streams its share of the projections (an SM sustains ~50 GB/s
                                              // of bulk copies, so HBM is only saturated with all of them streaming)
   const uint32_t tag0 = *p.tag_base;         // written by the previous launch (stream order)
+  if (tid == 0) {
+    s_launch_key = tag0 + 1u;
+    g_mega_err = p.err_flag;
+  }
 
   for (int c = tid; c < n_gemv; c += kThreads) {
     sent_wo[c] = last_tile_row(slice_rows(mat_rows(1), mat_unit(1), mat_rot(1), c, n_gemv)) >> 1;

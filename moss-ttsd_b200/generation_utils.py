@@ -216,66 +216,195 @@ def undelay(outputs: torch.Tensor, channels: int = MAX_CHANNELS) -> torch.Tensor
     return speech
 
 
+def _prepare_item(item, start_idx, i, use_normalize):
+    """Host-only part of one item (generation_utils.py:362-392): schema, text normalisation, prompt-audio load/resample."""
+    p = process_jsonl_item(item)
+    full_text = p["prompt_text"] + p["text"] if p["prompt_text"] else p["text"]
+    original_full_text = full_text
+    if use_normalize:
+        full_text = normalize_text(full_text)
+    final_text = full_text.replace("[S1]", "<speaker1>").replace("[S2]", "<speaker2>")
+    meta = {
+        "index": start_idx + i,
+        "original_text": original_full_text,
+        "normalized_text": normalize_text(original_full_text) if use_normalize else None,
+        "final_text": final_text,
+        "use_normalize": use_normalize,
+    }
+    audio = load_audio_data(p["prompt_audio"]) if p["prompt_audio"] else None
+    return meta, final_text, audio
+
+
+def encode_prompt_audios(spt, audios, device, group: int = 32):
+    """All prompt audios of a batch through `spt.encode` in groups of `group` items instead of one call per item
+    (generation_utils.py:198): the codec treats every item of a call independently (own log-mel, own length mask), so
+    the codes equal the per-item calls'. -> list aligned with `audios` of (n_i, 8) numpy grids with channel 0 offset by
+    151665, or None."""
+    out = [None] * len(audios)
+    todo = [(i, a) for i, a in enumerate(audios) if a is not None]
+    for g0 in range(0, len(todo), group):
+        part = todo[g0:g0 + group]
+        wavs = []
+        for _, wav in part:
+            silence = torch.zeros(wav.shape[0], int(SILENCE_DURATION * 16000))
+            wavs.append(torch.cat([wav, silence], dim=1).squeeze().to(device))
+        with torch.no_grad():
+            codes = spt.encode(wavs)["codes_list"]
+        for (i, _), c in zip(part, codes):
+            tok = c.permute(1, 0).cpu().numpy()
+            tok[:, 0] = tok[:, 0] + SPEECH_OFFSET
+            out[i] = tok
+    return out
+
+
+def prepare_batch(batch_items, tokenizer, spt, device, system_prompt, start_idx, use_normalize=False, pool=None):
+    """Prompt side of `process_batch` (generation_utils.py:362-404): -> (actual_texts_data, input_ids (B,T,8) int64,
+    attention_mask (B,T) float64). Host work per item (schema, normalisation, audio file load + resample) runs on `pool`
+    (a concurrent.futures executor) when given; all prompt audios are encoded in batched `spt.encode` calls."""
+    n = len(batch_items)
+    if pool is not None:
+        prepared = list(pool.map(lambda t: _prepare_item(t[1], start_idx, t[0], use_normalize), enumerate(batch_items)))
+    else:
+        prepared = [_prepare_item(item, start_idx, i, use_normalize) for i, item in enumerate(batch_items)]
+    metas = [p[0] for p in prepared]
+    try:
+        audio_tokens = encode_prompt_audios(spt, [p[2] for p in prepared], device)
+    except Exception as e:
+        print(f"Error processing audio data: {e}")
+        raise
+    grids = []
+    for (meta, text, _), tok in zip(prepared, audio_tokens):
+        g = process_inputs(tokenizer, spt, system_prompt, text, device, None)
+        if tok is not None:
+            g = np.concatenate([g, tok])
+        grids.append(shifting_inputs(g, tokenizer))
+    input_ids, attention_mask = rpadding(grids, MAX_CHANNELS, tokenizer)
+    return metas, input_ids, attention_mask
+
+
+def finish_batch(speech_ids, ends, wavs, spt, start_idx):
+    """(speech ids, per-row end, decoded waveforms or None) -> the reference's audio_results list (:456-467)."""
+    audio_results = [None] * len(ends)
+    for i, (e, w) in enumerate(zip(ends, wavs)):
+        if e <= 0:
+            print(f"Sample {start_idx + i} has no valid speech tokens")
+            continue
+        if w is None:
+            continue
+        w = w.cpu().detach()
+        if w.ndim == 1:
+            w = w.unsqueeze(0)
+        audio_results[i] = {"audio_data": w, "sample_rate": spt.output_sample_rate, "index": start_idx + i}
+        print(f"Audio generation completed: sample {start_idx + i}")
+    return audio_results
+
+
+def _decode_rows(spt, speech_ids, ends, start_idx):
+    """Codec decode of every row with speech; rows of EQUAL length share one call (they see exactly what they would see
+    alone). A failing group is retried row by row, so that — like the reference, which decodes one sample per call and
+    skips the one that raised (generation_utils.py:448-467) — only the failing sample yields None."""
+    wavs = [None] * len(ends)
+    by_len = defaultdict(list)
+    for i, e in enumerate(ends):
+        if e > 0:
+            by_len[e].append(i)
+    for e, idxs in by_len.items():
+        try:
+            got = spt.decode([speech_ids[i, :e].permute(1, 0) for i in idxs], overlap_seconds=10)["syn_wav_list"]
+            for i, w in zip(idxs, got):
+                wavs[i] = w
+        except Exception:
+            for i in idxs:
+                try:
+                    wavs[i] = spt.decode([speech_ids[i, :e].permute(1, 0)], overlap_seconds=10)["syn_wav_list"][0]
+                except Exception as ex:
+                    print(f"Error processing sample {start_idx + i}: {str(ex)}, skipping...")
+                    import traceback
+                    traceback.print_exc()
+    return wavs
+
+
 def process_batch(batch_items, tokenizer, model, spt, device, system_prompt, start_idx, use_normalize=False):
     """-> (actual_texts_data, audio_results); see the reference for the dict layouts (generation_utils.py:374-380,456-460)."""
     try:
         batch_size = len(batch_items)
-        texts, prompt_audios, actual_texts_data = [], [], []
         print(f"Processing {batch_size} samples starting from index {start_idx}...")
-        for i, item in enumerate(batch_items):
-            p = process_jsonl_item(item)
-            full_text = p["prompt_text"] + p["text"] if p["prompt_text"] else p["text"]
-            original_full_text = full_text
-            if use_normalize:
-                full_text = normalize_text(full_text)
-            final_text = full_text.replace("[S1]", "<speaker1>").replace("[S2]", "<speaker2>")
-            texts.append(final_text)
-            actual_texts_data.append({
-                "index": start_idx + i,
-                "original_text": original_full_text,
-                "normalized_text": normalize_text(original_full_text) if use_normalize else None,
-                "final_text": final_text,
-                "use_normalize": use_normalize,
-            })
-            prompt_audios.append(p["prompt_audio"])
-
-        grids = []
-        for text, audio_path in zip(texts, prompt_audios):
-            audio_data = load_audio_data(audio_path) if audio_path else None
-            g = process_inputs(tokenizer, spt, system_prompt, text, device, audio_data)
-            grids.append(shifting_inputs(g, tokenizer))
-        input_ids, attention_mask = rpadding(grids, MAX_CHANNELS, tokenizer)
-
+        actual_texts_data, input_ids, attention_mask = prepare_batch(batch_items, tokenizer, spt, device, system_prompt,
+                                                                     start_idx, use_normalize)
         print("Starting batch audio generation...")
         start = input_ids.shape[1] - MAX_CHANNELS + 1
         outputs = model.generate(input_ids=input_ids.to(device), attention_mask=attention_mask.to(device))
         print(f"Original outputs shape: {outputs.shape}")
         speech_ids = undelay(outputs[:, start:])
         ends = (find_max_valid_positions(speech_ids) + 1).cpu().tolist()
-
-        audio_results = [None] * batch_size
-        by_len = defaultdict(list)
-        for i, e in enumerate(ends):
-            if e <= 0:
-                print(f"Sample {start_idx + i} has no valid speech tokens")
-            else:
-                by_len[e].append(i)
-        for e, idxs in by_len.items():
-            try:
-                codes_list = [speech_ids[i, :e].permute(1, 0) for i in idxs]
-                wavs = spt.decode(codes_list, overlap_seconds=10)["syn_wav_list"]
-                for i, w in zip(idxs, wavs):
-                    w = w.cpu().detach()
-                    if w.ndim == 1:
-                        w = w.unsqueeze(0)
-                    audio_results[i] = {"audio_data": w, "sample_rate": spt.output_sample_rate, "index": start_idx + i}
-                    print(f"Audio generation completed: sample {start_idx + i}")
-            except Exception as ex:  # per-sample failures yield None, like the reference (generation_utils.py:463-467)
-                print(f"Error processing samples {[start_idx + i for i in idxs]}: {ex}, skipping...")
-                import traceback
-                traceback.print_exc()
+        wavs = _decode_rows(spt, speech_ids, ends, start_idx)
+        audio_results = finish_batch(speech_ids, ends, wavs, spt, start_idx)
         torch.cuda.empty_cache()
         return actual_texts_data, audio_results
     except Exception as e:
         print(f"Error during batch processing: {str(e)}")
         raise
+
+
+def process_batches(items, tokenizer, model, spt, device, system_prompt, batch_size, start_idx=0, use_normalize=False,
+                    bucket_by_length=True, overlap=True, workers=4):
+    """Pipelined form of the reference's driver loop (inference.py:73-101 calls `process_batch` once per batch): yields
+    `(actual_texts_data, audio_results)` per batch, with three stages in flight —
+      * prompt side of batch i+1 (JSONL schema, text normalisation, audio load/resample) on a host thread pool (§8f-3),
+      * LM decode of batch i on the main stream,
+      * codec decode of batch i-1 on a second stream (§8f-4, `pipeline.CodecStage`).
+    bucket_by_length: batches are formed from scripts of similar text length (`scheduler.length_bucketed_batches`; a batch
+    decodes until its longest row is done) instead of arrival order; every result carries its item's `index`."""
+    from concurrent.futures import ThreadPoolExecutor
+    from .pipeline import CodecStage
+    from . import scheduler
+    n = len(items)
+    if n == 0:
+        return
+    if bucket_by_length:
+        est = [len(process_jsonl_item(it)["text"]) for it in items]
+        groups = scheduler.length_bucketed_batches(list(range(n)), est, batch_size)
+    else:
+        groups = scheduler.batches(list(range(n)), batch_size)
+    stage = CodecStage(spt, device, overlap=overlap)
+    host_pool = ThreadPoolExecutor(max_workers=max(1, workers))
+
+    def prep_host(idxs):
+        return [_prepare_item(items[j], start_idx + j, 0, use_normalize) for j in idxs]
+
+    def collect(job, metas, idxs):
+        job.wait()
+        res = [None] * len(idxs)
+        for k, (e, w) in enumerate(zip(job.ends, job.wavs)):
+            if e <= 0:
+                print(f"Sample {metas[k]['index']} has no valid speech tokens")
+            elif w is not None:
+                w = w.cpu().detach()
+                res[k] = {"audio_data": w.unsqueeze(0) if w.ndim == 1 else w, "sample_rate": spt.output_sample_rate,
+                          "index": metas[k]["index"]}
+        return metas, res
+
+    try:
+        fut = host_pool.submit(prep_host, groups[0])
+        prev = None
+        for gi, idxs in enumerate(groups):
+            prepared = fut.result()
+            if gi + 1 < len(groups):
+                fut = host_pool.submit(prep_host, groups[gi + 1])
+            metas = [p[0] for p in prepared]
+            audio_tokens = encode_prompt_audios(spt, [p[2] for p in prepared], device)
+            grids = []
+            for (meta, text, _), tok in zip(prepared, audio_tokens):
+                g = process_inputs(tokenizer, spt, system_prompt, text, device, None)
+                grids.append(shifting_inputs(np.concatenate([g, tok]) if tok is not None else g, tokenizer))
+            input_ids, attention_mask = rpadding(grids, MAX_CHANNELS, tokenizer)
+            start = input_ids.shape[1] - MAX_CHANNELS + 1
+            outputs = model.generate(input_ids=input_ids.to(device), attention_mask=attention_mask.to(device))
+            job = stage.submit(outputs, start, index=gi)
+            if prev is not None:
+                yield collect(*prev)
+            prev = (job, metas, idxs)
+        if prev is not None:
+            yield collect(*prev)
+    finally:
+        host_pool.shutdown(wait=False)

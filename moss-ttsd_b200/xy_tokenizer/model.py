@@ -573,28 +573,35 @@ class XY_Tokenizer:
         batch_size = len(codes_list)
         lens = [int(c.shape[-1]) for c in codes_list]
         max_code_length = max(lens) if lens else 0
-        codes_tensor = torch.zeros(self.nq, batch_size, max_code_length, device=device, dtype=torch.long)
-        for i, c in enumerate(codes_list):
-            codes_tensor[:, i, :c.shape[-1]] = c.to(device)
+        if batch_size and min(lens) == max_code_length:
+            codes_tensor = torch.stack([c.to(device) for c in codes_list], dim=1).contiguous()   # (nq, B, T), one launch
+        else:
+            codes_tensor = torch.zeros(self.nq, batch_size, max_code_length, device=device, dtype=torch.long)
+            for i, c in enumerate(codes_list):
+                codes_tensor[:, i, :c.shape[-1]] = c.to(device)
         max_chunks = (max_code_length + duration_code_length - 1) // duration_code_length if duration_code_length > 0 else 0
-        wav_chunks = []
+        n_windows = sum(1 for k in range(max_chunks) if max(lens) - k * duration_code_length > 0)
+        wav_tensor = torch.empty(batch_size, max(n_windows, 1) * duration_wav_length, device=device) if batch_size else None
+        w_idx = 0
         for chunk_idx in range(max_chunks):
             start = chunk_idx * duration_code_length
             end = min(start + chunk_code_length, max_code_length)
             chunk_lens = [min(max(l - start, 0), end - start) for l in lens]
             if max(chunk_lens) == 0:
                 continue
-            wav = self.detokenize_tokens(codes_tensor[:, :, start:end].contiguous(),
-                                         torch.tensor(chunk_lens, dtype=torch.int32, device=device))
-            valid = torch.zeros(batch_size, 1, duration_wav_length, device=device)
-            for b in range(batch_size):
-                n = min(chunk_lens[b] * self.decoder_upsample_rate, duration_wav_length)
-                if n > 0:
-                    valid[b, 0, :n] = wav[b, :n]
-            wav_chunks.append(valid)
-        if wav_chunks:
-            wav_tensor = torch.cat(wav_chunks, dim=-1)
-            syn = [wav_tensor[i, 0, :lens[i] * self.decoder_upsample_rate] for i in range(batch_size)]
+            chunk_lens_dev = torch.tensor(chunk_lens, dtype=torch.int32, device=device)
+            wav = self.detokenize_tokens(codes_tensor[:, :, start:end].contiguous(), chunk_lens_dev)
+            # keep each item's own samples of the hop (zeros beyond its length): one launch for the whole window
+            keep = torch.clamp(chunk_lens_dev * self.decoder_upsample_rate, max=duration_wav_length).contiguous()
+            dst = wav_tensor[:, w_idx * duration_wav_length:(w_idx + 1) * duration_wav_length]
+            n = min(duration_wav_length, wav.shape[1])
+            if n < duration_wav_length:
+                dst.zero_()
+            check(self.L.mtts_rows_prefix_copy(ptr(wav), wav.stride(0), ptr(dst), dst.stride(0), ptr(keep), batch_size, n, 4,
+                                               stream_ptr()))
+            w_idx += 1
+        if w_idx:
+            syn = [wav_tensor[i, :lens[i] * self.decoder_upsample_rate] for i in range(batch_size)]
         else:
             syn = [torch.zeros(0, device=device) for _ in range(batch_size)]
         return {"syn_wav_list": syn}

@@ -81,3 +81,82 @@ def test_process_batch_sample_without_audio_returns_none():
     speech = torch.full((2, 6, 8), 1024)
     speech[1, :3, 1] = 7
     assert gu.find_max_valid_positions(speech).tolist() == [-1, 2]
+
+
+def _items(rng, n):
+    wav = torch.from_numpy((0.1 * rng.standard_normal(16000 * 2)).astype(np.float32))[None]
+    items = []
+    for i in range(n):
+        it = {"text": "[S1]" + "word " * int(rng.integers(2, 14)) + f"item {i}."}
+        if i % 2:
+            it.update(prompt_audio=(wav * (0.5 + 0.1 * i), 16000), prompt_text="[S1]ref")
+        items.append(it)
+    return items
+
+
+def test_process_batches_pipelined_equals_process_batch():
+    """The pipelined driver (host worker pool -> LM on the main stream -> codec on a second stream) yields, batch by
+    batch, what `process_batch` returns for the same batches (arrival-order batches so that batch composition is equal)."""
+    from moss_ttsd_b200 import generation_utils as gu
+    model, _ = tiny_model()
+    model.generation_config.eos_token_id = 152694
+    model.generation_config.max_new_tokens = 10
+    spt = _codec()
+    items = _items(np.random.default_rng(3), 7)
+    sys_prompt = "You are a speech synthesizer."
+    want = []
+    for b0 in range(0, len(items), 3):
+        want.append(gu.process_batch(items[b0:b0 + 3], Tok(), model, spt, "cuda", sys_prompt, start_idx=b0))
+    for overlap in (True, False):
+        got = list(gu.process_batches(items, Tok(), model, spt, "cuda", sys_prompt, batch_size=3, bucket_by_length=False,
+                                      overlap=overlap, workers=2))
+        assert len(got) == len(want)
+        for (tw, aw), (tg, ag) in zip(want, got):
+            assert tw == tg
+            for a, b in zip(aw, ag):
+                assert (a is None) == (b is None)
+                if a is not None:
+                    assert a["index"] == b["index"] and torch.equal(a["audio_data"], b["audio_data"])
+    # length-bucketed batches: every item comes back exactly once, under its own index
+    got = list(gu.process_batches(items, Tok(), model, spt, "cuda", sys_prompt, batch_size=3, bucket_by_length=True))
+    idx = sorted(t["index"] for texts, _ in got for t in texts)
+    assert idx == list(range(len(items)))
+    lens = [[len(t["final_text"]) for t in texts] for texts, _ in got]
+    assert all(min(a) >= max(b) for a, b in zip(lens, lens[1:]))           # longest scripts first, similar lengths together
+
+
+def test_batched_prompt_encode_equals_per_item_encode():
+    """All prompt audios of a batch in one `spt.encode` call give the codes of the reference's one-call-per-item loop
+    (generation_utils.py:198)."""
+    from moss_ttsd_b200 import generation_utils as gu
+    spt = _codec()
+    rng = np.random.default_rng(8)
+    audios = [torch.from_numpy((0.1 * rng.standard_normal(n)).astype(np.float32))[None] for n in (16000 * 2, 16000 * 5, 9000)]
+    audios.insert(1, None)
+    batched = gu.encode_prompt_audios(spt, audios, "cuda")
+    assert batched[1] is None
+    for a, tok in zip(audios, batched):
+        if a is None:
+            continue
+        alone = spt.encode([a.squeeze().cuda()])["codes_list"][0].permute(1, 0).cpu().numpy()
+        alone[:, 0] += 151665
+        assert tok.shape == alone.shape and (tok == alone).all()
+
+
+def test_decode_failure_nulls_only_the_failing_sample(monkeypatch):
+    """A codec failure on one sample yields None for that sample only (generation_utils.py:463-467), also when equal-length
+    samples were grouped into one decode call."""
+    from moss_ttsd_b200 import generation_utils as gu
+    spt = _codec()
+    speech = torch.randint(0, 1024, (3, 6, 8), device="cuda")
+    real = spt.decode
+    poisoned = int(speech[1, 0, 0])
+
+    def flaky(codes_list, **kw):
+        if any(int(c[0, 0]) == poisoned and c.shape[-1] == 6 and torch.equal(c, speech[1].permute(1, 0)) for c in codes_list):
+            raise RuntimeError("injected codec failure")
+        return real(codes_list, **kw)
+
+    monkeypatch.setattr(spt, "decode", flaky)
+    wavs = gu._decode_rows(spt, speech, [6, 6, 6], 0)
+    assert wavs[1] is None and wavs[0] is not None and wavs[2] is not None
