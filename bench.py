@@ -316,7 +316,7 @@ def main():
                 local_res[i] = (rank, int(e) * 1920)
             job.wavs = None
         merged = scheduler.gather_results(local_res, world)
-        assert len(merged) == len(bs) * BATCH * world
+        assert len(merged) == len({id(b["ids_host"]) for b in bs}) * BATCH * world, (len(merged), len(bs))
         return frames
 
     def timed(fn):

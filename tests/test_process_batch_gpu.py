@@ -121,7 +121,7 @@ def test_process_batches_pipelined_equals_process_batch():
     got = list(gu.process_batches(items, Tok(), model, spt, "cuda", sys_prompt, batch_size=3, bucket_by_length=True))
     idx = sorted(t["index"] for texts, _ in got for t in texts)
     assert idx == list(range(len(items)))
-    lens = [[len(t["final_text"]) for t in texts] for texts, _ in got]
+    lens = [[len(items[t["index"]]["text"]) for t in texts] for texts, _ in got]
     assert all(min(a) >= max(b) for a, b in zip(lens, lens[1:]))           # longest scripts first, similar lengths together
 
 
