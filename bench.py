@@ -666,7 +666,16 @@ def ragged_leg(model, dev):
     got = sum(o.shape[0] - (g.shape[0] - 7) - 7 for o, g in zip(outs, grids)) * FRAME_S
     res["continuous"] = {"s": dt, "decode_steps": cd.steps_done, "audio_s_per_s": audio_s / dt,
                          "idle_slot_step_frac": cd.idle_slot_steps / max(1, cd.steps_done * BATCH), "audio_s_check": got}
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    model.generate_continuous(grids, queue_order="longest_first", **kw)
+    torch.cuda.synchronize()
+    dt2 = time.perf_counter() - t0
+    cd = model._continuous[1]
+    res["continuous_longest_first"] = {"s": dt2, "decode_steps": cd.steps_done, "audio_s_per_s": audio_s / dt2,
+                                       "idle_slot_step_frac": cd.idle_slot_steps / max(1, cd.steps_done * BATCH)}
     res["continuous_vs_arrival_order"] = res["static_arrival_order"]["s"] / dt
+    res["continuous_longest_first_vs_arrival_order"] = res["static_arrival_order"]["s"] / dt2
     res["scripts"] = n
     res["target"] = "uniform 125..750 frames (10..60 s) per script; LM only"
     free_sessions(model)

@@ -65,6 +65,22 @@ int mtts_gemm(const void* x, long long ldx, const void* w, long long ldw, void* 
               int K, int in_dtype, int out_dtype, int flags, const float* bias, const float* gamma,
               const void* residual, long long ldr, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Split-K projection for the decode step (1 <= M <= 256, bf16) with the reduction moved into the consumer: every CTA
+ * owns all M rows of one (128-row weight tile, k-slice) and stores its fp32 partial tile into `partials`
+ * [splits][M][N] (no cluster, no barrier); mtts_splitk_reduce / mtts_splitk_reduce_rmsnorm sum the slices in ascending
+ * order. Replaces `aten::linear` of q/k/v, o_proj and down_proj in HF Qwen3Attention / Qwen3MLP as invoked from
+ * modeling_asteroid.py:226,273-284 together with the residual add + RMSNorm that follow them
+ * (modeling_qwen3.py:50-66,327-333). */
+int mtts_gemm_splitk_splits(int M, int N, int K);
+size_t mtts_gemm_splitk_workspace_bytes(int M, int N, int K);
+int mtts_gemm_splitk(const void* x, long long ldx, const void* w, long long ldw, float* partials, size_t partial_bytes,
+                     int M, int N, int K, int* splits_out, void* stream);
+/* out[M, N] bf16 = bf16(sum_s partials[s]) */
+int mtts_splitk_reduce(const float* partials, int splits, int M, int N, void* out, long long ldo, void* stream);
+/* x[M, N] bf16 (residual stream, in place) <- bf16(x + bf16(sum_s partials[s]));  xn <- RMSNorm(x, eps) * norm_w */
+int mtts_splitk_reduce_rmsnorm(const float* partials, int splits, int M, int N, void* x, long long ldx, const void* norm_w,
+                               void* xn, long long ldxn, float eps, void* stream);
+
 /* Exact-fp32 CUDA-core GEMM with generic strides (used where TF32 would break bit-exact parity, i.e. the
  * RVQ input projection quantizer.py:224,245, and as the in-library cross-check of mtts_gemm).
  *   x element (m, k) at x[(m / rows_per_batch) * x_batch_stride + (m % rows_per_batch) * x_row_stride + k * x_k_stride]

@@ -68,6 +68,12 @@ SIGNATURES = {
     "mtts_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "mtts_gemm": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_size_t, c_void_p]),
+    "mtts_gemm_splitk_splits": (c_int, [c_int, c_int, c_int]),
+    "mtts_gemm_splitk_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mtts_gemm_splitk": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mtts_splitk_reduce": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "mtts_splitk_reduce_rmsnorm": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_float,
+                                           c_void_p]),
     "mtts_gemm_simt": (c_int, [c_void_p, c_int, c_ll, c_ll, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int,
                                c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "mtts_rvq_codebook_norms": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -58,6 +58,7 @@ struct GemmParams {
   int flags;
   int vec_ok;     // output / residual rows allow 4-wide vector access
   int pair_tiles_n;  // > 0: CTA-pair kernel, number of 256-row weight tiles
+  float* partials;   // split-K with the reduction in the consumer: [splits][M][N] fp32
 };
 
 template <typename T>
@@ -368,6 +369,146 @@ __global__ void __launch_bounds__(kNumThreads) gemm_tc_kernel(const __grid_const
     tc_fence_after();
     tmem_dealloc<kCols>(tmem_base);
     if (lane == 0) GEMM_TRACE(10);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Split-K with the reduction moved into the CONSUMER kernel (decode-step projections, M <= 256).
+//
+// At M = 129..256 a decode projection is no longer bound by HBM but by what an SM can pull over the L2 -> SM crossbar:
+// per CTA the weight slice (128 rows x K/S), the activation slice (M rows x K/S) AND the fp32 partial tile (128 x M x 4 B,
+// as large as the weight slice) all cross it. The cluster variant above moves the partial tiles twice more (DSMEM reads
+// by the reducing CTAs) behind two cluster-wide barriers, which is more than half of every launch.
+// Here a CTA owns ALL batch rows of its (weight tile, k-slice) — one 128 x BN accumulator, BN up to 256, so weights
+// cross the crossbar exactly once — and simply stores its fp32 partial tile to an L2-resident workspace
+// [split][m][n] with coalesced 128-byte warp stores: no cluster, no barrier, no DSMEM. The kernel that consumes the
+// projection anyway (residual add + RMSNorm for o_proj / down_proj: mtts_splitk_reduce_rmsnorm; the bf16 cast in front
+// of attention for q/k/v: mtts_splitk_reduce) sums the S slices in fixed order (bitwise deterministic) while it reads
+// its input, spread over all SMs.
+// ---------------------------------------------------------------------------------------------
+template <int BN, int kStages>
+__global__ void __launch_bounds__(kNumThreads) gemm_tc_partial_kernel(const __grid_constant__ CUtensorMap tmap_w,
+                                                                      const __grid_constant__ CUtensorMap tmap_x,
+                                                                      const GemmParams p) {
+  using T = bf16;
+  constexpr int BK = Traits<T>::kBlockK;
+  constexpr int UK = Traits<T>::kUmmaK;
+  constexpr uint32_t kABytes = kBlockW * kSwizzleBytes;
+  constexpr uint32_t kBBytes = BN * kSwizzleBytes;
+  constexpr uint32_t kCols = tmem_cols<BN>();
+  constexpr uint32_t kIdesc = make_idesc(Traits<T>::kFmt, kBlockW, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + kStages * kBBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
+  const int kb_begin = split * p.kb_per_split;
+  const int kb_end = min(p.kb_total, kb_begin + p.kb_per_split);
+  const int num_kb = kb_end - kb_begin;  // host guarantees >= 1
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_x);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc<kCols>(tmem_ptr_smem);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_launch_dependents();  // after the TMEM allocation (see gemm_tc_kernel)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int pre = min(num_kb, kStages);
+      for (int it = 0; it < pre; ++it) {  // weights never depend on the predecessor: stream them before the PDL wait
+        mbar_arrive_expect_tx(&full_bar[it], kABytes + kBBytes);
+        tma_load_2d(smem_a + it * kABytes, &tmap_w, &full_bar[it], (kb_begin + it) * BK, n_tile * kBlockW, kEvictFirst);
+      }
+      pdl_wait();
+      for (int it = 0; it < pre; ++it)
+        tma_load_2d(smem_b + it * kBBytes, &tmap_x, &full_bar[it], (kb_begin + it) * BK, m_tile * BN, kEvictLast);
+      for (int it = pre; it < num_kb; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], kABytes + kBBytes);
+        const int kc = (kb_begin + it) * BK;
+        tma_load_2d(smem_a + s * kABytes, &tmap_w, &full_bar[s], kc, n_tile * kBlockW, kEvictFirst);
+        tma_load_2d(smem_b + s * kBBytes, &tmap_x, &full_bar[s], kc, m_tile * BN, kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < num_kb; ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + s * kABytes);
+        const uint32_t b_addr = smem_u32(smem_b + s * kBBytes);
+#pragma unroll
+        for (int k = 0; k < BK / UK; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a_addr + k * UK * (int)sizeof(T));
+          const uint64_t db = make_smem_desc_sw128(b_addr + k * UK * (int)sizeof(T));
+          umma_bf16(tmem_base, da, db, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ---- epilogue warps 2..5 (TMEM lane quarters 2,3,0,1): lane = weight row n, TMEM column = batch row m
+    const int quarter = warp & 3;
+    const int n = n_tile * kBlockW + quarter * 32 + lane;
+    const int m_base = m_tile * BN;
+    const int mv = min(BN, p.M - m_base);
+    pdl_wait();  // the workspace may still be read by the predecessor's predecessor's consumer: write only after it
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    float* dst = p.partials + ((long long)split * p.M + m_base) * p.N + n;
+    const bool n_ok = n < p.N;
+#pragma unroll 1
+    for (int c = 0; c < mv; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr + c, r);
+      tmem_ld_wait();
+      if (n_ok) {
+        if (c + 32 <= mv) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dst[(long long)(c + j) * p.N] = __uint_as_float(r[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c + j < mv) dst[(long long)(c + j) * p.N] = __uint_as_float(r[j]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<kCols>(tmem_base);
   }
 }
 
@@ -868,6 +1009,30 @@ int launch(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, di
   return MTTS_OK;
 }
 
+// Ring depth of the partial-tile kernel: BN <= 128 keeps two CTAs per SM (<= ~100 KB each), BN = 256 owns the SM.
+template <int BN> struct PStages;
+template <> struct PStages<16> { static constexpr int v = 5; };
+template <> struct PStages<32> { static constexpr int v = 5; };
+template <> struct PStages<64> { static constexpr int v = 4; };
+template <> struct PStages<128> { static constexpr int v = 3; };
+template <> struct PStages<256> { static constexpr int v = 4; };  // 4 x 48 KB
+
+template <int BN>
+int launch_partial(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, dim3 grid, cudaStream_t stream) {
+  constexpr int kStages = PStages<BN>::v;
+  MTTS_CUDA_CHECK(mtts_launch(gemm_tc_partial_kernel<BN, kStages>, grid, dim3(kNumThreads), smem_bytes<BN, kStages>(), stream,
+                              tw, tx, p));
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+template <int BN>
+int configure_partial() {
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_partial_kernel<BN, PStages<BN>::v>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       smem_bytes<BN, PStages<BN>::v>()));
+  return MTTS_OK;
+}
+
 static bool persist_disabled() {
   static int v = -1;
   if (v < 0) {
@@ -947,6 +1112,11 @@ int mtts_configure_gemm_tc() {
   if ((rc = configure_one<float, 64>())) return rc;
   if ((rc = configure_one<float, 128>())) return rc;
   if ((rc = configure_one<float, 256>())) return rc;
+  if ((rc = configure_partial<16>())) return rc;
+  if ((rc = configure_partial<32>())) return rc;
+  if ((rc = configure_partial<64>())) return rc;
+  if ((rc = configure_partial<128>())) return rc;
+  if ((rc = configure_partial<256>())) return rc;
   MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persist_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        smem_bytes<kPBN, kPStages>()));
   MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persist_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1064,6 +1234,73 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   dim3 grid(tiles_n, tiles_m, splits);
   if (in_dtype == MTTS_DTYPE_BF16) return dispatch<bf16>(bn, tw, tx, p, grid, stream);
   return dispatch<float>(bn, tw, tx, p, grid, stream);
+}
+
+// ---- split-K with the reduction in the consumer -------------------------------------------------------------------
+static int splitk_bn(int M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256; }
+
+// k-blocks per slice / number of slices: aim at one CTA per SM for the 256-row tile (it owns the SM's shared memory)
+// and two for the smaller tiles; every slice keeps >= 2 k-blocks (128 of K).
+static void splitk_plan(int M, int N, int K, int* kb_per_split, int* splits) {
+  const int bn = splitk_bn(M);
+  const int kb_total = ceil_div(K, Traits<bf16>::kBlockK);
+  const int tiles = ceil_div(N, kBlockW) * ceil_div(M, bn);
+  static int target_env = -1;
+  if (target_env < 0) {
+    const char* e = getenv("MTTS_SPLITK_TARGET");
+    target_env = e ? atoi(e) : 0;
+  }
+  const int target = target_env > 0 ? target_env : (bn == 256 ? 1 : 2) * mtts_num_sms();
+  int s = target / (tiles > 0 ? tiles : 1);
+  if (s < 1) s = 1;
+  if (s > 16) s = 16;
+  int per = ceil_div(kb_total, s);
+  if (per < 2) per = kb_total < 2 ? kb_total : 2;
+  *kb_per_split = per;
+  *splits = ceil_div(kb_total, per);
+}
+
+extern "C" int mtts_gemm_splitk_splits(int M, int N, int K) {
+  int per, s;
+  splitk_plan(M, N, K, &per, &s);
+  return s;
+}
+
+extern "C" size_t mtts_gemm_splitk_workspace_bytes(int M, int N, int K) {
+  return (size_t)mtts_gemm_splitk_splits(M, N, K) * (size_t)M * (size_t)N * sizeof(float);
+}
+
+extern "C" int mtts_gemm_splitk(const void* x, long long ldx, const void* w, long long ldw, float* partials,
+                                size_t partial_bytes, int M, int N, int K, int* splits_out, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(M > 0 && M <= 256 && N > 0 && K > 0, "mtts_gemm_splitk: needs 1 <= M <= 256 (got M=%d N=%d K=%d)", M, N, K);
+  MTTS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
+               "mtts_gemm_splitk: x and w must be 16-byte aligned");
+  MTTS_REQUIRE((ldx * 2) % 16 == 0 && (ldw * 2) % 16 == 0 && ldx >= K && ldw >= K, "mtts_gemm_splitk: bad leading dimensions");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.kb_total = ceil_div(K, Traits<bf16>::kBlockK);
+  splitk_plan(M, N, K, &p.kb_per_split, &p.splits);
+  MTTS_REQUIRE(partials != nullptr && partial_bytes >= (size_t)p.splits * M * N * sizeof(float),
+               "mtts_gemm_splitk: workspace too small (%zu bytes, need %zu)", partial_bytes,
+               (size_t)p.splits * M * N * sizeof(float));
+  p.partials = partials;
+  if (splits_out) *splits_out = p.splits;
+  const int bn = splitk_bn(M);
+  CUtensorMap tw, tx;
+  int rc = get_tmap(w, N, K, ldw, kBlockW, 2, &tw);
+  if (rc) return rc;
+  rc = get_tmap(x, M, K, ldx, bn, 2, &tx);
+  if (rc) return rc;
+  dim3 grid(ceil_div(N, kBlockW), ceil_div(M, bn), p.splits);
+  switch (bn) {
+    case 16: return launch_partial<16>(tw, tx, p, grid, stream);
+    case 32: return launch_partial<32>(tw, tx, p, grid, stream);
+    case 64: return launch_partial<64>(tw, tx, p, grid, stream);
+    case 128: return launch_partial<128>(tw, tx, p, grid, stream);
+    default: return launch_partial<256>(tw, tx, p, grid, stream);
+  }
 }
 
 #ifdef MTTS_GEMM_TRACE

@@ -141,6 +141,90 @@ __global__ void __launch_bounds__(256) rmsnorm_warp_kernel(const bf16* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// Consumers of mtts_gemm_splitk's fp32 partial tiles [S][M][N] (gemm_tc.cu): the S slices are summed in ascending
+// order (bitwise deterministic) by the kernel that reads the projection anyway.
+//   splitk_reduce:          out = bf16(sum_s P_s)                                    (q/k/v in front of attention)
+//   splitk_reduce_rmsnorm:  x  <- bf16(x + bf16(sum_s P_s))     residual stream, the reference's two roundings
+//                           xn <- RMSNorm(x) * w                (o_proj -> post-attention norm, down_proj -> next input norm)
+// One CTA per row; a thread owns 8 consecutive columns per pass.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sum_slices8(const float* __restrict__ P, int S, long long slice, float (&a)[8]) {
+  const float4 u0 = __ldcg(reinterpret_cast<const float4*>(P)), u1 = __ldcg(reinterpret_cast<const float4*>(P) + 1);
+  a[0] = u0.x; a[1] = u0.y; a[2] = u0.z; a[3] = u0.w; a[4] = u1.x; a[5] = u1.y; a[6] = u1.z; a[7] = u1.w;
+  for (int s = 1; s < S; ++s) {
+    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(P + s * slice));
+    const float4 v1 = __ldcg(reinterpret_cast<const float4*>(P + s * slice) + 1);
+    a[0] += v0.x; a[1] += v0.y; a[2] += v0.z; a[3] += v0.w; a[4] += v1.x; a[5] += v1.y; a[6] += v1.z; a[7] += v1.w;
+  }
+}
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ P, int S, int M, int N,
+                                                            bf16* __restrict__ out, long long ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long row = blockIdx.x;
+  const long long slice = (long long)M * N;
+  for (int v = threadIdx.x; v < (N >> 3); v += blockDim.x) {
+    float a[8];
+    sum_slices8(P + row * N + v * 8, S, slice, a);
+    *reinterpret_cast<uint4*>(out + row * ldo + v * 8) =
+        make_uint4(pack_bf16(a[0], a[1]), pack_bf16(a[2], a[3]), pack_bf16(a[4], a[5]), pack_bf16(a[6], a[7]));
+  }
+}
+
+template <int kVecPerThread>
+__global__ void __launch_bounds__(256) splitk_reduce_rmsnorm_kernel(const float* __restrict__ P, int S, int M, int N,
+                                                                    bf16* __restrict__ x, long long ldx,
+                                                                    const bf16* __restrict__ w, bf16* __restrict__ xn,
+                                                                    long long ldxn, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[33];
+  const long long row = blockIdx.x;
+  const long long slice = (long long)M * N;
+  const int nvec = N >> 3;
+  uint32_t keep[kVecPerThread][4];  // the new residual row, packed bf16
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecPerThread; ++i) {
+    const int v = threadIdx.x + i * 256;
+    if (v < nvec) {
+      float a[8];
+      sum_slices8(P + row * N + v * 8, S, slice, a);
+      const uint4 r = *reinterpret_cast<const uint4*>(x + row * ldx + v * 8);
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = bf16_round(bf16lo(rr[j]) + bf16_round(a[2 * j]));
+        const float hi = bf16_round(bf16hi(rr[j]) + bf16_round(a[2 * j + 1]));
+        ss = fmaf(lo, lo, ss);
+        ss = fmaf(hi, hi, ss);
+        keep[i][j] = pack_bf16(lo, hi);
+      }
+      *reinterpret_cast<uint4*>(x + row * ldx + v * 8) = make_uint4(keep[i][0], keep[i][1], keep[i][2], keep[i][3]);
+    }
+  }
+  ss = block_sum(ss, red);
+  const float inv = rsqrtf(ss / (float)N + eps);
+#pragma unroll
+  for (int i = 0; i < kVecPerThread; ++i) {
+    const int v = threadIdx.x + i * 256;
+    if (v < nvec) {
+      const uint4 wv = *reinterpret_cast<const uint4*>(w + v * 8);
+      const uint32_t b[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lo = bf16_round(bf16lo(keep[i][j]) * inv) * bf16lo(b[j]);
+        const float hi = bf16_round(bf16hi(keep[i][j]) * inv) * bf16hi(b[j]);
+        o[j] = pack_bf16(lo, hi);
+      }
+      *reinterpret_cast<uint4*>(xn + row * ldxn + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Per-head q/k RMSNorm + RoPE + KV-cache append (HF Qwen3Attention.forward, installed
 // modeling_qwen3.py:236-271; apply_rotary_pos_emb :86-181; DynamicCache.update replaced by an in-place
 // paged store). One warp per (row, head); head_dim == 128: lane l owns elements {2l, 2l+1} and their
@@ -294,6 +378,40 @@ extern "C" int mtts_rmsnorm(const void* x, long long ldx, const void* w, void* o
   }
   MTTS_CUDA_CHECK(mtts_launch(rmsnorm_kernel, dim3(rows), dim3(256), 0, stream, reinterpret_cast<const bf16*>(x), ldx,
                               reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(out), ldo, hidden, eps));
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_splitk_reduce(const float* partials, int splits, int M, int N, void* out, long long ldo, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(splits >= 1 && N % 8 == 0 && ldo % 8 == 0, "mtts_splitk_reduce: N and ldo must be multiples of 8");
+  if (M <= 0) return MTTS_OK;
+  MTTS_REQUIRE(partials && out, "mtts_splitk_reduce: null pointer");
+  MTTS_CUDA_CHECK(mtts_launch(splitk_reduce_kernel, dim3(M), dim3(256), 0, stream, partials, splits, M, N,
+                              reinterpret_cast<bf16*>(out), ldo));
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_splitk_reduce_rmsnorm(const float* partials, int splits, int M, int N, void* x, long long ldx,
+                                          const void* norm_w, void* xn, long long ldxn, float eps, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(splits >= 1 && N % 8 == 0 && N <= 8192 && ldx % 8 == 0 && ldxn % 8 == 0,
+               "mtts_splitk_reduce_rmsnorm: N (<= 8192) and strides must be multiples of 8");
+  if (M <= 0) return MTTS_OK;
+  MTTS_REQUIRE(partials && x && norm_w && xn, "mtts_splitk_reduce_rmsnorm: null pointer");
+  const bf16* w = reinterpret_cast<const bf16*>(norm_w);
+  bf16* xp = reinterpret_cast<bf16*>(x);
+  bf16* xnp = reinterpret_cast<bf16*>(xn);
+  if (N <= 2048)
+    MTTS_CUDA_CHECK(mtts_launch(splitk_reduce_rmsnorm_kernel<1>, dim3(M), dim3(256), 0, stream, partials, splits, M, N, xp, ldx,
+                                w, xnp, ldxn, eps));
+  else if (N <= 4096)
+    MTTS_CUDA_CHECK(mtts_launch(splitk_reduce_rmsnorm_kernel<2>, dim3(M), dim3(256), 0, stream, partials, splits, M, N, xp, ldx,
+                                w, xnp, ldxn, eps));
+  else
+    MTTS_CUDA_CHECK(mtts_launch(splitk_reduce_rmsnorm_kernel<4>, dim3(M), dim3(256), 0, stream, partials, splits, M, N, xp, ldx,
+                                w, xnp, ldxn, eps));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }

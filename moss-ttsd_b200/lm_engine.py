@@ -270,6 +270,10 @@ class DecoderEngine:
                                   and s.head_dim == 128 and s.num_attention_heads // s.num_key_value_heads in (1, 2, 4))
         self.mega_max_b = int(os.environ.get("MTTS_MEGA_MAX_B", "4"))
         self.prefill_tile_rows = int(os.environ.get("MTTS_PREFILL_TILE", "64"))  # 64: tensor-core tiles, 4: CUDA cores
+        # decode steps of the kernel chain with splitk_min_rows <= batch <= 256: q/k/v, o_proj and down_proj store fp32
+        # split-K partial tiles and the consumer (bf16 cast / residual + RMSNorm) sums them (mtts_gemm_splitk*)
+        self.splitk_min_rows = int(os.environ.get("MTTS_SPLITK_MIN_ROWS", "65"))
+        self.use_splitk = os.environ.get("MTTS_SPLITK", "1") != "0"
         self.graph_replayed_launches = 0  # kernels executed through graph replays (not seen by mtts_launch_count)
 
     # ------------------------------------------------------------------ primitive launches
@@ -325,6 +329,48 @@ class DecoderEngine:
                        (s.vpad, s.hidden_size)):
             need = max(need, self.L.mtts_gemm_workspace_bytes(R, n, k, ops.BF16))
         return torch.zeros(need, dtype=torch.uint8, device=self.dev)
+
+    def _splitk(self, x, w, ws):
+        splits = ctypes.c_int(0)
+        check(self.L.mtts_gemm_splitk(ptr(x), x.stride(0), ptr(w), w.stride(0), ptr(ws), ws.numel() * 4, x.shape[0], w.shape[0],
+                                      x.shape[1], ctypes.byref(splits), stream_ptr()))
+        return splits.value
+
+    def _splitk_ws(self, R):
+        s = self.s
+        nqkv = (s.num_attention_heads + 2 * s.num_key_value_heads) * s.head_dim
+        need = max(self.L.mtts_gemm_splitk_workspace_bytes(R, n, k) for (n, k) in
+                   ((nqkv, s.hidden_size), (s.hidden_size, s.num_attention_heads * s.head_dim), (s.hidden_size, s.intermediate_size)))
+        return torch.empty(need // 4 + 64, dtype=torch.float32, device=self.dev)
+
+    def _layers_splitk(self, a, cache, positions, attn_kw, gws, pws):
+        """Decode step (one row per sequence) with consumer-side split-K reduction: per layer
+        q/k/v partials -> bf16 cast -> fused norm/RoPE/append/attention -> o_proj partials -> (+residual, RMSNorm) ->
+        gate/up + SwiGLU -> down_proj partials -> (+residual, next RMSNorm)."""
+        x, xn, qkv, ao, h = a["x"], a["xn"], a["qkv"], a["ao"], a["h"]
+        s, L = self.s, self.L
+        R, H = x.shape
+        eps = s.rms_norm_eps
+        ws = attn_kw["ws"]
+        layers = self.w.layers
+        self._rmsnorm(x, layers[0]["ln1"], xn)
+        for l, lw in enumerate(layers):
+            S = self._splitk(xn, lw["wqkv"], pws)
+            check(L.mtts_splitk_reduce(ptr(pws), S, R, qkv.shape[1], ptr(qkv), qkv.stride(0), stream_ptr()))
+            check(L.mtts_gqa_decode_fused(
+                ptr(qkv), qkv.stride(0), ptr(lw["q_norm"]), ptr(lw["k_norm"]), ptr(self.w.inv_freq), eps,
+                ptr(cache.k[l]), ptr(cache.v[l]), ptr(cache.block_table), cache.max_pages, cache.page_size,
+                cache.num_pages, ptr(positions), ptr(ao), R, s.num_attention_heads, s.num_key_value_heads, s.head_dim,
+                attn_kw["nsplit"], ptr(ws), ws.numel() if ws is not None else 0, ptr(self.err), stream_ptr()))
+            S = self._splitk(ao, lw["wo"], pws)
+            check(L.mtts_splitk_reduce_rmsnorm(ptr(pws), S, R, H, ptr(x), x.stride(0), ptr(lw["ln2"]), ptr(xn), xn.stride(0), eps,
+                                               stream_ptr()))
+            ops.gemm(xn, lw["wgu"], out=h, swiglu=True, workspace=gws)
+            S = self._splitk(h, lw["wd"], pws)
+            nw = layers[l + 1]["ln1"] if l + 1 < len(layers) else self.w.final_norm
+            check(L.mtts_splitk_reduce_rmsnorm(ptr(pws), S, R, H, ptr(x), x.stride(0), ptr(nw), ptr(xn), xn.stride(0), eps,
+                                               stream_ptr()))
+        return xn
 
     def _layers(self, a, cache, positions, row_seq, attn_kw, gws, want_output=True):
         x, xn, qkv, q, ao, h = a["x"], a["xn"], a["qkv"], a["q"], a["ao"], a["h"]
@@ -433,6 +479,7 @@ class DecoderEngine:
         st["logits"] = torch.empty((B, self.s.vpad), dtype=torch.bfloat16, device=self.dev)
         st["acts"] = self._alloc_acts(B)
         st["gws"] = self._gemm_ws(B)
+        st["pws"] = self._splitk_ws(B) if (self.use_splitk and self.fused_decode_attn and self.splitk_min_rows <= B <= 256) else None
         s = self.s
         # split-KV only while (rows x kv heads) cannot fill the machine by itself: measured at B=64 the combine costs
         # more than it gains (29 us unsplit vs 36 us with 2 splits), at B=1 eight splits are 2.3x faster than none
@@ -517,7 +564,10 @@ class DecoderEngine:
             return
         attn_kw = dict(tiles=st["B"], rows_per_tile=1, tile_row0=None, tile_nrows=None, nsplit=st["nsplit"],
                        ws=st["attn_ws"] if st["nsplit"] > 1 else None)
-        xn = self._layers(a, st["cache"], st["positions"], None, attn_kw, st["gws"])
+        if st.get("pws") is not None:
+            xn = self._layers_splitk(a, st["cache"], st["positions"], attn_kw, st["gws"], st["pws"])
+        else:
+            xn = self._layers(a, st["cache"], st["positions"], None, attn_kw, st["gws"])
         ops.gemm(xn, self.w.heads, out=st["logits"], workspace=st["gws"])
         self.sample_and_advance(st, st["logits"])
 

@@ -272,14 +272,18 @@ class AsteroidTTSInstruct:
     @torch.no_grad()
     def generate_continuous(self, prompts, max_new_tokens=None, max_length=None, max_batch: int = 256, eos_at=None,
                             generation_config: Optional[GenerationConfig] = None, seed: Optional[int] = None,
-                            pool_pages: Optional[int] = None, sync_every: int = 8, **kwargs):
+                            pool_pages: Optional[int] = None, sync_every: int = 8, queue_order: str = "fifo", **kwargs):
         """Decode a QUEUE of scripts through `max_batch` slots, refilling a slot as soon as its row has finished
         (continuous.ContinuousDecoder) instead of padding every batch to its longest row (modeling_asteroid.py:155-169).
         prompts: list of (T_i, 8) int64 delay-shifted grids WITHOUT left padding (last 7 rows = teacher-forced tail);
         max_new_tokens / max_length: scalar or per-prompt list with generate()'s meaning; eos_at: optional per-prompt
         length budgets (sequence row from which channel 0 is forced to EOS). Returns a list of (L_i, 8) LongTensors: for
-        every prompt the rows a solo generate() call returns."""
+        every prompt the rows a solo generate() call returns. queue_order: "fifo" admits in arrival order;
+        "longest_first" admits the scripts with the largest row budget first (the makespan of a finite job is bounded by
+        the longest script that starts late) — results are returned in prompt order either way."""
         from .continuous import ContinuousDecoder, Request
+        if queue_order not in ("fifo", "longest_first"):
+            raise ValueError(f"queue_order must be 'fifo' or 'longest_first', got {queue_order!r}")
         gc = copy.deepcopy(generation_config if generation_config is not None else self.generation_config)
         gc.update(**kwargs)
         n = len(prompts)
@@ -297,6 +301,9 @@ class AsteroidTTSInstruct:
             reqs.append(Request(i, g.to(self.device).contiguous(), int(ml), int(per(eos_at, i)) if eos_at is not None else 0))
         if not reqs:
             return []
+        if queue_order == "longest_first":
+            budget = lambda r: (r.eos_at if r.eos_at > 0 else r.max_length) - r.grid.shape[0]
+            reqs.sort(key=lambda r: (-budget(r), r.index))
         eos = gc.eos_token_id
         if isinstance(eos, (list, tuple)):
             eos = eos[0] if len(eos) else None

@@ -84,6 +84,17 @@ def test_evicted_and_refilled_rows_equal_solo_runs(margin_model, slots, pool_pag
     assert cd.admitted == len(grids) and cd.pool.available == cd.pool.num_pages - 1 and cd.pool.reserved == 0
     if slots < len(grids):
         assert cd.decode_steps < sum(s.shape[0] for s in solo)      # rows really shared steps
+        # longest-first admission: same rows per request (results come back in prompt order), no more steps than FIFO
+        fifo_steps = cd.decode_steps
+        m.kv_page_size = 16
+        try:
+            outs2 = m.generate_continuous(grids, max_new_tokens=40, max_batch=slots, do_sample=False, pool_pages=pool_pages,
+                                          eos_at=[g.shape[0] - 7 + nb for g, nb in zip(grids, budgets)], sync_every=4,
+                                          queue_order="longest_first")
+        finally:
+            m.kv_page_size = 64
+        assert all(torch.equal(a.cpu(), b) for a, b in zip(outs2, solo))
+        assert m._continuous[1].decode_steps - fifo_steps <= fifo_steps
 
 
 @pytest.mark.gpu

@@ -147,3 +147,52 @@ def test_3xtf32_gemm_is_fp32_accurate():
     g_ref = torch.nn.functional.gelu(ref)
     g = ops.gemm_exact(x, ops.ExactWeight(w), bias=b, gelu=True).double()
     assert (g - g_ref).abs().max().item() / g_ref.abs().max().item() <= 3e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 4096, 2048), (200, 2048, 6144), (129, 2048, 2048), (64, 4096, 2048), (17, 2048, 6144),
+                                   (1, 2048, 2048), (256, 1000, 2048 + 64)])
+def test_splitk_partials_and_consumer_side_reduction(M, N, K):
+    """mtts_gemm_splitk + mtts_splitk_reduce / mtts_splitk_reduce_rmsnorm against torch fp32 (same bf16 rounding points as
+    the fused-epilogue GEMM followed by mtts_rmsnorm: those two paths must agree bit for bit up to fp32 summation order)."""
+    import ctypes
+    from moss_ttsd_b200 import _lib, ops
+    L = _lib.load()
+    ops.ensure_init()
+    torch.manual_seed(M + N)
+    x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    S = L.mtts_gemm_splitk_splits(M, N, K)
+    ws = torch.empty(L.mtts_gemm_splitk_workspace_bytes(M, N, K) // 4, dtype=torch.float32, device="cuda")
+    got_s = ctypes.c_int(0)
+    _lib.check(L.mtts_gemm_splitk(x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), ws.data_ptr(), ws.numel() * 4, M, N, K,
+                                  ctypes.byref(got_s), _lib.stream_ptr()))
+    assert got_s.value == S >= 1
+    ref = x.float() @ w.float().t()
+    part = ws[:S * M * N].view(S, M, N)
+    assert (part.sum(0) - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    if S > 1:
+        assert part[0].abs().max().item() > 0 and (part[0] - ref).abs().max().item() > 1e-3      # really partial sums
+    out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.mtts_splitk_reduce(ws.data_ptr(), S, M, N, out.data_ptr(), out.stride(0), _lib.stream_ptr()))
+    want = part.sum(0) if S == 1 else None
+    acc = part[0].clone()
+    for s in range(1, S):
+        acc += part[s]
+    assert torch.equal(out, acc.to(torch.bfloat16))                      # ascending-order fp32 sum, one bf16 rounding
+    fused = ops.gemm(x, w)
+    assert (out.float() - fused.float()).abs().max().item() <= 0.02 * ref.abs().max().item()
+    if N % 8 == 0 and N <= 8192:
+        res = torch.randn(M, N, device="cuda").to(torch.bfloat16)
+        nw = (1 + 0.1 * torch.randn(N, device="cuda")).to(torch.bfloat16)
+        xr = res.clone()
+        xn = torch.empty_like(xr)
+        _lib.check(L.mtts_splitk_reduce_rmsnorm(ws.data_ptr(), S, M, N, xr.data_ptr(), xr.stride(0), nw.data_ptr(), xn.data_ptr(),
+                                                xn.stride(0), 1e-6, _lib.stream_ptr()))
+        x_want = (res.float() + acc.to(torch.bfloat16).float()).to(torch.bfloat16)
+        assert torch.equal(xr, x_want)
+        xn_want = torch.empty_like(xr)
+        _lib.check(L.mtts_rmsnorm(x_want.data_ptr(), x_want.stride(0), nw.data_ptr(), xn_want.data_ptr(), xn_want.stride(0), M, N,
+                                  1e-6, _lib.stream_ptr()))
+        d = (xn.float() - xn_want.float()).abs()
+        assert d.max().item() <= 2.0 ** -6 * xn_want.float().abs().max().item()         # block- vs warp-order sum of squares
+        assert (d > 0).float().mean().item() <= 0.01
