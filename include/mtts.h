@@ -33,6 +33,7 @@ extern "C" {
 /* element types */
 #define MTTS_DTYPE_BF16 0
 #define MTTS_DTYPE_F32 1
+#define MTTS_DTYPE_F16 2 /* mtts_gemm operands / GELU output of the codec fp16-operand path */
 
 /* GEMM epilogue flags (bitmask). Order of application:
  *   v = acc; +bias[n]; gelu; round to out dtype; *gamma[n]; residual[m,n] + v.
@@ -262,6 +263,14 @@ int mtts_gqa_decode_fused(const void* qkv, long long ld_qkv, const void* q_norm_
                           int max_pages, int page_size, int num_pages, const int* positions, void* out, int rows,
                           int num_q_heads, int num_kv_heads, int head_dim, int nsplit, void* workspace,
                           size_t workspace_bytes, int* err_flag, void* stream);
+/* Same, with q/k/v taken as the fp32 split-K partial tiles [splits][rows][(Hq + 2 Hkv) * 128] of mtts_gemm_splitk: the
+ * slices are summed in ascending order and rounded to bf16 once inside the prologue (== mtts_splitk_reduce + the call
+ * above, one launch and one 2 MB round trip fewer per layer). */
+int mtts_gqa_decode_fused_splitk(const float* qkv_partials, int qkv_splits, const void* q_norm_w, const void* k_norm_w,
+                                 const float* inv_freq, float eps, void* k_pool, void* v_pool, const int* block_table,
+                                 int max_pages, int page_size, int num_pages, const int* positions, void* out, int rows,
+                                 int num_q_heads, int num_kv_heads, int head_dim, int nsplit, void* workspace,
+                                 size_t workspace_bytes, int* err_flag, void* stream);
 
 /* ---- Small-batch decode step as one persistent kernel (batch 1..4; hidden 2048, intermediate 6144, 16/8 heads x 128).
  * Runs, for ONE new row per sequence, everything between the embedding sum and the sampler: the Qwen3 layer stack that

@@ -114,6 +114,9 @@ SIGNATURES = {
     "mtts_gqa_decode_fused": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                       c_size_t, c_void_p, c_void_p]),
+    "mtts_gqa_decode_fused_splitk": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                             c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                             c_size_t, c_void_p, c_void_p]),
     "mtts_decode_mega_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "mtts_decode_mega_workspace_bytes": (c_ll, [c_int, c_int]),
     "mtts_decode_mega": (c_int, [ctypes.POINTER(DecodeMegaArgs), c_void_p]),

@@ -41,6 +41,10 @@ struct AttnParams {
   // fused decode (mtts_gqa_decode_fused): q/k/v of the new row come straight from the projection output
   const bf16* qkv;        // [rows, (Hq + 2 Hkv) * 128]
   long long ld_qkv;
+  // ... or as fp32 split-K partial tiles [splits][rows][(Hq + 2 Hkv) * 128] of mtts_gemm_splitk, summed here in
+  // ascending slice order and rounded to bf16 once (== mtts_splitk_reduce followed by the bf16 path above)
+  const float* qkv_partials;
+  int qkv_splits;
   const bf16* q_norm_w;
   const bf16* k_norm_w;
   const float* inv_freq;
@@ -569,10 +573,25 @@ __global__ void __launch_bounds__(128, STAGES == 1 ? 4 : 3) gqa_decode_tc_kernel
     const bool owner = pos >= k_begin && pos < k_end;
     for (int item = warp; item < G + 2; item += 4) {  // G query heads, then k, then v of this kv head
       const int col = item < G ? (hk * G + item) * kD : (item == G ? p.Hq * kD + hk * kD : (p.Hq + p.Hkv) * kD + hk * kD);
-      const bf16* src = p.qkv + (long long)row * p.ld_qkv + col;
-      const uint32_t a = *reinterpret_cast<const uint32_t*>(src + 2 * lane);       // elements 2l, 2l+1
-      const uint32_t b = *reinterpret_cast<const uint32_t*>(src + 64 + 2 * lane);  // elements 64+2l, 65+2l
-      float x0 = bf16lo(a), x1 = bf16hi(a), x2 = bf16lo(b), x3 = bf16hi(b);
+      float x0, x1, x2, x3;
+      if (p.qkv_partials) {
+        const long long nq = (long long)(p.Hq + 2 * p.Hkv) * kD;
+        const long long slice = (long long)gridDim.x * nq;   // rows x columns of one partial tile (grid.x == rows)
+        const float* P = p.qkv_partials + (long long)row * nq + col + 2 * lane;
+        float2 a = make_float2(0.f, 0.f), b = a;
+#pragma unroll 4
+        for (int sidx = 0; sidx < p.qkv_splits; ++sidx) {
+          const float2 u = __ldcg(reinterpret_cast<const float2*>(P + sidx * slice));
+          const float2 v = __ldcg(reinterpret_cast<const float2*>(P + sidx * slice + 64));
+          a.x += u.x; a.y += u.y; b.x += v.x; b.y += v.y;
+        }
+        x0 = bf16_round(a.x); x1 = bf16_round(a.y); x2 = bf16_round(b.x); x3 = bf16_round(b.y);
+      } else {
+        const bf16* src = p.qkv + (long long)row * p.ld_qkv + col;
+        const uint32_t a = *reinterpret_cast<const uint32_t*>(src + 2 * lane);       // elements 2l, 2l+1
+        const uint32_t b = *reinterpret_cast<const uint32_t*>(src + 64 + 2 * lane);  // elements 64+2l, 65+2l
+        x0 = bf16lo(a); x1 = bf16hi(a); x2 = bf16lo(b); x3 = bf16hi(b);
+      }
       if (item <= G) {  // same arithmetic, in the same order, as qknorm_rope_kv_kernel (lm_ops.cu)
         const bf16* nw = item < G ? p.q_norm_w : p.k_norm_w;
         float ss = x0 * x0;
@@ -1249,7 +1268,7 @@ extern "C" int mtts_gqa_attention(const void* q, const void* k_pool, const void*
   return mtts_set_error(MTTS_ERR_UNSUPPORTED, "mtts_gqa_attention: unsupported configuration");
 }
 
-extern "C" int mtts_gqa_decode_fused(const void* qkv, long long ld_qkv, const void* q_norm_w, const void* k_norm_w,
+static int gqa_decode_fused_impl(const void* qkv, long long ld_qkv, const float* qkv_partials, int qkv_splits, const void* q_norm_w, const void* k_norm_w,
                                      const float* inv_freq, float eps, void* k_pool, void* v_pool, const int* block_table,
                                      int max_pages, int page_size, int num_pages, const int* positions, void* out, int rows,
                                      int num_q_heads, int num_kv_heads, int head_dim, int nsplit, void* workspace,
@@ -1262,7 +1281,7 @@ extern "C" int mtts_gqa_decode_fused(const void* qkv, long long ld_qkv, const vo
   MTTS_REQUIRE(G == 1 || G == 2 || G == 4, "mtts_gqa_decode_fused: q heads per kv head must be 1, 2 or 4 (got %d)", G);
   MTTS_REQUIRE(nsplit >= 1 && nsplit <= 64, "mtts_gqa_decode_fused: nsplit out of range");
   if (rows <= 0) return MTTS_OK;
-  MTTS_REQUIRE(qkv && q_norm_w && k_norm_w && inv_freq && k_pool && v_pool && positions && out,
+  MTTS_REQUIRE((qkv || qkv_partials) && q_norm_w && k_norm_w && inv_freq && k_pool && v_pool && positions && out,
                "mtts_gqa_decode_fused: null pointer");
   AttnParams p;
   memset(&p, 0, sizeof(p));
@@ -1283,9 +1302,32 @@ extern "C" int mtts_gqa_decode_fused(const void* qkv, long long ld_qkv, const vo
     p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kAttnCounterBytes);
   }
   p.qkv = reinterpret_cast<const bf16*>(qkv); p.ld_qkv = ld_qkv;
+  p.qkv_partials = qkv_partials; p.qkv_splits = qkv_splits;
   p.q_norm_w = reinterpret_cast<const bf16*>(q_norm_w); p.k_norm_w = reinterpret_cast<const bf16*>(k_norm_w);
   p.inv_freq = inv_freq; p.eps = eps; p.num_pages = num_pages; p.err_flag = err_flag;
   if (G == 1) return launch_decode_tc<1, true>(p, rows, stream);
   if (G == 2) return launch_decode_tc<2, true>(p, rows, stream);
   return launch_decode_tc<4, true>(p, rows, stream);
+}
+
+extern "C" int mtts_gqa_decode_fused(const void* qkv, long long ld_qkv, const void* q_norm_w, const void* k_norm_w,
+                                     const float* inv_freq, float eps, void* k_pool, void* v_pool, const int* block_table,
+                                     int max_pages, int page_size, int num_pages, const int* positions, void* out, int rows,
+                                     int num_q_heads, int num_kv_heads, int head_dim, int nsplit, void* workspace,
+                                     size_t workspace_bytes, int* err_flag, void* stream_) {
+  return gqa_decode_fused_impl(qkv, ld_qkv, nullptr, 0, q_norm_w, k_norm_w, inv_freq, eps, k_pool, v_pool, block_table,
+                               max_pages, page_size, num_pages, positions, out, rows, num_q_heads, num_kv_heads, head_dim,
+                               nsplit, workspace, workspace_bytes, err_flag, stream_);
+}
+
+extern "C" int mtts_gqa_decode_fused_splitk(const float* qkv_partials, int qkv_splits, const void* q_norm_w,
+                                            const void* k_norm_w, const float* inv_freq, float eps, void* k_pool, void* v_pool,
+                                            const int* block_table, int max_pages, int page_size, int num_pages,
+                                            const int* positions, void* out, int rows, int num_q_heads, int num_kv_heads,
+                                            int head_dim, int nsplit, void* workspace, size_t workspace_bytes, int* err_flag,
+                                            void* stream_) {
+  MTTS_REQUIRE(qkv_partials != nullptr && qkv_splits >= 1, "mtts_gqa_decode_fused_splitk: needs partial tiles and splits >= 1");
+  return gqa_decode_fused_impl(nullptr, 0, qkv_partials, qkv_splits, q_norm_w, k_norm_w, inv_freq, eps, k_pool, v_pool,
+                               block_table, max_pages, page_size, num_pages, positions, out, rows, num_q_heads, num_kv_heads,
+                               head_dim, nsplit, workspace, workspace_bytes, err_flag, stream_);
 }

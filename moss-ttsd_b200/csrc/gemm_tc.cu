@@ -29,6 +29,7 @@
 #include "sm100.cuh"
 #include "mtts_internal.h"
 
+#include <cuda_fp16.h>
 #include <mutex>
 #include <unordered_map>
 #include <string>
@@ -50,7 +51,8 @@ struct GemmParams {
   int splits;
   void* out;
   long long ldo;
-  int out_bf16;  // 1: bf16 output, 0: fp32
+  int out_bf16;  // 1: bf16 output, 0: fp32 (or fp16, see out_f16)
+  int out_f16;   // 1: fp16 output (codec fp16-operand path: no residual / SwiGLU, plain rounding)
   const float* bias;
   const float* gamma;
   const void* residual;
@@ -70,6 +72,12 @@ struct Traits<bf16> {
 template <>
 struct Traits<float> {
   static constexpr int kBlockK = 32, kUmmaK = 8, kFmt = 2;
+};
+// fp16 operands (kind::f16, 10-bit mantissa like TF32 at twice the tensor rate and half the operand bytes): the codec's
+// large GEMMs, whose inputs are LayerNorm / GELU outputs and weights well inside the fp16 range
+template <>
+struct Traits<__half> {
+  static constexpr int kBlockK = 64, kUmmaK = 16, kFmt = 0;
 };
 
 template <int BN>
@@ -141,6 +149,12 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int 
     v[j] = x;
   }
   const long long o = (long long)m * p.ldo + n;
+  if (p.out_f16) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < p.N) reinterpret_cast<__half*>(p.out)[o + j] = __float2half_rn(v[j]);
+    return;
+  }
   if (full) {
     if (p.out_bf16)
       *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + o) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
@@ -564,6 +578,15 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
             reinterpret_cast<float*>(p.out)[o] = h;
         }
       }
+    } else if (p.flags == (MTTS_EPI_BIAS | MTTS_EPI_GELU) && p.out_f16) {
+      // fp16-operand codec path: the GELU'd intermediate goes straight out as fp16 (half the bytes of the largest tensor)
+      __half* op = reinterpret_cast<__half*>(p.out) + (long long)(m0 + c) * p.ldo + n;
+      if (n_ok) {
+        const int lim = min(32, p.M - (m0 + c));
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < lim) op[(long long)j * p.ldo] = __float2half_rn(gelu_fast(__uint_as_float(r[j]) + bias_n));
+      }
     } else if (p.flags == (MTTS_EPI_BIAS | MTTS_EPI_GELU) && !p.out_bf16) {
       // the codec's MLP up-projections: the flag tests are hoisted, nothing but bias + GELU + one store per element
       float* op = reinterpret_cast<float*>(p.out) + (long long)(m0 + c) * p.ldo + n;
@@ -577,7 +600,7 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
             if (m0 + c + j < p.M) op[(long long)j * p.ldo] = gelu_fast(__uint_as_float(r[j]) + bias_n);
         }
       }
-    } else if (!p.out_bf16 && !(p.flags & MTTS_EPI_GELU)) {
+    } else if (!p.out_bf16 && !p.out_f16 && !(p.flags & MTTS_EPI_GELU)) {
       // fp32 bias / layer-scale / residual (the codec's down-projections and attention outputs). The residual may
       // alias the output (x += ...), so its 32 loads are issued explicitly BEFORE the first store: left to the
       // compiler every load waits behind the previous element's store (one L2 round trip per element).
@@ -625,7 +648,9 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
         if (n_ok && m < p.M) {
           const float v = epilogue_scalar(p, __uint_as_float(r[j]), m, n, bias_n, gamma_n);
           const long long o = (long long)m * p.ldo + n;
-          if (p.out_bf16)
+          if (p.out_f16)
+            reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(v);
+          else if (p.out_bf16)
             reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(v);
           else
             reinterpret_cast<float*>(p.out)[o] = v;
@@ -829,18 +854,33 @@ __global__ void __launch_bounds__(kPThreads, 1) gemm_tc_pair_kernel(const __grid
   if (warp == 0) {
     // ================= TMA producer (both CTAs): own halves, byte counts land on the leader's full barrier =================
     if (lane == 0) {
-      pdl_wait();
       const uint32_t leader_full = mapa_u32(smem_u32(full_bar), 0);
+      // weights never depend on the predecessor kernel: the first ring fill of the first tile is requested before the
+      // PDL wait (a decode-step gate/up projection then starts streaming while the RMSNorm in front of it still runs)
+      const uint64_t pol_w = num_tiles <= num_pairs ? kEvictFirst : kEvictLast;  // one tile per pair: weights are read once
+      int pre = 0;
+      if (pair < num_tiles) {
+        pre = min(num_kb, kP2Stages);
+        const int n_tile0 = pair % tiles_n;
+        for (int kb = 0; kb < pre; ++kb) {
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[kb], 4 * kHalfBytes);
+          tma_load_2d_2sm(smem_a + kb * kHalfBytes, &tmap_w, leader_full + kb * 8, kb * BK,
+                          n_tile0 * 2 * kBlockW + (int)rank * kBlockW, pol_w);
+        }
+      }
+      pdl_wait();
       int it = 0;
       for (int t = pair; t < num_tiles; t += num_pairs) {
         const int n_tile = t % tiles_n, m_tile = t / tiles_n;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kP2Stages;
           const uint32_t ph = (it / kP2Stages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 4 * kHalfBytes);
-          tma_load_2d_2sm(smem_a + s * kHalfBytes, &tmap_w, leader_full + s * 8, kb * BK,
-                          n_tile * 2 * kBlockW + (int)rank * kBlockW, kEvictLast);
+          if (it >= pre) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 4 * kHalfBytes);
+            tma_load_2d_2sm(smem_a + s * kHalfBytes, &tmap_w, leader_full + s * 8, kb * BK,
+                            n_tile * 2 * kBlockW + (int)rank * kBlockW, pol_w);
+          }
           tma_load_2d_2sm(smem_b + s * kHalfBytes, &tmap_x, leader_full + s * 8, kb * BK,
                           m_tile * kPBN + (int)rank * (kPBN / 2), kEvictNormal);
         }
@@ -934,7 +974,7 @@ EncodeTiledFn get_encode_fn() {
 struct TmapKey {
   const void* ptr;
   long long rows, cols, ld;
-  int box_rows, elem_bytes;
+  int box_rows, elem_bytes;  // elem_bytes: 2 = bf16, 4 = fp32, -2 = fp16
   bool operator==(const TmapKey& o) const {
     return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
            elem_bytes == o.elem_bytes;
@@ -956,9 +996,10 @@ struct TmapKeyHash {
 std::mutex g_tmap_mu;
 std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
 
-int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int box_rows, int elem_bytes,
+int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int box_rows, int elem_code,
              CUtensorMap* out) {
-  TmapKey key{ptr, rows, cols, ld, box_rows, elem_bytes};
+  TmapKey key{ptr, rows, cols, ld, box_rows, elem_code};
+  const int elem_bytes = elem_code < 0 ? -elem_code : elem_code;
   {
     std::lock_guard<std::mutex> g(g_tmap_mu);
     auto it = g_tmap_cache.find(key);
@@ -974,7 +1015,8 @@ int get_tmap(const void* ptr, long long rows, long long cols, long long ld, int 
   cuuint32_t box[2] = {(cuuint32_t)(kSwizzleBytes / elem_bytes), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = enc(&m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult r = enc(&m, elem_code == -2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                       : (elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2,
                    const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1112,6 +1154,14 @@ int mtts_configure_gemm_tc() {
   if ((rc = configure_one<float, 64>())) return rc;
   if ((rc = configure_one<float, 128>())) return rc;
   if ((rc = configure_one<float, 256>())) return rc;
+  if ((rc = configure_one<__half, 16>())) return rc;
+  if ((rc = configure_one<__half, 32>())) return rc;
+  if ((rc = configure_one<__half, 64>())) return rc;
+  if ((rc = configure_one<__half, 128>())) return rc;
+  if ((rc = configure_one<__half, 256>())) return rc;
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_persist_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       smem_bytes<kPBN, kPStages>()));
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_pair_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2Bytes));
   if ((rc = configure_partial<16>())) return rc;
   if ((rc = configure_partial<32>())) return rc;
   if ((rc = configure_partial<64>())) return rc;
@@ -1176,9 +1226,14 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
                          size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(M > 0 && N > 0 && K > 0, "mtts_gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  MTTS_REQUIRE(in_dtype == MTTS_DTYPE_BF16 || in_dtype == MTTS_DTYPE_F32, "mtts_gemm: bad in_dtype %d", in_dtype);
-  MTTS_REQUIRE(out_dtype == MTTS_DTYPE_BF16 || out_dtype == MTTS_DTYPE_F32, "mtts_gemm: bad out_dtype %d", out_dtype);
-  const int eb = in_dtype == MTTS_DTYPE_BF16 ? 2 : 4;
+  MTTS_REQUIRE(in_dtype == MTTS_DTYPE_BF16 || in_dtype == MTTS_DTYPE_F32 || in_dtype == MTTS_DTYPE_F16,
+               "mtts_gemm: bad in_dtype %d", in_dtype);
+  MTTS_REQUIRE(out_dtype == MTTS_DTYPE_BF16 || out_dtype == MTTS_DTYPE_F32 || out_dtype == MTTS_DTYPE_F16,
+               "mtts_gemm: bad out_dtype %d", out_dtype);
+  if (out_dtype == MTTS_DTYPE_F16)
+    MTTS_REQUIRE(!(flags & (MTTS_EPI_RESIDUAL | MTTS_EPI_SWIGLU)), "mtts_gemm: fp16 output supports bias / GELU / layer-scale only");
+  const int eb = in_dtype == MTTS_DTYPE_F32 ? 4 : 2;
+  const int ecode = in_dtype == MTTS_DTYPE_F16 ? -2 : eb;
   MTTS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0,
                "mtts_gemm: x and w must be 16-byte aligned");
   MTTS_REQUIRE((ldx * eb) % 16 == 0 && (ldw * eb) % 16 == 0, "mtts_gemm: row strides must be multiples of 16 bytes");
@@ -1198,6 +1253,17 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   // tile per CTA in the persistent kernel (batch 128: 145 us against 176 us; batch 256: 165 us against 330 us with
   // two 128-row tiles per weight tile).
   if (bn == 128 && ceil_div(N, kBlockW) >= 4 * mtts_num_sms()) bn = 256;
+  // The gate/up projection of a decode step at batch 129..256 (96 weight tiles x 2 activation tiles = 192 CTAs = 1.3
+  // waves of one CTA per SM: the SMs that get two CTAs pull 2 MB over the crossbar and set the launch time, 29 us):
+  // as 48 CTA-pair tiles of 256 x 256 every busy SM pulls 1 MB (its 128 weight rows + its 128 activation rows).
+  static int wide_pair = -1;
+  if (wide_pair < 0) {
+    const char* e = getenv("MTTS_GEMM_WIDE_PAIR");
+    wide_pair = e ? atoi(e) : 1;
+  }
+  if (wide_pair && bn == 128 && M > 128 && ceil_div(N, 2 * kBlockW) >= mtts_num_sms() / 4 &&
+      ceil_div(N, 2 * kBlockW) <= mtts_num_sms() / 2)
+    bn = 256;
   const int bk = kSwizzleBytes / eb;
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -1212,14 +1278,14 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
     p.kb_per_split = ceil_div(p.kb_total, splits);
   }
   p.splits = splits;
-  p.out = out; p.ldo = ldo; p.out_bf16 = out_dtype == MTTS_DTYPE_BF16;
+  p.out = out; p.ldo = ldo; p.out_bf16 = out_dtype == MTTS_DTYPE_BF16; p.out_f16 = out_dtype == MTTS_DTYPE_F16;
   p.bias = bias; p.gamma = gamma; p.residual = residual; p.ldr = ldr; p.flags = flags;
-  const int oeb = p.out_bf16 ? 2 : 4;
+  const int oeb = (p.out_bf16 || p.out_f16) ? 2 : 4;
   p.vec_ok = (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) % (4 * oeb)) == 0) &&
              (!(flags & MTTS_EPI_RESIDUAL) || ((ldr % 4 == 0) && (reinterpret_cast<uintptr_t>(residual) % (4 * oeb)) == 0));
   (void)workspace; (void)workspace_bytes;
   CUtensorMap tw, tx;
-  int rc = get_tmap(w, N, K, ldw, kBlockW, eb, &tw);
+  int rc = get_tmap(w, N, K, ldw, kBlockW, ecode, &tw);
   if (rc) return rc;
   // large problems on the persistent route: CTA pairs (cta_group::2) on 256 x 256 tiles
   static int pair_mode = -1;
@@ -1229,10 +1295,11 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   }
   const bool pair = pair_mode > 0 && bn == 256 && !persist_disabled();
   if (pair) p.pair_tiles_n = ceil_div(N, 2 * kBlockW);
-  rc = get_tmap(x, M, K, ldx, pair ? kPBN / 2 : bn, eb, &tx);
+  rc = get_tmap(x, M, K, ldx, pair ? kPBN / 2 : bn, ecode, &tx);
   if (rc) return rc;
   dim3 grid(tiles_n, tiles_m, splits);
   if (in_dtype == MTTS_DTYPE_BF16) return dispatch<bf16>(bn, tw, tx, p, grid, stream);
+  if (in_dtype == MTTS_DTYPE_F16) return dispatch<__half>(bn, tw, tx, p, grid, stream);
   return dispatch<float>(bn, tw, tx, p, grid, stream);
 }
 

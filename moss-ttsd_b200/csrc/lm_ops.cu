@@ -148,13 +148,35 @@ __global__ void __launch_bounds__(256) rmsnorm_warp_kernel(const bf16* __restric
 //                           xn <- RMSNorm(x) * w                (o_proj -> post-attention norm, down_proj -> next input norm)
 // One CTA per row; a thread owns 8 consecutive columns per pass.
 // ------------------------------------------------------------------------------------------------
+// All slice loads of a group of 4 are issued before the first add (the partial tiles sit in L2: one round trip per
+// group instead of one per slice), the adds run in ascending slice order.
 __device__ __forceinline__ void sum_slices8(const float* __restrict__ P, int S, long long slice, float (&a)[8]) {
-  const float4 u0 = __ldcg(reinterpret_cast<const float4*>(P)), u1 = __ldcg(reinterpret_cast<const float4*>(P) + 1);
-  a[0] = u0.x; a[1] = u0.y; a[2] = u0.z; a[3] = u0.w; a[4] = u1.x; a[5] = u1.y; a[6] = u1.z; a[7] = u1.w;
-  for (int s = 1; s < S; ++s) {
-    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(P + s * slice));
-    const float4 v1 = __ldcg(reinterpret_cast<const float4*>(P + s * slice) + 1);
-    a[0] += v0.x; a[1] += v0.y; a[2] += v0.z; a[3] += v0.w; a[4] += v1.x; a[5] += v1.y; a[6] += v1.z; a[7] += v1.w;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  for (int s0 = 0; s0 < S; s0 += 4) {
+    float4 v[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (s0 + i < S) {
+        v[i][0] = __ldcg(reinterpret_cast<const float4*>(P + (s0 + i) * slice));
+        v[i][1] = __ldcg(reinterpret_cast<const float4*>(P + (s0 + i) * slice) + 1);
+      } else {
+        v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i][1] = v[i][0];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (s0 + i < S) {
+        if (s0 + i == 0) {
+          a[0] = v[i][0].x; a[1] = v[i][0].y; a[2] = v[i][0].z; a[3] = v[i][0].w;
+          a[4] = v[i][1].x; a[5] = v[i][1].y; a[6] = v[i][1].z; a[7] = v[i][1].w;
+        } else {
+          a[0] += v[i][0].x; a[1] += v[i][0].y; a[2] += v[i][0].z; a[3] += v[i][0].w;
+          a[4] += v[i][1].x; a[5] += v[i][1].y; a[6] += v[i][1].z; a[7] += v[i][1].w;
+        }
+      }
+    }
   }
 }
 

@@ -356,9 +356,8 @@ class DecoderEngine:
         self._rmsnorm(x, layers[0]["ln1"], xn)
         for l, lw in enumerate(layers):
             S = self._splitk(xn, lw["wqkv"], pws)
-            check(L.mtts_splitk_reduce(ptr(pws), S, R, qkv.shape[1], ptr(qkv), qkv.stride(0), stream_ptr()))
-            check(L.mtts_gqa_decode_fused(
-                ptr(qkv), qkv.stride(0), ptr(lw["q_norm"]), ptr(lw["k_norm"]), ptr(self.w.inv_freq), eps,
+            check(L.mtts_gqa_decode_fused_splitk(
+                ptr(pws), S, ptr(lw["q_norm"]), ptr(lw["k_norm"]), ptr(self.w.inv_freq), eps,
                 ptr(cache.k[l]), ptr(cache.v[l]), ptr(cache.block_table), cache.max_pages, cache.page_size,
                 cache.num_pages, ptr(positions), ptr(ao), R, s.num_attention_heads, s.num_key_value_heads, s.head_dim,
                 attn_kw["nsplit"], ptr(ws), ws.numel() if ws is not None else 0, ptr(self.err), stream_ptr()))

@@ -163,3 +163,58 @@ def test_full_width_decode_logits_match_the_fp32_oracle():
     # bf16 activations / weights against an fp32 reference: a few bf16 ulps of the largest logit
     assert worst["chain"] <= 0.03 * max(1.0, scale), (worst, scale)
     assert worst["mega"] <= 0.03 * max(1.0, scale), (worst, scale)
+
+
+@pytest.mark.parametrize("B", [70, 130, 256])
+def test_splitk_decode_chain_matches_the_fused_epilogue_chain(B):
+    """Decode steps at batch 65..256 through the consumer-side split-K path (mtts_gemm_splitk -> attention prologue /
+    residual+RMSNorm reducers; gate/up on the CTA-pair kernel above batch 128) against the cluster split-K chain with
+    fused epilogues: same bf16 rounding points, different fp32 summation order -> logits within a few bf16 ulps and
+    the same greedy tokens wherever the top-2 gap is not a near-tie; and against the fp32 oracle for a few rows."""
+    from moss_ttsd_b200.lm_engine import DecoderEngine, KVCache, LMShape, LMWeights, SamplerSetup
+    from oracle import lm_oracle
+    shape_d = dict(hidden_size=2048, intermediate_size=6144, num_hidden_layers=2, num_attention_heads=16,
+                   num_key_value_heads=8, head_dim=128, rms_norm_eps=1e-6, rope_theta=1e6, vocab_size=152697,
+                   speech_vocab_size=1025, channels=8, speech_token_range=[151665, 152689])
+    sd = lm_oracle.make_weights(shape_d, 78, tied=True)
+    shape = LMShape(num_hidden_layers=2)
+    w = LMWeights(shape, "cuda").load_state_dict(sd, tie_word_embeddings=True)
+    rng = np.random.default_rng(B)
+    P, n = 12, 3
+    full = np.zeros((B, P + n, 8), dtype=np.int64)
+    full[:, :, 0] = rng.integers(151665, 152689, (B, P + n))
+    full[:, :, 1:] = rng.integers(0, 1024, (B, P + n, 7))
+    mask = np.ones((B, P + n), dtype=np.int64)
+    mask[1::3, :2] = 0
+    ids, m = torch.from_numpy(full).cuda(), torch.from_numpy(mask).cuda()
+    got = {}
+    for name, use in (("fused", False), ("splitk", True)):
+        eng = DecoderEngine(w)
+        eng.use_splitk, eng.use_graph = use, False
+        cache = KVCache(shape, B, 64, "cuda")
+        st = eng.make_decode_state(B, cache, SamplerSetup(shape, [False] * 8, None), 64, (151665, 152689), 152694, False)
+        assert (st["pws"] is not None) == use
+        eng.reset_decode_state(st, 0, P, 100)
+        lg, lens = eng.prefill(ids[:, :P], m[:, :P], cache)
+        st["positions"].copy_((lens - 1).to(torch.int32))
+        eng.sample_and_advance(st, lg)
+        steps = []
+        for k in range(n):
+            st["tokens"].copy_(ids[:, P + k])
+            eng.decode_step(st)
+            steps.append(st["logits"].float().clone())
+        got[name] = torch.stack(steps, 1)            # (B, n, vpad)
+        assert not eng.err.cpu().any()
+    a, b = got["fused"], got["splitk"]
+    scale = a.abs().max().item()
+    assert (a - b).abs().max().item() <= 0.02 * max(1.0, scale), ((a - b).abs().max().item(), scale)
+    offs = shape.head_offsets
+    sl = a[..., offs[1]:offs[1] + 1024], b[..., offs[1]:offs[1] + 1024]
+    flips = sl[0].argmax(-1) != sl[1].argmax(-1)
+    top2 = sl[0].topk(2, -1).values
+    assert ((top2[..., 0] - top2[..., 1])[flips] <= 0.05 * max(1.0, scale)).all()
+    # fp32 oracle on the first 3 sequences
+    ref = lm_oracle.OracleLM(shape_d, sd, torch.float32).logits_all(torch.from_numpy(full[:3]), torch.from_numpy(mask[:3]))
+    ref = torch.cat([r for r in ref], dim=-1)[:, P:]
+    ours = torch.cat([b[:3, :, offs[c]:offs[c] + shape.vocabs[c]].cpu() for c in range(8)], dim=-1)
+    assert (ours - ref).abs().max().item() <= 0.03 * max(1.0, ref.abs().max().item())
