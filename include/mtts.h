@@ -220,6 +220,14 @@ int mtts_delay_step_rows(long long* tokens, const long long* tf_tail, long long*
 int mtts_layernorm(const float* x, const float* w, const float* b, float* out, long long rows, int C, float eps,
                    const int* lengths, int rows_per_item, void* stream);
 
+/* fp16-operand path of the decoder's large GEMMs (mtts_gemm with MTTS_DTYPE_F16 operands: the 10-bit mantissa of the TF32
+ * path at twice the tensor rate and half the operand bytes): the normalisations write their output — the next GEMM's
+ * activation operand — directly as fp16. Same arithmetic as mtts_layernorm / mtts_dwconv7_ln, one rounding at the store. */
+int mtts_layernorm_f16(const float* x, const float* w, const float* b, void* out_f16, long long rows, int C, float eps,
+                       const int* lengths, int rows_per_item, void* stream);
+int mtts_dwconv7_ln_f16(const float* x, const float* conv_w, const float* conv_b, const float* ln_w, const float* ln_b,
+                        void* out_f16, int B, int T, int C, float eps, void* stream);
+
 /* VarLenAttention core (modules.py:117-160), non-causal, head_dim 64: qkv [B*T, 3*H*64] (q|k|v incl. biases, q NOT yet
  * scaled), out [B*T, H*64]; keys >= lengths[b] are masked. */
 int mtts_mha_varlen(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads, int head_dim,

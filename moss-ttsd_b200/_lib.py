@@ -97,6 +97,9 @@ SIGNATURES = {
     "mtts_sample8_rows": (c_int, [c_void_p, c_ll, c_int, _cfg_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
     "mtts_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p, c_int, c_void_p]),
+    "mtts_layernorm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p, c_int, c_void_p]),
+    "mtts_dwconv7_ln_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                    c_void_p]),
     "mtts_mha_varlen": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mtts_mha_varlen_fp32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mtts_rows_prefix_copy": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -2,6 +2,7 @@
 // ([batch * frames, channels], channels contiguous) everywhere, so every projection is a plain mtts_gemm and no
 // (B,C,T)<->(B,T,C) transposes are ever materialised (the reference transposes around every block,
 // XY_Tokenizer/xy_tokenizer/nn/modules.py:1144-1153,1399-1409).
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "mtts_internal.h"
 #include <stdlib.h>
@@ -13,19 +14,26 @@ namespace {
 // zeroing rows at or beyond each item's length (`torch.where(attention_mask, hidden_states, 0)`,
 // modules.py:407,626). One warp per row.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store4(float* p, float4 o) { *reinterpret_cast<float4*>(p) = o; }
+__device__ __forceinline__ void store4(__half* p, float4 o) {  // fp16-operand path of the decoder GEMMs (mtts.h)
+  __half2 a = __floats2half2_rn(o.x, o.y), b = __floats2half2_rn(o.z, o.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
+template <typename OutT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ b, float* __restrict__ out,
+                                                        const float* __restrict__ b, OutT* __restrict__ out,
                                                         long long rows, int C, float eps,
                                                         const int* __restrict__ lengths, int rows_per_item) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* xr = x + row * C;
-  float* orow = out + row * C;
+  OutT* orow = out + row * C;
   if (lengths) {
     const int item = (int)(row / rows_per_item), t = (int)(row % rows_per_item);
     if (t >= lengths[item]) {
-      for (int c = lane * 4; c < C; c += 128) *reinterpret_cast<float4*>(orow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = lane * 4; c < C; c += 128) store4(orow + c, make_float4(0.f, 0.f, 0.f, 0.f));
       return;
     }
   }
@@ -51,7 +59,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     o.y = (v.y - mean) * inv * ww.y + bb.y;
     o.z = (v.z - mean) * inv * ww.z + bb.z;
     o.w = (v.w - mean) * inv * ww.w + bb.w;
-    *reinterpret_cast<float4*>(orow + c) = o;
+    store4(orow + c, o);
   }
 }
 
@@ -349,8 +357,9 @@ __global__ void __launch_bounds__(128) mha_varlen_tc_kernel(const float* __restr
 // ------------------------------------------------------------------------------------------------
 constexpr int kDwTokens = 16;
 
+template <typename OutT>
 __global__ void dwconv7_ln_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ cb,
-                                  const float* __restrict__ lw, const float* __restrict__ lb, float* __restrict__ out,
+                                  const float* __restrict__ lw, const float* __restrict__ lb, OutT* __restrict__ out,
                                   int T, int C, float eps) {
   __shared__ float red[2][2][32];  // [mean | var][parity][warp]
   const int tiles = (T + kDwTokens - 1) / kDwTokens;
@@ -401,8 +410,8 @@ __global__ void dwconv7_ln_kernel(const float* __restrict__ x, const float* __re
     tot = 0.f;
     for (int k = 0; k < nw; ++k) tot += red[1][par][k];
     const float inv = rsqrtf(tot * invC + eps);
-    *reinterpret_cast<float4*>(out + ((long long)b * T + t) * C + c) =
-        make_float4(d0 * inv * g.x + bb.x, d1 * inv * g.y + bb.y, d2 * inv * g.z + bb.z, d3 * inv * g.w + bb.w);
+    store4(out + ((long long)b * T + t) * C + c,
+           make_float4(d0 * inv * g.x + bb.x, d1 * inv * g.y + bb.y, d2 * inv * g.z + bb.z, d3 * inv * g.w + bb.w));
   }
 }
 
@@ -606,8 +615,21 @@ extern "C" int mtts_layernorm(const float* x, const float* w, const float* b, fl
   if (rows <= 0) return MTTS_OK;
   MTTS_REQUIRE(x && w && b && out, "mtts_layernorm: null pointer");
   MTTS_REQUIRE(lengths == nullptr || rows_per_item > 0, "mtts_layernorm: rows_per_item must be positive with lengths");
-  layernorm_kernel<<<(unsigned)ceil_div_ll(rows, 8), 256, 0, stream>>>(x, w, b, out, rows, C, eps, lengths,
-                                                                      rows_per_item);
+  layernorm_kernel<float><<<(unsigned)ceil_div_ll(rows, 8), 256, 0, stream>>>(x, w, b, out, rows, C, eps, lengths,
+                                                                             rows_per_item);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_layernorm_f16(const float* x, const float* w, const float* b, void* out_f16, long long rows, int C,
+                                  float eps, const int* lengths, int rows_per_item, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(C > 0 && C % 4 == 0, "mtts_layernorm_f16: C must be a multiple of 4");
+  if (rows <= 0) return MTTS_OK;
+  MTTS_REQUIRE(x && w && b && out_f16, "mtts_layernorm_f16: null pointer");
+  MTTS_REQUIRE(lengths == nullptr || rows_per_item > 0, "mtts_layernorm_f16: rows_per_item must be positive with lengths");
+  layernorm_kernel<__half><<<(unsigned)ceil_div_ll(rows, 8), 256, 0, stream>>>(x, w, b, reinterpret_cast<__half*>(out_f16),
+                                                                              rows, C, eps, lengths, rows_per_item);
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }
@@ -684,7 +706,20 @@ extern "C" int mtts_dwconv7_ln(const float* x, const float* conv_w, const float*
   if (B <= 0 || T <= 0) return MTTS_OK;
   MTTS_REQUIRE(x && conv_w && conv_b && ln_w && ln_b && out, "mtts_dwconv7_ln: null pointer");
   const int tiles = ceil_div(T, kDwTokens);
-  dwconv7_ln_kernel<<<(unsigned)((long long)B * tiles), C / 4, 0, stream>>>(x, conv_w, conv_b, ln_w, ln_b, out, T, C, eps);
+  dwconv7_ln_kernel<float><<<(unsigned)((long long)B * tiles), C / 4, 0, stream>>>(x, conv_w, conv_b, ln_w, ln_b, out, T, C, eps);
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_dwconv7_ln_f16(const float* x, const float* conv_w, const float* conv_b, const float* ln_w,
+                                   const float* ln_b, void* out_f16, int B, int T, int C, float eps, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(C % 128 == 0 && C <= 4096, "mtts_dwconv7_ln_f16: C must be a multiple of 128 and <= 4096");
+  if (B <= 0 || T <= 0) return MTTS_OK;
+  MTTS_REQUIRE(x && conv_w && conv_b && ln_w && ln_b && out_f16, "mtts_dwconv7_ln_f16: null pointer");
+  const int tiles = ceil_div(T, kDwTokens);
+  dwconv7_ln_kernel<__half><<<(unsigned)((long long)B * tiles), C / 4, 0, stream>>>(
+      x, conv_w, conv_b, ln_w, ln_b, reinterpret_cast<__half*>(out_f16), T, C, eps);
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }

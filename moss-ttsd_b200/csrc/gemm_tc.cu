@@ -1254,12 +1254,14 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   // two 128-row tiles per weight tile).
   if (bn == 128 && ceil_div(N, kBlockW) >= 4 * mtts_num_sms()) bn = 256;
   // The gate/up projection of a decode step at batch 129..256 (96 weight tiles x 2 activation tiles = 192 CTAs = 1.3
-  // waves of one CTA per SM: the SMs that get two CTAs pull 2 MB over the crossbar and set the launch time, 29 us):
-  // as 48 CTA-pair tiles of 256 x 256 every busy SM pulls 1 MB (its 128 weight rows + its 128 activation rows).
+  // waves: the SMs that get two CTAs pull 2 MB over the crossbar and set the launch time, 29 us in isolation) as 48
+  // CTA-pair tiles of 256 x 256 (every busy SM pulls 1 MB: its 128 weight rows + its 128 activation rows) — measured
+  // SLOWER inside the decode step on B200 (batch 256: 4.67 against 4.49 ms per step): only 96 SMs pull, and a
+  // one-CTA-per-SM kernel keeps its neighbours from becoming resident early. Kept behind MTTS_GEMM_WIDE_PAIR=1.
   static int wide_pair = -1;
   if (wide_pair < 0) {
     const char* e = getenv("MTTS_GEMM_WIDE_PAIR");
-    wide_pair = e ? atoi(e) : 1;
+    wide_pair = e ? atoi(e) : 0;
   }
   if (wide_pair && bn == 128 && M > 128 && ceil_div(N, 2 * kBlockW) >= mtts_num_sms() / 4 &&
       ceil_div(N, 2 * kBlockW) <= mtts_num_sms() / 2)

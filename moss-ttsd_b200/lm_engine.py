@@ -272,7 +272,9 @@ class DecoderEngine:
         self.prefill_tile_rows = int(os.environ.get("MTTS_PREFILL_TILE", "64"))  # 64: tensor-core tiles, 4: CUDA cores
         # decode steps of the kernel chain with splitk_min_rows <= batch <= 256: q/k/v, o_proj and down_proj store fp32
         # split-K partial tiles and the consumer (bf16 cast / residual + RMSNorm) sums them (mtts_gemm_splitk*)
-        self.splitk_min_rows = int(os.environ.get("MTTS_SPLITK_MIN_ROWS", "65"))
+        # (measured ms per decode step, cluster split-K with fused epilogues -> this path: batch 64 2.32 -> 2.21,
+        # batch 128 3.42 -> 3.20, batch 256 4.91 -> 4.49; batch 16 is slower this way, 1.46 -> 1.57)
+        self.splitk_min_rows = int(os.environ.get("MTTS_SPLITK_MIN_ROWS", "64"))
         self.use_splitk = os.environ.get("MTTS_SPLITK", "1") != "0"
         self.graph_replayed_launches = 0  # kernels executed through graph replays (not seen by mtts_launch_count)
 

@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import check, ptr, stream_ptr
 
-BF16, F32 = 0, 1
+BF16, F32, F16 = 0, 1, 2
 EPI_BIAS, EPI_GELU, EPI_GAMMA, EPI_RESIDUAL, EPI_SWIGLU, EPI_EXACT_ACT = 1, 2, 4, 8, 16, 32
 
 
@@ -19,6 +19,8 @@ def _dt(t: torch.Tensor) -> int:
         return BF16
     if t.dtype == torch.float32:
         return F32
+    if t.dtype == torch.float16:
+        return F16
     raise TypeError(f"unsupported dtype {t.dtype}")
 
 

@@ -188,6 +188,12 @@ class XY_Tokenizer:
         # whose two best candidates are closer than that — the rate is reported by tests/test_codec_gpu.py).
         self.encode_exact = True
         self._exact_w = {}
+        # decode(): the large GEMMs of the decoder (transformer q/k/v + MLP, ConvNeXt point-wise convs: ~90 % of its
+        # FLOPs) take fp16 operands with fp32 accumulation — the same 10-bit mantissa as the TF32 path they replace
+        # ("tf32"), at twice the tensor rate and half the operand bytes; LayerNorm / GELU outputs and the weights are
+        # well inside the fp16 range. Waveform parity is gated by SNR against the reference (tests/test_codec_gpu.py).
+        self.decode_gemm = "f16"
+        self._half_w = {}
 
     # ------------------------------------------------------------------ loading
     @classmethod
@@ -340,6 +346,7 @@ class XY_Tokenizer:
         sd, dev, gp = self._sd, self.device, self.params
         f = lambda k: sd[k].to(dev, torch.float32).contiguous()
         self._exact_w = {}
+        self._half_w = {}
         self.quantizer.load(sd, "quantizer.", dev)
         # post-RVQ adapter (Transformer, modules.py:519-640)
         pk = gp["post_rvq_adapter_kwargs"]
@@ -482,7 +489,35 @@ class XY_Tokenizer:
             self._exact_w[w.data_ptr()] = ew
         return ops.gemm_exact(x, ew, **kw)
 
-    def _stack(self, h, st: _TransformerStack, heads, lengths, B, T, exact=False):
+    def _half(self, w):
+        hw = self._half_w.get(w.data_ptr())
+        if hw is None or hw[0] is not w:
+            hw = (w, w.to(torch.float16).contiguous())
+            self._half_w[w.data_ptr()] = hw
+        return hw[1]
+
+    def _ln16(self, x, w, b, eps=1e-5):
+        out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+        check(self.L.mtts_layernorm_f16(ptr(x), ptr(w), ptr(b), ptr(out), x.shape[0], x.shape[1], eps, None, 0, stream_ptr()))
+        return out
+
+    def _stack_f16(self, h, st: _TransformerStack, heads, lengths, B, T):
+        """_stack with fp16 operands for the q/k/v projection and the MLP (fp32 residual stream, fp32 attention I/O)."""
+        E = h.shape[1]
+        for lw in st.layers:
+            xn = self._ln16(h, lw["ln1_w"], lw["ln1_b"])
+            qkv = ops.gemm(xn, self._half(lw["wqkv"]), bias=lw["bqkv"], out_dtype=torch.float32)
+            ao = torch.empty((B * T, E), dtype=torch.float32, device=h.device)
+            check(self.L.mtts_mha_varlen(ptr(qkv), ptr(ao), ptr(lengths), B, T, heads, E // heads, stream_ptr()))
+            ops.gemm(ao, lw["wo"], bias=lw["bo"], residual=h, out=h)
+            xn = self._ln16(h, lw["ln2_w"], lw["ln2_b"])
+            ff = ops.gemm(xn, self._half(lw["fc1_w"]), bias=lw["fc1_b"], gelu=True, out_dtype=torch.float16)
+            ops.gemm(ff, self._half(lw["fc2_w"]), bias=lw["fc2_b"], residual=h, out=h)
+        return self._ln(h, st.ln_w, st.ln_b, lengths=lengths, rows_per_item=T)
+
+    def _stack(self, h, st: _TransformerStack, heads, lengths, B, T, exact=False, half=False):
+        if half and not exact:
+            return self._stack_f16(h, st, heads, lengths, B, T)
         E = h.shape[1]
         mha = self.L.mtts_mha_varlen_fp32 if exact else self.L.mtts_mha_varlen
         for lw in st.layers:
@@ -509,7 +544,8 @@ class XY_Tokenizer:
         # post-RVQ adapter
         h = ops.gemm(z, self.pr_in_w, bias=self.pr_in_b)                        # (B*T, 768)
         check(L.mtts_add_rows_mod(ptr(h), ptr(self.pr_pos), B * T, h.shape[1], T, stream_ptr()))
-        h = self._stack(h, self.pr_stack, self.pr_heads, len1, B, T)
+        half = self.decode_gemm == "f16"
+        h = self._stack(h, self.pr_stack, self.pr_heads, len1, B, T, half=half)
         z = ops.gemm(h, self.pr_out_w, bias=self.pr_out_b)                      # (B*T, 3072)
         # upsample x4 (tap-major rows -> a plain reshape gives (B*4T, 768))
         s = self.up_stride
@@ -517,7 +553,7 @@ class XY_Tokenizer:
         T2 = T * s
         len2 = (len1 * s).contiguous()
         check(L.mtts_add_rows_mod(ptr(h), ptr(self.ad_pos), B * T2, h.shape[1], T2, stream_ptr()))
-        h = self._stack(h, self.ad_stack, self.ad_heads, len2, B, T2)
+        h = self._stack(h, self.ad_stack, self.ad_heads, len2, B, T2, half=half)
         # deconv1 (k3 s2) + GELU, deconv2 (k3 s1) + GELU, trim to 2*T2
         K, st = self.dc_k, self.dc1_stride
         T3 = (T2 - 1) * st + K
@@ -535,12 +571,19 @@ class XY_Tokenizer:
         check(L.mtts_im2col(ptr(mel), ptr(col), B, T4, self.mel_bins, self.v_k, self.v_embed_ld, 1, stream_ptr()))
         x = ops.gemm(col, self.v_embed_w, bias=self.v_embed_b)                  # (B*T4, 512)
         x = self._ln(x, self.v_norm_w, self.v_norm_b, eps=1e-6)
-        t = torch.empty_like(x)
+        t = torch.empty(x.shape, dtype=torch.float16 if half else torch.float32, device=dev)
+        ff = None
         for bl in self.v_blocks:
-            check(L.mtts_dwconv7_ln(ptr(x), ptr(bl["dw_w"]), ptr(bl["dw_b"]), ptr(bl["ln_w"]), ptr(bl["ln_b"]), ptr(t), B, T4,
-                                    self.v_dim, 1e-6, stream_ptr()))
-            ff = ops.gemm(t, bl["pw1_w"], bias=bl["pw1_b"], gelu=True)
-            ops.gemm(ff, bl["pw2_w"], bias=bl["pw2_b"], gamma=bl["gamma"], residual=x, out=x)
+            if half:
+                check(L.mtts_dwconv7_ln_f16(ptr(x), ptr(bl["dw_w"]), ptr(bl["dw_b"]), ptr(bl["ln_w"]), ptr(bl["ln_b"]), ptr(t), B,
+                                            T4, self.v_dim, 1e-6, stream_ptr()))
+                ff = ops.gemm(t, self._half(bl["pw1_w"]), out=ff, bias=bl["pw1_b"], gelu=True, out_dtype=torch.float16)
+                ops.gemm(ff, self._half(bl["pw2_w"]), bias=bl["pw2_b"], gamma=bl["gamma"], residual=x, out=x)
+            else:
+                check(L.mtts_dwconv7_ln(ptr(x), ptr(bl["dw_w"]), ptr(bl["dw_b"]), ptr(bl["ln_w"]), ptr(bl["ln_b"]), ptr(t), B, T4,
+                                        self.v_dim, 1e-6, stream_ptr()))
+                ff = ops.gemm(t, bl["pw1_w"], out=ff, bias=bl["pw1_b"], gelu=True)
+                ops.gemm(ff, bl["pw2_w"], bias=bl["pw2_b"], gamma=bl["gamma"], residual=x, out=x)
         x = self._ln(x, self.v_fln_w, self.v_fln_b, eps=1e-6)
         # ISTFT head
         F = self.n_fft // 2 + 1
