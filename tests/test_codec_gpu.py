@@ -55,6 +55,28 @@ def test_decode_full_config_matches_reference_golden():
     assert s >= SNR_DB, s
 
 
+@pytest.mark.parametrize("mode", ["f16", "tf32"])
+def test_decode_gemm_modes_keep_the_snr(mode):
+    """Both operand modes of the decoder's large GEMMs — fp16 (default) and TF32 — against the reference waveforms (tiny
+    two-window ragged golden and the shipped-config golden): stated gate 40 dB for either (both carry a 10-bit mantissa)."""
+    from oracle.codec_weights import TINY_CODEC, full_codec_params
+    g = gold("codec_decode.npz")
+    worst = 1e9
+    for name, gp, n_items in (("tiny_long", TINY_CODEC, 2), ("full", full_codec_params(), 1)):
+        spt = _spt(gp, int(g[f"{name}_seed"]))
+        assert spt.decode_gemm == "f16"
+        spt.decode_gemm = mode
+        codes = [torch.from_numpy(g[f"{name}_codes{i}"].astype(np.int64)).cuda() for i in range(n_items)]
+        wavs = spt.decode(codes, overlap_seconds=10)["syn_wav_list"]
+        for i in range(n_items):
+            w = wavs[i].cpu().numpy()
+            ref = g[f"{name}_wav{i}"]
+            s = snr_db(ref, w[::8] if name == "tiny_long" else w)
+            print(f"decode_gemm={mode} {name}[{i}] SNR {s:.1f} dB")
+            worst = min(worst, s)
+    assert worst >= 40.0, worst
+
+
 def test_inference_detokenize_shapes_and_empty():
     from oracle.codec_weights import TINY_CODEC
     spt = _spt(TINY_CODEC, 21)
