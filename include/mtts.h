@@ -186,6 +186,20 @@ int mtts_sample8(const void* logits, long long ld, int B, const mtts_sampler_con
                  const int* step_ptr, const unsigned long long* seed_ptr, long long* out_tokens, int* err_flag,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* The 8 LM heads FUSED with the sampler (replaces `lm_heads[i](hidden)` modeling_asteroid.py:412 + the mask /
+ * processor / draw block :123-138 for the last position). hidden [B, hidden_size] bf16 (final-norm output), heads
+ * [vpad, hidden_size] bf16 (the 8 head matrices stacked, each padded to a multiple of 32 rows). When every channel is
+ * greedy without a repetition penalty and B > 64, the [B, vpad] logits are never written: the heads GEMM's epilogue
+ * reduces every 32-row quarter to its best and second-best bf16 logit (warp-level integer max over order-preserving
+ * keys) and a (row, channel) pick kernel applies the step's pad / EOS mask and takes the argmax (lowest index on
+ * ties). Otherwise it is mtts_gemm -> `logits` -> mtts_sample8_rows. mtts_heads8_sample_fused() tells which. */
+size_t mtts_heads8_sample_workspace_bytes(int B, int vpad, int channels);
+int mtts_heads8_sample_fused(const mtts_sampler_config* cfg, int B);
+int mtts_heads8_sample(const void* hidden, long long ld_hidden, const void* heads, long long ld_heads, int B, int hidden_size,
+                       int vpad, const mtts_sampler_config* cfg, const uint32_t* seen, const int* step_ptr, const int* row_ctl,
+                       const unsigned long long* seed_ptr, void* logits, long long ld_logits, long long* out_tokens,
+                       int* err_flag, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The per-row state machine after the draw: wind-down trigger, teacher forcing (tf_tail [B, channels-1, channels] =
  * prompt[:, P:P+channels-1, :]), wind-down fill, finished fill, append to sequences [B, max_len_rows, channels] at row
  * P + s (P = dyn_params[0], max_length = dyn_params[1]; device ints, so a captured graph survives a new prompt), history bitmap update, counters/stopping, positions[b] += 1, unfinished_hist[s] = #unfinished rows,

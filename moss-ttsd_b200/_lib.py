@@ -96,6 +96,10 @@ SIGNATURES = {
                              c_void_p]),
     "mtts_sample8_rows": (c_int, [c_void_p, c_ll, c_int, _cfg_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_size_t, c_void_p]),
+    "mtts_heads8_sample_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "mtts_heads8_sample_fused": (c_int, [_cfg_p, c_int]),
+    "mtts_heads8_sample": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, _cfg_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mtts_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p, c_int, c_void_p]),
     "mtts_layernorm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p, c_int, c_void_p]),
     "mtts_dwconv7_ln_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,

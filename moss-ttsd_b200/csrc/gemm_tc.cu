@@ -61,6 +61,12 @@ struct GemmParams {
   int vec_ok;     // output / residual rows allow 4-wide vector access
   int pair_tiles_n;  // > 0: CTA-pair kernel, number of 256-row weight tiles
   float* partials;   // split-K with the reduction in the consumer: [splits][M][N] fp32
+  // fused LM heads + greedy pick (mtts_heads8_sample): instead of logits, every 32-row quarter of the stacked head matrix
+  // reports, per batch row, its best and second-best bf16 logit as sortable keys: [M][n_quarters][2] u32
+  uint32_t* argmax_keys;
+  int n_quarters;
+  int n_chan;
+  int chan_lo[8], chan_hi[8];  // real rows of channel c in the stacked matrix: [chan_lo, chan_hi)
 };
 
 template <typename T>
@@ -554,6 +560,36 @@ __device__ __forceinline__ float epilogue_scalar(const GemmParams& p, float v, i
 // lane = output column n, TMEM column = activation row m0 + c.
 __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t taddr, int m0, int n, bool n_ok, float bias_n,
                                               float gamma_n, int lane) {
+  if (p.argmax_keys) {
+    // lane = vocabulary row n (one 32-row quarter per warp, never straddling two channels: heads are padded to 32 rows),
+    // TMEM column = batch row. key = (order-preserving 16-bit image of the bf16 logit) << 16 | (31 - lane): the warp-wide
+    // integer maximum is the best logit, the lowest row on ties (torch.argmax); 0 marks padding rows / "no candidate".
+    bool real = false;
+    if (n_ok)
+      for (int ch = 0; ch < p.n_chan; ++ch) real = real || (n >= p.chan_lo[ch] && n < p.chan_hi[ch]);
+    const int q = n >> 5;
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      if (m0 + c >= p.M) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(taddr + c, r);
+      tmem_ld_wait();
+      uint32_t best_mine = 0u, second_mine = 0u;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(r[j])));
+        const uint32_t ord = (hb & 0x8000u) ? (~hb & 0xffffu) : (hb | 0x8000u);
+        const uint32_t key = real ? ((ord << 16) | (uint32_t)(31 - lane)) : 0u;
+        const uint32_t best = __reduce_max_sync(0xffffffffu, key);
+        const uint32_t second = __reduce_max_sync(0xffffffffu, key == best ? 0u : key);
+        if (lane == j) { best_mine = best; second_mine = second; }
+      }
+      const int m = m0 + c + lane;
+      if (m < p.M)
+        *reinterpret_cast<uint2*>(p.argmax_keys + ((long long)m * p.n_quarters + q) * 2) = make_uint2(best_mine, second_mine);
+    }
+    return;
+  }
 #pragma unroll 1
   for (int c = 0; c < 128; c += 32) {
     if (m0 + c >= p.M) break;  // warp-uniform
@@ -1303,6 +1339,32 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   if (in_dtype == MTTS_DTYPE_BF16) return dispatch<bf16>(bn, tw, tx, p, grid, stream);
   if (in_dtype == MTTS_DTYPE_F16) return dispatch<__half>(bn, tw, tx, p, grid, stream);
   return dispatch<float>(bn, tw, tx, p, grid, stream);
+}
+
+// ---- fused LM heads: per-quarter best / second-best logit keys instead of logits (called by mtts_heads8_sample) ------------
+int mtts_gemm_heads_argmax(const void* x, long long ldx, const void* w, long long ldw, int M, int N, int K, int n_chan,
+                           const int* chan_lo, const int* chan_hi, unsigned int* keys, cudaStream_t stream) {
+  MTTS_REQUIRE(M > 64 && N % 32 == 0 && n_chan >= 1 && n_chan <= 8, "heads argmax: needs M > 64, N %% 32 == 0");
+  MTTS_REQUIRE(!persist_disabled(), "heads argmax: needs the CTA-pair kernel (MTTS_GEMM_NO_PERSIST is set)");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.kb_total = ceil_div(K, Traits<bf16>::kBlockK);
+  p.kb_per_split = p.kb_total;
+  p.splits = 1;
+  p.out_bf16 = 1;
+  p.argmax_keys = keys;
+  p.n_quarters = N / 32;
+  p.n_chan = n_chan;
+  for (int c = 0; c < n_chan; ++c) { p.chan_lo[c] = chan_lo[c]; p.chan_hi[c] = chan_hi[c]; }
+  p.pair_tiles_n = ceil_div(N, 2 * kBlockW);
+  CUtensorMap tw, tx;
+  int rc = get_tmap(w, N, K, ldw, kBlockW, 2, &tw);
+  if (rc) return rc;
+  rc = get_tmap(x, M, K, ldx, kPBN / 2, 2, &tx);
+  if (rc) return rc;
+  dim3 grid(ceil_div(N, kBlockW), ceil_div(M, kPBN), 1);
+  return dispatch<bf16>(256, tw, tx, p, grid, stream);
 }
 
 // ---- split-K with the reduction in the consumer -------------------------------------------------------------------

@@ -3,6 +3,12 @@
 #include "../../include/mtts.h"
 
 int mtts_gemm_tc_pick_bn(int M);
+#ifdef __CUDACC__
+// LM-heads GEMM whose epilogue reports, per batch row and 32-row quarter of the stacked head matrix, the best and the
+// second-best bf16 logit as sortable keys [M][N/32][2] (gemm_tc.cu; used by mtts_heads8_sample, sampler.cu)
+int mtts_gemm_heads_argmax(const void* x, long long ldx, const void* w, long long ldw, int M, int N, int K, int n_chan,
+                           const int* chan_lo, const int* chan_hi, unsigned int* keys, cudaStream_t stream);
+#endif
 
 // one-time per-device kernel attribute setup, called by mtts_init()
 int mtts_configure_gemm_tc();

@@ -556,6 +556,67 @@ __global__ void init_seen_kernel(const long long* __restrict__ ids, int B, int r
   atomicOr(seen + b * cfg.seen_words_per_row + cfg.seen_offset_words[c] + (tok >> 5), 1u << (tok & 31));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused LM heads + greedy pick: the heads GEMM (gemm_tc.cu, argmax epilogue) left, per batch row and 32-row quarter of
+// the stacked head matrix, the best and second-best bf16 logit as keys (order-preserving value image << 16 | 31 - lane).
+// One CTA per (row, channel) scans the channel's quarters, skips the one index the reference masks at this step
+// (pad for a live speech channel, EOS while the prompt tail is forced: modeling_asteroid.py:124-128) — which is why two
+// candidates per quarter are enough — and keeps the best value, lowest index on ties (torch.argmax).
+// ------------------------------------------------------------------------------------------------
+struct PickParams {
+  const uint32_t* keys;  // [B][n_quarters][2]
+  int n_quarters;
+  mtts_sampler_config cfg;
+  const int* step_ptr;
+  const int* row_ctl;
+  long long* out_tokens;
+};
+
+__global__ void __launch_bounds__(256) heads_pick_kernel(const PickParams p) {
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, c = blockIdx.y;
+  const mtts_sampler_config& cfg = p.cfg;
+  const int step = *p.step_ptr - (p.row_ctl ? p.row_ctl[b * 4] : 0);
+  int mask_idx = -1;
+  if (c != 0 && step >= c) mask_idx = cfg.pad_token;
+  if (c == 0 && step <= cfg.channels - 2) mask_idx = cfg.eos_mask_token;
+  const int lo = cfg.logit_offset[c], V = cfg.vocab[c];
+  const int q0 = lo >> 5, q1 = (lo + V + 31) >> 5;
+  const uint32_t* kp = p.keys + ((long long)b * p.n_quarters) * 2;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = q0 * 2 + threadIdx.x; i < q1 * 2; i += 256) {
+    const uint32_t key = __ldcg(kp + i);
+    if (key == 0u) continue;
+    const int idx = (i >> 1) * 32 + (31 - (int)(key & 31u)) - lo;
+    if (idx < 0 || idx >= V || idx == mask_idx) continue;
+    const uint32_t ord = key >> 16;
+    const uint32_t hb = (ord & 0x8000u) ? (ord & 0x7fffu) : (~ord & 0xffffu);
+    const float v = __uint_as_float(hb << 16);
+    if (better(v, idx, bv, bi)) { bv = v; bi = idx; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = bv; s_idx[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    bv = threadIdx.x < 8 ? s_val[threadIdx.x] : -INFINITY;
+    bi = threadIdx.x < 8 ? s_idx[threadIdx.x] : 0x7fffffff;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) p.out_tokens[(long long)b * cfg.channels + c] = bi == 0x7fffffff ? 0 : bi;
+  }
+}
+
 int validate_cfg(const mtts_sampler_config* cfg) {
   MTTS_REQUIRE(cfg != nullptr, "sampler: null config");
   MTTS_REQUIRE(cfg->channels >= 1 && cfg->channels <= 8, "sampler: channels must be in [1,8]");
@@ -711,4 +772,62 @@ extern "C" int mtts_delay_step_rows(long long* tokens, const long long* tf_tail,
   MTTS_CUDA_CHECK(mtts_launch(delay_step_kernel, dim3(1), dim3(threads), 0, stream, p));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
+}
+
+// ---- fused LM heads + sampler (mtts_heads8_sample) -----------------------------------------------------
+static bool heads_fusable(const mtts_sampler_config* cfg, int B) {
+  if (B <= 64) return false;  // the argmax epilogue lives in the CTA-pair GEMM that batches above 64 use
+  for (int c = 0; c < cfg->channels; ++c) {
+    if (cfg->do_sample[c] || cfg->has_rep[c]) return false;  // a repetition penalty rescales arbitrary logits
+    if (cfg->logit_offset[c] % 32 != 0) return false;
+  }
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("MTTS_FUSE_HEADS");
+    off = (e && e[0] == '0') ? 1 : 0;
+  }
+  return off == 0;
+}
+
+extern "C" size_t mtts_heads8_sample_workspace_bytes(int B, int vpad, int channels) {
+  return mtts_sample8_workspace_bytes(B, channels) + (size_t)B * (size_t)(vpad / 32 + 1) * 2 * sizeof(uint32_t) + 256;
+}
+
+extern "C" int mtts_heads8_sample_fused(const mtts_sampler_config* cfg, int B) {
+  return (validate_cfg(cfg) == MTTS_OK && heads_fusable(cfg, B)) ? 1 : 0;
+}
+
+extern "C" int mtts_heads8_sample(const void* hidden, long long ld_hidden, const void* heads, long long ld_heads, int B,
+                                  int hidden_size, int vpad, const mtts_sampler_config* cfg, const uint32_t* seen,
+                                  const int* step_ptr, const int* row_ctl, const unsigned long long* seed_ptr,
+                                  void* logits, long long ld_logits, long long* out_tokens, int* err_flag, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = validate_cfg(cfg);
+  if (rc) return rc;
+  if (B <= 0) return MTTS_OK;
+  MTTS_REQUIRE(hidden && heads && step_ptr && out_tokens && workspace, "mtts_heads8_sample: null pointer");
+  MTTS_REQUIRE(workspace_bytes >= mtts_heads8_sample_workspace_bytes(B, vpad, cfg->channels),
+               "mtts_heads8_sample: workspace too small");
+  const size_t sample_ws = mtts_sample8_workspace_bytes(B, cfg->channels);
+  if (heads_fusable(cfg, B) && vpad % 32 == 0) {
+    // greedy rows: the [B, vpad] logits are never written; the GEMM epilogue leaves 2 candidates per 32-row quarter
+    uint32_t* keys = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(workspace) + sample_ws + 255) & ~uintptr_t(255));
+    int lo[8], hi[8];
+    for (int c = 0; c < cfg->channels; ++c) { lo[c] = cfg->logit_offset[c]; hi[c] = cfg->logit_offset[c] + cfg->vocab[c]; }
+    rc = mtts_gemm_heads_argmax(hidden, ld_hidden, heads, ld_heads, B, vpad, hidden_size, cfg->channels, lo, hi, keys, stream);
+    if (rc) return rc;
+    PickParams pp;
+    pp.keys = keys; pp.n_quarters = vpad / 32; pp.cfg = *cfg; pp.step_ptr = step_ptr; pp.row_ctl = row_ctl;
+    pp.out_tokens = out_tokens;
+    MTTS_CUDA_CHECK(mtts_launch(heads_pick_kernel, dim3(B, cfg->channels), dim3(256), 0, stream, pp));
+    MTTS_LAUNCH_CHECK();
+    return MTTS_OK;
+  }
+  MTTS_REQUIRE(logits != nullptr && seen != nullptr && seed_ptr != nullptr, "mtts_heads8_sample: the unfused path needs logits / seen / seed");
+  rc = mtts_gemm(hidden, ld_hidden, heads, ld_heads, logits, ld_logits, B, vpad, hidden_size, MTTS_DTYPE_BF16, MTTS_DTYPE_BF16, 0,
+                 nullptr, nullptr, nullptr, 0, nullptr, 0, stream_);
+  if (rc) return rc;
+  return mtts_sample8_rows(logits, ld_logits, B, cfg, seen, step_ptr, row_ctl, seed_ptr, out_tokens, err_flag, workspace,
+                           sample_ws, stream_);
 }

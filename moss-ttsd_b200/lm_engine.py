@@ -6,7 +6,7 @@ Reference behaviour being replaced: AsteroidTTSInstruct.forward + HF Qwen3Model 
 337-426) and the per-step part of CustomMixin._sample (modeling_asteroid.py:110-169).
 
 HBM layout (one replica per GPU):
-  heads   [Vpad, H] bf16   the 8 LM heads stacked (each head's rows padded to a multiple of 8); when the
+  heads   [Vpad, H] bf16   the 8 LM heads stacked (each head's rows padded to a multiple of 32); when the
                            checkpoint ties heads and embedding tables (tie_weights, modeling_asteroid.py:315-317)
                            the 8 embedding tables are views into this buffer
   layer l : wqkv [(Hq+2Hkv)*D, H]   q|k|v rows stacked -> one GEMM
@@ -31,8 +31,11 @@ from . import _lib, ops
 from ._lib import check, ptr, stream_ptr
 
 
-def _pad8(n: int) -> int:
-    return (n + 7) // 8 * 8
+def _pad_rows(n: int) -> int:
+    """Rows each LM head is padded to in the stacked head matrix: a multiple of 32, so that no 32-row quarter of a
+    weight tile straddles two channels (the fused heads + greedy pick reports candidates per quarter) and every
+    channel's logits start 16-byte aligned."""
+    return (n + 31) // 32 * 32
 
 
 @dataclass
@@ -70,12 +73,12 @@ class LMShape:
         offs, o = [], 0
         for v in self.vocabs:
             offs.append(o)
-            o += _pad8(v)
+            o += _pad_rows(v)
         return offs
 
     @property
     def vpad(self) -> int:
-        return sum(_pad8(v) for v in self.vocabs)
+        return sum(_pad_rows(v) for v in self.vocabs)
 
 
 class LMWeights:
@@ -180,7 +183,7 @@ class LMWeights:
             self.embeds = None
         for c in range(self.shape.channels):  # padding rows between heads stay zero
             o, v = self.shape.head_offsets[c], self.shape.vocabs[c]
-            self.heads[o + v:o + _pad8(v)].zero_()
+            self.heads[o + v:o + _pad_rows(v)].zero_()
         if speech_only_head0 is not None:
             lo, hi = speech_only_head0
             self.heads[:lo].zero_()
@@ -275,6 +278,9 @@ class DecoderEngine:
         # (measured ms per decode step, cluster split-K with fused epilogues -> this path: batch 64 2.32 -> 2.21,
         # batch 128 3.42 -> 3.20, batch 256 4.91 -> 4.49; batch 16 is slower this way, 1.46 -> 1.57)
         self.splitk_min_rows = int(os.environ.get("MTTS_SPLITK_MIN_ROWS", "64"))
+        # decode steps: LM heads fused with the sampler (mtts_heads8_sample); False keeps the [B, vpad] logits in
+        # st["logits"] (tests that inspect them)
+        self.fuse_heads = os.environ.get("MTTS_FUSE_HEADS", "1") != "0"
         self.use_splitk = os.environ.get("MTTS_SPLITK", "1") != "0"
         self.graph_replayed_launches = 0  # kernels executed through graph replays (not seen by mtts_launch_count)
 
@@ -487,8 +493,8 @@ class DecoderEngine:
         nsplit = max(1, min(8, -(-(2 * 148) // max(1, B * s.num_key_value_heads))))
         st["nsplit"] = nsplit
         st["attn_ws"] = self._attn_workspace(B, 1, nsplit)
-        st["sample_ws"] = torch.zeros(self.L.mtts_sample8_workspace_bytes(B, self.s.channels), dtype=torch.uint8,
-                                      device=self.dev)
+        st["sample_ws"] = torch.zeros(self.L.mtts_heads8_sample_workspace_bytes(B, self.s.vpad, self.s.channels),
+                                      dtype=torch.uint8, device=self.dev)
         st["mega"] = self._make_mega(st) if self.mega_supported(B) else None
         st["graph"] = None
         return st
@@ -556,6 +562,25 @@ class DecoderEngine:
                                           st["B"], ptr(st["dyn"]), ptr(rc), st["speech"][0], st["speech"][1], st["eos"],
                                           1 if st["has_eos"] else 0, ctypes.byref(sm.cfg), stream_ptr()))
 
+    def heads_sample_and_advance(self, st, xn):
+        """LM heads + sampler + delay-pattern state machine from the final-norm output `xn` [B, H]. Greedy rows without a
+        repetition penalty at batch > 64 never materialise the logits (mtts_heads8_sample)."""
+        if not self.fuse_heads:
+            ops.gemm(xn, self.w.heads, out=st["logits"], workspace=st["gws"])
+            return self.sample_and_advance(st, st["logits"])
+        sm = st["sampler"]
+        rc = st.get("row_ctl")
+        s = self.s
+        check(self.L.mtts_heads8_sample(ptr(xn), xn.stride(0), ptr(self.w.heads), self.w.heads.stride(0), st["B"], s.hidden_size,
+                                        s.vpad, ctypes.byref(sm.cfg), ptr(st["seen"]), ptr(st["step"]), ptr(rc),
+                                        ptr(st["seed_dev"]), ptr(st["logits"]), st["logits"].stride(0), ptr(st["tokens"]),
+                                        ptr(self.err), ptr(st["sample_ws"]), st["sample_ws"].numel(), stream_ptr()))
+        check(self.L.mtts_delay_step_rows(ptr(st["tokens"]), ptr(st["tf_tail"]), ptr(st["sequences"]), st["max_len_rows"],
+                                          ptr(st["unfinished"]), ptr(st["needs"]), ptr(st["positions"]), ptr(st["seen"]),
+                                          ptr(st["step"]), ptr(st["hist"]), st.get("hist_len", 0), ptr(st["finish_len"]),
+                                          st["B"], ptr(st["dyn"]), ptr(rc), st["speech"][0], st["speech"][1], st["eos"],
+                                          1 if st["has_eos"] else 0, ctypes.byref(sm.cfg), stream_ptr()))
+
     def _decode_body(self, st):
         a = st["acts"]
         self._embed(st["tokens"], a["x"])
@@ -569,8 +594,7 @@ class DecoderEngine:
             xn = self._layers_splitk(a, st["cache"], st["positions"], attn_kw, st["gws"], st["pws"])
         else:
             xn = self._layers(a, st["cache"], st["positions"], None, attn_kw, st["gws"])
-        ops.gemm(xn, self.w.heads, out=st["logits"], workspace=st["gws"])
-        self.sample_and_advance(st, st["logits"])
+        self.heads_sample_and_advance(st, xn)
 
     def decode_step(self, st):
         """Feed the row appended by the previous step, sample the next one. Replays a CUDA graph after the

@@ -12,12 +12,17 @@ spt.init_random_weights(seed=5, device="cuda")
 codes = [torch.randint(0, 1024, (8, 375), device="cuda") for _ in range(B)]
 out = {}
 ref = None
-for mode in ("tf32", "f16"):
+for mode in (sys.argv[2].split(",") if len(sys.argv) > 2 else ("tf32", "f16")):
     spt.decode_gemm = mode
     for _ in range(2):
         w = spt.decode(codes)["syn_wav_list"]
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    if os.environ.get("MTTS_PROFILE_RANGE") == mode:      # ncu --profile-from-start off: exactly one decode call
+        torch.cuda.profiler.start()
+        w = spt.decode(codes)["syn_wav_list"]
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     e0.record()
     for _ in range(3):
         w = spt.decode(codes)["syn_wav_list"]

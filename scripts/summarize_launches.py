@@ -1,29 +1,26 @@
-"""Summarise an ncu `--metrics gpu__time_duration.sum --csv` launch list: per-kernel totals of the last decode step."""
-import collections, csv, re, sys
+"""Per-kernel totals of an `ncu --metrics gpu__time_duration.sum --csv` launch list (shares, not absolutes)."""
+import collections, csv, sys
 
-def load(f):
-    with open(f) as fh:
-        lines = [l for l in fh if not l.startswith("==")]
-    rows = []
+def load(path):
+    with open(path) as f:
+        lines = [l for l in f if l.startswith('"')]
+    out = []
     for row in csv.DictReader(lines):
-        if row.get("Metric Name") == "gpu__time_duration.sum":
-            rows.append((row["Kernel Name"], float(row["Metric Value"].replace(",", "")), row.get("Grid Size", "")))
-    return rows
+        t = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        t = t / 1000 if u == "ns" else (t * 1000 if u == "ms" else t)
+        out.append((row["Kernel Name"], row.get("Grid Size", ""), t))
+    return out
 
-for f in sys.argv[1:]:
-    rows = load(f)
-    idx = [i for i, (n, _, _) in enumerate(rows) if "embed_sum" in n]
-    last = rows[idx[-1]:]
-    agg = collections.defaultdict(lambda: [0, 0.0])
-    for n, v, g in last:
-        key = re.sub(r"\(.*", "", n)[:64]
-        agg[key][0] += 1
-        agg[key][1] += v
-    tot = sum(v for _, v, _ in last)
-    print(f"{f}: last decode step = {len(last)} kernels, {tot/1e3:.1f} us")
-    for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"   {v/1e3:9.1f} us  {100*v/tot:5.1f}%  x{c:4d}  avg {v/c/1e3:7.2f} us  {k}")
-    # per-GEMM detail
-    for n, v, g in last:
-        if "gemm_tc" in n:
-            print(f"      gemm grid={g} {v/1e3:.2f} us")
+if __name__ == "__main__":
+    seq = load(sys.argv[1])
+    lo = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    hi = int(sys.argv[3]) if len(sys.argv) > 3 else len(seq)
+    seq = seq[lo:hi]
+    per = collections.OrderedDict()
+    for n, g, t in seq:
+        per.setdefault((n[:90], g), []).append(t)
+    tot = sum(t for _, _, t in seq)
+    print(f"total {tot:.1f} us over {len(seq)} launches")
+    for k, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
+        print(f"{sum(v):10.1f} us {100 * sum(v) / tot:5.1f}%  n={len(v):4d}  avg={sum(v) / len(v):9.2f}  {k[0]} {k[1]}")

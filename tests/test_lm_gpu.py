@@ -401,3 +401,59 @@ def test_generate_early_stop_tied_weights_streamer_and_dict():
     assert torch.equal(plain.cpu(), seq)
     with pytest.raises(ValueError):
         m.generate(input_ids=ids[:, :5].cuda(), attention_mask=mask[:, :5].cuda())
+
+
+@pytest.mark.parametrize("B,step", [(65, 0), (96, 3), (256, 9)])
+def test_fused_heads_greedy_pick_equals_logits_then_argmax(B, step):
+    """mtts_heads8_sample (heads GEMM with the per-quarter best / second-best epilogue + pick kernel, logits never
+    written) against the unfused pair mtts_gemm -> mtts_sample8_rows on the same hidden states: identical tokens for all
+    8 channels, including exact ties (lowest index), the step's pad / EOS masks, and a winner that is the masked index."""
+    import ctypes
+    from moss_ttsd_b200 import _lib, ops
+    from moss_ttsd_b200.lm_engine import LMShape, LMWeights, SamplerSetup
+    L = _lib.load()
+    ops.ensure_init()
+    shape = LMShape(num_hidden_layers=1)
+    w = LMWeights(shape, "cuda").init_random_(seed=5, std=0.02)
+    offs, vocabs = shape.head_offsets, shape.vocabs
+    assert all(o % 32 == 0 for o in offs) and shape.vpad % 32 == 0
+    # exact ties: two identical head rows in channel 0 and in channel 3; make the pad row of channel 2 and the EOS row of
+    # channel 0 the strongest rows, so that the mask decides
+    w.heads[offs[0] + 151900] = w.heads[offs[0] + 151700]
+    w.heads[offs[3] + 700] = w.heads[offs[3] + 5]
+    torch.manual_seed(B)
+    xn = torch.randn(B, shape.hidden_size, device="cuda").to(torch.bfloat16)
+    w.heads[offs[2] + 1024] = (xn[:8].float().mean(0) * 4).to(torch.bfloat16)
+    w.heads[offs[0] + 152694] = (xn[:8].float().mean(0) * 4).to(torch.bfloat16)
+    sm = SamplerSetup(shape, [False] * 8, None)
+    assert L.mtts_heads8_sample_fused(ctypes.byref(sm.cfg), B) == 1 and L.mtts_heads8_sample_fused(ctypes.byref(sm.cfg), 64) == 0
+    seen = torch.zeros((B, sm.words_per_row), dtype=torch.int32, device="cuda")
+    stp = torch.tensor([step], dtype=torch.int32, device="cuda")
+    seed = torch.zeros(1, dtype=torch.int64, device="cuda")
+    err = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ws = torch.zeros(L.mtts_heads8_sample_workspace_bytes(B, shape.vpad, 8), dtype=torch.uint8, device="cuda")
+    logits = torch.empty((B, shape.vpad), dtype=torch.bfloat16, device="cuda")
+    want = torch.zeros((B, 8), dtype=torch.int64, device="cuda")
+    ops.gemm(xn, w.heads, out=logits)
+    _lib.check(L.mtts_sample8_rows(logits.data_ptr(), logits.stride(0), B, ctypes.byref(sm.cfg), seen.data_ptr(), stp.data_ptr(),
+                                   None, seed.data_ptr(), want.data_ptr(), err.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   _lib.stream_ptr()))
+    got = torch.full((B, 8), -1, dtype=torch.int64, device="cuda")
+    logits2 = torch.full_like(logits, float("nan"))
+    _lib.check(L.mtts_heads8_sample(xn.data_ptr(), xn.stride(0), w.heads.data_ptr(), w.heads.stride(0), B, shape.hidden_size,
+                                    shape.vpad, ctypes.byref(sm.cfg), seen.data_ptr(), stp.data_ptr(), None, seed.data_ptr(),
+                                    logits2.data_ptr(), logits2.stride(0), got.data_ptr(), err.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), _lib.stream_ptr()))
+    assert torch.equal(got, want), (got != want).nonzero()[:5]
+    assert torch.isnan(logits2.float()).all()                       # the fused path never wrote logits
+    # the crafted cases really occur: the tie picks the lower row; masked rows lose exactly when the step masks them
+    lg = logits.float()
+    assert (lg[:, offs[0] + 151900] == lg[:, offs[0] + 151700]).all()
+    if step >= 2:
+        assert (got[:8, 2] != 1024).all()
+    else:
+        assert (got[:8, 2] == 1024).all()
+    assert ((got[:8, 0] == 152694) == (step > 6)).all()
+    # a repetition penalty or a sampled channel takes the logits path
+    sm2 = SamplerSetup(shape, [False] * 8, [dict(repetition_penalty=1.1)] * 8)
+    assert L.mtts_heads8_sample_fused(ctypes.byref(sm2.cfg), B) == 0

@@ -190,7 +190,7 @@ def test_splitk_decode_chain_matches_the_fused_epilogue_chain(B):
     got = {}
     for name, use in (("fused", False), ("splitk", True)):
         eng = DecoderEngine(w)
-        eng.use_splitk, eng.use_graph = use, False
+        eng.use_splitk, eng.use_graph, eng.fuse_heads = use, False, False
         cache = KVCache(shape, B, 64, "cuda")
         st = eng.make_decode_state(B, cache, SamplerSetup(shape, [False] * 8, None), 64, (151665, 152689), 152694, False)
         assert (st["pws"] is not None) == use
