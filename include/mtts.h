@@ -247,6 +247,11 @@ int mtts_dwconv7_ln_f16(const float* x, const float* conv_w, const float* conv_b
 int mtts_mha_varlen(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads, int head_dim,
                     void* stream);
 
+/* Same contraction with fp16 tensor-core operands (Q, K, V, probabilities; fp32 accumulate and softmax): the attention of
+ * the decoder's fp16-operand path. */
+int mtts_mha_varlen_f16(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads, int head_dim,
+                        void* stream);
+
 /* Same contraction with fp32 CUDA-core products, fp32 softmax and expf(): the exact mode of XY_Tokenizer.encode, whose
  * integer codes must match the reference's fp32 matmuls (model.py:54-101 -> modules.py:117-160). */
 int mtts_mha_varlen_fp32(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads, int head_dim,

@@ -349,6 +349,161 @@ __global__ void __launch_bounds__(128) mha_varlen_tc_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp16-operand version of the tensor-core attention (mma.sync m16n8k16, fp32 accumulate / softmax): Q, K, V and the
+// probabilities carry the same 10-bit mantissa as the TF32 kernel above at twice the MMA rate and half the shared-memory
+// traffic. CTA = 64 queries x one head, 4 warps x 16 query rows; K/V tiles of 64 keys staged as fp16 [key][dim], pitch
+// 72 halfs (conflict-free for the 32-bit K fragment loads and for ldmatrix). S = Q K^T reads K fragments directly;
+// O += P V takes P from the score accumulators (two adjacent 8-key blocks form one 16-key A fragment, no shuffles) and
+// V through ldmatrix.trans.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHPitch = 72;  // halfs per staged row
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void mma_f16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+__global__ void __launch_bounds__(128) mha_varlen_h_kernel(const float* __restrict__ qkv, float* __restrict__ out,
+                                                           const int* __restrict__ lengths, int T, int H,
+                                                           float scale_log2) {
+  __shared__ __align__(16) __half sk[kKT * kHPitch];
+  __shared__ __align__(16) __half sv[kKT * kHPitch];
+  const int E = H * kHD;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kQT;
+  const int len = lengths ? min(lengths[b], T) : T;
+  const int kv_len = len > 0 ? len : T;  // all-masked item: uniform over every key, as in the reference
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const float* base = qkv + (long long)b * T * 3 * E;
+
+  uint32_t qa[4][4];  // 4 k-steps of 16 dims
+  {
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+    const float* p0 = base + (long long)min(r0, T - 1) * 3 * E + h * kHD;
+    const float* p1 = base + (long long)min(r1, T - 1) * 3 * E + h * kHD;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const float2 a0 = *reinterpret_cast<const float2*>(p0 + ks * 16 + 2 * t);
+      const float2 a1 = *reinterpret_cast<const float2*>(p1 + ks * 16 + 2 * t);
+      const float2 a2 = *reinterpret_cast<const float2*>(p0 + ks * 16 + 2 * t + 8);
+      const float2 a3 = *reinterpret_cast<const float2*>(p1 + ks * 16 + 2 * t + 8);
+      qa[ks][0] = pack_h2(a0.x * scale_log2, a0.y * scale_log2);
+      qa[ks][1] = pack_h2(a1.x * scale_log2, a1.y * scale_log2);
+      qa[ks][2] = pack_h2(a2.x * scale_log2, a2.y * scale_log2);
+      qa[ks][3] = pack_h2(a3.x * scale_log2, a3.y * scale_log2);
+    }
+  }
+  float o[8][4];
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[nb][i] = 0.f;
+  float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
+  const uint32_t sv_addr = (uint32_t)__cvta_generic_to_shared(sv);
+  // ldmatrix.x4.trans lane address inside a 16-key x 16-dim block: key = (l % 8) + 8 * ((l / 8) % 2), dim = 8 * (l / 16)
+  const uint32_t ldm_off = (uint32_t)((((lane & 7) + 8 * ((lane >> 3) & 1)) * kHPitch + 8 * (lane >> 4)) * 2);
+
+  for (int k0 = 0; k0 < kv_len; k0 += kKT) {
+    __syncthreads();
+    for (int i = tid; i < kKT * (kHD / 4); i += 128) {
+      const int r = i >> 4, c4 = (i & 15) * 4;
+      float4 kv4 = make_float4(0.f, 0.f, 0.f, 0.f), vv4 = kv4;
+      if (k0 + r < kv_len) {
+        const float* p = base + (long long)(k0 + r) * 3 * E + h * kHD + c4;
+        kv4 = *reinterpret_cast<const float4*>(p + E);
+        vv4 = *reinterpret_cast<const float4*>(p + 2 * E);
+      }
+      *reinterpret_cast<uint2*>(sk + r * kHPitch + c4) = make_uint2(pack_h2(kv4.x, kv4.y), pack_h2(kv4.z, kv4.w));
+      *reinterpret_cast<uint2*>(sv + r * kHPitch + c4) = make_uint2(pack_h2(vv4.x, vv4.y), pack_h2(vv4.z, vv4.w));
+    }
+    __syncthreads();
+    float sc[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[nb][i] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const __half* kp = sk + (nb * 8 + g) * kHPitch + ks * 16 + 2 * t;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kp);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kp + 8);
+        mma_f16_16x8x16(sc[nb], qa[ks], b0, b1);
+      }
+    }
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int key = k0 + nb * 8 + 2 * t;
+      if (key >= kv_len) { sc[nb][0] = -INFINITY; sc[nb][2] = -INFINITY; }
+      if (key + 1 >= kv_len) { sc[nb][1] = -INFINITY; sc[nb][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(sc[nb][0], sc[nb][1]));
+      mx1 = fmaxf(mx1, fmaxf(sc[nb][2], sc[nb][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = exp2f(m0 - mx0), c1 = exp2f(m1 - mx1);
+    m0 = mx0;
+    m1 = mx1;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      sc[nb][0] = exp2f(sc[nb][0] - mx0);
+      sc[nb][1] = exp2f(sc[nb][1] - mx0);
+      sc[nb][2] = exp2f(sc[nb][2] - mx1);
+      sc[nb][3] = exp2f(sc[nb][3] - mx1);
+      ps0 += sc[nb][0] + sc[nb][1];
+      ps1 += sc[nb][2] + sc[nb][3];
+    }
+    l0 = l0 * c0 + ps0;
+    l1 = l1 * c1 + ps1;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // 16-key blocks
+      uint32_t pa[4];
+      pa[0] = pack_h2(sc[2 * j][0], sc[2 * j][1]);
+      pa[1] = pack_h2(sc[2 * j][2], sc[2 * j][3]);
+      pa[2] = pack_h2(sc[2 * j + 1][0], sc[2 * j + 1][1]);
+      pa[3] = pack_h2(sc[2 * j + 1][2], sc[2 * j + 1][3]);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {  // pairs of 8-dim blocks
+        uint32_t vb[4];
+        ldmatrix_x4_trans(vb, sv_addr + (uint32_t)((j * 16 * kHPitch + np * 16) * 2) + ldm_off);
+        mma_f16_16x8x16(o[2 * np], pa, vb[0], vb[1]);
+        mma_f16_16x8x16(o[2 * np + 1], pa, vb[2], vb[3]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    if (r0 < T)
+      *reinterpret_cast<float2*>(out + ((long long)b * T + r0) * E + h * kHD + nb * 8 + 2 * t) = make_float2(o[nb][0] * i0, o[nb][1] * i0);
+    if (r1 < T)
+      *reinterpret_cast<float2*>(out + ((long long)b * T + r1) * E + h * kHD + nb * 8 + 2 * t) = make_float2(o[nb][2] * i1, o[nb][3] * i1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // ConvNeXt front half: depthwise Conv1d(k=7, pad=3, groups=C) + LayerNorm(C, eps) fused
 // (ConvNeXtBlock.forward modules.py:1142-1150). x/out: [B, T, C]; w: [C, 7]; zero padding at each item's ends.
 // One CTA (C/4 threads, 4 channels each) walks kDwTokens consecutive tokens of one item with a 7-row sliding window in
@@ -652,6 +807,18 @@ extern "C" int mtts_mha_varlen(const float* qkv, float* out, const int* lengths,
   else
     mha_varlen_kernel<false><<<grid, 256, 4 * kQT * kPitch * sizeof(float), stream>>>(qkv, out, lengths, T, num_heads,
                                                                                      1.0f / sqrtf((float)head_dim));
+  MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+extern "C" int mtts_mha_varlen_f16(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads,
+                                   int head_dim, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  MTTS_REQUIRE(head_dim == kHD, "mtts_mha_varlen_f16: head_dim must be 64 (got %d)", head_dim);
+  if (B <= 0 || T <= 0) return MTTS_OK;
+  MTTS_REQUIRE(qkv && out, "mtts_mha_varlen_f16: null pointer");
+  dim3 grid(ceil_div(T, kQT), num_heads, B);
+  mha_varlen_h_kernel<<<grid, 128, 0, stream>>>(qkv, out, lengths, T, num_heads, 1.4426950408889634f / sqrtf((float)head_dim));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }

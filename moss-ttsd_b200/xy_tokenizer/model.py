@@ -508,7 +508,7 @@ class XY_Tokenizer:
             xn = self._ln16(h, lw["ln1_w"], lw["ln1_b"])
             qkv = ops.gemm(xn, self._half(lw["wqkv"]), bias=lw["bqkv"], out_dtype=torch.float32)
             ao = torch.empty((B * T, E), dtype=torch.float32, device=h.device)
-            check(self.L.mtts_mha_varlen(ptr(qkv), ptr(ao), ptr(lengths), B, T, heads, E // heads, stream_ptr()))
+            check(self.L.mtts_mha_varlen_f16(ptr(qkv), ptr(ao), ptr(lengths), B, T, heads, E // heads, stream_ptr()))
             ops.gemm(ao, lw["wo"], bias=lw["bo"], residual=h, out=h)
             xn = self._ln16(h, lw["ln2_w"], lw["ln2_b"])
             ff = ops.gemm(xn, self._half(lw["fc1_w"]), bias=lw["fc1_b"], gelu=True, out_dtype=torch.float16)

@@ -173,6 +173,19 @@ def test_codec_kernels_against_torch_functional():
     # TF32 tensor-core attention (10-bit mantissa operands, fp32 accumulate / softmax)
     assert (got[0] - ref[0]).abs().max().item() <= 4e-3 * ref.abs().max().item()
     assert (got[1, :77] - ref[1, :77]).abs().max().item() <= 4e-3 * ref.abs().max().item()
+    # fp16-operand kernel (same mantissa width) and the fp32 CUDA-core kernel of the exact encode mode
+    for fn, tol in ((L.mtts_mha_varlen_f16, 4e-3), (L.mtts_mha_varlen_fp32, 2e-6)):
+        ao2 = torch.full_like(ao, float("nan"))
+        _lib.check(fn(qkv.data_ptr(), ao2.data_ptr(), lens.data_ptr(), B, T, H, 64, sp()))
+        got2 = ao2.view(B, T, H * 64).double()
+        assert (got2[0] - ref[0]).abs().max().item() <= tol * ref.abs().max().item()
+        assert (got2[1, :77] - ref[1, :77]).abs().max().item() <= tol * ref.abs().max().item()
+    # LayerNorm with fp16 output
+    o16 = torch.empty(100, 768, dtype=torch.float16, device="cuda")
+    x_ln = torch.randn(100, 768, device="cuda", generator=g)
+    _lib.check(L.mtts_layernorm_f16(x_ln.data_ptr(), w.data_ptr(), b.data_ptr(), o16.data_ptr(), 100, 768, 1e-5, None, 0, sp()))
+    assert torch.equal(o16, F.layer_norm(x_ln, (768,), w, b, 1e-5).half()) or \
+        (o16.float() - F.layer_norm(x_ln, (768,), w, b, 1e-5)).abs().max().item() <= 4e-3
     # dwconv7 + LN
     Bc, Tc, C = 2, 40, 512
     x = torch.randn(Bc, Tc, C, device="cuda", generator=g)
