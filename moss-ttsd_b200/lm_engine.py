@@ -220,6 +220,19 @@ class KVCache:
         return self.k.numel() * 4
 
 
+class MttsCache:
+    """`past_key_values` of the drop-in model: the bf16 K/V pools of one batch plus, per sequence, how many (real, i.e.
+    unpadded) tokens they hold. Returned by `forward(use_cache=True)`, accepted by `forward(past_key_values=...)`."""
+
+    def __init__(self, cache: KVCache, lengths, capacity: int):
+        self.cache = cache
+        self.lengths = np.asarray(lengths, dtype=np.int64).copy()
+        self.capacity = capacity
+
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        return int(self.lengths.max()) if self.lengths.size else 0
+
+
 class SamplerSetup:
     """Host-side description of the per-channel processors -> `mtts_sampler_config`."""
 
@@ -422,17 +435,22 @@ class DecoderEngine:
             return out, flat_idx, lens
         return out, lens
 
-    def prefill_packed(self, ids: torch.Tensor, lens_h, slots_h, cache: KVCache, logits: Optional[str] = "last"):
+    def prefill_packed(self, ids: Optional[torch.Tensor], lens_h, slots_h, cache: KVCache, logits: Optional[str] = "last",
+                       pos0_h=None, embeds: Optional[torch.Tensor] = None):
         """Packed prefill: `ids` (R, C) int64 holds the rows of len(lens_h) sequences back to back; sequence i has
         lens_h[i] rows at positions 0 .. lens_h[i]-1 and its K/V go to cache slot slots_h[i] (a row of the page table:
         with continuous batching the slot is wherever a finished request made room). logits: "last" -> [n, Vpad] of each
-        sequence's last row, "all" -> [R, Vpad], None -> only the K/V side effect (admission of a queued request)."""
+        sequence's last row, "all" -> [R, Vpad], None -> only the K/V side effect (admission of a queued request).
+        pos0_h: first position of each sequence's rows (continuing a cache that already holds pos0 tokens, i.e.
+        `forward(past_key_values=...)`); embeds: (R, H) bf16 rows used instead of the embedding sum (`inputs_embeds=`)."""
         lens_h = np.asarray(lens_h, dtype=np.int64)
         n = len(lens_h)
         R = int(lens_h.sum())
         cu = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(lens_h, out=cu[1:])
-        pos_h = np.concatenate([np.arange(k, dtype=np.int32) for k in lens_h]) if R else np.zeros(0, np.int32)
+        p0 = np.zeros(n, dtype=np.int64) if pos0_h is None else np.asarray(pos0_h, dtype=np.int64)
+        pos_h = (np.concatenate([np.arange(a, a + k, dtype=np.int32) for a, k in zip(p0, lens_h)]) if R
+                 else np.zeros(0, np.int32)).astype(np.int32)
         seq_h = np.repeat(np.asarray(slots_h, dtype=np.int32), lens_h)
         row0_h, nrows_h = [], []
         tile_rows = self.prefill_tile_rows
@@ -446,7 +464,10 @@ class DecoderEngine:
         tile_nrows = torch.tensor(nrows_h, dtype=torch.int32, device=self.dev)
         a = self._alloc_acts(R)
         gws = self._gemm_ws(R)
-        self._embed(ids, a["x"])
+        if embeds is not None:
+            a["x"].copy_(embeds.to(self.dev, torch.bfloat16))
+        else:
+            self._embed(ids, a["x"])
         attn_kw = dict(tiles=len(row0_h), rows_per_tile=tile_rows, tile_row0=tile_row0, tile_nrows=tile_nrows, nsplit=1, ws=None)
         xn = self._layers(a, cache, positions, row_seq, attn_kw, gws, want_output=logits is not None)
         if logits is None:
@@ -565,7 +586,7 @@ class DecoderEngine:
     def heads_sample_and_advance(self, st, xn):
         """LM heads + sampler + delay-pattern state machine from the final-norm output `xn` [B, H]. Greedy rows without a
         repetition penalty at batch > 64 never materialise the logits (mtts_heads8_sample)."""
-        if not self.fuse_heads:
+        if not self.fuse_heads or st.get("keep_logits"):
             ops.gemm(xn, self.w.heads, out=st["logits"], workspace=st["gws"])
             return self.sample_and_advance(st, st["logits"])
         sm = st["sampler"]

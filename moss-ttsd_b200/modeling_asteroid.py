@@ -17,7 +17,7 @@ from typing import List, Optional, Tuple, Union
 
 import torch
 
-from .lm_engine import DecoderEngine, KVCache, LMShape, LMWeights, SamplerSetup
+from .lm_engine import DecoderEngine, KVCache, LMShape, LMWeights, MttsCache, SamplerSetup
 
 
 class AsteroidTTSConfig:
@@ -234,30 +234,62 @@ class AsteroidTTSInstruct:
                 position_ids=None, past_key_values=None, inputs_embeds=None, labels=None, use_cache=None,
                 output_attentions=None, output_hidden_states=None, return_dict=None, cache_position=None,
                 skip_logits=None, **kwargs):
+        """Teacher-forced logits of every position for (B, S, 8) ids (or (B, S, H) `inputs_embeds`), optionally continuing
+        a `past_key_values` cache returned by an earlier call with `use_cache=True` (modeling_asteroid.py:337-426,
+        inference branch; `attention_mask` then covers past + new positions, as HF passes it). Positions are
+        cumsum(mask) - 1 (`position_ids` / `cache_position` are accepted and must be consistent with that)."""
         if (input_ids is None) ^ (inputs_embeds is not None):
             raise ValueError("You must specify exactly one of input_ids or inputs_embeds")
-        if inputs_embeds is not None:
-            raise NotImplementedError("inputs_embeds is not supported by the B200 path (the embedding sum is fused)")
         if labels is not None:
             raise NotImplementedError("training loss is out of scope of the B200 inference path")
-        if past_key_values is not None:
-            raise NotImplementedError("forward() is the teacher-forced full-sequence pass; use generate() for decoding")
-        B, S, C = input_ids.shape
-        if C != self.config.channels:
-            raise ValueError(f"Expected {self.config.channels} channels, got {C}")
+        if output_attentions or output_hidden_states:
+            raise NotImplementedError("attention / hidden-state capture is not supported by the fused kernels")
         eng = self.engine
-        input_ids = input_ids.to(self.device)
+        if input_ids is not None:
+            B, S, C = input_ids.shape
+            if C != self.config.channels:
+                raise ValueError(f"Expected {self.config.channels} channels, got {C}")
+            input_ids = input_ids.to(self.device)
+        else:
+            B, S, Hd = inputs_embeds.shape
+            if Hd != self.shape.hidden_size:
+                raise ValueError(f"inputs_embeds must have hidden size {self.shape.hidden_size}, got {Hd}")
+        past = past_key_values
+        if past is not None and not isinstance(past, MttsCache):
+            raise TypeError("past_key_values must be the object returned by forward(use_cache=True) of this model")
         if attention_mask is None:
-            attention_mask = torch.ones((B, S), device=self.device)
+            attention_mask = torch.ones((B, S + (past.get_seq_length() if past is not None else 0)), device=self.device)
         attention_mask = attention_mask.to(self.device)
-        cache = KVCache(self.shape, B, S, self.device, paged=self.kv_paged, page_size=self.kv_page_size)
-        logits, flat_idx, _ = eng.prefill(input_ids, attention_mask, cache, all_logits=True)
+        if attention_mask.shape[1] < S:
+            raise ValueError("attention_mask must cover at least the new positions")
+        new_mask = (attention_mask[:, -S:] != 0)
+        lens_h = new_mask.sum(1).cpu().numpy().astype("int64")
+        if past is None:
+            cap = S + (int(getattr(self, "forward_cache_rows", 512)) if use_cache else 0)
+            cache = KVCache(self.shape, B, cap, self.device, paged=self.kv_paged, page_size=self.kv_page_size)
+            pos0 = lens_h * 0
+        else:
+            cache, cap, pos0 = past.cache, past.capacity, past.lengths
+            if (pos0 + lens_h).max() > cap:
+                raise RuntimeError(f"past_key_values holds {int(pos0.max())} rows of a {cap}-row cache; set "
+                                   f"model.forward_cache_rows before the first call to reserve more")
+        flat_idx = new_mask.reshape(-1).nonzero(as_tuple=False).squeeze(1)
+        import numpy as np
+        slots = np.arange(B, dtype=np.int32)
+        if input_ids is not None:
+            ids = input_ids.reshape(B * S, C).index_select(0, flat_idx).contiguous()
+            logits = eng.prefill_packed(ids, lens_h, slots, cache, "all", pos0_h=pos0)
+        else:
+            emb = inputs_embeds.to(self.device).reshape(B * S, -1).index_select(0, flat_idx).contiguous()
+            logits = eng.prefill_packed(None, lens_h, slots, cache, "all", pos0_h=pos0, embeds=emb)
         self._check_err()
         full = torch.zeros((B * S, self.shape.vpad), dtype=torch.bfloat16, device=self.device)
         full.index_copy_(0, flat_idx, logits)
         full = full.view(B, S, -1)
         logits_all = tuple(full[..., o:o + v] for o, v in zip(self.shape.head_offsets, self.shape.vocabs))
-        return AsteroidTTSOutputWithPast(loss=None, logits=logits_all[0], loss_all=None, logits_all=logits_all)
+        pkv = MttsCache(cache, pos0 + lens_h, cap) if use_cache else None
+        return AsteroidTTSOutputWithPast(loss=None, logits=logits_all[0], loss_all=None, logits_all=logits_all,
+                                         past_key_values=pkv)
 
     __call__ = forward
 
@@ -266,7 +298,8 @@ class AsteroidTTSInstruct:
         if any(e):
             self.engine.err.zero_()
             raise RuntimeError(f"libmtts device-side error flags {e} (1: token id out of range, 2: KV page out of range, "
-                               f"3: sampler candidate overflow, 4: full-vocabulary nucleus larger than the candidate list)")
+                               f"3: sampler candidate overflow, 4: full-vocabulary nucleus larger than the candidate list, "
+                               f"5: the persistent decode kernel gave up waiting)")
 
     # ------------------------------------------------------------------ continuous batching (not in the reference)
     @torch.no_grad()
@@ -358,8 +391,9 @@ class AsteroidTTSInstruct:
         channel 0 of row b is forced to EOS, after which the row winds down as after a sampled EOS; 0 = no budget."""
         gc = copy.deepcopy(generation_config if generation_config is not None else self.generation_config)
         gc.update(**kwargs)
-        if gc.output_attentions or gc.output_hidden_states or gc.output_scores or gc.output_logits:
-            raise NotImplementedError("per-step scores/attentions capture is not supported by the fused decode step")
+        if gc.output_attentions or gc.output_hidden_states:
+            raise NotImplementedError("attention / hidden-state capture is not supported by the fused decode step")
+        capture = bool(gc.return_dict_in_generate and (gc.output_scores or gc.output_logits))
         B, T, C = input_ids.shape
         if C != self.config.channels:
             raise ValueError(f"Expected {self.config.channels} channels, got {C}")
@@ -383,6 +417,10 @@ class AsteroidTTSInstruct:
         # A row in wind-down ignores max_length for up to C-2 extra rows; allocate for it.
         max_rows = max(max_length, P + 1) + C + 2 * self.sync_every
         sampler = self._sampler_setup(gc)
+        if capture and gc.output_scores and any(sampler.cfg.has_rep[c] or sampler.cfg.has_temp[c] or sampler.cfg.top_k[c] or
+                                                sampler.cfg.has_top_p[c] for c in range(C)):
+            raise NotImplementedError("output_scores with logits processors: the processed scores never leave the sampler "
+                                      "kernel; use output_logits (masked raw logits, modeling_asteroid.py:123-128,176)")
         if seed is None:
             seed = int(torch.initial_seed() & 0x7FFFFFFFFFFFFFFF)  # follows torch.manual_seed / accelerate set_seed
         # One decode session (KV pool, state buffers, captured graph) is kept and re-used while the batch size, the
@@ -390,7 +428,7 @@ class AsteroidTTSInstruct:
         # neither re-allocate ~10 GB nor re-capture the 230-kernel graph.
         cfg_key = bytes(sampler.cfg)
         key = (B, self.kv_paged, self.kv_page_size, cfg_key, tuple(self.config.speech_token_range), int(eos_fill), has_eos,
-               eng.use_graph, eos_at is not None)
+               eng.use_graph, eos_at is not None, capture)
         sess = getattr(self, "_session", None)
         if sess is None or sess["key"] != key or sess["rows"] < max_rows:
             self._session = None
@@ -404,6 +442,7 @@ class AsteroidTTSInstruct:
                 st["row_ctl"] = torch.zeros((B, 4), dtype=torch.int32, device=dev)
                 st["hist_len"] = st["hist"].numel()
                 st["mega"] = None
+            st["keep_logits"] = capture
             sess = dict(key=key, rows=rows_cap, st=st, cache=cache)
             self._session = sess
         st, cache = sess["st"], sess["cache"]
@@ -427,6 +466,7 @@ class AsteroidTTSInstruct:
         st["positions"].copy_((lens - 1).to(torch.int32))
         eng.sample_and_advance(st, logits)
         ev_t[1].record()
+        step_logits = [logits.clone()] if capture else None
         if streamer is not None:
             streamer.put(st["tokens"][:, 0].cpu())
         # ---- steps 1..: one graph replay per frame. The host never waits for the GPU inside the loop: after every
@@ -437,16 +477,22 @@ class AsteroidTTSInstruct:
         final_len = None
         max_steps = max_rows - P - 1
         hard_stop = max(1, max_length - P)  # rows that are not winding down all stop here: check synchronously
-        block = 1 if streamer is not None else max(1, int(self.sync_every))
+        block = 1 if (streamer is not None or capture) else max(1, int(self.sync_every))
         pinned = torch.empty(st["hist"].numel(), dtype=torch.int32).pin_memory()
+        pinned_err = torch.zeros(4, dtype=torch.int32).pin_memory()
         pending = []
 
         def scan(upto):
+            # device-side error flags travel with every block: a bad token id / page / sampler overflow surfaces at the
+            # next check (<= two blocks of `sync_every` steps later), not after the whole loop
+            if int(pinned_err.max()) != 0:
+                self._check_err()
             zero = (pinned[:upto] == 0).nonzero()
             return P + int(zero[0]) + 1 if zero.numel() else None
 
         def post_check():
             pinned[:steps_done].copy_(st["hist"][:steps_done], non_blocking=True)
+            pinned_err.copy_(eng.err, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             pending.append((ev, steps_done))
@@ -472,6 +518,8 @@ class AsteroidTTSInstruct:
             for _ in range(n):
                 eng.decode_step(st)
                 steps_done += 1
+                if capture:
+                    step_logits.append(st["logits"].clone())
                 if streamer is not None:
                     streamer.put(st["tokens"][:, 0].cpu())
             post_check()
@@ -488,5 +536,21 @@ class AsteroidTTSInstruct:
         out = st["sequences"][:, :final_len].clone()
         self._last_state = st
         if gc.return_dict_in_generate:
-            return GenerateDecoderOnlyOutput(sequences=out, past_key_values=None)
+            raw = None
+            if capture:
+                # one entry per generated row: the list of 8 fp32 (B, V_c) last-position logits with the step's pad / EOS
+                # mask applied in place, exactly what the reference appends (modeling_asteroid.py:123-128,176)
+                raw = []
+                offs, vocabs = self.shape.head_offsets, self.shape.vocabs
+                for s_i, lg in enumerate(step_logits[:final_len - P]):
+                    per = [lg[:, o:o + v].float() for o, v in zip(offs, vocabs)]
+                    for c in range(1, C):
+                        if s_i >= c:
+                            per[c][:, 1024] = float("-inf")
+                    if s_i <= C - 2:
+                        per[0][:, 152694] = float("-inf")
+                    raw.append(per)
+                raw = tuple(raw)
+            return GenerateDecoderOnlyOutput(sequences=out, past_key_values=None, logits=raw if gc.output_logits else None,
+                                             scores=raw if gc.output_scores else None)
         return out

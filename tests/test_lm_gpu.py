@@ -457,3 +457,60 @@ def test_fused_heads_greedy_pick_equals_logits_then_argmax(B, step):
     # a repetition penalty or a sampled channel takes the logits path
     sm2 = SamplerSetup(shape, [False] * 8, [dict(repetition_penalty=1.1)] * 8)
     assert L.mtts_heads8_sample_fused(ctypes.byref(sm2.cfg), B) == 0
+
+
+def test_forward_with_past_key_values_and_inputs_embeds(model):
+    """HF-style incremental use of the drop-in class (modeling_asteroid.py:252-285,337-376): forward(use_cache=True) then
+    forward(past_key_values=...) continues the cache; inputs_embeds replaces the 8-table embedding sum."""
+    g = gold("lm_tiny.npz")
+    ids, mask = torch.from_numpy(g["ids"]).cuda(), torch.from_numpy(g["mask"]).cuda()
+    T = ids.shape[1]
+    whole = model.forward(input_ids=ids, attention_mask=mask)
+    cut = T - 5
+    first = model.forward(input_ids=ids[:, :cut], attention_mask=mask[:, :cut], use_cache=True)
+    assert first.past_key_values is not None and first.past_key_values.get_seq_length() == int(mask[:, :cut].sum(1).max())
+    second = model.forward(input_ids=ids[:, cut:], attention_mask=mask, past_key_values=first.past_key_values, use_cache=True)
+    assert second.past_key_values.get_seq_length() == int(mask.sum(1).max())
+    for c in (0, 1, 7):
+        a, b = whole.logits_all[c][:, cut:].float(), second.logits_all[c].float()
+        assert a.shape == b.shape
+        assert (a - b).abs().max().item() <= 0.03          # same arithmetic, different tile shapes
+        assert (whole.logits_all[c][:, :cut].float() - first.logits_all[c].float()).abs().max().item() <= 0.03
+    # inputs_embeds: the embedding sum done by hand with the reference's bf16 rounding after every add (:244-248)
+    w = model._w
+    acc = torch.zeros(ids.shape[0], T, model.shape.hidden_size, dtype=torch.bfloat16, device="cuda")
+    for c in range(8):
+        acc += w.embed_view(c)[ids[..., c]]
+    emb = model.forward(inputs_embeds=acc, attention_mask=mask)
+    assert torch.equal(emb.logits_all[3], whole.logits_all[3])
+    with pytest.raises(ValueError):
+        model.forward(input_ids=ids, inputs_embeds=acc)
+    with pytest.raises(TypeError):
+        model.forward(input_ids=ids[:, cut:], attention_mask=mask, past_key_values=object())
+
+
+def test_generate_output_logits_capture(model):
+    """return_dict_in_generate + output_logits: one list of 8 masked fp32 last-position logits per generated row
+    (modeling_asteroid.py:123-128,176); greedy tokens are their argmax on every free channel."""
+    g = gold("lm_tiny.npz")
+    ids, mask = torch.from_numpy(g["ids"]).cuda(), torch.from_numpy(g["mask"]).cuda()
+    T = ids.shape[1]
+    P = T - 7
+    model.generation_config.eos_token_id = 152694
+    out = model.generate(input_ids=ids, attention_mask=mask, max_length=T + 5, do_sample=False, return_dict_in_generate=True,
+                         output_logits=True, output_scores=True)
+    plain = model.generate(input_ids=ids, attention_mask=mask, max_length=T + 5, do_sample=False)
+    assert torch.equal(out.sequences, plain)
+    n = out.sequences.shape[1] - P
+    assert len(out.logits) == n == len(out.scores)
+    for s_i, per in enumerate(out.logits):
+        assert len(per) == 8 and per[0].shape == (ids.shape[0], 152697) and per[1].dtype == torch.float32
+        assert torch.isinf(per[0][:, 152694]).all() == (s_i <= 6)
+        for c in range(8):
+            if c >= 1:
+                assert torch.isinf(per[c][:, 1024]).all() == (s_i >= c)
+            if c <= s_i:                                            # channel c is free from step c on
+                assert torch.equal(per[c].argmax(-1), out.sequences[:, P + s_i, c])
+    with pytest.raises(NotImplementedError):
+        model.generate(input_ids=ids, attention_mask=mask, max_length=T + 2, do_sample=True, top_k=5,
+                       return_dict_in_generate=True, output_scores=True)
