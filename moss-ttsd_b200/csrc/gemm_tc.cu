@@ -585,7 +585,7 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
         if (lane == j) { best_mine = best; second_mine = second; }
       }
       const int m = m0 + c + lane;
-      if (m < p.M)
+      if (m < p.M && q < p.n_quarters)  // the last tile's quarters beyond N must not alias the next row's first slots
         *reinterpret_cast<uint2*>(p.argmax_keys + ((long long)m * p.n_quarters + q) * 2) = make_uint2(best_mine, second_mine);
     }
     return;

@@ -421,6 +421,9 @@ def test_fused_heads_greedy_pick_equals_logits_then_argmax(B, step):
     # channel 0 the strongest rows, so that the mask decides
     w.heads[offs[0] + 151900] = w.heads[offs[0] + 151700]
     w.heads[offs[3] + 700] = w.heads[offs[3] + 5]
+    # winners in the very first and the very last quarters of the stacked matrix (tile-boundary handling of the epilogue)
+    w.heads[offs[0] + 3] *= 3.0
+    w.heads[offs[7] + 1020] *= 3.0
     torch.manual_seed(B)
     xn = torch.randn(B, shape.hidden_size, device="cuda").to(torch.bfloat16)
     w.heads[offs[2] + 1024] = (xn[:8].float().mean(0) * 4).to(torch.bfloat16)
