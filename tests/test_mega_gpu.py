@@ -71,9 +71,16 @@ def test_mega_step_matches_kernel_chain(B, paged, P):
         assert d <= 0.04 * max(1.0, lc.abs().max().item()), f"step {step}: max|dlogit| {d}"
         agree += int((st_c["tokens"] == st_m["tokens"]).sum())
         total += st_c["tokens"].numel()
+        # a differing pick must be a near-tie of the chain's own logits (random-init weights: top-2 gaps below the
+        # bf16 noise between the two summation orders do occur), never a different decision on a clear margin
+        for b, c in (st_c["tokens"] != st_m["tokens"]).nonzero().tolist():
+            off = shape.head_offsets[c]
+            tc, tm = int(st_c["tokens"][b, c]), int(st_m["tokens"][b, c])
+            gap = (lc[b, off + tc] - lc[b, off + tm]).abs().item()
+            assert gap <= 2 * d + 1e-6, f"step {step} row {b} channel {c}: picks {tc}/{tm} differ on a gap of {gap} (noise {d})"
         assert torch.equal(st_c["positions"], st_m["positions"])
         st_m["tokens"].copy_(st_c["tokens"])  # keep both paths on the same token stream
-    assert agree >= 0.97 * total, (agree, total)
+    assert agree >= 0.9 * total, (agree, total)
     # the K/V rows appended by both paths agree to bf16 rounding of near-identical inputs
     for l in range(shape.num_hidden_layers):
         kc, km = cache_c.k[l].float(), cache_m.k[l].float()
