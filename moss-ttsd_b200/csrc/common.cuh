@@ -185,6 +185,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// The same value without the IEEE-division subroutine (its slow-path branch keeps the compiler from interleaving
+// independent evaluations): q = x * rcp(y) refined by one Newton step on the residual fma(-q, y, x) — correctly rounded
+// like x / y except for rare last-bit cases, which sit 16 bits below the bf16 rounding that follows. y = 1 + e^-x >= 1;
+// y = inf (x < -88.7) keeps the unrefined quotient -0, as x / inf gives.
+__device__ __forceinline__ float silu_nb(float x) {
+  const float y = 1.0f + expf(-x);
+  float rc;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(rc) : "f"(y));
+  const float q = x * rc;
+  const float q2 = fmaf(fmaf(-q, y, x), rc, q);
+  return y < 3.0e38f ? q2 : q;
+}
 // erf-GELU for the epilogue of the TF32 tensor-core GEMMs (nn.GELU() of the codec, modules.py ConvNeXt / transformer
 // MLPs): erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, three orders below the TF32 product error it is applied
 // to), evaluated as q = x/2 * erfc(|x|/sqrt2) so that the negative tail keeps its relative accuracy:

@@ -107,7 +107,7 @@ __device__ __forceinline__ void epilogue_store4(const GemmParams& p, int m, int 
     for (int h = 0; h < 2; ++h) {
       float g = v[2 * h], u = v[2 * h + 1];
       if (p.out_bf16) { g = bf16_round(g); u = bf16_round(u); }
-      float s = silu_f(g);
+      float s = silu_nb(g);  // branch-free: the two evaluations of a call (and the unrolled rows around it) interleave
       if (p.out_bf16) s = bf16_round(s);
       o2[h] = s * u;
     }
@@ -556,6 +556,60 @@ __device__ __forceinline__ float epilogue_scalar(const GemmParams& p, float v, i
   return v;
 }
 
+// SwiGLU epilogue of one TMEM chunk (32 batch rows x this lane's weight row; rows interleaved: even lane = gate row of
+// output column n / 2, odd lane = its up row). Lane pairs exchange ONE value per two batch rows, so that the even lane
+// finishes batch row j and the odd lane batch row j + 1: all 32 lanes work. Written as four straight-line phases (round,
+// exchange, activate, store) over register arrays: the warp issues in order, so 16 independent ~200-cycle chains
+// (cvt -> shfl -> ex2 -> rcp -> fma -> cvt) only overlap if the code interleaves them. The first form — per row: shuffle,
+// then expf and an IEEE division behind a branch on the even lanes — ran them back to back: 23 us to drain one
+// 128 x 256 tile per SM, more than the tile's MMAs take (globaltimer phase trace of the drain, round 2).
+template <bool kBf16>
+__device__ __forceinline__ void swiglu_chunk(const GemmParams& p, const uint32_t (&r)[32], int mrow0, int n, bool n_ok, int lane) {
+  const bool odd = lane & 1;
+  float keep[16], send[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float a = __uint_as_float(r[2 * i]), b = __uint_as_float(r[2 * i + 1]);
+    if (kBf16) {  // bf16(gate), bf16(up): one packed conversion for the two rows
+      const __nv_bfloat162 ab = __floats2bfloat162_rn(a, b);
+      a = __low2float(ab);
+      b = __high2float(ab);
+    }
+    keep[i] = odd ? b : a;  // even lane: gate of row 2i; odd lane: up of row 2i + 1
+    send[i] = odd ? a : b;  // even lane: gate of row 2i + 1 (for the odd lane); odd lane: up of row 2i (for the even lane)
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) send[i] = __shfl_xor_sync(0xffffffffu, send[i], 1);
+  float h[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float g = odd ? send[i] : keep[i], u = odd ? keep[i] : send[i];
+    float sg = silu_nb(g);
+    if (kBf16) sg = bf16_round(sg);
+    h[i] = sg * u;
+  }
+  const int m = mrow0 + (odd ? 1 : 0);
+  const long long o = (long long)m * p.ldo + (n >> 1);
+  if (n_ok) {
+    if (kBf16) {
+      bf16* op = reinterpret_cast<bf16*>(p.out) + o;
+      if (mrow0 + 32 <= p.M) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) op[(long long)(2 * i) * p.ldo] = __float2bfloat16_rn(h[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (m + 2 * i < p.M) op[(long long)(2 * i) * p.ldo] = __float2bfloat16_rn(h[i]);
+      }
+    } else {
+      float* op = reinterpret_cast<float*>(p.out) + o;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (m + 2 * i < p.M) op[(long long)(2 * i) * p.ldo] = h[i];
+    }
+  }
+}
+
 // Drains 32 TMEM lanes x 128 accumulator columns (one epilogue warp's share of a tile) through the fused epilogue:
 // lane = output column n, TMEM column = activation row m0 + c.
 __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t taddr, int m0, int n, bool n_ok, float bias_n,
@@ -597,23 +651,10 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
     tmem_ld_32x32b_x32(taddr + c, r);
     tmem_ld_wait();
     if (p.flags & MTTS_EPI_SWIGLU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int m = m0 + c + j;
-        float v = __uint_as_float(r[j]);
-        if (p.out_bf16) v = bf16_round(v);
-        const float other = __shfl_xor_sync(0xffffffffu, v, 1);
-        if ((lane & 1) == 0 && n_ok && m < p.M) {
-          float sg = silu_f(v);
-          if (p.out_bf16) sg = bf16_round(sg);
-          const float h = sg * other;
-          const long long o = (long long)m * p.ldo + (n >> 1);
-          if (p.out_bf16)
-            reinterpret_cast<bf16*>(p.out)[o] = __float2bfloat16_rn(h);
-          else
-            reinterpret_cast<float*>(p.out)[o] = h;
-        }
-      }
+      if (p.out_bf16)
+        swiglu_chunk<true>(p, r, m0 + c, n, n_ok, lane);
+      else
+        swiglu_chunk<false>(p, r, m0 + c, n, n_ok, lane);
     } else if (p.flags == (MTTS_EPI_BIAS | MTTS_EPI_GELU) && p.out_f16) {
       // fp16-operand codec path: the GELU'd intermediate goes straight out as fp16 (half the bytes of the largest tensor)
       // lane pairs exchange one value per two rows so that every lane stores a half2 (even lanes row j, odd lanes row
@@ -1302,15 +1343,17 @@ extern "C" int mtts_gemm(const void* x, long long ldx, const void* w, long long 
   // tile per CTA in the persistent kernel (batch 128: 145 us against 176 us; batch 256: 165 us against 330 us with
   // two 128-row tiles per weight tile).
   if (bn == 128 && ceil_div(N, kBlockW) >= 4 * mtts_num_sms()) bn = 256;
-  // The gate/up projection of a decode step at batch 129..256 (96 weight tiles x 2 activation tiles = 192 CTAs = 1.3
-  // waves: the SMs that get two CTAs pull 2 MB over the crossbar and set the launch time, 29 us in isolation) as 48
-  // CTA-pair tiles of 256 x 256 (every busy SM pulls 1 MB: its 128 weight rows + its 128 activation rows) — measured
-  // SLOWER inside the decode step on B200 (batch 256: 4.67 against 4.49 ms per step): only 96 SMs pull, and a
-  // one-CTA-per-SM kernel keeps its neighbours from becoming resident early. Kept behind MTTS_GEMM_WIDE_PAIR=1.
+  // The gate/up projection of a decode step at batch 129..256: 96 weight tiles x 2 activation tiles = 192 CTAs = 1.3 waves of
+  // the cluster kernel (the SMs that get two CTAs pull 2 MB over the crossbar: 25.4 us per launch inside a 28-layer graph)
+  // against 48 CTA-pair tiles of 256 x 256 (every busy SM pulls 1 MB: its 128 weight rows + its 128 activation rows): 18.6 us,
+  // decode step at batch 256 4.46 -> 4.33 ms. (Before the SwiGLU epilogue was restructured — swiglu_chunk — the pair route
+  // LOST, 32.5 us: its MMAs took 14.7 us and the drain of the 128 x 256 tile 23 us. A stream-K split of the 48 tiles over
+  // all 74 pairs with fp32 contributions through an L2 workspace balanced the MMA phase to 10 us but its owner epilogue
+  // — contribution loads in front of every chunk — ended at 25.5 us; dropped.) MTTS_GEMM_WIDE_PAIR=0 restores the cluster route.
   static int wide_pair = -1;
   if (wide_pair < 0) {
     const char* e = getenv("MTTS_GEMM_WIDE_PAIR");
-    wide_pair = e ? atoi(e) : 0;
+    wide_pair = e ? atoi(e) : 1;
   }
   if (wide_pair && bn == 128 && M > 128 && ceil_div(N, 2 * kBlockW) >= mtts_num_sms() / 4 &&
       ceil_div(N, 2 * kBlockW) <= mtts_num_sms() / 2)

@@ -148,36 +148,33 @@ __global__ void __launch_bounds__(256) rmsnorm_warp_kernel(const bf16* __restric
 //                           xn <- RMSNorm(x) * w                (o_proj -> post-attention norm, down_proj -> next input norm)
 // One CTA per row; a thread owns 8 consecutive columns per pass.
 // ------------------------------------------------------------------------------------------------
-// All slice loads of a group of 4 are issued before the first add (the partial tiles sit in L2: one round trip per
-// group instead of one per slice), the adds run in ascending slice order.
-__device__ __forceinline__ void sum_slices8(const float* __restrict__ P, int S, long long slice, float (&a)[8]) {
+// All slice loads of a thread are issued before the first add (the partial tiles sit in L2: ONE round trip, the warp
+// issues in order and would otherwise wait for each group before requesting the next); the adds run in ascending slice
+// order. S <= 16 (mtts_gemm_splitk's limit): up to 32 float4 in flight per thread.
+template <int kMaxS>
+__device__ __forceinline__ void sum_slices8_t(const float* __restrict__ P, int S, long long slice, float (&a)[8]) {
+  float4 v[kMaxS][2];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] = 0.f;
-  for (int s0 = 0; s0 < S; s0 += 4) {
-    float4 v[4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (s0 + i < S) {
-        v[i][0] = __ldcg(reinterpret_cast<const float4*>(P + (s0 + i) * slice));
-        v[i][1] = __ldcg(reinterpret_cast<const float4*>(P + (s0 + i) * slice) + 1);
-      } else {
-        v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        v[i][1] = v[i][0];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (s0 + i < S) {
-        if (s0 + i == 0) {
-          a[0] = v[i][0].x; a[1] = v[i][0].y; a[2] = v[i][0].z; a[3] = v[i][0].w;
-          a[4] = v[i][1].x; a[5] = v[i][1].y; a[6] = v[i][1].z; a[7] = v[i][1].w;
-        } else {
-          a[0] += v[i][0].x; a[1] += v[i][0].y; a[2] += v[i][0].z; a[3] += v[i][0].w;
-          a[4] += v[i][1].x; a[5] += v[i][1].y; a[6] += v[i][1].z; a[7] += v[i][1].w;
-        }
-      }
+  for (int i = 0; i < kMaxS; ++i) {
+    if (i < S) {
+      v[i][0] = __ldcg(reinterpret_cast<const float4*>(P + i * slice));
+      v[i][1] = __ldcg(reinterpret_cast<const float4*>(P + i * slice) + 1);
     }
   }
+  a[0] = v[0][0].x; a[1] = v[0][0].y; a[2] = v[0][0].z; a[3] = v[0][0].w;
+  a[4] = v[0][1].x; a[5] = v[0][1].y; a[6] = v[0][1].z; a[7] = v[0][1].w;
+#pragma unroll
+  for (int i = 1; i < kMaxS; ++i) {
+    if (i < S) {
+      a[0] += v[i][0].x; a[1] += v[i][0].y; a[2] += v[i][0].z; a[3] += v[i][0].w;
+      a[4] += v[i][1].x; a[5] += v[i][1].y; a[6] += v[i][1].z; a[7] += v[i][1].w;
+    }
+  }
+}
+__device__ __forceinline__ void sum_slices8(const float* __restrict__ P, int S, long long slice, float (&a)[8]) {
+  if (S <= 4) sum_slices8_t<4>(P, S, slice, a);
+  else if (S <= 9) sum_slices8_t<9>(P, S, slice, a);
+  else sum_slices8_t<16>(P, S, slice, a);
 }
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ P, int S, int M, int N,
@@ -206,14 +203,16 @@ __global__ void __launch_bounds__(256) splitk_reduce_rmsnorm_kernel(const float*
   const long long slice = (long long)M * N;
   const int nvec = N >> 3;
   uint32_t keep[kVecPerThread][4];  // the new residual row, packed bf16
+  uint4 wv[kVecPerThread];
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < kVecPerThread; ++i) {
     const int v = threadIdx.x + i * 256;
     if (v < nvec) {
+      const uint4 r = *reinterpret_cast<const uint4*>(x + row * ldx + v * 8);  // requested before the slice sums wait
+      wv[i] = *reinterpret_cast<const uint4*>(w + v * 8);
       float a[8];
       sum_slices8(P + row * N + v * 8, S, slice, a);
-      const uint4 r = *reinterpret_cast<const uint4*>(x + row * ldx + v * 8);
       const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -232,8 +231,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_rmsnorm_kernel(const float*
   for (int i = 0; i < kVecPerThread; ++i) {
     const int v = threadIdx.x + i * 256;
     if (v < nvec) {
-      const uint4 wv = *reinterpret_cast<const uint4*>(w + v * 8);
-      const uint32_t b[4] = {wv.x, wv.y, wv.z, wv.w};
+      const uint32_t b[4] = {wv[i].x, wv[i].y, wv[i].z, wv[i].w};
       uint32_t o[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -406,7 +404,7 @@ extern "C" int mtts_rmsnorm(const void* x, long long ldx, const void* w, void* o
 
 extern "C" int mtts_splitk_reduce(const float* partials, int splits, int M, int N, void* out, long long ldo, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  MTTS_REQUIRE(splits >= 1 && N % 8 == 0 && ldo % 8 == 0, "mtts_splitk_reduce: N and ldo must be multiples of 8");
+  MTTS_REQUIRE(splits >= 1 && splits <= 16 && N % 8 == 0 && ldo % 8 == 0, "mtts_splitk_reduce: N and ldo must be multiples of 8, splits <= 16");
   if (M <= 0) return MTTS_OK;
   MTTS_REQUIRE(partials && out, "mtts_splitk_reduce: null pointer");
   MTTS_CUDA_CHECK(mtts_launch(splitk_reduce_kernel, dim3(M), dim3(256), 0, stream, partials, splits, M, N,
@@ -418,7 +416,7 @@ extern "C" int mtts_splitk_reduce(const float* partials, int splits, int M, int 
 extern "C" int mtts_splitk_reduce_rmsnorm(const float* partials, int splits, int M, int N, void* x, long long ldx,
                                           const void* norm_w, void* xn, long long ldxn, float eps, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  MTTS_REQUIRE(splits >= 1 && N % 8 == 0 && N <= 8192 && ldx % 8 == 0 && ldxn % 8 == 0,
+  MTTS_REQUIRE(splits >= 1 && splits <= 16 && N % 8 == 0 && N <= 8192 && ldx % 8 == 0 && ldxn % 8 == 0,
                "mtts_splitk_reduce_rmsnorm: N (<= 8192) and strides must be multiples of 8");
   if (M <= 0) return MTTS_OK;
   MTTS_REQUIRE(partials && x && norm_w && xn, "mtts_splitk_reduce_rmsnorm: null pointer");
