@@ -612,8 +612,11 @@ __device__ __forceinline__ void swiglu_chunk(const GemmParams& p, const uint32_t
 
 // Drains 32 TMEM lanes x 128 accumulator columns (one epilogue warp's share of a tile) through the fused epilogue:
 // lane = output column n, TMEM column = activation row m0 + c.
+// `release_bar` != 0 (CTA-pair kernel): cluster address of the leader's tmem_empty barrier; the warp arrives on it as
+// soon as its LAST tcgen05.ld has returned — before the arithmetic and the global stores of that chunk — so the MMA warp
+// gets the accumulator back while the epilogue is still writing.
 __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t taddr, int m0, int n, bool n_ok, float bias_n,
-                                              float gamma_n, int lane) {
+                                              float gamma_n, int lane, uint32_t release_bar = 0) {
   if (p.argmax_keys) {
     // lane = vocabulary row n (one 32-row quarter per warp, never straddling two channels: heads are padded to 32 rows),
     // TMEM column = batch row. key = (order-preserving 16-bit image of the bf16 logit) << 16 | (31 - lane): the warp-wide
@@ -642,14 +645,26 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
       if (m < p.M && q < p.n_quarters)  // the last tile's quarters beyond N must not alias the next row's first slots
         *reinterpret_cast<uint2*>(p.argmax_keys + ((long long)m * p.n_quarters + q) * 2) = make_uint2(best_mine, second_mine);
     }
+    if (release_bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(release_bar);
+    }
     return;
   }
+  bool released = false;
 #pragma unroll 1
   for (int c = 0; c < 128; c += 32) {
     if (m0 + c >= p.M) break;  // warp-uniform
     uint32_t r[32];
     tmem_ld_32x32b_x32(taddr + c, r);
     tmem_ld_wait();
+    if (release_bar && (c == 96 || m0 + c + 32 >= p.M)) {  // last chunk of this warp: the accumulator is free
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(release_bar);
+      released = true;
+    }
     if (p.flags & MTTS_EPI_SWIGLU) {
       if (p.out_bf16)
         swiglu_chunk<true>(p, r, m0 + c, n, n_ok, lane);
@@ -663,19 +678,31 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
       const int lim = min(32, p.M - (m0 + c));
       const int odd = lane & 1;
       if ((p.ldo & 1) == 0 && (p.N & 1) == 0) {
+        // straight-line phases (activate, exchange, pack, store) so that the 32 independent chains interleave
         __half* op = reinterpret_cast<__half*>(p.out) + (long long)(m0 + c + odd) * p.ldo + (n - odd);
+        float g[32], rv[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float a = gelu_fast(__uint_as_float(r[j]) + bias_n), b = gelu_fast(__uint_as_float(r[j + 1]) + bias_n);
-          const float recv = __shfl_xor_sync(0xffffffffu, odd ? a : b, 1);
-          const __half2 h = odd ? __floats2half2_rn(recv, b) : __floats2half2_rn(a, recv);
-          if (n_ok && j + odd < lim) *reinterpret_cast<__half2*>(op + (long long)j * p.ldo) = h;
+        for (int j = 0; j < 32; ++j) g[j] = gelu_tanh5(__uint_as_float(r[j]) + bias_n);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rv[i] = __shfl_xor_sync(0xffffffffu, odd ? g[2 * i] : g[2 * i + 1], 1);
+        __half2 h[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) h[i] = odd ? __floats2half2_rn(rv[i], g[2 * i + 1]) : __floats2half2_rn(g[2 * i], rv[i]);
+        if (n_ok) {
+          if (lim == 32) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) *reinterpret_cast<__half2*>(op + (long long)(2 * i) * p.ldo) = h[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (2 * i + odd < lim) *reinterpret_cast<__half2*>(op + (long long)(2 * i) * p.ldo) = h[i];
+          }
         }
       } else if (n_ok) {
         __half* op = reinterpret_cast<__half*>(p.out) + (long long)(m0 + c) * p.ldo + n;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < lim) op[(long long)j * p.ldo] = __float2half_rn(gelu_fast(__uint_as_float(r[j]) + bias_n));
+          if (j < lim) op[(long long)j * p.ldo] = __float2half_rn(gelu_tanh5(__uint_as_float(r[j]) + bias_n));
       }
     } else if (p.flags == (MTTS_EPI_BIAS | MTTS_EPI_GELU) && !p.out_bf16) {
       // the codec's MLP up-projections: the flag tests are hoisted, nothing but bias + GELU + one store per element
@@ -711,12 +738,43 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
           if (j < lim) op[(long long)j * p.ldo] = fmaf(__uint_as_float(r[j]) + bias_n, gamma_n, res[j]);
       }
     } else if (p.out_bf16 && !(p.flags & MTTS_EPI_GELU)) {
-      // bf16 linear (+ residual): prefill projections. Same hoisting of the (possibly aliasing) residual loads.
-      if (n_ok) {
+      // bf16 linear (+ residual): prefill projections. Lane pairs exchange one value per two rows so that every lane
+      // stores (and, for the residual, loads) a bf16x2: even lanes finish row j, odd lanes row j + 1 of columns
+      // (n & ~1, n | 1) — 16 four-byte accesses per 32 rows instead of 32 two-byte ones, in straight-line phases. The
+      // residual may alias the output (x += ...): all of its loads are issued before the first store.
+      const int lim = min(32, p.M - (m0 + c));
+      const bool has_res = (p.flags & MTTS_EPI_RESIDUAL) != 0;
+      const int odd = lane & 1;
+      const bool pairs_ok = (p.ldo & 1) == 0 && (p.N & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 3) == 0 &&
+                            (!has_res || ((p.ldr & 1) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 3) == 0));
+      if (pairs_ok) {
+        float g[32], rv[16];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) g[j] = bf16_round(__uint_as_float(r[j]) + bias_n) * gamma_n;  // the bf16 linear output first
+#pragma unroll
+        for (int i = 0; i < 16; ++i) rv[i] = __shfl_xor_sync(0xffffffffu, odd ? g[2 * i] : g[2 * i + 1], 1);
+        uint32_t res[16];
+        if (has_res && n_ok) {
+          const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + (long long)(m0 + c + odd) * p.ldr + (n - odd);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            res[i] = (2 * i + odd < lim) ? __ldcg(reinterpret_cast<const unsigned int*>(rp + (long long)(2 * i) * p.ldr)) : 0u;
+        }
+        if (n_ok) {
+          bf16* op = reinterpret_cast<bf16*>(p.out) + (long long)(m0 + c + odd) * p.ldo + (n - odd);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float lo = odd ? rv[i] : g[2 * i], hi = odd ? g[2 * i + 1] : rv[i];
+            if (has_res) {
+              lo += bf16lo(res[i]);
+              hi += bf16hi(res[i]);
+            }
+            if (2 * i + odd < lim) *reinterpret_cast<uint32_t*>(op + (long long)(2 * i) * p.ldo) = pack_bf16(lo, hi);
+          }
+        }
+      } else if (n_ok) {
         bf16* op = reinterpret_cast<bf16*>(p.out) + (long long)(m0 + c) * p.ldo + n;
-        const int lim = min(32, p.M - (m0 + c));
         float res[32];
-        const bool has_res = (p.flags & MTTS_EPI_RESIDUAL) != 0;
         if (has_res) {
           const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + (long long)(m0 + c) * p.ldr + n;
 #pragma unroll
@@ -747,6 +805,11 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
         }
       }
     }
+  }
+  if (release_bar && !released) {  // nothing to drain (rows beyond M)
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_cluster_relaxed(release_bar);
   }
 }
 
@@ -1026,10 +1089,7 @@ __global__ void __launch_bounds__(kPThreads, 1) gemm_tc_pair_kernel(const __grid
       tc_fence_after();
       const uint32_t taddr = tmem_base + a * kPBN + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
       const int m0 = m_tile * kPBN + half * 128;
-      persist_drain(p, taddr, m0, n, n_ok, bias_n, gamma_n, lane);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(leader_empty + a * 8);
+      persist_drain(p, taddr, m0, n, n_ok, bias_n, gamma_n, lane, leader_empty + a * 8);
     }
   }
 

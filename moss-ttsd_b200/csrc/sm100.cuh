@@ -131,6 +131,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t laddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same without memory ordering: enough when the arrival only says "my tcgen05.ld reads of this accumulator are done"
+// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync order those). The release form compiles to ERRBAR + a wait for
+// every global store the thread has in flight — in a GEMM epilogue that is 1-2 us per tile during which the accumulator
+// stays blocked (ncu: the top stall of the CTA-pair kernel's epilogue warps, tensor pipe 49 % active).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load into THIS CTA's shared memory whose bytes are counted on the LEADER's mbarrier (shared::cluster address)
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
                                                 int c1, uint64_t cache_policy) {
