@@ -294,6 +294,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    lm_timings = []   # (events, steps) of every generate call: prefill / decode split of the timed job
+
     def run_job(bs, resident):
         """The hot path over a list of batches: generate (main stream) -> un-delay + codec decode (codec stream, overlapping
         the next batch's generate) [-> waveforms to pinned host memory], then the host-side merge of per-script results."""
@@ -305,6 +307,7 @@ def main():
                 ids = b["ids_host"].to(dev, non_blocking=True)
                 mask = b["mask_host"].to(dev, non_blocking=True)
             out = model.generate(input_ids=ids, attention_mask=mask, max_new_tokens=NEW_FRAMES, do_sample=False)
+            lm_timings.append(model._last_timing)
             host = None if resident else (wav_host if k % 2 == 0 else wav_host2)
             if len(jobs) >= 2:
                 jobs[-2][0].wait()          # a pinned buffer / a batch of waveforms is reused two batches later
@@ -371,7 +374,10 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    del lm_timings[:]
     ms, frames, launches = timed(lambda: run_job(batches, True))
+    job_prefill_ms = float(np.mean([t[0][0].elapsed_time(t[0][1]) for t in lm_timings]))
+    job_decode_step_ms = float(np.mean([t[0][1].elapsed_time(t[0][2]) / max(1, t[1] - 1) for t in lm_timings]))
     clk = clocks.stop() if rank == 0 else None
     value = frames * FRAME_S / (ms / 1e3)
     e2e_steps = min(args.steps, int(os.environ.get("MTTS_BENCH_E2E_STEPS", 10)))
@@ -414,7 +420,10 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e / e2e_steps, "steps": e2e_steps},
             "phases_ms_per_step": {"serial_lm_generate": gen_ms, "serial_prefill": prefill_ms, "serial_codec_decode": codec_ms,
-                                   "serial_total": gen_ms + codec_ms, "overlapped_total": ms / args.steps},
+                                   "serial_total": gen_ms + codec_ms, "overlapped_total": ms / args.steps,
+                                   "note": "serial_* = batch 0 alone (the group with the longest prompts); job_* = mean over "
+                                           "the batches of the timed job (codec of the previous batch running underneath)",
+                                   "job_prefill_mean": job_prefill_ms, "job_decode_step_mean": job_decode_step_ms},
             "decode_step_latency": lat,
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_other": roof_other, "cpu_baseline": cpu,
             "extras": extras, "nccl": nccl_summary() if world > 1 else None,
@@ -466,12 +475,27 @@ def roofline_legs(model, L, dev, text_lens):
     o_i = torch.empty(BATCH, SHAPE["intermediate_size"], device=dev, dtype=torch.bfloat16)
     gws = model.engine._gemm_ws(BATCH)
 
+    eng = model.engine
+    acts = eng._alloc_acts(BATCH)
+    for t in acts.values():
+        t.normal_(0, 1)
+    pws = eng._splitk_ws(BATCH)
+    H, eps = SHAPE["hidden_size"], SHAPE["rms_norm_eps"]
+
     def gemm_sweep():
+        """The dense-projection chain of a decode step exactly as DecoderEngine._layers_splitk launches it at this batch
+        (q/k/v, o_proj and down_proj as split-K partial GEMMs whose fp32 slices are summed by the residual + RMSNorm
+        kernels; gate/up + SwiGLU on CTA-pair tiles) — everything but the attention kernel."""
+        xx, xn, ao, h = acts["x"], acts["xn"], acts["ao"], acts["h"]
         for lw in w.layers:
-            ops.gemm(x, lw["wqkv"], out=o_qkv, workspace=gws)
-            ops.gemm(hq, lw["wo"], out=o_h, residual=o_h, workspace=gws)
-            ops.gemm(x, lw["wgu"], out=o_i, swiglu=True, workspace=gws)
-            ops.gemm(hi, lw["wd"], out=o_h, residual=o_h, workspace=gws)
+            eng._splitk(xn, lw["wqkv"], pws)
+            S = eng._splitk(ao, lw["wo"], pws)
+            _lib.check(L.mtts_splitk_reduce_rmsnorm(pws.data_ptr(), S, BATCH, H, xx.data_ptr(), xx.stride(0), lw["ln2"].data_ptr(),
+                                                    xn.data_ptr(), xn.stride(0), eps, _lib.stream_ptr()))
+            ops.gemm(xn, lw["wgu"], out=h, swiglu=True, workspace=gws)
+            S = eng._splitk(h, lw["wd"], pws)
+            _lib.check(L.mtts_splitk_reduce_rmsnorm(pws.data_ptr(), S, BATCH, H, xx.data_ptr(), xx.stride(0), lw["ln1"].data_ptr(),
+                                                    xn.data_ptr(), xn.stride(0), eps, _lib.stream_ptr()))
 
     def replay_ms(fn, n_launch, reps=10):
         fn()
@@ -498,13 +522,15 @@ def roofline_legs(model, L, dev, text_lens):
     ach = (algo / nl) / (per_launch_ms * 1e-3) / 1e9
     tr = _traffic("gemm_traffic.json")
     tpeak = float(peaks.get("bf16_tflops", 1624.2))
-    gemm_roof = {"kernel": f"decode-step dense projections (tcgen05 weight-streaming GEMM, M = {BATCH} rows)", "bound": "hbm",
+    gemm_roof = {"kernel": f"decode-step dense projections at M = {BATCH} rows: 4 tcgen05 GEMMs per layer (q/k/v, o_proj, down_proj "
+                           "as split-K partial tiles, gate/up + SwiGLU on cta_group::2 tiles) with the 2 split-K reducers "
+                           "(residual + RMSNorm) counted in; avg_launch_us = chain time / 4 GEMMs", "bound": "hbm",
                  "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": psrc,
                  "algorithmic_bytes_per_launch": algo / nl, "avg_launch_us": per_launch_ms * 1e3,
                  "traffic": tr.get("dram_bytes_per_launch"), "xbar_l2_to_sm_bytes_per_launch": tr.get("xbar_bytes_per_launch"),
                  "traffic_source": tr.get("source"),
                  "tensor_tflops": flops / nl / (per_launch_ms * 1e-3) / 1e12, "tensor_frac_of_burst": flops / nl / (per_launch_ms * 1e-3) / 1e12 / tpeak,
-                 "launches_per_decode_step": nl + 1, "us_per_decode_step": per_launch_ms * 1e3 * nl}
+                 "launches_per_decode_step": 6 * len(w.layers), "us_per_decode_step": per_launch_ms * 1e3 * nl}
     sess = model._session
     cache = sess["cache"]
     ctx_rows = torch.from_numpy((text_lens[:BATCH] + AUDIO_ROWS + 7 + NEW_FRAMES // 2).astype(np.int32)).to(dev)
