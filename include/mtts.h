@@ -252,6 +252,12 @@ int mtts_mha_varlen(const float* qkv, float* out, const int* lengths, int B, int
 int mtts_mha_varlen_f16(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads, int head_dim,
                         void* stream);
 
+/* The same contraction on the 5th-gen tensor cores (tcgen05.mma with S and O in TMEM, Q / K / V tiles by TMA, one thread
+ * per query row for the softmax), fp16 in and out: qkv [B*T, 3*H*64] fp16, out [B*T, H*64] fp16. The attention of the
+ * decoder's fp16-operand path (modules.py:117-160 as called from model.py:103-128). */
+int mtts_mha_varlen_tc(const void* qkv_f16, void* out_f16, const int* lengths, int B, int T, int num_heads, int head_dim,
+                       void* stream);
+
 /* Same contraction with fp32 CUDA-core products, fp32 softmax and expf(): the exact mode of XY_Tokenizer.encode, whose
  * integer codes must match the reference's fp32 matmuls (model.py:54-101 -> modules.py:117-160). */
 int mtts_mha_varlen_fp32(const float* qkv, float* out, const int* lengths, int B, int T, int num_heads, int head_dim,

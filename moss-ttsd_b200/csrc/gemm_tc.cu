@@ -670,7 +670,7 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
         swiglu_chunk<true>(p, r, m0 + c, n, n_ok, lane);
       else
         swiglu_chunk<false>(p, r, m0 + c, n, n_ok, lane);
-    } else if (p.flags == (MTTS_EPI_BIAS | MTTS_EPI_GELU) && p.out_f16) {
+    } else if (p.out_f16 && (p.flags & ~(MTTS_EPI_BIAS | MTTS_EPI_GELU)) == 0) {
       // fp16-operand codec path: the GELU'd intermediate goes straight out as fp16 (half the bytes of the largest tensor)
       // lane pairs exchange one value per two rows so that every lane stores a half2 (even lanes row j, odd lanes row
       // j + 1): 16 four-byte store instructions per 32 rows instead of 32 two-byte ones (1660 -> ~1130 us on the
@@ -681,8 +681,13 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
         // straight-line phases (activate, exchange, pack, store) so that the 32 independent chains interleave
         __half* op = reinterpret_cast<__half*>(p.out) + (long long)(m0 + c + odd) * p.ldo + (n - odd);
         float g[32], rv[16];
+        if (p.flags & MTTS_EPI_GELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) g[j] = gelu_tanh5(__uint_as_float(r[j]) + bias_n);
+          for (int j = 0; j < 32; ++j) g[j] = gelu_tanh5(__uint_as_float(r[j]) + bias_n);
+        } else {  // plain fp16 linear (+ bias): the q/k/v projection in front of the tcgen05 attention
+#pragma unroll
+          for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(r[j]) + bias_n;
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) rv[i] = __shfl_xor_sync(0xffffffffu, odd ? g[2 * i] : g[2 * i + 1], 1);
         __half2 h[16];
@@ -702,7 +707,10 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
         __half* op = reinterpret_cast<__half*>(p.out) + (long long)(m0 + c) * p.ldo + n;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < lim) op[(long long)j * p.ldo] = __float2half_rn(gelu_tanh5(__uint_as_float(r[j]) + bias_n));
+          if (j < lim) {
+            const float x = __uint_as_float(r[j]) + bias_n;
+            op[(long long)j * p.ldo] = __float2half_rn((p.flags & MTTS_EPI_GELU) ? gelu_tanh5(x) : x);
+          }
       }
     } else if (p.flags == (MTTS_EPI_BIAS | MTTS_EPI_GELU) && !p.out_bf16) {
       // the codec's MLP up-projections: the flag tests are hoisted, nothing but bias + GELU + one store per element
@@ -1290,6 +1298,12 @@ int configure_one() {
 }
 
 }  // namespace
+
+// 2-D tiled tensor map with 128-byte-swizzled boxes of `box_rows` rows x 128 bytes (cached per pointer / shape); used by
+// the other tcgen05 kernels of the library (mha_tc5.cu). elem_code: 2 = bf16, 4 = fp32, -2 = fp16.
+int mtts_get_tmap_2d(const void* ptr, long long rows, long long cols, long long ld, int box_rows, int elem_code, CUtensorMap* out) {
+  return get_tmap(ptr, rows, cols, ld, box_rows, elem_code, out);
+}
 
 // Opt every instantiation into its dynamic shared-memory size (called from mtts_init, outside any graph capture).
 int mtts_configure_gemm_tc() {

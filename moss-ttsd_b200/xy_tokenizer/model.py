@@ -12,6 +12,7 @@ re-packed once at load time so that each of them is one mtts_gemm (TF32 tensor c
 """
 from __future__ import annotations
 
+import os
 import math
 from typing import Dict, List, Optional
 
@@ -502,14 +503,22 @@ class XY_Tokenizer:
         return out
 
     def _stack_f16(self, h, st: _TransformerStack, heads, lengths, B, T):
-        """_stack with fp16 operands for the q/k/v projection and the MLP (fp32 residual stream, fp32 attention I/O)."""
+        """_stack with fp16 operands for every projection (q/k/v, attention output, MLP) and the tcgen05 attention kernel
+        (fp16 q/k/v in, fp16 out); the residual stream stays fp32."""
         E = h.shape[1]
+        tc_attn = E // heads == 64 and os.environ.get("MTTS_CODEC_ATTN_TC", "1") != "0"
         for lw in st.layers:
             xn = self._ln16(h, lw["ln1_w"], lw["ln1_b"])
-            qkv = ops.gemm(xn, self._half(lw["wqkv"]), bias=lw["bqkv"], out_dtype=torch.float32)
-            ao = torch.empty((B * T, E), dtype=torch.float32, device=h.device)
-            check(self.L.mtts_mha_varlen_f16(ptr(qkv), ptr(ao), ptr(lengths), B, T, heads, E // heads, stream_ptr()))
-            ops.gemm(ao, lw["wo"], bias=lw["bo"], residual=h, out=h)
+            if tc_attn:
+                qkv = ops.gemm(xn, self._half(lw["wqkv"]), bias=lw["bqkv"], out_dtype=torch.float16)
+                ao = torch.empty((B * T, E), dtype=torch.float16, device=h.device)
+                check(self.L.mtts_mha_varlen_tc(ptr(qkv), ptr(ao), ptr(lengths), B, T, heads, 64, stream_ptr()))
+                ops.gemm(ao, self._half(lw["wo"]), bias=lw["bo"], residual=h, out=h)
+            else:
+                qkv = ops.gemm(xn, self._half(lw["wqkv"]), bias=lw["bqkv"], out_dtype=torch.float32)
+                ao = torch.empty((B * T, E), dtype=torch.float32, device=h.device)
+                check(self.L.mtts_mha_varlen_f16(ptr(qkv), ptr(ao), ptr(lengths), B, T, heads, E // heads, stream_ptr()))
+                ops.gemm(ao, lw["wo"], bias=lw["bo"], residual=h, out=h)
             xn = self._ln16(h, lw["ln2_w"], lw["ln2_b"])
             ff = ops.gemm(xn, self._half(lw["fc1_w"]), bias=lw["fc1_b"], gelu=True, out_dtype=torch.float16)
             ops.gemm(ff, self._half(lw["fc2_w"]), bias=lw["fc2_b"], residual=h, out=h)

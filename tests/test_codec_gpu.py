@@ -350,3 +350,31 @@ def test_encode_then_decode_round_trip_shapes():
     rec = spt.decode(codes)["syn_wav_list"][0]
     assert rec.shape == (50 * 1920,) and torch.isfinite(rec).all()
     assert spt.encode([])["codes_list"] == []
+
+
+@pytest.mark.parametrize("B,T,H,lens", [(3, 300, 12, [300, 117, 0]), (2, 1500, 12, [1500, 1337]), (4, 64, 2, [64, 1, 33, 64]),
+                                        (1, 129, 12, [129])])
+def test_mha_varlen_tcgen05_matches_fp32_softmax(B, T, H, lens):
+    """tcgen05 attention (S and O in TMEM, fp16 operands, fp16 in/out) against an fp64 softmax(QK^T/8)V of the same fp16
+    inputs: padded batch, ragged lengths incl. an all-masked item (uniform attention, as the reference computes it), query
+    tiles and key tiles that end inside an item."""
+    from moss_ttsd_b200 import _lib
+    L = _lib.load()
+    _lib.check(L.mtts_init())
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + T)
+    E = H * 64
+    qkv = (torch.randn(B * T, 3 * E, device="cuda", generator=g) * 1.5).half()
+    out = torch.full((B * T, E), float("nan"), device="cuda", dtype=torch.float16)
+    lengths = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    _lib.check(L.mtts_mha_varlen_tc(qkv.data_ptr(), out.data_ptr(), lengths.data_ptr(), B, T, H, 64, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    q, k, v = qkv.double().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)          # (B, H, T, 64)
+    s = q @ k.transpose(-1, -2) / 8.0
+    for b, n in enumerate(lens):
+        if 0 < n < T:
+            s[b, :, :, n:] = float("-inf")
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * T, E)
+    got = out.double()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs().max().item()
+    assert err <= 6e-3, err      # fp16 probabilities (2^-11 relative) and fp16 output rounding on values of magnitude <= ~4
