@@ -285,6 +285,16 @@ int mtts_dwconv7_ln(const float* x, const float* conv_w, const float* conv_b, co
 int mtts_convt_gather(const float* y, const float* bias, float* out, int B, int Tin, int Cout, int K, int stride,
                       int Tout, int gelu, void* stream);
 
+/* Prefill attention on the 5th-gen tensor cores (tcgen05.mma with S and O in TMEM, Q tiles and the K/V tiles of the paged
+ * pool by TMA): the same contraction as mtts_gqa_attention for packed prompt rows (HF Qwen3Attention.forward, installed
+ * modeling_qwen3.py:236-288 as invoked from modeling_asteroid.py:226,273-284), causal, GQA, head_dim 128. Tiles are up to
+ * 128 consecutive rows of ONE sequence (tile_row0 / tile_nrows [tiles]); q [rows, Hq * 128] bf16; the keys of every row,
+ * incl. the rows of this call, are already in the pools (mtts_qknorm_rope_kvappend runs first); page_size >= 64. */
+int mtts_gqa_prefill_tc(const void* q, long long rows, const void* k_pool, const void* v_pool, const int* block_table,
+                        int max_pages, int page_size, int num_pages, const int* tile_row0, const int* tile_nrows,
+                        const int* row_seq, const int* positions, void* out, int tiles, int num_q_heads, int num_kv_heads,
+                        int head_dim, void* stream);
+
 /* Decode attention fused with its prologue: for ONE new row per sequence it does what mtts_qknorm_rope_kvappend +
  * mtts_gqa_attention do (HF Qwen3Attention.forward, installed modeling_qwen3.py:236-288: q/k RMSNorm, RoPE, cache
  * update, attention), bit-identically, in one launch: q and the new K/V row never travel through global memory and the

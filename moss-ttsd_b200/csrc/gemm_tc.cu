@@ -40,6 +40,9 @@ using namespace sm100;
 
 namespace {
 
+#ifndef MTTS_PSTAGES256
+#define MTTS_PSTAGES256 4
+#endif
 constexpr int kBlockW = 128;      // weight rows per tile == UMMA M
 constexpr int kSwizzleBytes = 128;
 constexpr int kNumThreads = 192;  // warp0: TMA, warp1: MMA + TMEM alloc, warps 2-5: epilogue
@@ -1215,7 +1218,7 @@ template <> struct PStages<16> { static constexpr int v = 5; };
 template <> struct PStages<32> { static constexpr int v = 5; };
 template <> struct PStages<64> { static constexpr int v = 4; };
 template <> struct PStages<128> { static constexpr int v = 3; };
-template <> struct PStages<256> { static constexpr int v = 4; };  // 4 x 48 KB
+template <> struct PStages<256> { static constexpr int v = MTTS_PSTAGES256; };  // x 48 KB
 
 template <int BN>
 int launch_partial(const CUtensorMap& tw, const CUtensorMap& tx, const GemmParams& p, dim3 grid, cudaStream_t stream) {

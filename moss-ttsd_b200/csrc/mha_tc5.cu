@@ -185,8 +185,14 @@ __global__ void __launch_bounds__(128, 3) mha_varlen_tc5_kernel(const __grid_con
       mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
     }
     const float m_new = fmaxf(m_run, mx);
-    const float alpha = ex2((m_run - m_new) * c);  // 0 on the first tile (m_run = -inf)
-    const float mc = m_new * c;
+    // LAZY rescaling: the reference maximum of a row moves only when the true maximum has outgrown it by more than 2^8
+    // (in the exp2 domain) somewhere in the warp; until then probabilities may exceed 1 (<= 256: harmless in fp16 / fp32)
+    // and O, l keep their scale — the result is the same quotient. Without it almost every tile pays a TMEM round trip
+    // of O, because some row of the 32 sees a new maximum in most tiles.
+    const bool move = j == 0 || __any_sync(0xffffffffu, (m_new - m_run) * c > 8.0f);
+    const float m_use = move ? m_new : m_run;
+    const float alpha = ex2((m_run - m_use) * c);  // 0 on the first tile (m_run = -inf), 1 when nothing moves
+    const float mc = m_use * c;
     float sum = 0.f;
     uint32_t ph[32];  // 64 probabilities as fp16 pairs
 #pragma unroll
@@ -200,8 +206,7 @@ __global__ void __launch_bounds__(128, 3) mha_varlen_tc5_kernel(const __grid_con
       ph[16 + i] = *reinterpret_cast<const uint32_t*>(&hb);
     }
     l_run = l_run * alpha + sum;
-    const bool grew = m_new > m_run;
-    m_run = m_new;
+    m_run = m_use;
     // ---- O += P V of the previous tile has retired: P, V stage (j - 1) % 2 and O are ours
     if (j > 0) {
       mbar_wait(pv_done, (j - 1) & 1);
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(128, 3) mha_varlen_tc5_kernel(const __grid_con
         tma_load_2d(sV + st * kTileBytes, &tmap, &v_full[st], cv, row_base + (j + 1) * kK, kEvictLast);
       }
       __syncwarp();
-      if (__any_sync(0xffffffffu, grew)) {  // rescale this warp's 32 rows of O in place
+      if (move) {  // warp-uniform: rescale this warp's 32 rows of O in place
         uint32_t o[32];
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {

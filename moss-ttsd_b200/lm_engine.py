@@ -285,7 +285,10 @@ class DecoderEngine:
         self.fused_decode_attn = (os.environ.get("MTTS_ATTN_FUSED", "1") != "0" and os.environ.get("MTTS_ATTN_SIMT", "0") != "1"
                                   and s.head_dim == 128 and s.num_attention_heads // s.num_key_value_heads in (1, 2, 4))
         self.mega_max_b = int(os.environ.get("MTTS_MEGA_MAX_B", "4"))
-        self.prefill_tile_rows = int(os.environ.get("MTTS_PREFILL_TILE", "64"))  # 64: tensor-core tiles, 4: CUDA cores
+        # 128: tcgen05 flash attention (mtts_gqa_prefill_tc), 64: mma.sync flash kernel, 4: CUDA cores
+        self.prefill_tile_rows = int(os.environ.get("MTTS_PREFILL_TILE", "128"))
+        if s.head_dim != 128 and self.prefill_tile_rows == 128:
+            self.prefill_tile_rows = 64
         # decode steps of the kernel chain with splitk_min_rows <= batch <= 256: q/k/v, o_proj and down_proj store fp32
         # split-K partial tiles and the consumer (bf16 cast / residual + RMSNorm) sums them (mtts_gemm_splitk*)
         # (measured ms per decode step, cluster split-K with fused epilogues -> this path: batch 64 2.32 -> 2.21,
@@ -318,6 +321,12 @@ class DecoderEngine:
     def _attention(self, q, cache: KVCache, layer: int, positions, row_seq, out, tiles, rows_per_tile, tile_row0,
                    tile_nrows, nsplit, ws):
         s = self.s
+        if rows_per_tile == 128:
+            check(self.L.mtts_gqa_prefill_tc(
+                ptr(q), q.shape[0], ptr(cache.k[layer]), ptr(cache.v[layer]), ptr(cache.block_table), cache.max_pages,
+                cache.page_size, cache.num_pages, ptr(tile_row0), ptr(tile_nrows), ptr(row_seq), ptr(positions), ptr(out), tiles,
+                s.num_attention_heads, s.num_key_value_heads, s.head_dim, stream_ptr()))
+            return
         check(self.L.mtts_gqa_attention(
             ptr(q), ptr(cache.k[layer]), ptr(cache.v[layer]), ptr(cache.block_table), cache.max_pages, cache.page_size,
             ptr(tile_row0), ptr(tile_nrows), ptr(row_seq), ptr(positions), ptr(out), tiles, rows_per_tile,
@@ -454,6 +463,8 @@ class DecoderEngine:
         seq_h = np.repeat(np.asarray(slots_h, dtype=np.int32), lens_h)
         row0_h, nrows_h = [], []
         tile_rows = self.prefill_tile_rows
+        if tile_rows == 128 and cache.page_size < 64:   # the TMA key tiles of the tcgen05 kernel are 64 keys of ONE page
+            tile_rows = 64
         for b in range(n):
             for t in range(0, int(lens_h[b]), tile_rows):
                 row0_h.append(cu[b] + t)

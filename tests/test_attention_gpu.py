@@ -177,3 +177,61 @@ def test_prefill_attention_matches_fp32_reference(lens, Hq, Hkv, paged):
             worst = max(worst, (got[cu[b] + r] - ref).abs().max().item())
     assert worst <= 0.03, worst
     assert torch.isfinite(got).all()
+
+
+@pytest.mark.parametrize("lens,Hq,Hkv,paged,pos0", [([70, 1, 64, 65, 130], 16, 8, False, 0), ([457, 300], 16, 8, True, 0),
+                                                     ([33, 200, 17], 8, 8, True, 0), ([129, 64, 128, 127], 16, 4, False, 0),
+                                                     ([100, 31], 16, 8, True, 77)])
+def test_prefill_attention_tcgen05_matches_fp32_reference(lens, Hq, Hkv, paged, pos0):
+    """128-row causal tiles on tcgen05 (S and O in TMEM, K/V tiles of the paged pool by TMA) against fp32 eager attention:
+    packed ragged sequences, shuffled pages, rows that continue a cache holding pos0 tokens; pool rows past each sequence's
+    last key hold NaN bit patterns (an uninitialised pool) and must not reach the output."""
+    from moss_ttsd_b200 import _lib, ops
+    ops.ensure_init()
+    L = _lib.load()
+    D, page = 128, 64
+    B = len(lens)
+    g = torch.Generator(device="cuda").manual_seed(sum(lens) + pos0)
+    rng = np.random.default_rng(sum(lens))
+    max_ctx = max(lens) + pos0
+    max_pages = (max_ctx + page - 1) // page
+    num_pages = B * max_pages
+    ids = np.arange(num_pages, dtype=np.int32)
+    if paged:
+        rng.shuffle(ids)
+    table = torch.from_numpy(ids.reshape(B, max_pages)).cuda()
+    k_log = torch.randn((B, max_pages * page, Hkv, D), device="cuda", generator=g).to(torch.bfloat16)
+    v_log = torch.randn((B, max_pages * page, Hkv, D), device="cuda", generator=g).to(torch.bfloat16)
+    for b in range(B):  # keys past the sequence: NaN
+        k_log[b, pos0 + lens[b]:] = float("nan")
+        v_log[b, pos0 + lens[b]:] = float("nan")
+    k_pool = torch.empty((num_pages, Hkv, page, D), device="cuda", dtype=torch.bfloat16)
+    v_pool = torch.empty_like(k_pool)
+    k_pool[table.long().reshape(-1)] = k_log.view(B * max_pages, page, Hkv, D).permute(0, 2, 1, 3)
+    v_pool[table.long().reshape(-1)] = v_log.view(B * max_pages, page, Hkv, D).permute(0, 2, 1, 3)
+    R = sum(lens)
+    q = torch.randn((R, Hq, D), device="cuda", generator=g).to(torch.bfloat16)
+    pos_h = np.concatenate([np.arange(pos0, pos0 + n, dtype=np.int32) for n in lens])
+    seq_h = np.repeat(np.arange(B, dtype=np.int32), lens)
+    cu = np.concatenate([[0], np.cumsum(lens)])
+    row0_h, nrows_h = [], []
+    for b in range(B):
+        for t0 in range(0, lens[b], 128):
+            row0_h.append(cu[b] + t0)
+            nrows_h.append(min(128, lens[b] - t0))
+    dev = lambda a: torch.from_numpy(np.asarray(a, dtype=np.int32)).cuda()
+    positions, row_seq, tile_row0, tile_nrows = dev(pos_h), dev(seq_h), dev(row0_h), dev(nrows_h)
+    out = torch.full((R, Hq * D), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(L.mtts_gqa_prefill_tc(q.data_ptr(), R, k_pool.data_ptr(), v_pool.data_ptr(), table.data_ptr() if paged else None,
+                                     max_pages, page, num_pages, tile_row0.data_ptr(), tile_nrows.data_ptr(), row_seq.data_ptr(),
+                                     positions.data_ptr(), out.data_ptr(), len(row0_h), Hq, Hkv, D, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    got = out.float().view(R, Hq, D)
+    assert torch.isfinite(got).all()
+    kl, vl = k_log.float(), v_log.float()
+    worst = 0.0
+    for b in range(B):
+        for r in range(lens[b]):
+            ref = _reference(q[cu[b] + r:cu[b] + r + 1].float(), kl[b:b + 1], vl[b:b + 1], [pos0 + r + 1], Hq, Hkv)[0]
+            worst = max(worst, (got[cu[b] + r] - ref).abs().max().item())
+    assert worst <= 0.03, worst
