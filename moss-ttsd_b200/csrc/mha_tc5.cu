@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(128, 3) mha_varlen_tc5_kernel(const __grid_con
     // (in the exp2 domain) somewhere in the warp; until then probabilities may exceed 1 (<= 256: harmless in fp16 / fp32)
     // and O, l keep their scale — the result is the same quotient. Without it almost every tile pays a TMEM round trip
     // of O, because some row of the 32 sees a new maximum in most tiles.
-    const bool move = j == 0 || __any_sync(0xffffffffu, (m_new - m_run) * c > 8.0f);
+    // (only rows of this item vote: a row's arithmetic must not depend on the item that follows it in the batch)
+    const bool move = j == 0 || __any_sync(0xffffffffu, q0 + row < p.T && (m_new - m_run) * c > 8.0f);
     const float m_use = move ? m_new : m_run;
     const float alpha = ex2((m_run - m_use) * c);  // 0 on the first tile (m_run = -inf), 1 when nothing moves
     const float mc = m_use * c;

@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(128, 2) gqa_prefill_tc5_kernel(const __grid_co
     // (in the exp2 domain) somewhere in the warp; until then probabilities may exceed 1 (<= 256: harmless in bf16 / fp32)
     // and O, l keep their scale — the result is the same quotient. Without it almost every tile pays a TMEM round trip
     // of O (some row of 32 sees a new maximum in most tiles: 4400 cycles per key tile measured, mostly that).
-    const bool move = j == 0 || __any_sync(0xffffffffu, (m_new - m_run) * c > 8.0f);
+    // (only rows of this tile's sequence vote: a row's arithmetic must not depend on which other sequence follows it in
+    // the packed batch)
+    const bool move = j == 0 || __any_sync(0xffffffffu, row < nrows && (m_new - m_run) * c > 8.0f);
     const float m_use = move ? m_new : m_run;
     const float alpha = ex2((m_run - m_use) * c);
     const float mc = m_use * c;
