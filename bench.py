@@ -250,10 +250,14 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    ranks_seen = 1
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         nccl_env()
         dist.init_process_group("nccl", device_id=dev)
+        one = torch.ones(1, device=dev)
+        dist.all_reduce(one)            # every rank of the NCCL communicator contributes 1
+        ranks_seen = one.item()
 
     from moss_ttsd_b200 import _lib, scheduler
     from moss_ttsd_b200.modeling_asteroid import AsteroidTTSConfig, AsteroidTTSInstruct
@@ -426,7 +430,11 @@ def main():
                                    "job_prefill_mean": job_prefill_ms, "job_decode_step_mean": job_decode_step_ms},
             "decode_step_latency": lat,
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_other": roof_other, "cpu_baseline": cpu,
-            "extras": extras, "nccl": nccl_summary() if world > 1 else None,
+            "extras": extras, "nccl": (nccl_summary() or {"note": "NCCL_DEBUG was preset by the caller: NCCL's own init lines are wherever "
+                                                                    "that setting sends them", "NCCL_DEBUG": os.environ.get("NCCL_DEBUG"),
+                                                          "world_size": world, "ranks_counted_by_allreduce": int(ranks_seen),
+                                                          "nccl_version": ".".join(str(v) for v in torch.cuda.nccl.version())})
+            if world > 1 else None,
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -15,8 +15,9 @@
 //               folded in, P in bf16 (as the reference casts the probabilities) to shared memory, 128B-swizzled K-major
 //   O += P V    tcgen05.mma M=128 N=128 K=64, V tile MN-major as TMA stored it (two 64-dim blocks, LBO apart), O in TMEM
 //               (128 columns), rescaled in place only when a row of the warp saw a new maximum
-// K double-buffered (the next S is issued as soon as every thread holds its scores), V single-buffered (free once O += P V
-// has retired): 96 KB of shared memory and 256 TMEM columns per CTA, two CTAs per SM.
+// K and V in two-stage rings (a K tile is free once S is computed, a V tile once O += P V has retired); warps 0..3 are the
+// softmax threads, warp 4 issues every TMA copy and MMA, the two sides meet on mbarriers only (no block barrier in the key
+// loop). 112 KB of shared memory and 256 TMEM columns per CTA, two CTAs per SM.
 #include "common.cuh"
 #include "sm100.cuh"
 #include "mtts_internal.h"
@@ -27,7 +28,10 @@ namespace {
 
 constexpr int kQ = 128, kK = 64, kD = 128;
 constexpr uint32_t kSub = 64 * 128;  // 8 KB: 64 rows x 64 dims (128 B), one TMA box
-constexpr uint32_t kSmemBytes = 4 * kSub /*Q*/ + 2 * 2 * kSub /*K ring*/ + 2 * kSub /*V*/ + 2 * kSub /*P*/ + 1024 + 128;
+// Q 32 KB + K ring 32 KB + V ring 32 KB + P 16 KB + barriers. No alignment slack: two CTAs must fit one SM's 228 KB
+// (2 x (112 KB + 128 B + 1 KB reserved) = 226.25 KB), so the kernel checks that its dynamic shared memory starts 1024-aligned.
+constexpr uint32_t kSmemBytes = 4 * kSub /*Q*/ + 2 * 2 * kSub /*K ring*/ + 2 * 2 * kSub /*V ring*/ + 2 * kSub /*P*/ + 128;
+constexpr int kThreadsPf = 160;  // warps 0..3: softmax (thread = query row), warp 4: control (TMA + MMA issue)
 
 struct PrefillParams {
   bf16* out;
@@ -70,21 +74,22 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(128, 2) gqa_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q,
-                                                                 const __grid_constant__ CUtensorMap tm_k,
-                                                                 const __grid_constant__ CUtensorMap tm_v, const PrefillParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__global__ void __launch_bounds__(kThreadsPf, 2) gqa_prefill_tc5_kernel(const __grid_constant__ CUtensorMap tm_q,
+                                                                        const __grid_constant__ CUtensorMap tm_k,
+                                                                        const __grid_constant__ CUtensorMap tm_v, const PrefillParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                 // [2 dim halves][128 q][64 d]
   uint8_t* sK = sQ + 4 * kSub;        // [2 stages][2 dim halves][64 keys][64 d]
-  uint8_t* sV = sK + 4 * kSub;        // [2 dim halves][64 keys][64 d]
-  uint8_t* sP = sV + 2 * kSub;        // [128 q][64 keys]
+  uint8_t* sV = sK + 4 * kSub;        // [2 stages][2 dim halves][64 keys][64 d]
+  uint8_t* sP = sV + 4 * kSub;        // [128 q][64 keys]
   uint64_t* q_full = reinterpret_cast<uint64_t*>(sP + 2 * kSub);
   uint64_t* k_full = q_full + 1;      // [2]
-  uint64_t* v_full = k_full + 2;
-  uint64_t* s_full = v_full + 1;
+  uint64_t* v_full = k_full + 2;      // [2]
+  uint64_t* s_full = v_full + 2;
   uint64_t* pv_done = s_full + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* s_free = pv_done + 1;     // 4 arrivals: every softmax warp holds its scores of the current tile
+  uint64_t* p_ready = s_free + 1;     // 4 arrivals: every softmax warp has written its rows of P (and rescaled O)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(p_ready + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, hq = blockIdx.y;
@@ -96,18 +101,25 @@ __global__ void __launch_bounds__(128, 2) gqa_prefill_tc5_kernel(const __grid_co
   const int page_mask = (1 << p.page_shift) - 1;
 
   if (tid == 0) {
+    if (smem_u32(smem) & 1023u) {
+      printf("mtts: prefill attention: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
     prefetch_tmap(&tm_q);
     prefetch_tmap(&tm_k);
     prefetch_tmap(&tm_v);
     mbar_init(q_full, 1);
     mbar_init(&k_full[0], 1);
     mbar_init(&k_full[1], 1);
-    mbar_init(v_full, 1);
+    mbar_init(&v_full[0], 1);
+    mbar_init(&v_full[1], 1);
     mbar_init(s_full, 1);
     mbar_init(pv_done, 1);
+    mbar_init(s_free, 4);
+    mbar_init(p_ready, 4);
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (warp == 4) {
     __syncwarp();
     tmem_alloc<256>(tmem_ptr_smem);
   }
@@ -115,199 +127,195 @@ __global__ void __launch_bounds__(128, 2) gqa_prefill_tc5_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tS = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);  // columns 0..63: S
-  const uint32_t tO = tS + 64;                                               // columns 64..191: O
   pdl_launch_dependents();
   pdl_wait();
 
   constexpr uint32_t kIdescS = make_idesc(1, kQ, kK);               // bf16 x bf16 -> f32, both K-major
   constexpr uint32_t kIdescO = make_idesc(1, kQ, kD) | (1u << 16);  // B (the V tile) MN-major
 
-  // first row of key tile t in the [pages * Hkv * page_size, 128] view of the pools
-  auto kv_row = [&](int t) -> int {
-    const int key0 = t * kK;
-    const int lp = key0 >> p.page_shift;
-    const int page = p.block_table ? __ldg(p.block_table + (long long)seq * p.max_pages + lp) : seq * p.max_pages + lp;
-    return ((page * p.Hkv + hk) << p.page_shift) + (key0 & page_mask);
-  };
-  auto load_k = [&](int t, int st) {
-    const int r = kv_row(t);
-    mbar_arrive_expect_tx(&k_full[st], 2 * kSub);
-    tma_load_2d(sK + st * 2 * kSub, &tm_k, &k_full[st], 0, r, kEvictLast);
-    tma_load_2d(sK + st * 2 * kSub + kSub, &tm_k, &k_full[st], 64, r, kEvictLast);
-  };
-  auto load_v = [&](int t) {
-    const int r = kv_row(t);
-    mbar_arrive_expect_tx(v_full, 2 * kSub);
-    tma_load_2d(sV, &tm_v, v_full, 0, r, kEvictLast);
-    tma_load_2d(sV + kSub, &tm_v, v_full, 64, r, kEvictLast);
-  };
-  auto issue_s = [&](int st) {
-    const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * 2 * kSub);
-#pragma unroll
-    for (int k = 0; k < kD / 16; ++k) {
-      const uint32_t half = k >> 2, in = (k & 3) * 32;
-      umma_bf16(tmem_base, make_smem_desc_sw128(qa + half * 2 * kSub + in), make_smem_desc_sw128(ka + half * kSub + in), kIdescS,
-                k > 0 ? 1u : 0u);
-    }
-    umma_commit(s_full);
-  };
-
-  if (tid == 0) {
-    mbar_arrive_expect_tx(q_full, 4 * kSub);
-    const int cq = hq * kD;
-    tma_load_2d(sQ, &tm_q, q_full, cq, row0, kEvictNormal);
-    tma_load_2d(sQ + kSub, &tm_q, q_full, cq, row0 + 64, kEvictNormal);
-    tma_load_2d(sQ + 2 * kSub, &tm_q, q_full, cq + 64, row0, kEvictNormal);
-    tma_load_2d(sQ + 3 * kSub, &tm_q, q_full, cq + 64, row0 + 64, kEvictNormal);
-    load_k(0, 0);
-    if (n_tiles > 1) load_k(1, 1);
-    load_v(0);
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    issue_s(0);
-  }
-
-  float m_run = -INFINITY, l_run = 0.f;
-  const float c = p.scale_log2;
-  const int row = warp * 32 + lane;
-  const int my_pos = pos0 + row;  // keys <= my_pos are visible to this row
-  uint8_t* p_row = sP + row * 128;
-  const int sw = row & 7;
-
-  for (int j = 0; j < n_tiles; ++j) {
-    mbar_wait(s_full, j & 1);
-    tc_fence_after();
-    uint32_t s0[32], s1[32];
-    tmem_ld_32x32b_x32(tS, s0);
-    tmem_ld_32x32b_x32(tS + 32, s1);
-    tmem_ld_wait();
-    tc_fence_before();
-    __syncthreads();  // [A] scores are in registers: S columns and K stage j % 2 are free
-    if (tid == 0) {
-      tc_fence_after();
-      if (j > 0) {  // O += P V of the previous tile has all but certainly retired: request this tile's V now, a whole
-        mbar_wait(pv_done, (j - 1) & 1);  // softmax ahead of its use (requested after the softmax it stalled every tile)
-        load_v(j);
-      }
-      if (j + 2 < n_tiles) load_k(j + 2, j & 1);
-      if (j + 1 < n_tiles) {
-        mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+  if (warp == 4) {
+    // ================= control: TMA copies + MMA issue =================
+    if (lane == 0) {
+      // first row of key tile t in the [pages * Hkv * page_size, 128] view of the pools
+      auto kv_row = [&](int t) -> int {
+        const int key0 = t * kK;
+        const int lp = key0 >> p.page_shift;
+        const int page = p.block_table ? __ldg(p.block_table + (long long)seq * p.max_pages + lp) : seq * p.max_pages + lp;
+        return ((page * p.Hkv + hk) << p.page_shift) + (key0 & page_mask);
+      };
+      auto load_k = [&](int t) {
+        const int r = kv_row(t), st = t & 1;
+        mbar_arrive_expect_tx(&k_full[st], 2 * kSub);
+        tma_load_2d(sK + st * 2 * kSub, &tm_k, &k_full[st], 0, r, kEvictLast);
+        tma_load_2d(sK + st * 2 * kSub + kSub, &tm_k, &k_full[st], 64, r, kEvictLast);
+      };
+      auto load_v = [&](int t) {
+        const int r = kv_row(t), st = t & 1;
+        mbar_arrive_expect_tx(&v_full[st], 2 * kSub);
+        tma_load_2d(sV + st * 2 * kSub, &tm_v, &v_full[st], 0, r, kEvictLast);
+        tma_load_2d(sV + st * 2 * kSub + kSub, &tm_v, &v_full[st], 64, r, kEvictLast);
+      };
+      auto issue_s = [&](int t) {
+        mbar_wait(&k_full[t & 1], (t >> 1) & 1);
         tc_fence_after();
-        issue_s((j + 1) & 1);
-      }
-    }
-    __syncwarp();
-    // ---- causal mask (only tiles that reach this row's diagonal), row maximum, probabilities
-    const int lim = my_pos - j * kK;  // keys 0..lim of this tile are visible (lim >= 63: all)
-    float mx = -INFINITY;
-    if (lim < kK - 1) {
+        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + (t & 1) * 2 * kSub);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i > lim) s0[i] = __float_as_uint(-INFINITY);
-        if (32 + i > lim) s1[i] = __float_as_uint(-INFINITY);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
-    float m_new = fmaxf(m_run, mx);
-    // a row with nothing visible yet can only be a row beyond the tile's sequence (never stored): keep it finite
-    if (m_new == -INFINITY) m_new = 0.f;
-    // LAZY rescaling: the reference maximum of a row moves only when the true maximum has outgrown it by more than 2^8
-    // (in the exp2 domain) somewhere in the warp; until then probabilities may exceed 1 (<= 256: harmless in bf16 / fp32)
-    // and O, l keep their scale — the result is the same quotient. Without it almost every tile pays a TMEM round trip
-    // of O (some row of 32 sees a new maximum in most tiles: 4400 cycles per key tile measured, mostly that).
-    // (only rows of this tile's sequence vote: a row's arithmetic must not depend on which other sequence follows it in
-    // the packed batch)
-    const bool move = j == 0 || __any_sync(0xffffffffu, row < nrows && (m_new - m_run) * c > 8.0f);
-    const float m_use = move ? m_new : m_run;
-    const float alpha = ex2((m_run - m_use) * c);
-    const float mc = m_use * c;
-    float sum = 0.f;
-    uint32_t ph[32];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float a0 = ex2(fmaf(__uint_as_float(s0[2 * i]), c, -mc)), a1 = ex2(fmaf(__uint_as_float(s0[2 * i + 1]), c, -mc));
-      const float b0 = ex2(fmaf(__uint_as_float(s1[2 * i]), c, -mc)), b1 = ex2(fmaf(__uint_as_float(s1[2 * i + 1]), c, -mc));
-      const uint32_t pa = pack_bf16(a0, a1), pb = pack_bf16(b0, b1);
-      sum += (bf16lo(pa) + bf16hi(pa)) + (bf16lo(pb) + bf16hi(pb));  // the sum runs over the rounded probabilities
-      ph[i] = pa;
-      ph[16 + i] = pb;
-    }
-    l_run = l_run * alpha + sum;
-    m_run = m_use;
-    if (j > 0) {
-      mbar_wait(pv_done, (j - 1) & 1);  // O += P V of the previous tile retired: P, the V buffer and O are free
-      tc_fence_after();
-      if (move) {  // warp-uniform
-        uint32_t o[32];
-#pragma unroll 1
-        for (int q4 = 0; q4 < 4; ++q4) {
-          tmem_ld_32x32b_x32(tO + q4 * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32b_x32(tO + q4 * 32, o);
+        for (int k = 0; k < kD / 16; ++k) {
+          const uint32_t half = k >> 2, in = (k & 3) * 32;
+          umma_bf16(tmem_base, make_smem_desc_sw128(qa + half * 2 * kSub + in), make_smem_desc_sw128(ka + half * kSub + in), kIdescS,
+                    k > 0 ? 1u : 0u);
         }
-        tmem_st_wait();
+        umma_commit(s_full);
+      };
+      mbar_arrive_expect_tx(q_full, 4 * kSub);
+      const int cq = hq * kD;
+      tma_load_2d(sQ, &tm_q, q_full, cq, row0, kEvictNormal);
+      tma_load_2d(sQ + kSub, &tm_q, q_full, cq, row0 + 64, kEvictNormal);
+      tma_load_2d(sQ + 2 * kSub, &tm_q, q_full, cq + 64, row0, kEvictNormal);
+      tma_load_2d(sQ + 3 * kSub, &tm_q, q_full, cq + 64, row0 + 64, kEvictNormal);
+      for (int t = 0; t < 2 && t < n_tiles; ++t) {
+        load_k(t);
+        load_v(t);
       }
-    }
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(s_free, j & 1);  // S_j is in registers: its TMEM columns and K stage j % 2 are free
+        tc_fence_after();
+        if (j + 2 < n_tiles) load_k(j + 2);
+        if (j + 1 < n_tiles) issue_s(j + 1);  // runs under tile j's softmax
+        mbar_wait(p_ready, j & 1);            // (the softmax warps waited for v_full themselves on the last tile)
+        mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP), va = smem_u32(sV + (j & 1) * 2 * kSub);
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch)
-      *reinterpret_cast<uint4*>(p_row + ((ch ^ sw) << 4)) = make_uint4(ph[4 * ch], ph[4 * ch + 1], ph[4 * ch + 2], ph[4 * ch + 3]);
-    {
-      // keys past the last row of this prefill are not in the pool yet: their probabilities are 0, but 0 x stale NaN / Inf
-      // bits of V would still poison O — zero those V rows (a row's 128 bytes stay inside the row under the swizzle)
-      const int nvalid = pos0 + nrows - j * kK;
-      if (nvalid < kK) {  // uniform: last key tile only
-        mbar_wait(v_full, j & 1);
-        for (int i = tid; i < (kK - nvalid) * 16; i += 128) {
-          const int kr = nvalid + (i >> 4), part = i & 15;
-          *reinterpret_cast<uint4*>(sV + (part >> 3) * kSub + kr * 128 + (part & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        for (int k = 0; k < kK / 16; ++k)
+          umma_bf16(tmem_base + 64, make_smem_desc_sw128(pa + k * 32), make_smem_desc_mn_sw128(va + k * 2048), kIdescO,
+                    (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(pv_done);
+        if (j + 2 < n_tiles) {  // V stage j % 2 is free once this O += P V has retired
+          mbar_wait(pv_done, j & 1);
+          load_v(j + 2);
         }
       }
     }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();  // [B]
-    if (tid == 0) {
+  } else {
+    // ================= softmax: thread = query row =================
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);  // columns 0..63: S
+    const uint32_t tO = tS + 64;                                               // columns 64..191: O
+    float m_run = -INFINITY, l_run = 0.f;
+    const float c = p.scale_log2;
+    const int row = warp * 32 + lane;
+    const int my_pos = pos0 + row;  // keys <= my_pos are visible to this row
+    uint8_t* p_row = sP + row * 128;
+    const int sw = row & 7;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
-      mbar_wait(v_full, j & 1);
-      tc_fence_after();
-      const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32b_x32(tS, s0);
+      tmem_ld_32x32b_x32(tS + 32, s1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);
+      // ---- causal mask (only tiles that reach this row's diagonal), row maximum, probabilities
+      const int lim = my_pos - j * kK;  // keys 0..lim of this tile are visible (lim >= 63: all)
+      float mx = -INFINITY;
+      if (lim < kK - 1) {
 #pragma unroll
-      for (int k = 0; k < kK / 16; ++k)
-        umma_bf16(tmem_base + 64, make_smem_desc_sw128(pa + k * 32), make_smem_desc_mn_sw128(va + k * 2048), kIdescO,
-                  (j > 0 || k > 0) ? 1u : 0u);
-      umma_commit(pv_done);
-    }
-    __syncwarp();
-  }
-
-  mbar_wait(pv_done, (n_tiles - 1) & 1);
-  tc_fence_after();
-  const float inv = 1.0f / l_run;
-  bf16* op = p.out + ((long long)(row0 + row)) * (p.Hq * kD) + hq * kD;
+        for (int i = 0; i < 32; ++i) {
+          if (i > lim) s0[i] = __float_as_uint(-INFINITY);
+          if (32 + i > lim) s1[i] = __float_as_uint(-INFINITY);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+      float m_new = fmaxf(m_run, mx);
+      // a row with nothing visible yet can only be a row beyond the tile's sequence (never stored): keep it finite
+      if (m_new == -INFINITY) m_new = 0.f;
+      // LAZY rescaling: the reference maximum of a row moves only when the true maximum has outgrown it by more than 2^8
+      // (in the exp2 domain) somewhere in the warp; until then probabilities may exceed 1 (<= 256: harmless in bf16 / fp32)
+      // and O, l keep their scale — the result is the same quotient. Only rows of this tile's sequence vote: a row's
+      // arithmetic must not depend on which other sequence follows it in the packed batch.
+      const bool move = j == 0 || __any_sync(0xffffffffu, row < nrows && (m_new - m_run) * c > 8.0f);
+      const float m_use = move ? m_new : m_run;
+      const float alpha = ex2((m_run - m_use) * c);
+      const float mc = m_use * c;
+      float sum = 0.f;
+      uint32_t ph[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a0 = ex2(fmaf(__uint_as_float(s0[2 * i]), c, -mc)), a1 = ex2(fmaf(__uint_as_float(s0[2 * i + 1]), c, -mc));
+        const float b0 = ex2(fmaf(__uint_as_float(s1[2 * i]), c, -mc)), b1 = ex2(fmaf(__uint_as_float(s1[2 * i + 1]), c, -mc));
+        const uint32_t pa = pack_bf16(a0, a1), pb = pack_bf16(b0, b1);
+        sum += (bf16lo(pa) + bf16hi(pa)) + (bf16lo(pb) + bf16hi(pb));  // the sum runs over the rounded probabilities
+        ph[i] = pa;
+        ph[16 + i] = pb;
+      }
+      l_run = l_run * alpha + sum;
+      m_run = m_use;
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);  // O += P V of the previous tile retired: P and O are free
+        tc_fence_after();
+        if (move) {  // warp-uniform
+          uint32_t o[32];
 #pragma unroll 1
-  for (int q4 = 0; q4 < 4; ++q4) {
-    uint32_t o[32];
-    tmem_ld_32x32b_x32(tO + q4 * 32, o);
-    tmem_ld_wait();
-    if (row < nrows) {
+          for (int q4 = 0; q4 < 4; ++q4) {
+            tmem_ld_32x32b_x32(tO + q4 * 32, o);
+            tmem_ld_wait();
 #pragma unroll
-      for (int v4 = 0; v4 < 4; ++v4) {
-        uint32_t w[4];
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(tO + q4 * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          w[i] = pack_bf16(__uint_as_float(o[v4 * 8 + 2 * i]) * inv, __uint_as_float(o[v4 * 8 + 2 * i + 1]) * inv);
-        *reinterpret_cast<uint4*>(op + q4 * 32 + v4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+      for (int ch = 0; ch < 8; ++ch)
+        *reinterpret_cast<uint4*>(p_row + ((ch ^ sw) << 4)) = make_uint4(ph[4 * ch], ph[4 * ch + 1], ph[4 * ch + 2], ph[4 * ch + 3]);
+      {
+        // keys past the last row of this prefill are not in the pool yet: their probabilities are 0, but 0 x stale NaN / Inf
+        // bits of V would still poison O — zero those V rows (a row's 128 bytes stay inside the row under the swizzle)
+        const int nvalid = pos0 + nrows - j * kK;
+        if (nvalid < kK) {  // uniform: last key tile only
+          mbar_wait(&v_full[j & 1], (j >> 1) & 1);
+          uint8_t* vb = sV + (j & 1) * 2 * kSub;
+          for (int i = tid; i < (kK - nvalid) * 16; i += 128) {
+            const int kr = nvalid + (i >> 4), part = i & 15;
+            *reinterpret_cast<uint4*>(vb + (part >> 3) * kSub + kr * 128 + (part & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    }
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    bf16* op = p.out + ((long long)(row0 + row)) * (p.Hq * kD) + hq * kD;
+#pragma unroll 1
+    for (int q4 = 0; q4 < 4; ++q4) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tO + q4 * 32, o);
+      tmem_ld_wait();
+      if (row < nrows) {
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            w[i] = pack_bf16(__uint_as_float(o[v4 * 8 + 2 * i]) * inv, __uint_as_float(o[v4 * 8 + 2 * i + 1]) * inv);
+          *reinterpret_cast<uint4*>(op + q4 * 32 + v4 * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 4) {
     tc_fence_after();
     tmem_dealloc<256>(tmem_base);
   }
@@ -346,7 +354,7 @@ extern "C" int mtts_gqa_prefill_tc(const void* q, long long rows, const void* k_
   p.block_table = block_table; p.tile_row0 = tile_row0; p.tile_nrows = tile_nrows; p.row_seq = row_seq; p.positions = positions;
   p.max_pages = max_pages; p.page_shift = page_shift; p.Hq = Hq; p.Hkv = Hkv; p.rows = (int)rows;
   p.scale_log2 = scale_log2;
-  MTTS_CUDA_CHECK(mtts_launch(gqa_prefill_tc5_kernel, dim3(tiles, Hq), dim3(128), kSmemBytes, stream, tq, tk, tv, p));
+  MTTS_CUDA_CHECK(mtts_launch(gqa_prefill_tc5_kernel, dim3(tiles, Hq), dim3(kThreadsPf), kSmemBytes, stream, tq, tk, tv, p));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }
