@@ -274,88 +274,87 @@ struct RopeParams {
   int* err_flag;
 };
 
+// One CTA (8 warps) per ROW: the 64 angles of the row are evaluated once (the accurate cosf / sinf with arguments up to
+// ~12 000 rad were most of this kernel's time when every 8-head group of a row recomputed them), every warp takes heads
+// warp, warp + 8, ... and requests the loads of all its heads before it touches the first one.
 __global__ void __launch_bounds__(256) qknorm_rope_kv_kernel(const RopeParams p) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float s_cs[128];  // cos[64] | sin[64] of the block's row, bf16-rounded
-  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  __shared__ float s_cs[128];  // cos[64] | sin[64] of this row, bf16-rounded
+  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int heads = p.Hq + 2 * p.Hkv;
-  const int row = warp_global / heads;
-  const int h = warp_global % heads;
-  // When the 8 warps of a block work on heads of ONE row (heads % 8 == 0) the 64 angles of that row are evaluated once
-  // per block instead of once per head: the accurate cosf / sinf were 2/3 of this kernel's time at prefill.
-  const bool shared_angles = (heads % 8) == 0;
-  if (shared_angles) {
-    const int brow = (blockIdx.x * 8) / heads;
-    if (threadIdx.x < 64 && brow < p.rows) {
-      const float f = (float)p.positions[brow] * p.inv_freq[threadIdx.x];
-      s_cs[threadIdx.x] = bf16_round(cosf(f));
-      s_cs[64 + threadIdx.x] = bf16_round(sinf(f));
-    }
-    __syncthreads();
-  }
-  if (row >= p.rows) return;
-  const bf16* src = p.qkv + (long long)row * p.ld_qkv + h * 128;
-  const uint32_t a = *reinterpret_cast<const uint32_t*>(src + 2 * lane);        // elements 2l, 2l+1
-  const uint32_t b = *reinterpret_cast<const uint32_t*>(src + 64 + 2 * lane);   // elements 64+2l, 65+2l
   const int pos = p.positions[row];
+  if (threadIdx.x < 64) {
+    const float f = (float)pos * p.inv_freq[threadIdx.x];
+    s_cs[threadIdx.x] = bf16_round(cosf(f));
+    s_cs[64 + threadIdx.x] = bf16_round(sinf(f));
+  }
+  constexpr int kMaxPerWarp = 4;  // 32 heads over 8 warps; more heads run in further rounds
+  const bf16* src_row = p.qkv + (long long)row * p.ld_qkv;
   const int seq = p.row_seq ? p.row_seq[row] : row;
-
-  bf16* dst;
-  if (h < p.Hq) {
-    dst = p.q_out + ((long long)row * p.Hq + h) * 128;
-  } else {
-    const int hk = (h - p.Hq) % p.Hkv;
-    const bool is_v = (h - p.Hq) >= p.Hkv;
-    const int lp = pos >> p.page_shift;
-    int page = -1;
-    if (pos >= 0 && lp < p.max_pages) page = p.block_table ? p.block_table[(long long)seq * p.max_pages + lp] : seq * p.max_pages + lp;
-    if (page < 0 || page >= p.num_pages) {
-      if (p.err_flag && lane == 0) *p.err_flag = 2;
-      return;
+  const uint32_t wqa = *reinterpret_cast<const uint32_t*>(p.q_norm_w + 2 * lane), wqb = *reinterpret_cast<const uint32_t*>(p.q_norm_w + 64 + 2 * lane);
+  const uint32_t wka = *reinterpret_cast<const uint32_t*>(p.k_norm_w + 2 * lane), wkb = *reinterpret_cast<const uint32_t*>(p.k_norm_w + 64 + 2 * lane);
+  __syncthreads();
+  const float c0 = s_cs[2 * lane], c1 = s_cs[2 * lane + 1], s0 = s_cs[64 + 2 * lane], s1 = s_cs[65 + 2 * lane];
+  for (int h0 = warp; h0 < heads; h0 += 8 * kMaxPerWarp) {
+    uint32_t a[kMaxPerWarp], b[kMaxPerWarp];
+#pragma unroll
+    for (int i = 0; i < kMaxPerWarp; ++i) {
+      const int h = h0 + 8 * i;
+      if (h < heads) {
+        a[i] = *reinterpret_cast<const uint32_t*>(src_row + h * 128 + 2 * lane);       // elements 2l, 2l+1
+        b[i] = *reinterpret_cast<const uint32_t*>(src_row + h * 128 + 64 + 2 * lane);  // elements 64+2l, 65+2l
+      }
     }
-    bf16* pool = is_v ? p.v_pool : p.k_pool;
-    const int slot = pos & ((1 << p.page_shift) - 1);
-    dst = pool + (((long long)page * p.Hkv + hk) << p.page_shift) * 128 + (long long)slot * 128;
-    if (is_v) {  // V: plain copy
-      *reinterpret_cast<uint32_t*>(dst + 2 * lane) = a;
-      *reinterpret_cast<uint32_t*>(dst + 64 + 2 * lane) = b;
-      return;
+#pragma unroll
+    for (int i = 0; i < kMaxPerWarp; ++i) {
+      const int h = h0 + 8 * i;
+      if (h >= heads) break;
+      bf16* dst;
+      if (h < p.Hq) {
+        dst = p.q_out + ((long long)row * p.Hq + h) * 128;
+      } else {
+        const int hk = (h - p.Hq) % p.Hkv;
+        const bool is_v = (h - p.Hq) >= p.Hkv;
+        const int lp = pos >> p.page_shift;
+        int page = -1;
+        if (pos >= 0 && lp < p.max_pages) page = p.block_table ? p.block_table[(long long)seq * p.max_pages + lp] : seq * p.max_pages + lp;
+        if (page < 0 || page >= p.num_pages) {
+          if (p.err_flag && lane == 0) *p.err_flag = 2;
+          continue;
+        }
+        bf16* pool = is_v ? p.v_pool : p.k_pool;
+        const int slot = pos & ((1 << p.page_shift) - 1);
+        dst = pool + (((long long)page * p.Hkv + hk) << p.page_shift) * 128 + (long long)slot * 128;
+        if (is_v) {  // V: plain copy
+          *reinterpret_cast<uint32_t*>(dst + 2 * lane) = a[i];
+          *reinterpret_cast<uint32_t*>(dst + 64 + 2 * lane) = b[i];
+          continue;
+        }
+      }
+      const uint32_t wa = (h < p.Hq) ? wqa : wka, wb = (h < p.Hq) ? wqb : wkb;
+      float x0 = bf16lo(a[i]), x1 = bf16hi(a[i]), x2 = bf16lo(b[i]), x3 = bf16hi(b[i]);
+      float ss = x0 * x0;
+      ss = fmaf(x1, x1, ss);
+      ss = fmaf(x2, x2, ss);
+      ss = fmaf(x3, x3, ss);
+      ss = warp_sum(ss);
+      const float inv = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
+      // normed = w * bf16(x * inv), rounded to bf16 (it is a bf16 tensor in the reference)
+      x0 = bf16_round(bf16lo(wa) * bf16_round(x0 * inv));
+      x1 = bf16_round(bf16hi(wa) * bf16_round(x1 * inv));
+      x2 = bf16_round(bf16lo(wb) * bf16_round(x2 * inv));
+      x3 = bf16_round(bf16hi(wb) * bf16_round(x3 * inv));
+      // RoPE: out[i] = bf16(x[i]*cos) + bf16(-x[i+64]*sin) ; out[i+64] = bf16(x[i+64]*cos) + bf16(x[i]*sin)
+      const float o0 = bf16_round(x0 * c0) + bf16_round(-x2 * s0);
+      const float o1 = bf16_round(x1 * c1) + bf16_round(-x3 * s1);
+      const float o2 = bf16_round(x2 * c0) + bf16_round(x0 * s0);
+      const float o3 = bf16_round(x3 * c1) + bf16_round(x1 * s1);
+      *reinterpret_cast<uint32_t*>(dst + 2 * lane) = pack_bf16(o0, o1);
+      *reinterpret_cast<uint32_t*>(dst + 64 + 2 * lane) = pack_bf16(o2, o3);
     }
   }
-  const bf16* nw = (h < p.Hq) ? p.q_norm_w : p.k_norm_w;
-  float x0 = bf16lo(a), x1 = bf16hi(a), x2 = bf16lo(b), x3 = bf16hi(b);
-  float ss = x0 * x0;
-  ss = fmaf(x1, x1, ss);
-  ss = fmaf(x2, x2, ss);
-  ss = fmaf(x3, x3, ss);
-  ss = warp_sum(ss);
-  const float inv = rsqrtf(ss * (1.0f / 128.0f) + p.eps);
-  const uint32_t wa = *reinterpret_cast<const uint32_t*>(nw + 2 * lane);
-  const uint32_t wb = *reinterpret_cast<const uint32_t*>(nw + 64 + 2 * lane);
-  // normed = w * bf16(x * inv), rounded to bf16 (it is a bf16 tensor in the reference)
-  x0 = bf16_round(bf16lo(wa) * bf16_round(x0 * inv));
-  x1 = bf16_round(bf16hi(wa) * bf16_round(x1 * inv));
-  x2 = bf16_round(bf16lo(wb) * bf16_round(x2 * inv));
-  x3 = bf16_round(bf16hi(wb) * bf16_round(x3 * inv));
-  // RoPE: angle index i = 2l, 2l+1 (shared by element i and i+64)
-  float c0, s0, c1, s1;
-  if (shared_angles) {
-    c0 = s_cs[2 * lane]; c1 = s_cs[2 * lane + 1]; s0 = s_cs[64 + 2 * lane]; s1 = s_cs[65 + 2 * lane];
-  } else {
-    const float f0 = (float)pos * p.inv_freq[2 * lane];
-    const float f1 = (float)pos * p.inv_freq[2 * lane + 1];
-    c0 = bf16_round(cosf(f0)); s0 = bf16_round(sinf(f0));
-    c1 = bf16_round(cosf(f1)); s1 = bf16_round(sinf(f1));
-  }
-  // out[i] = bf16(x[i]*cos) + bf16(-x[i+64]*sin) ; out[i+64] = bf16(x[i+64]*cos) + bf16(x[i]*sin)
-  const float o0 = bf16_round(x0 * c0) + bf16_round(-x2 * s0);
-  const float o1 = bf16_round(x1 * c1) + bf16_round(-x3 * s1);
-  const float o2 = bf16_round(x2 * c0) + bf16_round(x0 * s0);
-  const float o3 = bf16_round(x3 * c1) + bf16_round(x1 * s1);
-  *reinterpret_cast<uint32_t*>(dst + 2 * lane) = pack_bf16(o0, o1);
-  *reinterpret_cast<uint32_t*>(dst + 64 + 2 * lane) = pack_bf16(o2, o3);
 }
 
 }  // namespace
@@ -457,8 +456,7 @@ extern "C" int mtts_qknorm_rope_kvappend(const void* qkv, long long ld_qkv, cons
   while ((1 << shift) < page_size) ++shift;
   p.page_shift = shift; p.num_pages = num_pages; p.rows = rows; p.Hq = num_q_heads; p.Hkv = num_kv_heads; p.eps = eps;
   p.err_flag = err_flag;
-  const long long warps = (long long)rows * (num_q_heads + 2 * num_kv_heads);
-  MTTS_CUDA_CHECK(mtts_launch(qknorm_rope_kv_kernel, dim3((unsigned)ceil_div_ll(warps, 8)), dim3(256), 0, stream, p));
+  MTTS_CUDA_CHECK(mtts_launch(qknorm_rope_kv_kernel, dim3((unsigned)rows), dim3(256), 0, stream, p));
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }
