@@ -200,12 +200,15 @@ __global__ void __launch_bounds__(kThreadsMha, 3) mha_varlen_tc5_kernel(const __
       if (lane == 0) mbar_arrive(s_free);
       const int valid = kv_len - j * kK;  // keys of this tile inside the item (>= 1)
       float mx = -INFINITY;
+      if (valid < kK) {  // uniform: only the item's last key tile is masked (ncu: the softmax warps are issue-bound, 62 %)
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        if (i >= valid) s0[i] = __float_as_uint(-INFINITY);
-        if (32 + i >= valid) s1[i] = __float_as_uint(-INFINITY);
-        mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
+        for (int i = 0; i < 32; ++i) {
+          if (i >= valid) s0[i] = __float_as_uint(-INFINITY);
+          if (32 + i >= valid) s1[i] = __float_as_uint(-INFINITY);
+        }
       }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i])));
       const float m_new = fmaxf(m_run, mx);
       // LAZY rescaling: the reference maximum of a row moves only when the true maximum has outgrown it by more than 2^8
       // (in the exp2 domain) somewhere in the warp; until then probabilities may exceed 1 (<= 256: harmless in fp16 / fp32)
