@@ -681,21 +681,25 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
       const int lim = min(32, p.M - (m0 + c));
       const int odd = lane & 1;
       if ((p.ldo & 1) == 0 && (p.N & 1) == 0) {
-        // straight-line phases (activate, exchange, pack, store) so that the 32 independent chains interleave
+        // straight-line phases (convert, activate, exchange, store). The arithmetic runs on PACKED fp16 pairs — rows
+        // 2i, 2i + 1 of this lane's column share a register — so the GELU costs 9 instructions per pair (gelu_tanh5_h2),
+        // and one shuffle + one byte permute per pair turns (two rows of one column) into (two columns of one row).
         __half* op = reinterpret_cast<__half*>(p.out) + (long long)(m0 + c + odd) * p.ldo + (n - odd);
-        float g[32], rv[16];
-        if (p.flags & MTTS_EPI_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) g[j] = gelu_tanh5(__uint_as_float(r[j]) + bias_n);
-        } else {  // plain fp16 linear (+ bias): the q/k/v projection in front of the tcgen05 attention
-#pragma unroll
-          for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(r[j]) + bias_n;
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) rv[i] = __shfl_xor_sync(0xffffffffu, odd ? g[2 * i] : g[2 * i + 1], 1);
         __half2 h[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) h[i] = odd ? __floats2half2_rn(rv[i], g[2 * i + 1]) : __floats2half2_rn(g[2 * i], rv[i]);
+        for (int i = 0; i < 16; ++i) h[i] = __floats2half2_rn(__uint_as_float(r[2 * i]) + bias_n, __uint_as_float(r[2 * i + 1]) + bias_n);
+        if (p.flags & MTTS_EPI_GELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) h[i] = gelu_tanh5_h2(h[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t mine = *reinterpret_cast<const uint32_t*>(&h[i]);
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+          // even lane: row 2i of columns (n, n + 1) = (mine.lo, other.lo); odd lane: row 2i + 1 of (n - 1, n) = (other.hi, mine.hi)
+          const uint32_t o = odd ? __byte_perm(mine, other, 0x3276) : __byte_perm(mine, other, 0x5410);
+          h[i] = *reinterpret_cast<const __half2*>(&o);
+        }
         if (n_ok) {
           if (lim == 32) {
 #pragma unroll
