@@ -26,6 +26,8 @@ SHAPES = [
     (1000, 512, 560),
     # >= 592 weight tiles at 65..256 rows: the LM-heads route (CTA-pair kernel with one, partly out-of-bounds, row tile)
     (200, 76032, 128), (77, 75900, 192),
+    # short K, many rows (the codec's ConvNeXt pw1 regime): many tiles per pair, last tiles partly out of bounds
+    (19000, 1100, 448), (40000, 2048, 512),
 ]
 
 
