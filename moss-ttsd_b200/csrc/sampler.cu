@@ -251,13 +251,29 @@ __global__ void __launch_bounds__(kThreads) sample_scan_kernel(const SampleParam
       p.ws.slice_idx[bc * kMaxSlices + slice] = bi;
     }
   } else if (S > 1) {
-    s_val[tid] = bv;
-    s_idx[tid] = bi;
-    __syncthreads();
-    bitonic_sort_desc(s_val, s_idx, kThreads);
-    if (tid < kReport) p.ws.reported[(bc * kMaxSlices + slice) * kReport + tid] = s_val[tid];
+    // Every warp reports its 4 largest thread maxima (4 rounds of a warp-wide max; the winner steps aside): 16 warps x 4 =
+    // kReport values per slice without a block-wide sort. Any set of real scores gives a valid threshold (the k-th largest
+    // of a SUBSET is a lower bound of the k-th largest score); it is as tight as the sorted top-64 unless more than four of
+    // the row's top k sit in one warp's 256 logits. (The 512-entry bitonic sort this replaces — 45 barrier stages per
+    // slice, 9728 slices at batch 256 — made the scan 984 us of a sampled decode step.)
+    static_assert(kReport == (kThreads / 32) * 4, "4 reported values per warp");
+    float cand = bv, wmax = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float m = cand;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (r == 0) wmax = m;
+      const unsigned who = __ballot_sync(0xffffffffu, cand == m);
+      if ((tid & 31) == __ffs(who) - 1) cand = -INFINITY;  // one winner per round (ties: the others stay for the next)
+      if ((tid & 31) == r) p.ws.reported[(bc * kMaxSlices + slice) * kReport + (tid >> 5) * 4 + r] = m;
+    }
     // slice softmax statistics (needed for top-p over the full vocabulary when no top-k precedes it)
-    const float smax = s_val[0];
+    if ((tid & 31) == 0) s_val[tid >> 5] = wmax;
+    __syncthreads();
+    float smax = s_val[0];
+#pragma unroll
+    for (int w = 1; w < kThreads / 32; ++w) smax = fmaxf(smax, s_val[w]);
     float se = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e)
@@ -339,39 +355,53 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
   const int j0 = slice * kSlice + tid * 8;
   float sv[8];
   scores8(sc, j0, V, sv);
+  int n, npad = 1;
+  if (S == 1 && V <= kCap) {
+    // a one-slice channel (the 1025-way speech channels): this CTA holds the whole row — the scores go straight into the
+    // sort buffer (the candidate list in global memory cost one atomic per score on a single counter: 1025 serialised
+    // atomics per (row, channel))
+    n = V;
+    while (npad < n) npad <<= 1;
+    for (int t = tid; t < npad; t += kThreads) { s_val[t] = -INFINITY; s_idx[t] = -1; }
+    __syncthreads();
 #pragma unroll
-  for (int e = 0; e < 8; ++e)
-    if (j0 + e < V && sv[e] >= thr) {
-      const int pos = atomicAdd(p.ws.cand_count + bc, 1);
-      if (pos < kCap) {
-        __stcg(p.ws.cand_val + bc * kCap + pos, sv[e]);
-        __stcg(p.ws.cand_idx + bc * kCap + pos, j0 + e);
+    for (int e = 0; e < 8; ++e)
+      if (j0 + e < V) { s_val[j0 + e] = sv[e]; s_idx[j0 + e] = j0 + e; }
+    __syncthreads();
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (j0 + e < V && sv[e] >= thr) {
+        const int pos = atomicAdd(p.ws.cand_count + bc, 1);
+        if (pos < kCap) {
+          __stcg(p.ws.cand_val + bc * kCap + pos, sv[e]);
+          __stcg(p.ws.cand_idx + bc * kCap + pos, j0 + e);
+        }
       }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int prev = atomicAdd(p.ws.tickets + bc * 2 + 1, 1);
+      s_last = (prev == S - 1);
+      if (s_last) p.ws.tickets[bc * 2 + 1] = 0;
     }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const int prev = atomicAdd(p.ws.tickets + bc * 2 + 1, 1);
-    s_last = (prev == S - 1);
-    if (s_last) p.ws.tickets[bc * 2 + 1] = 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    n = __ldcg(p.ws.cand_count + bc);
+    __syncthreads();
+    if (tid == 0) p.ws.cand_count[bc] = 0;
+    if (n > kCap) {
+      if (tid == 0 && p.err_flag) *p.err_flag = 3;  // candidate overflow (pathological ties); truncated
+      n = kCap;
+    }
+    while (npad < n) npad <<= 1;
+    for (int t = tid; t < npad; t += kThreads) {
+      s_val[t] = t < n ? __ldcg(p.ws.cand_val + bc * kCap + t) : -INFINITY;
+      s_idx[t] = t < n ? __ldcg(p.ws.cand_idx + bc * kCap + t) : -1;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  int n = __ldcg(p.ws.cand_count + bc);
-  __syncthreads();
-  if (tid == 0) p.ws.cand_count[bc] = 0;
-  if (n > kCap) {
-    if (tid == 0 && p.err_flag) *p.err_flag = 3;  // candidate overflow (pathological ties); truncated
-    n = kCap;
-  }
-  int npad = 1;
-  while (npad < n) npad <<= 1;
-  for (int t = tid; t < npad; t += kThreads) {
-    s_val[t] = t < n ? __ldcg(p.ws.cand_val + bc * kCap + t) : -INFINITY;
-    s_idx[t] = t < n ? __ldcg(p.ws.cand_idx + bc * kCap + t) : -1;
-  }
-  __syncthreads();
   bitonic_sort_desc(s_val, s_idx, npad);
   const int k = cfg.top_k[c] > 0 ? min(cfg.top_k[c], V) : V;
 
