@@ -73,6 +73,7 @@ extern "C" int mtts_init(void) {
     if ((rc = mtts_configure_decode_mega())) return rc;
     if ((rc = mtts_configure_mha_tc5())) return rc;
     if ((rc = mtts_configure_prefill_tc5())) return rc;
+    if ((rc = mtts_configure_sampler())) return rc;
     configured[dev] = true;
   }
   return MTTS_OK;

@@ -17,6 +17,7 @@ int mtts_get_tmap_2d(const void* ptr, long long rows, long long cols, long long 
 // one-time per-device kernel attribute setup, called by mtts_init()
 int mtts_configure_mha_tc5();
 int mtts_configure_prefill_tc5();
+int mtts_configure_sampler();
 int mtts_configure_gemm_tc();
 int mtts_configure_attention();
 int mtts_configure_rvq();

@@ -184,7 +184,9 @@ __device__ __forceinline__ void block_argmax(float& bv, int& bi, float* s_val, i
   }
 }
 
-__global__ void __launch_bounds__(kThreads) sample_scan_kernel(const SampleParams2 p) {
+// (two CTAs per SM: at 80 registers and the default shared-memory carve-out the 11 520 slice CTAs of a batch-256 step ran one
+// per SM — 78 waves; ncu: launch__occupancy_limit_registers = launch__occupancy_limit_shared_mem = 1)
+__global__ void __launch_bounds__(kThreads, 2) sample_scan_kernel(const SampleParams2 p) {
   __shared__ float s_val[kMaxSlices * kReport];
   __shared__ int s_idx[kMaxSlices * kReport];
   __shared__ int s_last;
@@ -250,7 +252,20 @@ __global__ void __launch_bounds__(kThreads) sample_scan_kernel(const SampleParam
       p.ws.slice_val[bc * kMaxSlices + slice] = bv;
       p.ws.slice_idx[bc * kMaxSlices + slice] = bi;
     }
-  } else if (S > 1) {
+  } else if (S == 1) {
+    // one-slice channel (the 1025-way speech channels, 5 warps of data): 16 rounds per warp, so that the reported set holds
+    // at least top_k real scores for the usual k (<= 80 here; a larger k finds -inf at position k and keeps every score)
+    float cand = bv;
+#pragma unroll 1
+    for (int r = 0; r < 16; ++r) {
+      float m = cand;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      const unsigned who = __ballot_sync(0xffffffffu, cand == m);
+      if ((tid & 31) == __ffs(who) - 1) cand = -INFINITY;
+      if ((tid & 31) == r) p.ws.reported[bc * kMaxSlices * kReport + (tid >> 5) * 16 + r] = m;
+    }
+  } else {
     // Every warp reports its 4 largest thread maxima (4 rounds of a warp-wide max; the winner steps aside): 16 warps x 4 =
     // kReport values per slice without a block-wide sort. Any set of real scores gives a valid threshold (the k-th largest
     // of a SUBSET is a lower bound of the k-th largest score); it is as tight as the sorted top-64 unless more than four of
@@ -322,8 +337,9 @@ __global__ void __launch_bounds__(kThreads) sample_scan_kernel(const SampleParam
     if (tid == 0) { p.ws.thr[bc * 4 + 1] = gm; p.ws.thr[bc * 4 + 2] = gz; }
     if (cfg.top_k[c] <= 0) k = min(S * kReport, (kCap * 3) / 4);
   }
-  if (S > 1 && k <= S * kReport) {
-    const int n = S * kReport;
+  const int n_rep = S > 1 ? S * kReport : (kThreads / 32) * 16;
+  if (k <= n_rep) {
+    const int n = n_rep;
     int npad = 1;
     while (npad < n) npad <<= 1;
     for (int t = tid; t < npad; t += kThreads) {
@@ -360,13 +376,22 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
     // a one-slice channel (the 1025-way speech channels): this CTA holds the whole row — the scores go straight into the
     // sort buffer (the candidate list in global memory cost one atomic per score on a single counter: 1025 serialised
     // atomics per (row, channel))
-    n = V;
-    while (npad < n) npad <<= 1;
-    for (int t = tid; t < npad; t += kThreads) { s_val[t] = -INFINITY; s_idx[t] = -1; }
+    // ... and only the scores at or above the scan's threshold (a lower bound of the k-th largest) are kept: ~50-150 of 1025,
+    // a 128/256-entry sort instead of a 2048-entry one (ncu: the finish kernel was issue-bound, 310 M instructions per step)
+    __shared__ int s_n;
+    if (tid == 0) s_n = 0;
     __syncthreads();
 #pragma unroll
     for (int e = 0; e < 8; ++e)
-      if (j0 + e < V) { s_val[j0 + e] = sv[e]; s_idx[j0 + e] = j0 + e; }
+      if (j0 + e < V && sv[e] >= thr) {
+        const int pos = atomicAdd(&s_n, 1);
+        s_val[pos] = sv[e];
+        s_idx[pos] = j0 + e;
+      }
+    __syncthreads();
+    n = s_n;
+    while (npad < n) npad <<= 1;
+    for (int t = n + tid; t < npad; t += kThreads) { s_val[t] = -INFINITY; s_idx[t] = -1; }
     __syncthreads();
   } else {
 #pragma unroll
@@ -680,6 +705,13 @@ extern "C" int mtts_sampler_init_history(const long long* ids, int B, int rows, 
   init_seen_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(ids, B, rows, row_stride_b, cfg->channels, seen,
                                                                          *cfg);
   MTTS_LAUNCH_CHECK();
+  return MTTS_OK;
+}
+
+// the slice kernels keep 32 KB of static shared memory; ask for the largest carve-out so that several CTAs share an SM
+int mtts_configure_sampler() {
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(sample_scan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  MTTS_CUDA_CHECK(cudaFuncSetAttribute(sample_finish_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   return MTTS_OK;
 }
 
