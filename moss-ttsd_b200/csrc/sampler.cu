@@ -91,13 +91,13 @@ __device__ void bitonic_sort_desc(float* val, int* idx, int n) {
 //           the last arriver sorts it and applies top-k (ties kept) / top-p / the Philox draw.
 // ------------------------------------------------------------------------------------------------
 constexpr int kSlice = kThreads * 8;  // 4096 logits per CTA, 16-byte loads
-constexpr int kReport = 64;
+constexpr int kReport = 256;  // reported scores per slice: the 16 largest thread maxima of each of its 16 warps
 constexpr int kMaxSlices = 64;
 
 struct SampleWs {
   float* slice_val;   // [B][C][kMaxSlices]
   int* slice_idx;     // [B][C][kMaxSlices]
-  float* reported;    // [B][C][kMaxSlices * kReport]
+  float* reported;    // [B][kMaxSlices (all channels' slices, launch order)][kReport]
   float* thr;         // [B][C][4]: threshold, global max, global sum of exp(score - max), unused
   int* tickets;       // [B][C][2]  (scan, finish) zero between launches
   int* cand_count;    // [B][C]     zero between launches
@@ -187,8 +187,8 @@ __device__ __forceinline__ void block_argmax(float& bv, int& bi, float* s_val, i
 // (two CTAs per SM: at 80 registers and the default shared-memory carve-out the 11 520 slice CTAs of a batch-256 step ran one
 // per SM — 78 waves; ncu: launch__occupancy_limit_registers = launch__occupancy_limit_shared_mem = 1)
 __global__ void __launch_bounds__(kThreads, 2) sample_scan_kernel(const SampleParams2 p) {
-  __shared__ float s_val[kMaxSlices * kReport];
-  __shared__ int s_idx[kMaxSlices * kReport];
+  __shared__ float s_val[kThreads];
+  __shared__ int s_idx[kThreads];
   __shared__ int s_last;
   pdl_launch_dependents();
   pdl_wait();
@@ -246,43 +246,35 @@ __global__ void __launch_bounds__(kThreads, 2) sample_scan_kernel(const SamplePa
       }
     }
   }
+  float wmax = -INFINITY;  // (sampled channels) largest score of this warp's 256 logits
   if (greedy) {
     block_argmax(bv, bi, s_val, s_idx);
     if (tid == 0) {
       p.ws.slice_val[bc * kMaxSlices + slice] = bv;
       p.ws.slice_idx[bc * kMaxSlices + slice] = bi;
     }
-  } else if (S == 1) {
-    // one-slice channel (the 1025-way speech channels, 5 warps of data): 16 rounds per warp, so that the reported set holds
-    // at least top_k real scores for the usual k (<= 80 here; a larger k finds -inf at position k and keeps every score)
-    float cand = bv;
-#pragma unroll 1
-    for (int r = 0; r < 16; ++r) {
-      float m = cand;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      const unsigned who = __ballot_sync(0xffffffffu, cand == m);
-      if ((tid & 31) == __ffs(who) - 1) cand = -INFINITY;
-      if ((tid & 31) == r) p.ws.reported[bc * kMaxSlices * kReport + (tid >> 5) * 16 + r] = m;
-    }
   } else {
-    // Every warp reports its 4 largest thread maxima (4 rounds of a warp-wide max; the winner steps aside): 16 warps x 4 =
-    // kReport values per slice without a block-wide sort. Any set of real scores gives a valid threshold (the k-th largest
-    // of a SUBSET is a lower bound of the k-th largest score); it is as tight as the sorted top-64 unless more than four of
-    // the row's top k sit in one warp's 256 logits. (The 512-entry bitonic sort this replaces — 45 barrier stages per
-    // slice, 9728 slices at batch 256 — made the scan 984 us of a sampled decode step.)
-    static_assert(kReport == (kThreads / 32) * 4, "4 reported values per warp");
-    float cand = bv, wmax = -INFINITY;
+    // Reports of a slice: the thread maxima are sorted inside every warp (bitonic network over shuffles: no barrier) and
+    // each warp writes its 16 largest — kReport = 256 scores per slice, no block-wide sort (the first version's 512-entry
+    // bitonic sort, 45 barrier stages per slice on 9728 slices at batch 256, made the scan 984 us of a sampled step).
+    // Any set of real scores gives a valid threshold (the k-th largest of a SUBSET is a lower bound of the k-th largest
+    // score); it has to stay tight when the whole top k sits in a few warps — a TTS step puts all of channel 0's mass
+    // into the 1024 contiguous speech tokens, four warps of one slice (with only 4 reports per warp the 50th largest
+    // report was a cold logit and every score of the row became a candidate: device flag 3).
+    const int lane = tid & 31, wid = tid >> 5;
+    float v = bv;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      float m = cand;
+    for (int k = 2; k <= 32; k <<= 1)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (r == 0) wmax = m;
-      const unsigned who = __ballot_sync(0xffffffffu, cand == m);
-      if ((tid & 31) == __ffs(who) - 1) cand = -INFINITY;  // one winner per round (ties: the others stay for the next)
-      if ((tid & 31) == r) p.ws.reported[(bc * kMaxSlices + slice) * kReport + (tid >> 5) * 4 + r] = m;
-    }
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const float o = __shfl_xor_sync(0xffffffffu, v, j);
+        const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);  // descending over the whole warp at k = 32
+        v = keep_max ? fmaxf(v, o) : fminf(v, o);
+      }
+    if (lane < 16) p.ws.reported[((long long)b * kMaxSlices + blockIdx.y) * kReport + wid * 16 + lane] = v;
+    wmax = __shfl_sync(0xffffffffu, v, 0);
+  }
+  if (!greedy && S > 1) {
     // slice softmax statistics (needed for top-p over the full vocabulary when no top-k precedes it)
     if ((tid & 31) == 0) s_val[tid >> 5] = wmax;
     __syncthreads();
@@ -337,18 +329,40 @@ __global__ void __launch_bounds__(kThreads, 2) sample_scan_kernel(const SamplePa
     if (tid == 0) { p.ws.thr[bc * 4 + 1] = gm; p.ws.thr[bc * 4 + 2] = gz; }
     if (cfg.top_k[c] <= 0) k = min(S * kReport, (kCap * 3) / 4);
   }
-  const int n_rep = S > 1 ? S * kReport : (kThreads / 32) * 16;
+  // k-th largest of the S * kReport reported scores, exactly, by a most-significant-bit-first radix select on
+  // order-preserving integer keys (32 rounds of count-and-decide over values held in registers; no sort, no big buffer)
+  const int n_rep = S * kReport;
   if (k <= n_rep) {
-    const int n = n_rep;
-    int npad = 1;
-    while (npad < n) npad <<= 1;
-    for (int t = tid; t < npad; t += kThreads) {
-      s_val[t] = t < n ? __ldcg(p.ws.reported + bc * kMaxSlices * kReport + t) : -INFINITY;
-      s_idx[t] = t;
+    const float* rep = p.ws.reported + ((long long)b * kMaxSlices + (blockIdx.y - slice)) * kReport;  // this channel's slices are contiguous
+    constexpr int kPer = kMaxSlices * kReport / kThreads;  // 32
+    uint32_t key[kPer];
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      const int t = tid + i * kThreads;
+      uint32_t u = 0u;  // below every real key (-inf maps to 0x007fffff)
+      if (t < n_rep) {
+        u = __float_as_uint(__ldcg(rep + t));
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      }
+      key[i] = u;
     }
-    __syncthreads();
-    bitonic_sort_desc(s_val, s_idx, npad);
-    thr = s_val[k - 1];
+    __shared__ int s_cnt[2];
+    uint32_t prefix = 0u;
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      if (tid == 0) s_cnt[bit & 1] = 0;
+      __syncthreads();
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) cnt += key[i] >= cand ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if ((tid & 31) == 0 && cnt) atomicAdd(&s_cnt[bit & 1], cnt);
+      __syncthreads();
+      if (s_cnt[bit & 1] >= k) prefix = cand;
+    }
+    const uint32_t u = (prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix;
+    thr = __uint_as_float(u);
   }
   if (tid == 0) p.ws.thr[bc * 4] = thr;
 }
@@ -728,7 +742,7 @@ static size_t sample_ws_layout(int B, int C, SampleWs* ws, uint8_t* base) {
   int* cand_count = reinterpret_cast<int*>(take(bc * sizeof(int)));
   float* slice_val = reinterpret_cast<float*>(take(bc * kMaxSlices * sizeof(float)));
   int* slice_idx = reinterpret_cast<int*>(take(bc * kMaxSlices * sizeof(int)));
-  float* reported = reinterpret_cast<float*>(take(bc * kMaxSlices * kReport * sizeof(float)));
+  float* reported = reinterpret_cast<float*>(take((size_t)B * kMaxSlices * kReport * sizeof(float)));
   float* thr = reinterpret_cast<float*>(take(bc * 4 * sizeof(float)));
   float* cand_val = reinterpret_cast<float*>(take(bc * kCap * sizeof(float)));
   int* cand_idx = reinterpret_cast<int*>(take(bc * kCap * sizeof(int)));

@@ -517,3 +517,41 @@ def test_generate_output_logits_capture(model):
     with pytest.raises(NotImplementedError):
         model.generate(input_ids=ids, attention_mask=mask, max_length=T + 2, do_sample=True, top_k=5,
                        return_dict_in_generate=True, output_scores=True)
+
+
+@pytest.mark.parametrize("lo", [151665, 4090, 131000])
+def test_sampling_with_all_mass_in_a_contiguous_token_range(model, lo):
+    """A TTS step puts the whole probability mass of channel 0 into the 1024 contiguous speech tokens (four warps of one
+    4096-logit slice) while every other logit of the 152,697-way row is an identical cold value: the top-k threshold of the
+    scan must still come out above the cold value (no candidate overflow, device flag 3), and every draw must be one of the
+    row's top-k tokens."""
+    from moss_ttsd_b200 import _lib
+    from moss_ttsd_b200.lm_engine import SamplerSetup
+    torch.manual_seed(lo)
+    shape, eng, C, B = model.shape, model.engine, 8, 16
+    cfg = dict(repetition_penalty=1.1, temperature=0.9, top_k=50, top_p=0.95)
+    logits = torch.zeros((B, shape.vpad), dtype=torch.bfloat16, device="cuda")
+    o0 = shape.head_offsets[0]
+    logits[:, o0 + lo:o0 + lo + 1024] = (torch.randn(B, 1024, device="cuda") * 2.0 + 1.0).to(torch.bfloat16)
+    for c in range(1, C):
+        o, v = shape.head_offsets[c], shape.vocabs[c]
+        logits[:, o:o + v] = torch.randn(B, v, device="cuda").to(torch.bfloat16)
+    sm = SamplerSetup(shape, [True] * C, [dict(cfg) for _ in range(C)])
+    seen = torch.zeros((B, sm.words_per_row), dtype=torch.int32, device="cuda")
+    step = torch.full((1,), 9, dtype=torch.int32, device="cuda")
+    toks = torch.zeros((B, C), dtype=torch.int64, device="cuda")
+    sws = torch.zeros(eng.L.mtts_sample8_workspace_bytes(B, C), dtype=torch.uint8, device="cuda")
+    seed_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
+    eng.err.zero_()
+    top50 = logits[:, o0:o0 + shape.vocabs[0]].float().topk(50, dim=-1)
+    for s in range(8):
+        seed_dev.fill_(1000 + s)
+        _lib.check(eng.L.mtts_sample8(logits.data_ptr(), logits.stride(0), B, ctypes.byref(sm.cfg), seen.data_ptr(),
+                                      step.data_ptr(), seed_dev.data_ptr(), toks.data_ptr(), eng.err.data_ptr(),
+                                      sws.data_ptr(), sws.numel(), _lib.stream_ptr()))
+        got = toks.cpu()
+        assert eng.err.cpu().sum().item() == 0, eng.err.cpu().tolist()
+        for b in range(B):
+            t0 = int(got[b, 0])
+            # inside the top 50 (ties with the 50th value are kept by HF's top-k, so compare values)
+            assert float(logits[b, o0 + t0]) >= float(top50.values[b, -1]), (b, t0)
