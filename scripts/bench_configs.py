@@ -1,5 +1,5 @@
 """Timings of the BASELINE.json configurations that are not the bench.py line (C2 codec round trip, C4 long-form
-KV-bound decode, C5 batch-256 decode + codec), on one GPU, synthetic data. Writes gpurun_out/r01_configs.json."""
+KV-bound decode, C5 batch-256 decode + codec), on one GPU, synthetic data. Writes gpurun_out/configs.json."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, yaml
@@ -95,7 +95,7 @@ def main():
     res["C5_e2e_b256_375frames_1gpu"] = dict(seconds=dt, audio_s_per_s=256 * 30 / dt, samples_per_item=int(w[0].numel()))
     print("C5 e2e", res["C5_e2e_b256_375frames_1gpu"], flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open("gpurun_out/r01_configs.json", "w"), indent=1)
+    json.dump(res, open("gpurun_out/configs.json", "w"), indent=1)
 
 
 if __name__ == "__main__":
