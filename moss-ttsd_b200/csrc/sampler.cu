@@ -205,10 +205,14 @@ __global__ void __launch_bounds__(kThreads, 2) sample_scan_kernel(const SamplePa
   float bv = -INFINITY;
   int bi = 0x7fffffff;
   if (!greedy) {
-    scores8(sc, j0, V, sv);
+    for (int q = 0; q < p.chunk; ++q) {  // `chunk` pieces of 4096 logits per CTA at large batch (fewer, fatter CTAs)
+      const int jq = j0 + q * kSlice;
+      if (jq >= V) break;
+      scores8(sc, jq, V, sv);
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (j0 + e < V && better(sv[e], j0 + e, bv, bi)) { bv = sv[e]; bi = j0 + e; }
+      for (int e = 0; e < 8; ++e)
+        if (jq + e < V && better(sv[e], jq + e, bv, bi)) { bv = sv[e]; bi = jq + e; }
+    }
   } else {
     // Greedy: the scan is issue-bound (ncu: 386 instructions per warp for 8 logits per thread), so a group of 8 raw
     // logits is first reduced with plain max and only searched for its index when it beats the running best; groups
@@ -274,7 +278,8 @@ __global__ void __launch_bounds__(kThreads, 2) sample_scan_kernel(const SamplePa
     if (lane < 16) p.ws.reported[((long long)b * kMaxSlices + blockIdx.y) * kReport + wid * 16 + lane] = v;
     wmax = __shfl_sync(0xffffffffu, v, 0);
   }
-  if (!greedy && S > 1) {
+  const bool need_mass = !greedy && S > 1 && cfg.top_k[c] <= 0;  // only a nucleus over the WHOLE vocabulary needs the row's softmax mass
+  if (need_mass) {
     // slice softmax statistics (needed for top-p over the full vocabulary when no top-k precedes it)
     if ((tid & 31) == 0) s_val[tid >> 5] = wmax;
     __syncthreads();
@@ -282,9 +287,14 @@ __global__ void __launch_bounds__(kThreads, 2) sample_scan_kernel(const SamplePa
 #pragma unroll
     for (int w = 1; w < kThreads / 32; ++w) smax = fmaxf(smax, s_val[w]);
     float se = 0.f;
+    for (int q = 0; q < p.chunk; ++q) {
+      const int jq = j0 + q * kSlice;
+      if (jq >= V) break;
+      scores8(sc, jq, V, sv);
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (j0 + e < V && sv[e] > -INFINITY) se += expf(sv[e] - smax);
+      for (int e = 0; e < 8; ++e)
+        if (jq + e < V && sv[e] > -INFINITY) se += expf(sv[e] - smax);
+    }
     __shared__ float s_red[33];
     se = block_sum(se, s_red);
     if (tid == 0) {
@@ -320,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 2) sample_scan_kernel(const SamplePa
   // it using the GLOBAL softmax mass (flagged if the nucleus does not fit).
   float thr = -INFINITY;
   int k = cfg.top_k[c] > 0 ? min(cfg.top_k[c], V) : V;
-  if (S > 1) {
+  if (need_mass) {
     float gm = -INFINITY;
     for (int t = 0; t < S; ++t) gm = fmaxf(gm, __ldcg(p.ws.slice_val + bc * kMaxSlices + t));
     float gz = 0.f;
@@ -382,7 +392,7 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
   const ScoreCtx sc = make_ctx(p, b, c, step);
   const long long bc = (long long)b * cfg.channels + c;
   const float thr = __ldcg(p.ws.thr + bc * 4);
-  const int j0 = slice * kSlice + tid * 8;
+  const int j0 = slice * p.chunk * kSlice + tid * 8;
   float sv[8];
   scores8(sc, j0, V, sv);
   int n, npad = 1;
@@ -408,15 +418,20 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
     for (int t = n + tid; t < npad; t += kThreads) { s_val[t] = -INFINITY; s_idx[t] = -1; }
     __syncthreads();
   } else {
+    for (int q = 0; q < p.chunk; ++q) {
+      const int jq = j0 + q * kSlice;
+      if (jq >= V) break;
+      if (q > 0) scores8(sc, jq, V, sv);
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (j0 + e < V && sv[e] >= thr) {
-        const int pos = atomicAdd(p.ws.cand_count + bc, 1);
-        if (pos < kCap) {
-          __stcg(p.ws.cand_val + bc * kCap + pos, sv[e]);
-          __stcg(p.ws.cand_idx + bc * kCap + pos, j0 + e);
+      for (int e = 0; e < 8; ++e)
+        if (jq + e < V && sv[e] >= thr) {
+          const int pos = atomicAdd(p.ws.cand_count + bc, 1);
+          if (pos < kCap) {
+            __stcg(p.ws.cand_val + bc * kCap + pos, sv[e]);
+            __stcg(p.ws.cand_idx + bc * kCap + pos, jq + e);
+          }
         }
-      }
+    }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -788,9 +803,11 @@ extern "C" int mtts_sample8_rows(const void* logits, long long ld, int B, const 
   for (int c = 0; c < cfg->channels; ++c) any_sample |= cfg->do_sample[c] != 0;
   // sampled channels keep one piece per CTA (their threshold search reports per-thread maxima of one piece)
   // batch 256: 127 us with one piece per CTA, 87 / 68 / 62 / 63 us with 2 / 4 / 8 / 16; batch 64: 34 / 24 / 20 / 19 / 20 us
-  int chunk = any_sample ? 1 : (B >= 128 ? 8 : B >= 32 ? 4 : B >= 16 ? 2 : 1);
+  // pieces of 4096 logits per CTA: a sampled step at batch 256 is 11 520 slice CTAs whose fixed cost (launch, ticket,
+  // fence) dominates; four pieces per CTA leave 10 CTAs per 152,697-way row
+  int chunk = any_sample ? (B >= 64 ? 4 : B >= 16 ? 2 : 1) : (B >= 128 ? 8 : B >= 32 ? 4 : B >= 16 ? 2 : 1);
   if (const char* e = getenv("MTTS_SAMPLE_CHUNK")) {  // experiment knob (scripts/bench_sampler.py)
-    if (!any_sample && atoi(e) >= 1 && atoi(e) <= 38) chunk = atoi(e);
+    if (atoi(e) >= 1 && atoi(e) <= (any_sample ? 8 : 38)) chunk = atoi(e);
   }
   p.chunk = chunk;
   for (int c = 0; c < cfg->channels; ++c) {
