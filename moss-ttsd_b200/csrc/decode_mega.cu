@@ -59,6 +59,10 @@ constexpr int kMaxB = 4;
 constexpr int kActPitch = kI + 8;             // bf16 elements; rows 12304 B apart -> conflict-free B-fragment loads
 constexpr int kWsStride = kD + 4;             // attention partial: [M, L, -, -, O[128]] (one LL word per float)
 constexpr int kTagsPerLayer = 8;
+#ifndef MTTS_MEGA_KV_DEPTH
+#define MTTS_MEGA_KV_DEPTH 1
+#endif
+constexpr int kKvDepth = MTTS_MEGA_KV_DEPTH;  // attention passes (32 keys) in flight per unit
 
 constexpr int kRedTile = kTileRows * kMaxB;   // floats one warp contributes to the tile reduction
 constexpr int kMaxCtas = 160;
@@ -114,6 +118,22 @@ __device__ __forceinline__ void mma_16x8x16(float (&c)[4], const uint32_t (&a)[4
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// K/V rows are read with an L2 evict_last hint: the weight stream (evict_first) pushes 3.5 GB through L2 every step and
+// keeps the DRAM queues full, so a K/V load that misses L2 waits behind ~19 MB of outstanding bulk copies.
+#ifndef MTTS_MEGA_KV_EVICT_LAST
+#define MTTS_MEGA_KV_EVICT_LAST 1
+#endif
+__device__ __forceinline__ uint4 ld_kv(const void* p) {
+#if MTTS_MEGA_KV_EVICT_LAST
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(kEvictLast));
+  return r;
+#else
+  return ld_nc_v4(p);
+#endif
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -161,6 +181,8 @@ __device__ __forceinline__ void ll_issue2(const uint2* p, uint32_t& d0, uint32_t
   d1 = (uint32_t)v1; t1 = (uint32_t)(v1 >> 32);
 }
 __shared__ uint32_t s_launch_key;  // tag0 + 1 of this launch
+// tags of layer l's words: +1 qkv, +2 attention partials, +3 x after o_proj, +4 h, +5 x after down
+__device__ __forceinline__ uint32_t layer_tag(int l) { return s_launch_key - 1u + (uint32_t)l * kTagsPerLayer; }
 struct LLSpin {
   uint32_t spins = 0;
   // true: give up (this launch has been aborted)
@@ -216,6 +238,32 @@ __device__ __noinline__ void sentinel_wait(const uint2* base, const int* offs, i
   }
 }
 
+// ---- shared-memory layout. The phase routines are not inlined (the step's code must stay within the instruction
+// cache), and anything handed to them by reference or beyond the register-passed arguments travels through the LOCAL
+// stack frame: 544 threads' frames do not fit the 60 KB of L1 the ring leaves over, and an LDL that misses sits at the
+// head of every phase. So the routines take two or three scalar arguments and find everything else here.
+extern __shared__ __align__(128) uint8_t mega_smem[];
+__shared__ MegaParams s_params;
+__shared__ Slice s_sl[5];  // this CTA's shares of the four per-layer matrices and of the LM heads
+// Ring chunks / 16-row tiles this CTA consumes before matrix m of a layer ([4] = per layer): the consumer's ring
+// position and reduction buffer follow from (layer, matrix), so no loop-carried state has to survive the phase calls
+// (values that live across a call are spilled to the stack frame: see above).
+__shared__ int s_cpre[5], s_tpre[5];
+__shared__ int s_unit;  // attention unit of this CTA, or -1
+__device__ __forceinline__ bf16* sm_act() { return reinterpret_cast<bf16*>(mega_smem + kSmemRing); }
+__device__ __forceinline__ float* sm_red() { return reinterpret_cast<float*>(mega_smem + kSmemRing + kSmemAct); }
+__device__ __forceinline__ uint64_t* sm_full() {
+  return reinterpret_cast<uint64_t*>(mega_smem + kSmemRing + kSmemAct + kSmemRed);
+}
+__device__ __forceinline__ uint64_t* sm_empty() { return sm_full() + kStages; }
+__device__ __forceinline__ float* sm_scratch() { return reinterpret_cast<float*>(sm_empty() + kStages + 2); }  // [16][kMaxB]
+__device__ __forceinline__ float* sm_res(int which) {  // [kMaxB][16] raw residual values of this CTA's o_proj (0) / down (1) rows
+  return sm_scratch() + kCW * kMaxB + which * (kMaxB * 16);
+}
+__device__ __forceinline__ float* sm_rope() { return sm_scratch() + kCW * kMaxB + 2 * (kMaxB * 16); }  // [128]
+// sentinel word offsets per producer CTA: 0 = o_proj output, 1 = down output, 2 = SwiGLU output
+__device__ __forceinline__ int* sm_sent(int which) { return reinterpret_cast<int*>(sm_rope() + 128) + which * kMaxCtas; }
+
 struct Ring {
   uint8_t* stages;
   uint64_t* full;
@@ -245,16 +293,25 @@ __device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
 // The loop is issue-bound if it is not kept lean (4 warps per scheduler, 64 KB of weights per trip): no modulo, no
 // select, no bookkeeping inside.
 template <int kB>
-__device__ __noinline__ void consume_matrix(Ring& rg, const MegaParams& p, Slice s, int kch, int epi, const bf16* act,
-                                            float* red, int& red_buf, uint2* out, int out_wpr, const float* res,
-                                            uint32_t tag) {
+__device__ __noinline__ void consume_matrix(int l, int epi) {
+  const MegaParams& p = s_params;
+  const Slice s = s_sl[epi];
+  const int kch = epi == EPI_WD ? kI / kChunkK : kH / kChunkK;
+  const bf16* act = sm_act();
+  float* red = sm_red();
+  const int m4 = epi & 3;  // the LM heads (epi 4) come first in "layer" num_layers
+  int red_buf = (l * s_tpre[4] + s_tpre[m4]) & 1;
+  Ring rg{mega_smem, sm_full(), sm_empty(), (uint32_t)(l * s_cpre[4] + s_cpre[m4])};
+  const uint32_t tag = layer_tag(l) + (epi == EPI_QKV ? 1u : (epi == EPI_WO ? 3u : (epi == EPI_GU ? 4u : 5u)));
+  uint2* out = epi == EPI_QKV ? p.qkv_ll : (epi == EPI_WO ? p.x_ll[1] : (epi == EPI_GU ? p.h_ll : p.x_ll[0]));
+  const int out_wpr = epi == EPI_QKV ? kNQKV / 2 : (epi == EPI_GU ? kI / 2 : kH / 2);
+  const float* res = sm_res(epi == EPI_WD ? 1 : 0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const uint32_t a_off = (uint32_t)((lane & 15) * kRowPitch + (warp * 64 + (lane >> 4) * 8) * 2);
   const bf16* b_src = g < kB ? act + g * kActPitch + warp * 64 + 2 * t : act + kMaxB * kActPitch + 2 * t;
   const int kmul = g < kB ? kChunkK : 0;
   uint32_t st = rg.it % kStages, par = (rg.it / kStages) & 1;
-  uint32_t n_done = 0;
   // B fragments (k16 x n8, "col") of this warp's 64-wide k slice of two chunks: batch row g, k = 2t,2t+1 and +8
   uint32_t bq[8][2];
   auto load_bq = [&](int kg) {
@@ -283,7 +340,6 @@ __device__ __noinline__ void consume_matrix(Ring& rg, const MegaParams& p, Slice
         __syncwarp();
         if (lane == 0) mbar_arrive(&rg.empty[st]);
         if (++st == kStages) { st = 0; par ^= 1; }
-        ++n_done;
       }
     }
     // 16-warp reduction of the [16 rows x 4 batch] tile (accumulator columns 2t, 2t+1; only t < 2 are real rows)
@@ -317,17 +373,28 @@ __device__ __noinline__ void consume_matrix(Ring& rg, const MegaParams& p, Slice
     }
     red_buf ^= 1;
   }
-  rg.it += n_done;
 }
 
 // Stage B rows of 2048 elements (LL words, or the plain embedding sum) into act with RMSNorm on the way (every CTA
 // does it redundantly: 8 KB per row from L2):
 //   v = mean(x^2); y = bf16(x * rsqrt(v + eps)); out = bf16(w * y)        (lm_ops.cu rmsnorm_kernel)
 // The raw values of rows [keep.r0, keep.r1) are kept in `res` for the residual add of the following projection.
+// `which`: 0 = layer input (x after down / the embedding sum) -> ln1, residual rows of the o_proj share kept;
+//          1 = x after o_proj -> ln2, residual rows of the down share kept;   2 = final norm (nothing kept)
 template <int kB>
-__device__ __noinline__ void stage_norm(const MegaParams& p, const uint2* src_ll, uint32_t tag, const int* sent, int n_gemv,
-                                        const bf16* x_plain, const bf16* __restrict__ w, bf16* act, float* scratch,
-                                        Slice keep, float* res) {
+__device__ __noinline__ void stage_norm(int which, int l) {
+  const MegaParams& p = s_params;
+  const uint32_t tag = which == 1 ? layer_tag(l) + 3u : layer_tag(l) - kTagsPerLayer + 5u;
+  const bf16* __restrict__ w = which == 2 ? p.final_norm
+                                          : reinterpret_cast<const bf16*>(which == 0 ? p.layers[l].ln1 : p.layers[l].ln2);
+  const bf16* x_plain = (which == 0 && l == 0) ? p.x_in : nullptr;
+  const uint2* src_ll = p.x_ll[which == 1 ? 1 : 0];
+  const int* sent = sm_sent(which == 1 ? 0 : 1);
+  const int n_gemv = (int)gridDim.x;
+  bf16* act = sm_act();
+  float* scratch = sm_scratch();
+  const Slice keep = which == 2 ? Slice{0, 0} : s_sl[which == 0 ? 1 : 3];
+  float* res = sm_res(which == 1 ? 1 : 0);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint2 xv[kB];
   const uint2 wv = *reinterpret_cast<const uint2*>(w + tid * 4);
@@ -383,7 +450,12 @@ __device__ __noinline__ void stage_norm(const MegaParams& p, const uint2* src_ll
 
 // Stage the B rows of the SwiGLU output (6144 elements each) into act, unchanged.
 template <int kB>
-__device__ __noinline__ void stage_h(const MegaParams& p, uint32_t tag, const int* sent, int n_gemv, bf16* act) {
+__device__ __noinline__ void stage_h(int l) {
+  const MegaParams& p = s_params;
+  const uint32_t tag = layer_tag(l) + 4u;
+  const int* sent = sm_sent(2);
+  const int n_gemv = (int)gridDim.x;
+  bf16* act = sm_act();
   const int tid = threadIdx.x, warp = tid >> 5;
   if (p.sentinel) {
     if (warp == 0) sentinel_wait(p.h_ll + (size_t)(kB - 1) * (kI / 2), sent, n_gemv, tag);
@@ -413,7 +485,10 @@ __device__ __noinline__ void stage_h(const MegaParams& p, uint32_t tag, const in
 
 // Merge the split-KV partials of the attention phase into act[b][head*128 + d] (bf16, as the o_proj input).
 template <int kB>
-__device__ __noinline__ void stage_attn_out(const MegaParams& p, bf16* act, uint32_t tag) {
+__device__ __noinline__ void stage_attn_out(int l) {
+  const MegaParams& p = s_params;
+  const uint32_t tag = layer_tag(l) + 2u;
+  bf16* act = sm_act();
   const int units = kB * kHkv * p.nsplit;
   if (p.sentinel && (threadIdx.x >> 5) == 0) {  // sentinel: the last O word of head g = 1 of every unit
     const int lane = threadIdx.x & 31;
@@ -497,18 +572,28 @@ struct AttnUnit {
   int b, hk, pos, k_begin, k_end, owner;  // k_end excludes the new key
 };
 struct AttnLayer { const bf16 *k_pool, *v_pool, *q_norm, *k_norm; };
+// Per-CTA constants of the attention unit and the current layer's pointers live in SHARED memory, not in the kernel's
+// stack frame: a struct handed to a non-inlined phase routine by reference is read back with LDL, the 544 threads' frames
+// do not fit the 60 KB of L1 the ring leaves over, and an LDL that misses L1 sits in front of every K/V address (measured:
+// ~1400 cycles per 32-key pass, which deeper K/V prefetching did not shorten).
+__shared__ AttnUnit s_un;
+__shared__ AttnLayer s_al;
 
-// one key row (this lane's 8 dims of K and V) folded into the online-softmax state of both q heads
-__device__ __forceinline__ void attn_fold(const float (&qf)[kG][8], uint4 kq, uint4 vq, bool valid, unsigned mask,
+// one key row (this lane's 8 dims of K and V) folded into the online-softmax state of both q heads. q (normed, roped,
+// pre-scaled) is re-read from shared memory in every pass: holding it in 16 registers next to the accumulators leaves no
+// room under the 96-register cap (17 warps) for a second K/V pass in flight.
+__device__ __forceinline__ void attn_fold(const float* s_qs, uint4 kq, uint4 vq, bool valid, unsigned mask,
                                        float (&m)[kG], float (&l)[kG], float (&acc)[kG][8]) {
   float kf[8], vf[8];
   unpack8(kq, kf);
   unpack8(vq, vf);
 #pragma unroll
   for (int g = 0; g < kG; ++g) {
-    float s = 0.f;
-#pragma unroll
-    for (int d = 0; d < 8; ++d) s = fmaf(qf[g][d], kf[d], s);
+    const float4 q0 = *reinterpret_cast<const float4*>(s_qs + g * kD);
+    const float4 q1 = *reinterpret_cast<const float4*>(s_qs + g * kD + 4);
+    float s = q0.x * kf[0];
+    s = fmaf(q0.y, kf[1], s); s = fmaf(q0.z, kf[2], s); s = fmaf(q0.w, kf[3], s);
+    s = fmaf(q1.x, kf[4], s); s = fmaf(q1.y, kf[5], s); s = fmaf(q1.z, kf[6], s); s = fmaf(q1.w, kf[7], s);
     s += __shfl_xor_sync(mask, s, 8);
     s += __shfl_xor_sync(mask, s, 4);
     s += __shfl_xor_sync(mask, s, 2);
@@ -523,8 +608,14 @@ __device__ __forceinline__ void attn_fold(const float (&qf)[kG][8], uint4 kq, ui
   }
 }
 
-__device__ __noinline__ void attention_layer(const MegaParams& p, const AttnLayer& L, const AttnUnit& un, int unit,
-                                                float* scr, const float* rope, uint32_t tag_in, uint32_t tag_out) {
+__device__ __noinline__ void attention_layer(int layer) {
+  const MegaParams& p = s_params;
+  const int unit = s_unit;
+  const uint32_t tag_in = layer_tag(layer) + 1u, tag_out = layer_tag(layer) + 2u;
+  float* scr = reinterpret_cast<float*>(sm_act());
+  const float* rope = sm_rope();
+  const AttnUnit un = s_un;
+  const AttnLayer L = s_al;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* s_q = scr;                 // [2][128] normed + roped q (bf16-rounded values)
   float* s_k = scr + 2 * kD;        // [128]
@@ -535,6 +626,18 @@ __device__ __noinline__ void attention_layer(const MegaParams& p, const AttnLaye
   const long long head_off = ((long long)hk << p.page_shift) * kD;
   const long long page_stride = ((long long)kHkv << p.page_shift) * kD;
   const int l16 = lane & 15, rgp = warp * 2 + (lane >> 4);
+#ifdef MTTS_MEGA_PROFILE
+  const bool prof = p.prof != nullptr && blockIdx.x == 0 && tid == 0;
+  long long tprev = prof ? clock64() : 0;
+#define ATTN_TICK(slot)                     \
+  if (prof) {                               \
+    const long long tn = clock64();         \
+    s_prof[slot] += tn - tprev;             \
+    tprev = tn;                             \
+  }
+#else
+#define ATTN_TICK(slot)
+#endif
 
   auto kv_offset = [&](int key) {
     key = min(key, k_end - 1);  // clamp: the load is always legal, the score is masked
@@ -542,12 +645,21 @@ __device__ __noinline__ void attention_layer(const MegaParams& p, const AttnLaye
     const int page = p.block_table ? __ldg(p.block_table + (long long)b * p.max_pages + lp) : b * p.max_pages + lp;
     return (long long)page * page_stride + head_off + (long long)(key & page_mask) * kD + l16 * 8;
   };
-  uint4 kq = make_uint4(0, 0, 0, 0), vq = kq;
-  if (un.k_begin < k_end) {  // in flight while q/k/v of the new token arrive
-    const long long off = kv_offset(un.k_begin + rgp);
-    kq = ld_nc_v4(L.k_pool + off);
-    vq = ld_nc_v4(L.v_pool + off);
+  // The first kKvDepth passes (32 keys each) are requested before the unit starts waiting for q: a pass costs one
+  // DRAM / L2 round trip (~1400 cycles under the weight stream), so with one pass in flight the key loop is a chain
+  // of round trips (measured: 5850 cycles for 4 passes); with all of them in flight it is one.
+  uint4 kb[kKvDepth], vb[kKvDepth];
+#pragma unroll
+  for (int i = 0; i < kKvDepth; ++i) {
+    kb[i] = make_uint4(0, 0, 0, 0);
+    vb[i] = kb[i];
+    if (un.k_begin + 32 * i < k_end) {
+      const long long off = kv_offset(un.k_begin + 32 * i + rgp);
+      kb[i] = ld_kv(L.k_pool + off);
+      vb[i] = ld_kv(L.v_pool + off);
+    }
   }
+  ATTN_TICK(16)
 
   if (warp < 4) {
     const int col = warp < 2 ? (hk * kG + warp) * kD : (warp == 2 ? kHq * kD + hk * kD : (kHq + kHkv) * kD + hk * kD);
@@ -578,6 +690,7 @@ __device__ __noinline__ void attention_layer(const MegaParams& p, const AttnLaye
         if (sp.miss(tag_in)) break;
       }
     }
+    ATTN_TICK(17)
     float x0 = bf16lo(a), x1 = bf16hi(a), x2 = bf16lo(c), x3 = bf16hi(c);
     float* so = warp < 2 ? s_q + warp * kD : (warp == 2 ? s_k : s_v);
     if (warp != 3) {
@@ -596,19 +709,18 @@ __device__ __noinline__ void attention_layer(const MegaParams& p, const AttnLaye
       const float o3 = bf16_round(bf16_round(x3 * c1) + bf16_round(x1 * s1));
       x0 = o0; x1 = o1; x2 = o2; x3 = o3;
     }
-    so[2 * lane] = x0; so[2 * lane + 1] = x1; so[64 + 2 * lane] = x2; so[65 + 2 * lane] = x3;
+    const float qs = warp < 2 ? p.scale_log2 : 1.0f;  // q is stored pre-scaled (softmax scale * log2 e)
+    so[2 * lane] = x0 * qs; so[2 * lane + 1] = x1 * qs; so[64 + 2 * lane] = x2 * qs; so[65 + 2 * lane] = x3 * qs;
     if (dst) {
       *reinterpret_cast<uint32_t*>(dst + 2 * lane) = pack_bf16(x0, x1);
       *reinterpret_cast<uint32_t*>(dst + 64 + 2 * lane) = pack_bf16(x2, x3);
     }
   }
+  ATTN_TICK(18)
   consumer_sync();
+  ATTN_TICK(19)
 
-  float qf[kG][8];
-#pragma unroll
-  for (int g = 0; g < kG; ++g)
-#pragma unroll
-    for (int d = 0; d < 8; ++d) qf[g][d] = s_q[g * kD + l16 * 8 + d] * p.scale_log2;
+  const float* s_qs = s_q + l16 * 8;  // this lane's 8 dims of both (pre-scaled) q heads
   float m[kG], l[kG], acc[kG][8];
 #pragma unroll
   for (int g = 0; g < kG; ++g) {
@@ -618,24 +730,28 @@ __device__ __noinline__ void attention_layer(const MegaParams& p, const AttnLaye
   }
 #pragma unroll 1
   for (int key = un.k_begin + rgp; key - rgp < k_end; key += 32) {
-    uint4 kn = kq, vn = vq;
-    if (key - rgp + 32 < k_end) {  // next pass in flight
-      const long long off = kv_offset(key + 32);
-      kn = ld_nc_v4(L.k_pool + off);
-      vn = ld_nc_v4(L.v_pool + off);
+    const uint4 kq = kb[0], vq = vb[0];
+#pragma unroll
+    for (int i = 0; i + 1 < kKvDepth; ++i) {
+      kb[i] = kb[i + 1];
+      vb[i] = vb[i + 1];
     }
-    attn_fold(qf, kq, vq, key < k_end, 0xffffffffu, m, l, acc);
-    kq = kn;
-    vq = vn;
+    if (key - rgp + 32 * kKvDepth < k_end) {  // keep kKvDepth passes in flight
+      const long long off = kv_offset(key + 32 * kKvDepth);
+      kb[kKvDepth - 1] = ld_kv(L.k_pool + off);
+      vb[kKvDepth - 1] = ld_kv(L.v_pool + off);
+    }
+    attn_fold(s_qs, kq, vq, key < k_end, 0xffffffffu, m, l, acc);
   }
   if (un.owner && rgp == 0) {  // the new token's key/value (never read back from global memory)
     const uint4 kn = make_uint4(pack_bf16(s_k[l16 * 8], s_k[l16 * 8 + 1]), pack_bf16(s_k[l16 * 8 + 2], s_k[l16 * 8 + 3]),
                                 pack_bf16(s_k[l16 * 8 + 4], s_k[l16 * 8 + 5]), pack_bf16(s_k[l16 * 8 + 6], s_k[l16 * 8 + 7]));
     const uint4 vn = make_uint4(pack_bf16(s_v[l16 * 8], s_v[l16 * 8 + 1]), pack_bf16(s_v[l16 * 8 + 2], s_v[l16 * 8 + 3]),
                                 pack_bf16(s_v[l16 * 8 + 4], s_v[l16 * 8 + 5]), pack_bf16(s_v[l16 * 8 + 6], s_v[l16 * 8 + 7]));
-    attn_fold(qf, kn, vn, true, 0x0000ffffu, m, l, acc);  // s_k / s_v hold bf16-rounded values: the packing is exact
+    attn_fold(s_qs, kn, vn, true, 0x0000ffffu, m, l, acc);  // s_k / s_v hold bf16-rounded values: the packing is exact
   }
   __syncwarp();
+  ATTN_TICK(20)
   // merge the two half-warps, then the 16 warps
 #pragma unroll
   for (int g = 0; g < kG; ++g) {
@@ -679,6 +795,8 @@ __device__ __noinline__ void attention_layer(const MegaParams& p, const AttnLaye
     }
   }
   consumer_sync();
+  ATTN_TICK(21)
+#undef ATTN_TICK
 }
 
 __device__ __noinline__ void rope_table(float pos, const float* inv_freq, float* rope) {
@@ -696,26 +814,19 @@ __device__ __noinline__ void rope_table(float pos, const float* inv_freq, float*
 // ------------------------------------------------------------------ the kernel
 template <int kB>
 __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaParams p_in) {
-  // The parameter block is handed to the (non-inlined) phase routines by reference. A reference to the kernel argument
-  // would make the compiler keep a per-thread copy in LOCAL memory (a 400-byte stack frame per thread, served by
-  // whatever L1 the 227 KB of shared memory leave over); one shared copy per CTA is read with LDS instead.
-  __shared__ MegaParams s_params;
+  // The (non-inlined) phase routines read the parameter block from one shared copy per CTA (LDS); a reference to the
+  // kernel argument would make the compiler keep a per-thread copy in LOCAL memory.
   if (threadIdx.x == 0) s_params = p_in;
   __syncthreads();
   const MegaParams& p = p_in;  // the kernel body itself reads the constant bank
-  extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* ring = smem;
-  bf16* act = reinterpret_cast<bf16*>(smem + kSmemRing);
-  float* red = reinterpret_cast<float*>(smem + kSmemRing + kSmemAct);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemRing + kSmemAct + kSmemRed);
-  uint64_t* empty = full + kStages;
-  float* scratch = reinterpret_cast<float*>(empty + kStages + 2);  // [16][kMaxB]
-  float* res_wo = scratch + kCW * kMaxB;   // [kMaxB][16] raw residual values of this CTA's o_proj rows ...
-  float* res_wd = res_wo + kMaxB * 16;     // ... and of its down-projection rows
-  float* rope = res_wd + kMaxB * 16;       // [128]
-  int* sent_wo = reinterpret_cast<int*>(rope + 128);  // sentinel word offsets per producer CTA: o_proj output,
-  int* sent_wd = sent_wo + kMaxCtas;                   // down output,
-  int* sent_gu = sent_wd + kMaxCtas;                   // SwiGLU output
+  uint8_t* ring = mega_smem;
+  bf16* act = sm_act();
+  uint64_t* full = sm_full();
+  uint64_t* empty = sm_empty();
+  float* rope = sm_rope();
+  int* sent_wo = sm_sent(0);
+  int* sent_wd = sm_sent(1);
+  int* sent_gu = sm_sent(2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x;
@@ -738,6 +849,23 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
     g_mega_err = p.err_flag;
   }
 
+  // this CTA's shares (4 per-layer matrices + the LM heads): shared, because the producer indexes them dynamically and a
+  // dynamically indexed local array would live in the stack frame
+  if (tid < 4) s_sl[tid] = slice_rows(mat_rows(tid), mat_unit(tid), mat_rot(tid), cta, n_gemv);
+  if (tid == 4) s_sl[4] = slice_rows(p.vpad, 2, 0, cta, n_gemv);
+  if (tid == 5) {
+    int c = 0, t = 0;
+    for (int m = 0; m < 4; ++m) {
+      const Slice sm = slice_rows(mat_rows(m), mat_unit(m), mat_rot(m), cta, n_gemv);
+      const int tiles = (sm.r1 - sm.r0 + kTileRows - 1) / kTileRows;
+      s_cpre[m] = c;
+      s_tpre[m] = t;
+      c += tiles * ((m == 3 ? kI : kH) / kChunkK);
+      t += tiles;
+    }
+    s_cpre[4] = c;
+    s_tpre[4] = t;
+  }
   for (int c = tid; c < n_gemv; c += kThreads) {
     sent_wo[c] = last_tile_row(slice_rows(mat_rows(1), mat_unit(1), mat_rot(1), c, n_gemv)) >> 1;
     sent_wd[c] = last_tile_row(slice_rows(mat_rows(3), mat_unit(3), mat_rot(3), c, n_gemv)) >> 1;
@@ -745,11 +873,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
   }
   __syncthreads();
 
-  Ring rg{ring, full, empty, 0u};
-  Slice sl[4];
-#pragma unroll
-  for (int m = 0; m < 4; ++m) sl[m] = slice_rows(mat_rows(m), mat_unit(m), mat_rot(m), cta, n_gemv);
-  const Slice s_heads = slice_rows(p.vpad, 2, 0, cta, n_gemv);
+  Ring rg{ring, full, empty, 0u};  // (the producer's view; the consumers carry their chunk count in `cstate`)
+  const Slice* sl = s_sl;
+  const Slice s_heads = s_sl[4];
 
   if (warp == kCW) {
     // ---------------- producer warp: the CTA's share of every matrix of the step, in consumption order
@@ -794,22 +920,28 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
 #define MTTS_MEGA_UNIT_STRIDE 1
 #endif
   const bool has_unit = (cta % MTTS_MEGA_UNIT_STRIDE) == 0 && cta / MTTS_MEGA_UNIT_STRIDE < n_attn;
-  const int unit_id = cta / MTTS_MEGA_UNIT_STRIDE;
-  AttnUnit un;
+  if (tid == 0) s_unit = has_unit ? cta / MTTS_MEGA_UNIT_STRIDE : -1;
   if (has_unit) {
-    const int split = unit_id % p.nsplit;
-    un.hk = (unit_id / p.nsplit) % kHkv;
-    un.b = unit_id / (p.nsplit * kHkv);
-    un.pos = p.positions[un.b];
-    const int kv_len = un.pos + 1;
-    const int per = ((kv_len + p.nsplit - 1) / p.nsplit + 31) / 32 * 32;
-    un.k_begin = min(kv_len, split * per);
-    const int k_end = min(kv_len, un.k_begin + per);
-    un.owner = (un.pos >= un.k_begin && un.pos < k_end) ? 1 : 0;
-    un.k_end = min(k_end, un.pos);
-    if (warp == 0) rope_table((float)un.pos, p.inv_freq, rope);
+    const int unit_id = cta / MTTS_MEGA_UNIT_STRIDE;
+    const int b = unit_id / (p.nsplit * kHkv);
+    const int pos = p.positions[b];
+    if (tid == 0) {
+      AttnUnit un;
+      const int split = unit_id % p.nsplit;
+      un.hk = (unit_id / p.nsplit) % kHkv;
+      un.b = b;
+      un.pos = pos;
+      const int kv_len = pos + 1;
+      const int per = ((kv_len + p.nsplit - 1) / p.nsplit + 31) / 32 * 32;
+      un.k_begin = min(kv_len, split * per);
+      const int k_end = min(kv_len, un.k_begin + per);
+      un.owner = (pos >= un.k_begin && pos < k_end) ? 1 : 0;
+      un.k_end = min(k_end, pos);
+      s_un = un;
+    }
+    if (warp == 0) rope_table((float)pos, p.inv_freq, rope);
   }
-  int red_buf = 0;
+  // (s_unit, s_un, s_al and rope are first read behind the consumer barriers of the first phase)
 #ifdef MTTS_MEGA_PROFILE
   const bool prof = p.prof != nullptr && cta == 0 && tid == 0;
   long long tprev = prof ? clock64() : 0;
@@ -835,50 +967,44 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
 #else
 #define MEGA_TICK(slot)
 #endif
+  // Nothing but the layer index lives across the phase calls.
 #pragma unroll 1
-  for (int l = 0; l <= NL; ++l) {
-    // tags of layer l's words: +1 qkv, +2 attention partials, +3 x after o_proj, +4 h, +5 x after down
-    const uint32_t tg = tag0 + (uint32_t)l * kTagsPerLayer;
+  for (int l = 0; l < NL; ++l) {
     MEGA_TICK(13)
-    if (l == NL) {  // final norm + LM heads
-      stage_norm<kB>(s_params, p.x_ll[0], tg - kTagsPerLayer + 5, sent_wd, n_gemv, nullptr, p.final_norm, act, scratch, Slice{0, 0},
-                     res_wo);
-      MEGA_TICK(14)
-      consume_matrix<kB>(rg, s_params, s_heads, 2, EPI_HEADS, act, red, red_buf, nullptr, 0, nullptr, 0u);
-      MEGA_TICK(15)
-      break;
+    if (threadIdx.x == 0 && s_unit >= 0) {
+      const mtts_lm_layer& L = p.layers[l];
+      s_al = AttnLayer{reinterpret_cast<const bf16*>(L.k_pool), reinterpret_cast<const bf16*>(L.v_pool),
+                       reinterpret_cast<const bf16*>(L.q_norm), reinterpret_cast<const bf16*>(L.k_norm)};
     }
-    const mtts_lm_layer& L = p.layers[l];
-    stage_norm<kB>(s_params, p.x_ll[0], tg - kTagsPerLayer + 5, sent_wd, n_gemv, l == 0 ? p.x_in : nullptr,
-                   reinterpret_cast<const bf16*>(L.ln1), act, scratch, sl[1], res_wo);
+    stage_norm<kB>(0, l);
     MEGA_TICK(0)
-    consume_matrix<kB>(rg, s_params, sl[0], 2, EPI_QKV, act, red, red_buf, p.qkv_ll, kNQKV / 2, nullptr, tg + 1);
+    consume_matrix<kB>(l, EPI_QKV);
     MEGA_TICK(1)
-    if (has_unit) {
-      const AttnLayer al{reinterpret_cast<const bf16*>(L.k_pool), reinterpret_cast<const bf16*>(L.v_pool),
-                         reinterpret_cast<const bf16*>(L.q_norm), reinterpret_cast<const bf16*>(L.k_norm)};
-      attention_layer(s_params, al, un, unit_id, reinterpret_cast<float*>(act), rope, tg + 1, tg + 2);
-    }
+    if (s_unit >= 0) attention_layer(l);
     MEGA_TICK(3)
-    stage_attn_out<kB>(s_params, act, tg + 2);
+    stage_attn_out<kB>(l);
     MEGA_TICK(5)
-    consume_matrix<kB>(rg, s_params, sl[1], 2, EPI_WO, act, red, red_buf, p.x_ll[1], kH / 2, res_wo, tg + 3);
+    consume_matrix<kB>(l, EPI_WO);
     MEGA_TICK(6)
-    stage_norm<kB>(s_params, p.x_ll[1], tg + 3, sent_wo, n_gemv, nullptr, reinterpret_cast<const bf16*>(L.ln2), act, scratch, sl[3],
-                   res_wd);
+    stage_norm<kB>(1, l);
     MEGA_TICK(8)
-    consume_matrix<kB>(rg, s_params, sl[2], 2, EPI_GU, act, red, red_buf, p.h_ll, kI / 2, nullptr, tg + 4);
+    consume_matrix<kB>(l, EPI_GU);
     MEGA_TICK(9)
-    stage_h<kB>(s_params, tg + 4, sent_gu, n_gemv, act);
+    stage_h<kB>(l);
     MEGA_TICK(11)
-    consume_matrix<kB>(rg, s_params, sl[3], 6, EPI_WD, act, red, red_buf, p.x_ll[0], kH / 2, res_wd, tg + 5);
+    consume_matrix<kB>(l, EPI_WD);
     MEGA_TICK(12)
   }
+  MEGA_TICK(13)
+  stage_norm<kB>(2, p.num_layers);  // final norm + LM heads
+  MEGA_TICK(14)
+  consume_matrix<kB>(p.num_layers, EPI_HEADS);
+  MEGA_TICK(15)
 #undef MEGA_TICK
 #undef MEGA_TRACE
   // CTA 0 can only be here after it consumed words of every CTA, i.e. after every CTA has read tag_base
-  if (cta == 0 && tid == 0) {
-    *p.tag_base = tag0 + (uint32_t)(NL + 1) * kTagsPerLayer;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *p.tag_base = s_launch_key - 1u + (uint32_t)(p.num_layers + 1) * kTagsPerLayer;
 #ifdef MTTS_MEGA_PROFILE
     if (p.prof)
       for (int i = 0; i < 32; ++i) p.prof[i] += s_prof[i];
