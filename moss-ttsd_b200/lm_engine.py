@@ -548,7 +548,12 @@ class DecoderEngine:
         layers = torch.from_numpy(tab).to(self.dev)
         # one attention unit (row, kv head, key range) per CTA; measured best: 4 key ranges up to batch 3, 3 at batch 4
         # (~115 keys = 4 passes per unit at ctx 460; more ranges cost more partial reads in every CTA's o_proj phase)
+        # At batch 1 a longer context gets 8 ranges: every 32-key pass of a unit is a serial ~0.7 us step on the critical
+        # path of all 148 CTAs (ctx 880: 1.000 ms with 4 ranges, 0.975 with 6, 0.965 with 8; ctx 460: 0.885 / 0.906 /
+        # 0.889; batch 2 is best with 4 at both lengths). `ctx_hint` = prompt + new rows of the call that opens the session.
         nsplit = 4 if B <= 3 else 3
+        if B == 1 and getattr(self, "ctx_hint", 0) >= 700:
+            nsplit = 8
         if os.environ.get("MTTS_MEGA_NSPLIT"):
             nsplit = int(os.environ["MTTS_MEGA_NSPLIT"])
         ws = torch.zeros(self.L.mtts_decode_mega_workspace_bytes(B, nsplit) + 256, dtype=torch.uint8, device=self.dev)

@@ -436,6 +436,7 @@ class AsteroidTTSInstruct:
             rows_cap = max_rows if not getattr(self, "session_headroom", True) else max(max_rows, 1024)
             cache = KVCache(self.shape, B, rows_cap + 1, dev, paged=self.kv_paged, page_size=self.kv_page_size,
                             shuffle_pages=self.kv_paged)
+            eng.ctx_hint = max_rows   # rows this call will reach (the session's KV capacity may be larger)
             st = eng.make_decode_state(B, cache, sampler, rows_cap, tuple(self.config.speech_token_range), int(eos_fill),
                                        has_eos)
             if eos_at is not None:

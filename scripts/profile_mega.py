@@ -19,7 +19,7 @@ def main():
     m.generation_config.eos_token_id = 152694
     rng = np.random.default_rng(0)
     for B in [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "1,8").split(",")]:
-        ids, mask = make_prompt(rng, B, 200, 250)
+        ids, mask = make_prompt(rng, B, int(os.environ.get("MTTS_PROFILE_TEXT_ROWS", "200")), 250)
         ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
         m.generate(input_ids=ids, attention_mask=mask, max_new_tokens=8)
         st = m._last_state
