@@ -180,7 +180,10 @@ int mtts_sampler_init_history(const long long* ids, int B, int rows, long long r
  * top-k -> top-p -> multinomial (Philox, stream = (*seed_ptr, step, row, channel); the seed lives in device memory so
  * that a captured CUDA graph can be replayed with a new seed) or argmax. out_tokens [B, channels] int64.
  * *step_ptr is the device-resident step counter s (0 = first generated row). `workspace`: mtts_sample8_workspace_bytes()
- * bytes, zero-filled once by the caller (the kernels leave it clean); logits rows and per-channel offsets 16-byte aligned. */
+ * bytes, zero-filled once by the caller (the kernels leave it clean); logits rows and per-channel offsets 16-byte aligned.
+ * Every HF combination is accepted: a channel wider than the 2048-entry candidate list (the 152,697-way text channel) with
+ * top_k > 512, with no filter at all, or with a nucleus that outgrows the list is drawn by an exact multi-pass kernel
+ * (radix-select top-k, bisection top-p, inverse CDF) instead of the candidate-list fast path. */
 size_t mtts_sample8_workspace_bytes(int B, int channels);
 int mtts_sample8(const void* logits, long long ld, int B, const mtts_sampler_config* cfg, const uint32_t* seen,
                  const int* step_ptr, const unsigned long long* seed_ptr, long long* out_tokens, int* err_flag,

@@ -101,6 +101,7 @@ struct SampleWs {
   float* thr;         // [B][C][4]: threshold, global max, global sum of exp(score - max), unused
   int* tickets;       // [B][C][2]  (scan, finish) zero between launches
   int* cand_count;    // [B][C]     zero between launches
+  int* redo;          // [B][C]     set by the finish phase when a nucleus does not fit the candidate list; cleared by sample_exact
   float* cand_val;    // [B][C][kCap]
   int* cand_idx;      // [B][C][kCap]
 };
@@ -117,6 +118,8 @@ struct SampleParams2 {
   int* err_flag;
   SampleWs ws;
   int total_slices;
+  unsigned int exact_mask;  // channels sampled by sample_exact_kernel alone (wide top-k / no filter on a wide vocabulary)
+  unsigned char exact_channels[8];  // the channels sample_exact_kernel is launched for (vocab > kCap, sampled)
   int chunk;  // kSlice-wide pieces one CTA scans (> 1 only when every channel is greedy and the batch is large)
   unsigned char slice_channel[kMaxSlices];
   unsigned char slice_index[kMaxSlices];
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(kThreads, 2) sample_scan_kernel(const SamplePa
   pdl_wait();
   const int b = blockIdx.x, c = p.slice_channel[blockIdx.y], slice = p.slice_index[blockIdx.y];
   const mtts_sampler_config& cfg = p.cfg;
+  if ((p.exact_mask >> c) & 1u) return;  // sampled by sample_exact_kernel
   const int V = cfg.vocab[c], S = p.slices_of[c];
   const int tid = threadIdx.x;
   const int step = *p.step_ptr - (p.row_ctl ? p.row_ctl[b * 4] : 0);
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
   pdl_wait();
   const int b = blockIdx.x, c = p.slice_channel[blockIdx.y], slice = p.slice_index[blockIdx.y];
   const mtts_sampler_config& cfg = p.cfg;
-  if (!cfg.do_sample[c]) return;
+  if (!cfg.do_sample[c] || ((p.exact_mask >> c) & 1u)) return;
   const int V = cfg.vocab[c], S = p.slices_of[c];
   const int tid = threadIdx.x;
   const int step = *p.step_ptr - (p.row_ctl ? p.row_ctl[b * 4] : 0);
@@ -509,8 +513,8 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
       }
       for (int o = 16; o > 0; o >>= 1) my_keep = max(my_keep, __shfl_xor_sync(0xffffffffu, my_keep, o));
       keep = max(my_keep, 1);
-      // full-vocabulary nucleus larger than the candidate list: cannot be represented -> flag (truncated to the list)
-      if (global_mass && keep >= nk && n >= (kCap * 3) / 4 && lane == 0 && p.err_flag) *p.err_flag = 4;
+      // full-vocabulary nucleus larger than the candidate list: this (row, channel) is drawn again by sample_exact_kernel
+      if (global_mass && keep >= nk && n >= (kCap * 3) / 4 && lane == 0) p.ws.redo[bc] = 1;
     }
     float kpart = 0.f;
     for (int t = t0; t < min(t1, keep); ++t) kpart += s_val[t];
@@ -536,6 +540,196 @@ __global__ void __launch_bounds__(kThreads) sample_finish_kernel(const SamplePar
     if (choice < 0) choice = keep - 1;  // rounding at the very end of the CDF
     if (lane == 0) p.out_tokens[bc] = s_idx[choice];
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact draw over a wide vocabulary (the 152,697-way text channel) for what the candidate-list path cannot represent:
+// top_k above the list's reach, no filter at all (plain temperature sampling), or a nucleus that outgrows the list. One
+// CTA per (row, channel) walks the row several times and never sorts or stores it:
+//   top-k   the k-th largest score by a radix select on order-preserving integer keys (4 passes, 256-bin counts);
+//           ties with the k-th value are kept (HF TopKLogitsWarper: scores < kth -> -inf)
+//   top-p   HF removes, in ascending order, every token whose cumulative probability is <= 1 - top_p: a token stays iff
+//           the mass of all kept-by-top-k scores <= its own exceeds (1 - top_p) Z -> the smallest such score is found by
+//           bisection on the integer keys (32 passes, fixed-order reductions: deterministic); equal scores stay together
+//   draw    inverse CDF over the surviving scores, thread-major order (the order only has to be fixed), own Philox stream
+// A slow path by design (~40 passes over 300 KB of L2-resident logits per row); the common configurations never get here.
+__device__ __forceinline__ uint32_t order_key(float v) {
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// fixed-order block sum (warp shuffles, then the 16 warp sums in index order): every thread gets the total
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) t += s_red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(kThreads) sample_exact_kernel(const SampleParams2 p) {
+  __shared__ float s_red[kThreads / 32];
+  __shared__ int s_hist[256];
+  __shared__ uint32_t s_sel[2];
+  __shared__ float s_scan[kThreads / 32];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, c = p.exact_channels[blockIdx.y];
+  const mtts_sampler_config& cfg = p.cfg;
+  const long long bc = (long long)b * cfg.channels + c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!((p.exact_mask >> c) & 1u)) {  // a channel of the candidate-list path: only rows it gave up on
+    if (__ldcg(p.ws.redo + bc) == 0) return;
+    __syncthreads();
+    if (tid == 0) p.ws.redo[bc] = 0;
+  }
+  const int V = cfg.vocab[c];
+  const int step = *p.step_ptr - (p.row_ctl ? p.row_ctl[b * 4] : 0);
+  const ScoreCtx sc = make_ctx(p, b, c, step);
+  const int pieces = (V + kSlice - 1) / kSlice;
+  float sv[8];
+
+  // ---- maximum
+  float m = -INFINITY;
+  for (int q = 0; q < pieces; ++q) {
+    scores8(sc, q * kSlice + tid * 8, V, sv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m = fmaxf(m, sv[e]);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  m = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kThreads / 32; ++w) m = fmaxf(m, s_red[w]);
+
+  // ---- top-k threshold key (0 = keep everything)
+  uint32_t kth_key = 0u;
+  const int k = cfg.top_k[c] > 0 ? min(cfg.top_k[c], V) : V;
+  if (k < V) {
+    uint32_t prefix = 0u;
+    int want = k;  // rank, among the keys that share `prefix`, of the key we are after (1 = largest)
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      __syncthreads();
+      if (tid < 256) s_hist[tid] = 0;
+      __syncthreads();
+      const uint32_t hi_mask = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+      for (int q = 0; q < pieces; ++q) {
+        const int j0 = q * kSlice + tid * 8;
+        scores8(sc, j0, V, sv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (j0 + e < V) {
+            const uint32_t key = order_key(sv[e]);
+            if ((key & hi_mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xffu], 1);
+          }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int acc = 0, d = 255;
+        for (; d > 0; --d) {
+          if (acc + s_hist[d] >= want) break;
+          acc += s_hist[d];
+        }
+        s_sel[0] = (uint32_t)d;
+        s_sel[1] = (uint32_t)(want - acc);
+      }
+      __syncthreads();
+      prefix |= s_sel[0] << shift;
+      want = (int)s_sel[1];
+    }
+    kth_key = prefix;
+  }
+
+  // ---- softmax mass of what top-k keeps
+  float z = 0.f;
+  for (int q = 0; q < pieces; ++q) {
+    const int j0 = q * kSlice + tid * 8;
+    scores8(sc, j0, V, sv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (j0 + e < V && order_key(sv[e]) >= kth_key) z += expf(sv[e] - m);
+  }
+  const float Z = block_sum(z, s_red);
+
+  // ---- top-p: the smallest key whose "mass at or below it" exceeds (1 - top_p) Z; the maximum always stays
+  uint32_t cut_key = kth_key;
+  if (cfg.has_top_p[c] && cfg.top_p[c] < 1.0f) {
+    const float limit = (1.0f - cfg.top_p[c]) * Z;
+    uint32_t lo = kth_key, hi = order_key(m);  // invariant: the answer is in [lo, hi]; "mass <= hi" = Z > limit, or the maximum is kept anyway
+#pragma unroll 1
+    while (lo < hi) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      float part = 0.f;
+      for (int q = 0; q < pieces; ++q) {
+        const int j0 = q * kSlice + tid * 8;
+        scores8(sc, j0, V, sv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint32_t key = order_key(sv[e]);
+          if (j0 + e < V && key >= kth_key && key <= mid) part += expf(sv[e] - m);
+        }
+      }
+      const float mass = block_sum(part, s_red);
+      if (mass > limit) hi = mid; else lo = mid + 1;
+    }
+    cut_key = lo;
+  }
+
+  // ---- draw: inverse CDF over the survivors, thread-major
+  float w = 0.f;
+  for (int q = 0; q < pieces; ++q) {
+    const int j0 = q * kSlice + tid * 8;
+    scores8(sc, j0, V, sv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (j0 + e < V && order_key(sv[e]) >= cut_key) w += expf(sv[e] - m);
+  }
+  float incl = w;
+  for (int o = 1; o < 32; o <<= 1) {
+    const float up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  __syncthreads();
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  float before = 0.f, total = 0.f;
+#pragma unroll
+  for (int i = 0; i < kThreads / 32; ++i) {
+    if (i < warp) before += s_scan[i];
+    total += s_scan[i];
+  }
+  const float lo_t = before + incl - w, hi_t = before + incl;
+  const float u = philox_uniform(*p.seed_ptr, (uint32_t)step, (uint32_t)(b * 8 + c));
+  const float target = u * total;
+  if (tid == 0) s_sel[0] = 0xffffffffu;
+  __syncthreads();
+  // the owner of `target`; rounding at the very end of the CDF falls to the last thread with any mass
+  const bool mine = w > 0.f && ((target >= lo_t && target < hi_t) || (target >= hi_t && hi_t == total));
+  if (mine) {
+    float acc = lo_t;
+    int choice = -1, last = -1;
+    for (int q = 0; q < pieces && choice < 0; ++q) {
+      const int j0 = q * kSlice + tid * 8;
+      scores8(sc, j0, V, sv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (choice < 0 && j0 + e < V && order_key(sv[e]) >= cut_key) {
+          acc += expf(sv[e] - m);
+          last = j0 + e;
+          if (target < acc) choice = j0 + e;
+        }
+    }
+    if (choice < 0) choice = last;
+    atomicMin(&s_sel[0], (uint32_t)choice);  // (two owners only if partial sums tie exactly: any of them is a legal draw)
+  }
+  __syncthreads();
+  if (tid == 0) p.out_tokens[bc] = s_sel[0] == 0xffffffffu ? 0 : (long long)s_sel[0];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -701,19 +895,22 @@ __global__ void __launch_bounds__(256) heads_pick_kernel(const PickParams p) {
   }
 }
 
+// A sampled channel wider than the candidate list is drawn by sample_exact_kernel when its top_k is beyond what the
+// list's threshold search reaches, or when it has no filter at all; a nucleus without top-k goes through the list first
+// and falls back per row (ws.redo).
+static bool exact_only(const mtts_sampler_config* cfg, int c) {
+  if (!cfg->do_sample[c] || cfg->vocab[c] <= kCap) return false;
+  const int k = cfg->top_k[c] > 0 ? (cfg->top_k[c] < cfg->vocab[c] ? cfg->top_k[c] : cfg->vocab[c]) : cfg->vocab[c];
+  const bool nucleus_only = cfg->top_k[c] <= 0 && cfg->has_top_p[c] && cfg->top_p[c] < 1.0f;
+  return k > kThreads && !nucleus_only;
+}
+
 int validate_cfg(const mtts_sampler_config* cfg) {
   MTTS_REQUIRE(cfg != nullptr, "sampler: null config");
   MTTS_REQUIRE(cfg->channels >= 1 && cfg->channels <= 8, "sampler: channels must be in [1,8]");
   for (int c = 0; c < cfg->channels; ++c) {
     MTTS_REQUIRE(cfg->vocab[c] > 0, "sampler: vocab[%d] must be positive", c);
     if (cfg->do_sample[c]) {
-      const int k = cfg->top_k[c] > 0 ? (cfg->top_k[c] < cfg->vocab[c] ? cfg->top_k[c] : cfg->vocab[c]) : cfg->vocab[c];
-      const bool nucleus_only = cfg->top_k[c] <= 0 && cfg->has_top_p[c] && cfg->top_p[c] < 1.0f;
-      if (cfg->vocab[c] > kCap && k > kThreads && !nucleus_only)
-        return mtts_set_error(MTTS_ERR_UNSUPPORTED,
-                              "sampler: channel %d samples over %d tokens with top_k=%d and no top_p < 1; this build needs "
-                              "top_k <= %d, a nucleus (top_p < 1), or vocab <= %d for sampled channels",
-                              c, cfg->vocab[c], cfg->top_k[c], kThreads, kCap);
       if (cfg->has_temp[c]) MTTS_REQUIRE(cfg->temperature[c] > 0.f, "sampler: temperature must be > 0");
       if (cfg->has_top_p[c]) MTTS_REQUIRE(cfg->top_p[c] >= 0.f && cfg->top_p[c] <= 1.f, "sampler: top_p must be in [0,1]");
     }
@@ -752,9 +949,10 @@ static size_t sample_ws_layout(int B, int C, SampleWs* ws, uint8_t* base) {
     return p;
   };
   const size_t bc = (size_t)B * C;
-  // integer state first: [tickets | cand_count] must be ZERO before the first launch (kernels leave them zero)
+  // integer state first: [tickets | cand_count | redo] must be ZERO before the first launch (kernels leave them zero)
   int* tickets = reinterpret_cast<int*>(take(bc * 2 * sizeof(int)));
   int* cand_count = reinterpret_cast<int*>(take(bc * sizeof(int)));
+  int* redo = reinterpret_cast<int*>(take(bc * sizeof(int)));
   float* slice_val = reinterpret_cast<float*>(take(bc * kMaxSlices * sizeof(float)));
   int* slice_idx = reinterpret_cast<int*>(take(bc * kMaxSlices * sizeof(int)));
   float* reported = reinterpret_cast<float*>(take((size_t)B * kMaxSlices * kReport * sizeof(float)));
@@ -762,7 +960,7 @@ static size_t sample_ws_layout(int B, int C, SampleWs* ws, uint8_t* base) {
   float* cand_val = reinterpret_cast<float*>(take(bc * kCap * sizeof(float)));
   int* cand_idx = reinterpret_cast<int*>(take(bc * kCap * sizeof(int)));
   if (ws) {
-    ws->tickets = tickets; ws->cand_count = cand_count; ws->slice_val = slice_val; ws->slice_idx = slice_idx;
+    ws->tickets = tickets; ws->cand_count = cand_count; ws->redo = redo; ws->slice_val = slice_val; ws->slice_idx = slice_idx;
     ws->reported = reported; ws->thr = thr; ws->cand_val = cand_val; ws->cand_idx = cand_idx;
   }
   return off;
@@ -810,6 +1008,12 @@ extern "C" int mtts_sample8_rows(const void* logits, long long ld, int B, const 
     if (atoi(e) >= 1 && atoi(e) <= (any_sample ? 8 : 38)) chunk = atoi(e);
   }
   p.chunk = chunk;
+  int n_exact = 0;  // sampled channels wider than the candidate list: sample_exact_kernel draws them, always or per row
+  for (int c = 0; c < cfg->channels; ++c) {
+    if (exact_only(cfg, c)) p.exact_mask |= 1u << c;
+    if (cfg->do_sample[c] && cfg->vocab[c] > kCap && (exact_only(cfg, c) || (cfg->top_k[c] <= 0 && cfg->has_top_p[c])))
+      p.exact_channels[n_exact++] = (unsigned char)c;
+  }
   for (int c = 0; c < cfg->channels; ++c) {
     MTTS_REQUIRE(cfg->logit_offset[c] % 8 == 0, "mtts_sample8: logit_offset[%d] must be a multiple of 8", c);
     const int S = (cfg->vocab[c] + kSlice * chunk - 1) / (kSlice * chunk);
@@ -826,6 +1030,10 @@ extern "C" int mtts_sample8_rows(const void* logits, long long ld, int B, const 
   MTTS_LAUNCH_CHECK();
   if (any_sample) {
     MTTS_CUDA_CHECK(mtts_launch(sample_finish_kernel, dim3(B, total), dim3(kThreads), 0, stream, p));
+    MTTS_LAUNCH_CHECK();
+  }
+  if (n_exact > 0) {
+    MTTS_CUDA_CHECK(mtts_launch(sample_exact_kernel, dim3(B, n_exact), dim3(kThreads), 0, stream, p));
     MTTS_LAUNCH_CHECK();
   }
   return MTTS_OK;

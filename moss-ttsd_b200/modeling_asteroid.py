@@ -298,7 +298,7 @@ class AsteroidTTSInstruct:
         if any(e):
             self.engine.err.zero_()
             raise RuntimeError(f"libmtts device-side error flags {e} (1: token id out of range, 2: KV page out of range, "
-                               f"3: sampler candidate overflow, 4: full-vocabulary nucleus larger than the candidate list, "
+                               f"3: sampler candidate overflow, 4: unused, "
                                f"5: the persistent decode kernel gave up waiting)")
 
     # ------------------------------------------------------------------ continuous batching (not in the reference)
