@@ -48,13 +48,18 @@ constexpr int kRowBytes = kChunkK * 2;
 constexpr int kRowPitch = kRowBytes + 16;     // 16-byte skew per row: ldmatrix phases hit 32 distinct banks
 constexpr int kTileRows = 16;
 constexpr int kStageBytes = kTileRows * kRowPitch;
-// Four stages, not five: with five the CTA needs the 228 KB shared-memory carve-out, which leaves 28 KB of L1 for the
-// stack frames of 544 threads and the read-only loads; four stages fit the 196 KB carve-out (60 KB of L1) and the
-// step is 5 % (batch 1) to 9 % (batch 2) faster. Three stages (164 KB) lose again: the ring gets too shallow.
+// Ring depth. Four stages at batch 2-4: with five the CTA would need the 228 KB shared-memory carve-out, which leaves 28 KB
+// of L1 for the stack frames of 544 threads and the read-only loads; four stages fit the 196 KB carve-out (60 KB of L1) and
+// the step is 5 % (batch 1) to 9 % (batch 2) faster. Three stages (164 KB) lose again: the ring gets too shallow. At batch 1
+// the activation buffer is a quarter of the size, so a fifth stage fits the same 196 KB carve-out.
 #ifndef MTTS_MEGA_STAGES
 #define MTTS_MEGA_STAGES 4
 #endif
-constexpr int kStages = MTTS_MEGA_STAGES;
+#ifndef MTTS_MEGA_STAGES_B1
+#define MTTS_MEGA_STAGES_B1 5
+#endif
+constexpr int kMaxStages = 6;
+__host__ __device__ constexpr int ring_stages(int B) { return B == 1 ? MTTS_MEGA_STAGES_B1 : MTTS_MEGA_STAGES; }
 constexpr int kMaxB = 4;
 constexpr int kActPitch = kI + 8;             // bf16 elements; rows 12304 B apart -> conflict-free B-fragment loads
 constexpr int kWsStride = kD + 4;             // attention partial: [M, L, -, -, O[128]] (one LL word per float)
@@ -67,12 +72,21 @@ constexpr int kKvDepth = MTTS_MEGA_KV_DEPTH;  // attention passes (32 keys) in f
 constexpr int kRedTile = kTileRows * kMaxB;   // floats one warp contributes to the tile reduction
 constexpr int kMaxCtas = 160;
 
-constexpr int kSmemRing = kStages * kStageBytes;
-constexpr int kSmemAct = kMaxB * kActPitch * 2 + 256;  // 49472 B (+256 zero bytes); also the attention scratch
-constexpr int kSmemRed = 2 * kCW * kRedTile * 4;     // double-buffered 16-warp tile reduction
+// Shared-memory layout: [misc | red | act(B) | ring(B)] -- everything the batch-size-independent routines touch sits at a
+// fixed offset; only the ring (consume_matrix<B>, the producer) moves with the batch size.
 constexpr int kSmemMisc = 4096;                      // barriers, block-reduce scratch, residual rows, RoPE + sentinel tables
-constexpr int kSmemTotal = kSmemRing + kSmemAct + kSmemRed + kSmemMisc;
-static_assert(kSmemTotal <= 227 * 1024, "shared memory budget");
+constexpr int kSmemRed = 2 * kCW * kRedTile * 4;     // double-buffered 16-warp tile reduction
+constexpr int kOffRed = kSmemMisc;
+constexpr int kOffAct = kSmemMisc + kSmemRed;        // B activation rows + 256 zero bytes
+__host__ __device__ constexpr int act_bytes(int B) { return (B * kActPitch * 2 + 256 + 127) / 128 * 128; }
+__host__ __device__ constexpr int ring_offset(int B) { return kOffAct + act_bytes(B); }
+__host__ __device__ constexpr int smem_total(int B) { return ring_offset(B) + ring_stages(B) * kStageBytes; }
+// the attention scratch (q, k, v of the new token + 16 warps x 2 heads of partials: 18.9 KB) lies over red + act; it ends
+// below the zero bytes that follow act row B-1 even at batch 1
+constexpr int kAttnScratch = (4 * kD + kCW * kG * kWsStride) * 4;
+static_assert(kAttnScratch <= kSmemRed + kActPitch * 2, "attention scratch must stay below the zero pad at batch 1");
+static_assert(smem_total(1) <= 196 * 1024 - 2048 && smem_total(kMaxB) <= 196 * 1024 - 2048, "196 KB carve-out");
+static_assert(ring_stages(1) <= kMaxStages && ring_stages(kMaxB) <= kMaxStages, "barrier arrays");
 
 struct MegaParams {
   const mtts_lm_layer* layers;
@@ -250,13 +264,13 @@ __shared__ Slice s_sl[5];  // this CTA's shares of the four per-layer matrices a
 // (values that live across a call are spilled to the stack frame: see above).
 __shared__ int s_cpre[5], s_tpre[5];
 __shared__ int s_unit;  // attention unit of this CTA, or -1
-__device__ __forceinline__ bf16* sm_act() { return reinterpret_cast<bf16*>(mega_smem + kSmemRing); }
-__device__ __forceinline__ float* sm_red() { return reinterpret_cast<float*>(mega_smem + kSmemRing + kSmemAct); }
+__device__ __forceinline__ bf16* sm_act() { return reinterpret_cast<bf16*>(mega_smem + kOffAct); }
+__device__ __forceinline__ float* sm_red() { return reinterpret_cast<float*>(mega_smem + kOffRed); }
 __device__ __forceinline__ uint64_t* sm_full() {
-  return reinterpret_cast<uint64_t*>(mega_smem + kSmemRing + kSmemAct + kSmemRed);
+  return reinterpret_cast<uint64_t*>(mega_smem);
 }
-__device__ __forceinline__ uint64_t* sm_empty() { return sm_full() + kStages; }
-__device__ __forceinline__ float* sm_scratch() { return reinterpret_cast<float*>(sm_empty() + kStages + 2); }  // [16][kMaxB]
+__device__ __forceinline__ uint64_t* sm_empty() { return sm_full() + kMaxStages; }
+__device__ __forceinline__ float* sm_scratch() { return reinterpret_cast<float*>(sm_empty() + kMaxStages + 2); }  // [16][kMaxB]
 __device__ __forceinline__ float* sm_res(int which) {  // [kMaxB][16] raw residual values of this CTA's o_proj (0) / down (1) rows
   return sm_scratch() + kCW * kMaxB + which * (kMaxB * 16);
 }
@@ -301,7 +315,8 @@ __device__ __noinline__ void consume_matrix(int l, int epi) {
   float* red = sm_red();
   const int m4 = epi & 3;  // the LM heads (epi 4) come first in "layer" num_layers
   int red_buf = (l * s_tpre[4] + s_tpre[m4]) & 1;
-  Ring rg{mega_smem, sm_full(), sm_empty(), (uint32_t)(l * s_cpre[4] + s_cpre[m4])};
+  constexpr int kStages = ring_stages(kB);
+  Ring rg{mega_smem + ring_offset(kB), sm_full(), sm_empty(), (uint32_t)(l * s_cpre[4] + s_cpre[m4])};
   const uint32_t tag = layer_tag(l) + (epi == EPI_QKV ? 1u : (epi == EPI_WO ? 3u : (epi == EPI_GU ? 4u : 5u)));
   uint2* out = epi == EPI_QKV ? p.qkv_ll : (epi == EPI_WO ? p.x_ll[1] : (epi == EPI_GU ? p.h_ll : p.x_ll[0]));
   const int out_wpr = epi == EPI_QKV ? kNQKV / 2 : (epi == EPI_GU ? kI / 2 : kH / 2);
@@ -309,7 +324,7 @@ __device__ __noinline__ void consume_matrix(int l, int epi) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const uint32_t a_off = (uint32_t)((lane & 15) * kRowPitch + (warp * 64 + (lane >> 4) * 8) * 2);
-  const bf16* b_src = g < kB ? act + g * kActPitch + warp * 64 + 2 * t : act + kMaxB * kActPitch + 2 * t;
+  const bf16* b_src = g < kB ? act + g * kActPitch + warp * 64 + 2 * t : act + kB * kActPitch + 2 * t;
   const int kmul = g < kB ? kChunkK : 0;
   uint32_t st = rg.it % kStages, par = (rg.it / kStages) & 1;
   // B fragments (k16 x n8, "col") of this warp's 64-wide k slice of two chunks: batch row g, k = 2t,2t+1 and +8
@@ -612,15 +627,19 @@ __device__ __noinline__ void attention_layer(int layer) {
   const MegaParams& p = s_params;
   const int unit = s_unit;
   const uint32_t tag_in = layer_tag(layer) + 1u, tag_out = layer_tag(layer) + 2u;
-  float* scr = reinterpret_cast<float*>(sm_act());
+  float* scr = sm_red();  // red + act: both idle between the q/k/v projection and the partial merge
   const float* rope = sm_rope();
   const AttnUnit un = s_un;
   const AttnLayer L = s_al;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* s_q = scr;                 // [2][128] normed + roped q (bf16-rounded values)
-  float* s_k = scr + 2 * kD;        // [128]
-  float* s_v = scr + 3 * kD;        // [128]
-  float* s_part = scr + 4 * kD;     // [16 warps][2][kWsStride]
+  // The partials come first (over `red`, whose last readers -- warps 0 and 1 in the epilogue of the q/k/v projection --
+  // are long past it when the partials are written behind this routine's first barrier); q, k, v are written at once by
+  // warps 0..3 and therefore lie in the act part, which nobody reads after the projection's last tile barrier.
+  float* s_part = scr;                            // [16 warps][2][kWsStride]
+  float* s_q = scr + kCW * kG * kWsStride;        // [2][128] normed + roped, pre-scaled q (bf16-rounded values)
+  float* s_k = s_q + 2 * kD;                      // [128]
+  float* s_v = s_q + 3 * kD;                      // [128]
+  static_assert(kCW * kG * kWsStride * 4 >= kSmemRed, "q / k / v must lie beyond the reduction buffers");
   const int page_mask = (1 << p.page_shift) - 1;
   const int b = un.b, hk = un.hk, pos = un.pos, k_end = un.k_end;
   const long long head_off = ((long long)hk << p.page_shift) * kD;
@@ -819,7 +838,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
   if (threadIdx.x == 0) s_params = p_in;
   __syncthreads();
   const MegaParams& p = p_in;  // the kernel body itself reads the constant bank
-  uint8_t* ring = mega_smem;
+  constexpr int kStages = ring_stages(kB);
+  uint8_t* ring = mega_smem + ring_offset(kB);
   bf16* act = sm_act();
   uint64_t* full = sm_full();
   uint64_t* empty = sm_empty();
@@ -838,7 +858,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
     fence_barrier_init();
   }
   if (tid < 32) s_prof[tid] = 0;
-  if (tid < 64) reinterpret_cast<uint32_t*>(act + kMaxB * kActPitch)[tid] = 0u;
+  if (tid < 64) reinterpret_cast<uint32_t*>(act + kB * kActPitch)[tid] = 0u;
   const int NL = p.num_layers;
   const int n_attn = kB * kHkv * p.nsplit;   // CTAs 0 .. n_attn-1 also own one attention unit each
   const int n_gemv = (int)gridDim.x;         // every CTA streams its share of the projections (an SM sustains ~50 GB/s
@@ -1041,7 +1061,7 @@ MegaLayout mega_layout(int B, int nsplit) {
 
 int mtts_configure_decode_mega() {
   for (int B = 1; B <= kMaxB; ++B) {
-    cudaError_t e = cudaFuncSetAttribute(mega_kernel_for(B), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
+    cudaError_t e = cudaFuncSetAttribute(mega_kernel_for(B), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total(B));
     if (e != cudaSuccess) return mtts_set_error(MTTS_ERR_CUDA, "decode_mega: smem attribute: %s", cudaGetErrorString(e));
   }
   return MTTS_OK;
@@ -1111,7 +1131,7 @@ extern "C" int mtts_decode_mega(const mtts_decode_mega_args* a, void* stream_) {
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)mtts_num_sms());
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemTotal;
+  cfg.dynamicSmemBytes = (size_t)smem_total(a->B);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident, or the launch fails (never a hung poll loop)
