@@ -278,6 +278,13 @@ __device__ __forceinline__ float* sm_rope() { return sm_scratch() + kCW * kMaxB 
 // sentinel word offsets per producer CTA: 0 = o_proj output, 1 = down output, 2 = SwiGLU output
 __device__ __forceinline__ int* sm_sent(int which) { return reinterpret_cast<int*>(sm_rope() + 128) + which * kMaxCtas; }
 
+// opaque identity: keeps the compiler from proving that a phase routine returns its argument (it would then re-read the
+// caller's stack copy instead of using the returned register)
+__device__ __forceinline__ int launder(int v) {
+  asm volatile("" : "+r"(v));
+  return v;
+}
+
 struct Ring {
   uint8_t* stages;
   uint64_t* full;
@@ -307,7 +314,7 @@ __device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
 // The loop is issue-bound if it is not kept lean (4 warps per scheduler, 64 KB of weights per trip): no modulo, no
 // select, no bookkeeping inside.
 template <int kB>
-__device__ __noinline__ void consume_matrix(int l, int epi) {
+__device__ __noinline__ int consume_matrix(int l, int epi) {
   const MegaParams& p = s_params;
   const Slice s = s_sl[epi];
   const int kch = epi == EPI_WD ? kI / kChunkK : kH / kChunkK;
@@ -388,6 +395,7 @@ __device__ __noinline__ void consume_matrix(int l, int epi) {
     }
     red_buf ^= 1;
   }
+  return launder(l);  // handed back so that the caller need not keep it across the call (it would live in the stack frame)
 }
 
 // Stage B rows of 2048 elements (LL words, or the plain embedding sum) into act with RMSNorm on the way (every CTA
@@ -397,7 +405,7 @@ __device__ __noinline__ void consume_matrix(int l, int epi) {
 // `which`: 0 = layer input (x after down / the embedding sum) -> ln1, residual rows of the o_proj share kept;
 //          1 = x after o_proj -> ln2, residual rows of the down share kept;   2 = final norm (nothing kept)
 template <int kB>
-__device__ __noinline__ void stage_norm(int which, int l) {
+__device__ __noinline__ int stage_norm(int which, int l) {
   const MegaParams& p = s_params;
   const uint32_t tag = which == 1 ? layer_tag(l) + 3u : layer_tag(l) - kTagsPerLayer + 5u;
   const bf16* __restrict__ w = which == 2 ? p.final_norm
@@ -461,11 +469,12 @@ __device__ __noinline__ void stage_norm(int which, int l) {
     *reinterpret_cast<uint2*>(act + b * kActPitch + tid * 4) = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
   }
   consumer_sync();
+  return launder(l);  // handed back so that the caller need not keep it across the call (it would live in the stack frame)
 }
 
 // Stage the B rows of the SwiGLU output (6144 elements each) into act, unchanged.
 template <int kB>
-__device__ __noinline__ void stage_h(int l) {
+__device__ __noinline__ int stage_h(int l) {
   const MegaParams& p = s_params;
   const uint32_t tag = layer_tag(l) + 4u;
   const int* sent = sm_sent(2);
@@ -496,19 +505,52 @@ __device__ __noinline__ void stage_h(int l) {
 #pragma unroll
     for (int b = 0; b < kB; ++b) *reinterpret_cast<uint2*>(act + b * kActPitch + pc * kH + tid * 4) = xv[pc][b];
   consumer_sync();
+  return launder(l);  // handed back so that the caller need not keep it across the call (it would live in the stack frame)
+}
+
+// One polling batch of the split-KV merge: M, L and four O values of up to four splits of one (row, head); absent splits
+// come back as M = -inf. The spin is bounded without a call (see stage_attn_out); true = gave up.
+__device__ __forceinline__ bool poll_partials(const uint2* base, int s0, int nsplit, int d4, uint32_t tag, float (&ms)[4],
+                                              float (&ls)[4], float4 (&ov)[4]) {
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t bad = 0u;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      uint32_t d0 = 0xff800000u, d1 = 0u, d2 = 0u, d3 = 0u, d4v = 0u, d5 = 0u;
+      if (s0 + s < nsplit) {
+        const uint2* w0 = base + (size_t)(s0 + s) * kG * kWsStride;
+        uint32_t t0, t1, t2, t3, t4, t5;
+        ll_issue2(w0, d0, t0, d1, t1);
+        ll_issue2(w0 + 4 + d4, d2, t2, d3, t3);
+        ll_issue2(w0 + 6 + d4, d4v, t4, d5, t5);
+        bad |= (t0 ^ tag) | (t1 ^ tag) | (t2 ^ tag) | (t3 ^ tag) | (t4 ^ tag) | (t5 ^ tag);
+      }
+      ms[s] = __uint_as_float(d0);
+      ls[s] = __uint_as_float(d1);
+      ov[s] = make_float4(__uint_as_float(d2), __uint_as_float(d3), __uint_as_float(d4v), __uint_as_float(d5));
+    }
+    if (bad == 0u) return false;
+    if (++spins > (1u << 21)) return true;  // ~2 s of L2 round trips
+    if ((spins & 1023u) == 0u && *reinterpret_cast<volatile unsigned int*>(&g_mega_abort) == s_launch_key) return true;
+  }
 }
 
 // Merge the split-KV partials of the attention phase into act[b][head*128 + d] (bf16, as the o_proj input).
+__shared__ int s_layer_keep;
 template <int kB>
-__device__ __noinline__ void stage_attn_out(int l) {
+__device__ __noinline__ int stage_attn_out(int l) {
   const MegaParams& p = s_params;
   const uint32_t tag = layer_tag(l) + 2u;
+  // this routine is short of registers at batch 1: the layer index waits in shared memory (not in the stack frame) for
+  // the return; written before the first barrier below, read behind the last one
+  if (threadIdx.x == 0) s_layer_keep = l;
   bf16* act = sm_act();
   const int units = kB * kHkv * p.nsplit;
   if (p.sentinel && (threadIdx.x >> 5) == 0) {  // sentinel: the last O word of head g = 1 of every unit
     const int lane = threadIdx.x & 31;
-    LLSpin sp;
-    while (true) {
+    uint32_t spins = 0;
+    while (true) {  // (call-free, like the polls below; the verified loads that follow report a real time-out)
       bool ok = true;
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
@@ -518,42 +560,35 @@ __device__ __noinline__ void stage_attn_out(int l) {
         ok = ok && (t == tag);
       }
       if (__all_sync(0xffffffffu, ok)) break;
-      if (sp.miss(tag)) break;
+      if (++spins > (1u << 21)) break;
+      if ((spins & 1023u) == 0u && *reinterpret_cast<volatile unsigned int*>(&g_mega_abort) == s_launch_key) break;
     }
   }
   consumer_sync();
+  bool timed_out = false;
 #pragma unroll 1
   for (int idx = threadIdx.x; idx < kB * (kH / 4); idx += kConsumers) {
     const int b = idx / (kH / 4), rem = idx % (kH / 4);
     const int head = rem >> 5, d4 = (rem & 31) * 4;
     const int hk = head / kG, g = head % kG;
     const uint2* base = p.ws_ll + ((size_t)((b * kHkv + hk) * p.nsplit) * kG + g) * kWsStride;
-    // splits are merged four at a time (one polling batch each), groups with a running online-softmax state
-    float M = -1e30f, L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+    // Splits are merged four at a time (one polling batch each), groups with a running online-softmax state. The first
+    // group is peeled and the poll loops contain no call (a call in a poll loop makes the compiler park everything that
+    // is live around it in the stack frame -- six accumulators and the layer index, reloaded on the critical path).
+    float ms[4], ls[4];
+    float4 ov[4];
+    timed_out |= poll_partials(base, 0, p.nsplit, d4, tag, ms, ls, ov);
+    float M = fmaxf(fmaxf(fmaxf(-1e30f, ms[0]), fmaxf(ms[1], ms[2])), ms[3]);
+    float L = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const float w = ex2(ms[s] - M);
+      L = fmaf(ls[s], w, L);
+      o[0] = fmaf(ov[s].x, w, o[0]); o[1] = fmaf(ov[s].y, w, o[1]); o[2] = fmaf(ov[s].z, w, o[2]); o[3] = fmaf(ov[s].w, w, o[3]);
+    }
 #pragma unroll 1
-    for (int s0 = 0; s0 < p.nsplit; s0 += 4) {
-      float ms[4], ls[4];
-      float4 ov[4];
-      LLSpin sp;
-      while (true) {
-        bool ok = true;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          uint32_t d[6] = {0xff800000u, 0u, 0u, 0u, 0u, 0u}, t[6] = {tag, tag, tag, tag, tag, tag};  // absent split: M = -inf
-          if (s0 + s < p.nsplit) {
-            const uint2* w0 = base + (size_t)(s0 + s) * kG * kWsStride;
-            ll_issue2(w0, d[0], t[0], d[1], t[1]);
-            ll_issue2(w0 + 4 + d4, d[2], t[2], d[3], t[3]);
-            ll_issue2(w0 + 6 + d4, d[4], t[4], d[5], t[5]);
-          }
-          ms[s] = __uint_as_float(d[0]); ls[s] = __uint_as_float(d[1]);
-          ov[s] = make_float4(__uint_as_float(d[2]), __uint_as_float(d[3]), __uint_as_float(d[4]), __uint_as_float(d[5]));
-#pragma unroll
-          for (int i = 0; i < 6; ++i) ok = ok && (t[i] == tag);
-        }
-        if (ok) break;
-        if (sp.miss(tag)) break;
-      }
+    for (int s0 = 4; s0 < p.nsplit; s0 += 4) {
+      timed_out |= poll_partials(base, s0, p.nsplit, d4, tag, ms, ls, ov);
       float Mn = M;
 #pragma unroll
       for (int s = 0; s < 4; ++s) Mn = fmaxf(Mn, ms[s]);
@@ -572,7 +607,9 @@ __device__ __noinline__ void stage_attn_out(int l) {
     *reinterpret_cast<uint2*>(act + b * kActPitch + head * kD + d4) =
         make_uint2(pack_bf16(o[0] * inv, o[1] * inv), pack_bf16(o[2] * inv, o[3] * inv));
   }
+  if (timed_out) ll_slow_check(tag, 1u << 25, s_launch_key);  // report + abort flag, with nothing live around the call
   consumer_sync();
+  return launder(s_layer_keep);  // handed back so that the caller need not keep it across the call (it would live in the stack frame)
 }
 
 // ------------------------------------------------------------------ attention CTAs
@@ -623,7 +660,7 @@ __device__ __forceinline__ void attn_fold(const float* s_qs, uint4 kq, uint4 vq,
   }
 }
 
-__device__ __noinline__ void attention_layer(int layer) {
+__device__ __noinline__ int attention_layer(int layer) {
   const MegaParams& p = s_params;
   const int unit = s_unit;
   const uint32_t tag_in = layer_tag(layer) + 1u, tag_out = layer_tag(layer) + 2u;
@@ -816,6 +853,7 @@ __device__ __noinline__ void attention_layer(int layer) {
   consumer_sync();
   ATTN_TICK(21)
 #undef ATTN_TICK
+  return launder(layer);  // handed back so that the caller need not keep it across the call (it would live in the stack frame)
 }
 
 __device__ __noinline__ void rope_table(float pos, const float* inv_freq, float* rope) {
@@ -989,30 +1027,30 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const MegaPara
 #endif
   // Nothing but the layer index lives across the phase calls.
 #pragma unroll 1
-  for (int l = 0; l < NL; ++l) {
+  for (int l = 0; l < p.num_layers; ++l) {
     MEGA_TICK(13)
     if (threadIdx.x == 0 && s_unit >= 0) {
       const mtts_lm_layer& L = p.layers[l];
       s_al = AttnLayer{reinterpret_cast<const bf16*>(L.k_pool), reinterpret_cast<const bf16*>(L.v_pool),
                        reinterpret_cast<const bf16*>(L.q_norm), reinterpret_cast<const bf16*>(L.k_norm)};
     }
-    stage_norm<kB>(0, l);
+    l = stage_norm<kB>(0, l);
     MEGA_TICK(0)
-    consume_matrix<kB>(l, EPI_QKV);
+    l = consume_matrix<kB>(l, EPI_QKV);
     MEGA_TICK(1)
-    if (s_unit >= 0) attention_layer(l);
+    if (s_unit >= 0) l = attention_layer(l);
     MEGA_TICK(3)
-    stage_attn_out<kB>(l);
+    l = stage_attn_out<kB>(l);
     MEGA_TICK(5)
-    consume_matrix<kB>(l, EPI_WO);
+    l = consume_matrix<kB>(l, EPI_WO);
     MEGA_TICK(6)
-    stage_norm<kB>(1, l);
+    l = stage_norm<kB>(1, l);
     MEGA_TICK(8)
-    consume_matrix<kB>(l, EPI_GU);
+    l = consume_matrix<kB>(l, EPI_GU);
     MEGA_TICK(9)
-    stage_h<kB>(l);
+    l = stage_h<kB>(l);
     MEGA_TICK(11)
-    consume_matrix<kB>(l, EPI_WD);
+    l = consume_matrix<kB>(l, EPI_WD);
     MEGA_TICK(12)
   }
   MEGA_TICK(13)
