@@ -546,14 +546,15 @@ class DecoderEngine:
             tab[l] = [lw[k].data_ptr() for k in ("wqkv", "wo", "wgu", "wd", "ln1", "ln2", "q_norm", "k_norm")] + \
                      [cache.k[l].data_ptr(), cache.v[l].data_ptr()]
         layers = torch.from_numpy(tab).to(self.dev)
-        # one attention unit (row, kv head, key range) per CTA; measured best: 4 key ranges up to batch 3, 3 at batch 4
-        # (~115 keys = 4 passes per unit at ctx 460; more ranges cost more partial reads in every CTA's o_proj phase)
-        # At batch 1 a longer context gets 8 ranges: every 32-key pass of a unit is a serial ~0.7 us step on the critical
-        # path of all 148 CTAs (ctx 880: 1.000 ms with 4 ranges, 0.975 with 6, 0.965 with 8; ctx 460: 0.885 / 0.906 /
-        # 0.889; batch 2 is best with 4 at both lengths). `ctx_hint` = prompt + new rows of the call that opens the session.
-        nsplit = 4 if B <= 3 else 3
-        if B == 1 and getattr(self, "ctx_hint", 0) >= 700:
-            nsplit = 8
+        # one attention unit (row, kv head, key range) per CTA. Measured (round 2, after the stack-frame work): 4 key ranges
+        # are best at every batch size at ctx 460 (batch 4: 1.058 ms against 1.071 with 3); from 700 rows of context on,
+        # batch 1 wants 8 (ctx 880: 1.000 ms with 4, 0.975 with 6, 0.965 with 8) and batch 2 wants 6 (1.038 -> 1.010):
+        # every 32-key pass of a unit is a serial ~0.7 us step on the critical path of all 148 CTAs, while more ranges
+        # cost more partial reads in every CTA's o_proj phase. `ctx_hint` = prompt + new rows of the call that opens the
+        # session.
+        nsplit = 4
+        if getattr(self, "ctx_hint", 0) >= 700:
+            nsplit = 8 if B == 1 else (6 if B == 2 else 4)
         if os.environ.get("MTTS_MEGA_NSPLIT"):
             nsplit = int(os.environ["MTTS_MEGA_NSPLIT"])
         ws = torch.zeros(self.L.mtts_decode_mega_workspace_bytes(B, nsplit) + 256, dtype=torch.uint8, device=self.dev)

@@ -52,7 +52,7 @@ def _session(eng, shape, B, ids, mask, paged, rows=256):
 
 
 @pytest.mark.parametrize("B,paged,P,hint", [(1, False, 70, 0), (3, True, 61, 0), (4, False, 130, 0), (2, True, 200, 0),
-                                            (1, True, 150, 900)])  # last: the 8-key-range layout of long contexts
+                                            (1, True, 150, 900), (2, False, 150, 900)])  # the 8 / 6 key-range layouts of long contexts
 def test_mega_step_matches_kernel_chain(B, paged, P, hint):
     shape, w, chain, mega = _engine_pair(3)
     ids, mask = _prompt(shape, B, P, seed=B)
@@ -61,7 +61,7 @@ def test_mega_step_matches_kernel_chain(B, paged, P, hint):
     st_m, cache_m = _session(mega, shape, B, ids, mask, paged)
     mega.ctx_hint = 0
     assert st_m["mega"] is not None and st_c["mega"] is None
-    assert st_m["mega"]["nsplit"] == (8 if hint >= 700 else (4 if B <= 3 else 3))
+    assert st_m["mega"]["nsplit"] == ({1: 8, 2: 6}.get(B, 4) if hint >= 700 else 4)
     assert torch.equal(st_c["tokens"], st_m["tokens"])
     worst, agree, total = 0.0, 0, 0
     for step in range(12):
