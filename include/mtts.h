@@ -382,6 +382,17 @@ int mtts_istft_spec(const float* x, long long ldx, float* spec, long long lds, l
  * (already windowed: the inverse-DFT-times-window basis is applied by mtts_gemm) -> out [B, T*hop]. */
 int mtts_istft_ola(const float* frames, const float* window, float* out, int B, int T, int n_fft, int hop, void* stream);
 
+/* ISTFTHead.forward in one call (XY_Tokenizer/xy_tokenizer/nn/modules.py:939-988, called from Vocos.forward :1451-1479;
+ * SURVEY.md 8b `mtts_istft_head`): wav [B, T*hop] = istft(x . head_w^T + head_b) with x [B*T, channels] fp32 (row stride
+ * ldx), head_w [n_fft + 2, channels] (row stride ld_head_w), head_b [n_fft + 2], basis [n_fft, lds] the inverse real DFT
+ * times the synthesis window over (Re | Im | 0-pad) columns, lds >= n_fft + 2 and a multiple of 4, window [n_fft].
+ * = mtts_gemm(bias) -> mtts_istft_spec -> mtts_gemm -> mtts_istft_ola on `stream`; the three fp32 intermediates live in
+ * `workspace` (mtts_istft_head_workspace_bytes() bytes, 256-byte aligned, caller-owned). */
+size_t mtts_istft_head_workspace_bytes(int B, int T, int n_fft, long long lds);
+int mtts_istft_head(const float* x, long long ldx, int channels, const float* head_w, long long ld_head_w,
+                    const float* head_b, const float* basis, long long lds, const float* window, float* wav, int B, int T,
+                    int n_fft, int hop, void* workspace, size_t workspace_bytes, void* stream);
+
 /* x[r,:] += table[r % mod,:]  (sinusoidal positional embedding, modules.py:398-402,600-606). */
 int mtts_add_rows_mod(float* x, const float* table, long long rows, int C, int mod, void* stream);
 

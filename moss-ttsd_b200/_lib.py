@@ -121,6 +121,9 @@ SIGNATURES = {
     "mtts_logmel_finish": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "mtts_istft_spec": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_ll, c_int, c_void_p]),
     "mtts_istft_ola": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mtts_istft_head_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_ll]),
+    "mtts_istft_head": (c_int, [c_void_p, c_ll, c_int, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_int,
+                                c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "mtts_add_rows_mod": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p]),
     "mtts_gqa_decode_fused": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                       c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,

@@ -989,6 +989,46 @@ extern "C" int mtts_istft_ola(const float* frames, const float* window, float* o
   return MTTS_OK;
 }
 
+// ISTFTHead.forward as ONE entry point (SURVEY.md 8b `mtts_istft_head`; modules.py:939-988): the head projection
+// x . head_w^T + head_b (TF32 tcgen05 GEMM), the (log-mag | phase) -> (Re | Im) map, the inverse DFT with the synthesis
+// window folded into `basis` (second GEMM) and the overlap-add / envelope normalisation / "same" trim. The three
+// intermediates live in the caller's workspace: [rows, 2F] | [rows, lds] | [rows, n_fft] fp32, each 256-byte aligned.
+static inline size_t istft_align(size_t n) { return (n + 255) & ~size_t(255); }
+
+extern "C" size_t mtts_istft_head_workspace_bytes(int B, int T, int n_fft, long long lds) {
+  if (B <= 0 || T <= 0 || n_fft <= 0) return 0;
+  const size_t rows = (size_t)B * T;
+  return istft_align(rows * (n_fft + 2) * 4) + istft_align(rows * (size_t)lds * 4) + istft_align(rows * (size_t)n_fft * 4);
+}
+
+extern "C" int mtts_istft_head(const float* x, long long ldx, int channels, const float* head_w, long long ld_head_w,
+                               const float* head_b, const float* basis, long long lds, const float* window, float* wav,
+                               int B, int T, int n_fft, int hop, void* workspace, size_t workspace_bytes, void* stream_) {
+  MTTS_REQUIRE(n_fft > 0 && n_fft % 2 == 0 && channels > 0, "mtts_istft_head: bad n_fft / channels");
+  const int F = n_fft / 2 + 1;
+  MTTS_REQUIRE(lds >= 2 * F, "mtts_istft_head: lds must hold 2 * (n_fft / 2 + 1) columns");
+  if (B <= 0 || T <= 0) return MTTS_OK;
+  MTTS_REQUIRE(x && head_w && head_b && basis && window && wav && workspace, "mtts_istft_head: null pointer");
+  MTTS_REQUIRE(workspace_bytes >= mtts_istft_head_workspace_bytes(B, T, n_fft, lds) &&
+                   (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "mtts_istft_head: workspace too small or not 256-byte aligned");
+  const long long rows = (long long)B * T;
+  MTTS_REQUIRE(rows <= 0x7fffffffLL, "mtts_istft_head: too many frames");
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* hx = reinterpret_cast<float*>(ws);
+  float* spec = reinterpret_cast<float*>(ws + istft_align((size_t)rows * 2 * F * 4));
+  float* frames = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(spec) + istft_align((size_t)rows * lds * 4));
+  int rc = mtts_gemm(x, ldx, head_w, ld_head_w, hx, 2 * F, (int)rows, 2 * F, channels, MTTS_DTYPE_F32, MTTS_DTYPE_F32,
+                     MTTS_EPI_BIAS, head_b, nullptr, nullptr, 0, nullptr, 0, stream_);
+  if (rc != MTTS_OK) return rc;
+  rc = mtts_istft_spec(hx, 2 * F, spec, lds, rows, F, stream_);  // also zeroes the lds - 2F padding columns
+  if (rc != MTTS_OK) return rc;
+  rc = mtts_gemm(spec, lds, basis, lds, frames, n_fft, (int)rows, n_fft, (int)lds, MTTS_DTYPE_F32, MTTS_DTYPE_F32, 0, nullptr,
+                 nullptr, nullptr, 0, nullptr, 0, stream_);
+  if (rc != MTTS_OK) return rc;
+  return mtts_istft_ola(frames, window, wav, B, T, n_fft, hop, stream_);
+}
+
 extern "C" int mtts_add_rows_mod(float* x, const float* table, long long rows, int C, int mod, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   MTTS_REQUIRE(C % 4 == 0 && mod > 0, "mtts_add_rows_mod: bad shape");

@@ -595,13 +595,12 @@ class XY_Tokenizer:
                 ops.gemm(ff, bl["pw2_w"], bias=bl["pw2_b"], gamma=bl["gamma"], residual=x, out=x)
         x = self._ln(x, self.v_fln_w, self.v_fln_b, eps=1e-6)
         # ISTFT head
-        F = self.n_fft // 2 + 1
-        hx = ops.gemm(x, self.head_w, bias=self.head_b)                         # (B*T4, 2F)
-        spec = torch.empty((B * T4, self.head_ld), dtype=torch.float32, device=dev)
-        check(L.mtts_istft_spec(ptr(hx), hx.stride(0), ptr(spec), self.head_ld, B * T4, F, stream_ptr()))
-        frames = ops.gemm(spec, self.basis)                                     # (B*T4, n_fft), already windowed
+        # head projection -> (log-mag | phase) -> (Re | Im) -> windowed inverse DFT (GEMM) -> overlap-add, one entry point
+        ws = torch.empty(L.mtts_istft_head_workspace_bytes(B, T4, self.n_fft, self.head_ld), dtype=torch.uint8, device=dev)
         wav = torch.empty((B, T4 * self.hop), dtype=torch.float32, device=dev)
-        check(L.mtts_istft_ola(ptr(frames), ptr(self.window), ptr(wav), B, T4, self.n_fft, self.hop, stream_ptr()))
+        check(L.mtts_istft_head(ptr(x), x.stride(0), x.shape[1], ptr(self.head_w), self.head_w.stride(0), ptr(self.head_b),
+                                ptr(self.basis), self.head_ld, ptr(self.window), ptr(wav), B, T4, self.n_fft, self.hop,
+                                ptr(ws), ws.numel(), stream_ptr()))
         return wav
 
     # ------------------------------------------------------------------ reference API

@@ -216,6 +216,28 @@ def test_codec_kernels_against_torch_functional():
     env = F.fold(win.square().expand(1, Ti, -1).transpose(1, 2), output_size=(1, size), kernel_size=(1, 960), stride=(1, 240)).squeeze()[360:-360]
     ref = yy / env
     assert (wav - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
+    # the same head as ONE C-ABI call (mtts_istft_head: projection + the three stages above, TF32 GEMMs) against
+    # torch: fp32 linear -> irfft -> fold
+    Cv = spt.head_w.shape[1]
+    xh = torch.randn(Bi * Ti, Cv, device="cuda", generator=g) * 0.5
+    ws = torch.empty(L.mtts_istft_head_workspace_bytes(Bi, Ti, 960, spt.head_ld), dtype=torch.uint8, device="cuda")
+    wav1 = torch.full((Bi, Ti * 240), float("nan"), device="cuda")
+    _lib.check(L.mtts_istft_head(xh.data_ptr(), xh.stride(0), Cv, spt.head_w.data_ptr(), spt.head_w.stride(0),
+                                 spt.head_b.data_ptr(), spt.basis.data_ptr(), spt.head_ld, spt.window.data_ptr(),
+                                 wav1.data_ptr(), Bi, Ti, 960, 240, ws.data_ptr(), ws.numel(), sp()))
+    o = (xh.double() @ spt.head_w.double().t() + spt.head_b.double()).float().view(Bi, Ti, 2 * Fb).transpose(1, 2)
+    mag, ph = o.chunk(2, dim=1)
+    S = torch.clip(torch.exp(mag), max=1e2) * (torch.cos(ph) + 1j * torch.sin(ph))
+    ifft = torch.fft.irfft(S, 960, dim=1, norm="backward") * win[None, :, None]
+    yy = F.fold(ifft, output_size=(1, size), kernel_size=(1, 960), stride=(1, 240))[:, 0, 0, 360:-360]
+    ref1 = yy / env
+    assert torch.isfinite(wav1).all()
+    assert (wav1 - ref1).abs().max().item() <= 5e-3 * ref1.abs().max().item()
+    # too-small workspace and an empty batch: an error code / a no-op, never a launch
+    assert L.mtts_istft_head(xh.data_ptr(), xh.stride(0), Cv, spt.head_w.data_ptr(), spt.head_w.stride(0),
+                             spt.head_b.data_ptr(), spt.basis.data_ptr(), spt.head_ld, spt.window.data_ptr(),
+                             wav1.data_ptr(), Bi, Ti, 960, 240, ws.data_ptr(), 16, sp()) != 0
+    assert L.mtts_istft_head(None, 0, Cv, None, 0, None, None, spt.head_ld, None, None, 0, Ti, 960, 240, None, 0, sp()) == 0
 
 
 def _spt_with_encoder(gp, seed):
