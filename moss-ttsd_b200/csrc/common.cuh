@@ -119,7 +119,15 @@ int mtts_num_sms();  // cached cudaDevAttrMultiProcessorCount of the current dev
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
 
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// Round to bf16 and back. cvt.rn.bf16x2.f32 d, a, b puts bf16(a) into the UPPER half of d: with b = +0 the word is the
+// fp32 bit pattern of the rounded value — one full-rate F2FP instead of F2F.BF16.F32 (+ a shift), which issues on the
+// quarter-rate conversion pipe and was what bounded the prompt-sized q/k-norm + RoPE kernel (65 per thread and row).
+// Same round-to-nearest-even result as __float2bfloat16_rn.
+__device__ __forceinline__ float bf16_round(float x) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(x), "f"(0.0f));
+  return __uint_as_float(d);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -637,7 +637,7 @@ __device__ __forceinline__ void persist_drain(const GemmParams& p, uint32_t tadd
       uint32_t best_mine = 0u, second_mine = 0u;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(__uint_as_float(r[j])));
+        const uint32_t hb = __float_as_uint(bf16_round(__uint_as_float(r[j]))) >> 16;  // full-rate F2FP, not F2F
         const uint32_t ord = (hb & 0x8000u) ? (~hb & 0xffffu) : (hb | 0x8000u);
         const uint32_t key = real ? ((ord << 16) | (uint32_t)(31 - lane)) : 0u;
         const uint32_t best = __reduce_max_sync(0xffffffffu, key);

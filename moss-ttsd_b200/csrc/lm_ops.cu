@@ -357,6 +357,124 @@ __global__ void __launch_bounds__(256) qknorm_rope_kv_kernel(const RopeParams p)
   }
 }
 
+
+// Prompt-sized variant (heads % 4 == 0, heads <= 32): the same arithmetic bit for bit, with 16-byte accesses. Eight lanes
+// share a head: lane j of the group holds elements 8j..8j+7 and 64+8j..64+8j+7, i.e. the data of the four lanes
+// 4j..4j+3 of the kernel above ("virtual lanes"), so the sum of squares is rebuilt in exactly that kernel's order: the
+// per-lane fma chain over (2v, 2v+1, 64+2v, 65+2v), the butterfly levels xor 16 / 8 / 4 as shuffles over lanes
+// xor 4 / 2 / 1, and the levels xor 2 / 1 inside the lane. A warp covers 4 heads, the 8 warps one row; a CTA walks
+// kWideRows consecutive rows: their 4 x 64 angles are evaluated by the 256 threads at once (one barrier per CTA instead
+// of one per row, a quarter of the CTA launches) and the loads of all four rows are requested before the first is used.
+// 2.2 GB per launch at a bench-sized prefill; the 4-byte kernel ran at 3.1 TB/s there.
+constexpr int kWideRows = 4;
+__global__ void __launch_bounds__(256, 3) qknorm_rope_kv_wide_kernel(const RopeParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ __align__(16) float s_cs[kWideRows][128];  // cos[64] | sin[64] per row, bf16-rounded
+  const int row0 = blockIdx.x * kWideRows;
+  const int nrows = min(kWideRows, p.rows - row0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane >> 3, j = lane & 7;
+  const int heads = p.Hq + 2 * p.Hkv;
+  const int h = warp * 4 + sub;          // this lane group's head; heads % 4 == 0 makes `h < heads` uniform per warp
+  const bool active = h < heads;
+  const long long col = (long long)h * 128 + 8 * j;
+  uint4 ra[kWideRows], rb[kWideRows];  // all rows of the CTA requested up front: 32 KB in flight per CTA
+#pragma unroll
+  for (int r = 0; r < kWideRows; ++r) {
+    ra[r] = make_uint4(0, 0, 0, 0);
+    rb[r] = ra[r];
+    if (active && r < nrows) {
+      const bf16* src = p.qkv + (long long)(row0 + r) * p.ld_qkv + col;
+      ra[r] = *reinterpret_cast<const uint4*>(src);
+      rb[r] = *reinterpret_cast<const uint4*>(src + 64);
+    }
+  }
+  {
+    const int r = threadIdx.x >> 6, i = threadIdx.x & 63;
+    if (r < nrows) {
+      const float f = (float)p.positions[row0 + r] * p.inv_freq[i];
+      s_cs[r][i] = bf16_round(cosf(f));
+      s_cs[r][64 + i] = bf16_round(sinf(f));
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+#pragma unroll
+  for (int r = 0; r < kWideRows; ++r) {
+    if (r >= nrows) break;
+    const int row = row0 + r;
+    const uint4 a = ra[r], b = rb[r];
+    const int pos = p.positions[row];
+    bf16* dst;
+    bool is_v = false, ok = true;
+    if (h < p.Hq) {
+      dst = p.q_out + ((long long)row * p.Hq + h) * 128;
+    } else {
+      const int seq = p.row_seq ? p.row_seq[row] : row;
+      const int hk = (h - p.Hq) % p.Hkv;
+      is_v = (h - p.Hq) >= p.Hkv;
+      const int lp = pos >> p.page_shift;
+      int page = -1;
+      if (pos >= 0 && lp < p.max_pages) page = p.block_table ? p.block_table[(long long)seq * p.max_pages + lp] : seq * p.max_pages + lp;
+      if (page < 0 || page >= p.num_pages) {
+        if (p.err_flag && j == 0) *p.err_flag = 2;
+        ok = false;
+        page = 0;
+      }
+      bf16* pool = is_v ? p.v_pool : p.k_pool;
+      const int slot = pos & ((1 << p.page_shift) - 1);
+      dst = pool + (((long long)page * p.Hkv + hk) << p.page_shift) * 128 + (long long)slot * 128;
+    }
+    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+    float s3[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const float x0 = bf16lo(ua[m]), x1 = bf16hi(ua[m]), x2 = bf16lo(ub[m]), x3 = bf16hi(ub[m]);
+      float ss = x0 * x0;
+      ss = fmaf(x1, x1, ss);
+      ss = fmaf(x2, x2, ss);
+      ss = fmaf(x3, x3, ss);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 4);  // virtual lanes v ^ 16
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);  // v ^ 8
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);  // v ^ 4
+      s3[m] = ss;
+    }
+    if (ok) {
+      if (is_v) {  // V: plain copy
+        *reinterpret_cast<uint4*>(dst + 8 * j) = a;
+        *reinterpret_cast<uint4*>(dst + 64 + 8 * j) = b;
+      } else {
+        const float ssum = (s3[0] + s3[2]) + (s3[1] + s3[3]);  // v ^ 2, then v ^ 1
+        const float inv = rsqrtf(ssum * (1.0f / 128.0f) + p.eps);
+        const bf16* nw = (h < p.Hq) ? p.q_norm_w : p.k_norm_w;
+        const uint4 w0 = *reinterpret_cast<const uint4*>(nw + 8 * j), w1 = *reinterpret_cast<const uint4*>(nw + 64 + 8 * j);
+        const uint32_t wa[4] = {w0.x, w0.y, w0.z, w0.w}, wb[4] = {w1.x, w1.y, w1.z, w1.w};
+        uint32_t oa[4], ob[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          float x0 = bf16lo(ua[m]), x1 = bf16hi(ua[m]), x2 = bf16lo(ub[m]), x3 = bf16hi(ub[m]);
+          x0 = bf16_round(bf16lo(wa[m]) * bf16_round(x0 * inv));
+          x1 = bf16_round(bf16hi(wa[m]) * bf16_round(x1 * inv));
+          x2 = bf16_round(bf16lo(wb[m]) * bf16_round(x2 * inv));
+          x3 = bf16_round(bf16hi(wb[m]) * bf16_round(x3 * inv));
+          const float2 cc = *reinterpret_cast<const float2*>(&s_cs[r][8 * j + 2 * m]);
+          const float2 tt = *reinterpret_cast<const float2*>(&s_cs[r][64 + 8 * j + 2 * m]);
+          const float c0 = cc.x, c1 = cc.y, s0 = tt.x, s1 = tt.y;
+          const float o0 = bf16_round(x0 * c0) + bf16_round(-x2 * s0);
+          const float o1 = bf16_round(x1 * c1) + bf16_round(-x3 * s1);
+          const float o2 = bf16_round(x2 * c0) + bf16_round(x0 * s0);
+          const float o3 = bf16_round(x3 * c1) + bf16_round(x1 * s1);
+          oa[m] = pack_bf16(o0, o1);
+          ob[m] = pack_bf16(o2, o3);
+        }
+        *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+        *reinterpret_cast<uint4*>(dst + 64 + 8 * j) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int mtts_embed_sum8(const long long* ids, int rows, int channels, const void* const* tables_host,
@@ -388,8 +506,9 @@ extern "C" int mtts_rmsnorm(const void* x, long long ldx, const void* w, void* o
                "mtts_rmsnorm: hidden and strides must be multiples of 8");
   if (rows <= 0) return MTTS_OK;
   MTTS_REQUIRE(x && w && out, "mtts_rmsnorm: null pointer");
-  if (hidden == 2048 && rows <= 1024) {  // decode steps: a warp per row, 2 rows per CTA (spread over the SMs)
-    MTTS_CUDA_CHECK(mtts_launch(rmsnorm_warp_kernel, dim3((rows + 1) / 2), dim3(64), 0, stream,
+  if (hidden == 2048) {  // a warp per row, the row in registers: 2 rows per CTA at decode sizes (spread over the SMs),
+    const int wpc = rows <= 1024 ? 2 : 8;  // 8 at prompt sizes (32 KB of loads in flight per CTA, one pass over the data)
+    MTTS_CUDA_CHECK(mtts_launch(rmsnorm_warp_kernel, dim3((rows + wpc - 1) / wpc), dim3(32 * wpc), 0, stream,
                                 reinterpret_cast<const bf16*>(x), ldx, reinterpret_cast<const bf16*>(w),
                                 reinterpret_cast<bf16*>(out), ldo, rows, eps));
     MTTS_LAUNCH_CHECK();
@@ -456,7 +575,16 @@ extern "C" int mtts_qknorm_rope_kvappend(const void* qkv, long long ld_qkv, cons
   while ((1 << shift) < page_size) ++shift;
   p.page_shift = shift; p.num_pages = num_pages; p.rows = rows; p.Hq = num_q_heads; p.Hkv = num_kv_heads; p.eps = eps;
   p.err_flag = err_flag;
-  MTTS_CUDA_CHECK(mtts_launch(qknorm_rope_kv_kernel, dim3((unsigned)rows), dim3(256), 0, stream, p));
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const int heads = num_q_heads + 2 * num_kv_heads;
+  const bool wide = heads % 4 == 0 && heads <= 32 && ld_qkv % 8 == 0 && al16(qkv) && al16(q_out) && al16(k_pool) &&
+                    al16(v_pool) && al16(q_norm_w) && al16(k_norm_w);
+  if (wide) {  // 16-byte accesses, same bits (see the kernel)
+    MTTS_CUDA_CHECK(mtts_launch(qknorm_rope_kv_wide_kernel, dim3((unsigned)((rows + kWideRows - 1) / kWideRows)), dim3(256), 0,
+                                stream, p));
+  } else {
+    MTTS_CUDA_CHECK(mtts_launch(qknorm_rope_kv_kernel, dim3((unsigned)rows), dim3(256), 0, stream, p));
+  }
   MTTS_LAUNCH_CHECK();
   return MTTS_OK;
 }
