@@ -148,7 +148,7 @@ def cpu_baseline_sample(threads):
     return one, sample
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
@@ -162,7 +162,7 @@ def run_reference(args, rank, world):
         audio += a
         secs += t
     v = audio / secs
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights, random prompt grids)",
@@ -170,7 +170,7 @@ def run_reference(args, rank, world):
                    "reference's outputs); the reference itself is Python/PyTorch and is not installable on the GPU box"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------ script list
@@ -233,7 +233,22 @@ def nccl_summary():
 
 
 # ------------------------------------------------------------------------------------------------ main arm
+def _claim_stdout():
+    """stdout of this process carries the JSON line and nothing else: file descriptor 1 is pointed at stderr for the
+    whole run (NCCL prints its version banner to fd 1 even with NCCL_DEBUG_FILE set; any library chatter follows it to
+    stderr) and the line is written to the saved descriptor by emit()."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(saved, (json.dumps(obj) + "\n").encode())
+    return emit
+
+
 def main():
+    emit = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -244,7 +259,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, emit)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
@@ -352,8 +367,8 @@ def main():
         run_job(warm, True)
         ms, frames, launches = timed(lambda: run_job(batches, True))
         if rank == 0:
-            print(json.dumps({"mode": "launch list (not a bench value)", "steps": args.steps, "warmup": args.warmup,
-                              "batch_per_gpu": BATCH, "new_frames": NEW_FRAMES, "gpu_launches": int(launches)}))
+            emit({"mode": "launch list (not a bench value)", "steps": args.steps, "warmup": args.warmup,
+                  "batch_per_gpu": BATCH, "new_frames": NEW_FRAMES, "gpu_launches": int(launches)})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -410,7 +425,7 @@ def main():
     if rank == 0:
         h2d = batches[0]["ids_host"].numel() * 8 + batches[0]["mask_host"].numel() * 8
         d2h = BATCH * NEW_FRAMES * 1920 * 4
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (random-init weights, random prompt grids)",
@@ -437,7 +452,7 @@ def main():
                                                           "world_size": world, "ranks_counted_by_allreduce": int(ranks_seen),
                                                           "nccl_version": ".".join(str(v) for v in torch.cuda.nccl.version())})
             if world > 1 else None,
-        }))
+        })
     if world > 1:
         dist.destroy_process_group()
 
