@@ -61,3 +61,20 @@ def test_bench_launch_list_summary_tool_reads_the_committed_list():
         per_step[sbl.short(name)] = per_step.get(sbl.short(name), 0.0) + us / nsteps
     top2 = sorted(per_step, key=per_step.get, reverse=True)[:2]
     assert any("gqa_decode_tc_kernel" in k for k in top2) and any("gemm_tc_kernel" in k for k in top2)
+
+
+def test_bench_stdout_is_one_json_line_even_when_a_library_writes_to_fd1():
+    """bench.py's contract: rank 0 prints ONE JSON line. Anything a native library writes to file descriptor 1 during the
+    run (NCCL's version banner does, under torchrun) must land on stderr, the line itself on the real stdout."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; emit = bench._claim_stdout(); "
+            "os.write(1, b'NCCL version 0.0.0\\n'); print('chatter'); emit({'metric': 'm', 'value': 1.5})" % root)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert json.loads(out.stdout) == {"metric": "m", "value": 1.5}
+    assert out.stdout.count("\n") == 1
+    assert "NCCL version 0.0.0" in out.stderr and "chatter" in out.stderr
