@@ -523,6 +523,8 @@ class DecoderEngine:
         # split-KV only while (rows x kv heads) cannot fill the machine by itself: measured at B=64 the combine costs
         # more than it gains (29 us unsplit vs 36 us with 2 splits), at B=1 eight splits are 2.3x faster than none
         nsplit = max(1, min(8, -(-(2 * 148) // max(1, B * s.num_key_value_heads))))
+        if os.environ.get("MTTS_ATTN_NSPLIT"):
+            nsplit = max(1, min(8, int(os.environ["MTTS_ATTN_NSPLIT"])))
         st["nsplit"] = nsplit
         st["attn_ws"] = self._attn_workspace(B, 1, nsplit)
         st["sample_ws"] = torch.zeros(self.L.mtts_heads8_sample_workspace_bytes(B, self.s.vpad, self.s.channels),

@@ -34,7 +34,7 @@ def main():
     rows = []
     batches = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1, 16, 64]
     for B, new in [(b, 64) for b in batches]:
-        ids, mask = make_prompt(rng, B, 200, 250)
+        ids, mask = make_prompt(rng, B, int(sys.argv[2]) if len(sys.argv) > 2 else 200, int(sys.argv[3]) if len(sys.argv) > 3 else 250)
         ids, mask = torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda()
         T = ids.shape[1]
         for it in range(2):
