@@ -4,6 +4,9 @@ import subprocess
 import sys
 import textwrap
 
+import numpy as np
+import pytest
+
 from moss_ttsd_b200 import scheduler
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -75,3 +78,41 @@ def test_two_rank_gloo_gather(tmp_path):
                          capture_output=True, text=True, env=env, timeout=180)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_page_pool_never_loses_or_duplicates_a_page():
+    """PagePool (continuous.py, the free list behind `block_table`): under a random admit / grow / retire schedule page 0
+    is never handed out, no page is owned twice, a reservation can always be drawn, and everything returns to the pool."""
+    from moss_ttsd_b200.continuous import PagePool
+    with pytest.raises(ValueError):
+        PagePool(1)
+    rng = np.random.default_rng(3)
+    pool = PagePool(97)
+    owners = []            # per live request: [pages owned, pages still reserved]
+    for _ in range(4000):
+        op = rng.integers(0, 3)
+        if op == 0:        # admit: reserve the worst case, take the pages the prompt needs now
+            need = int(rng.integers(1, 12))
+            before = pool.available
+            if pool.reserve(need):
+                first = int(rng.integers(0, need + 1))
+                owners.append([pool.take_reserved(first), need - first])
+                assert pool.available == before - need
+            else:
+                assert need > before and pool.available == before
+        elif op == 1 and owners:   # grow a running request out of its reservation
+            o = owners[int(rng.integers(0, len(owners)))]
+            if o[1]:
+                k = int(rng.integers(1, o[1] + 1))
+                o[0] += pool.take_reserved(k)
+                o[1] -= k
+        elif op == 2 and owners:   # retire: pages and the unused reservation go back
+            o = owners.pop(int(rng.integers(0, len(owners))))
+            pool.release(o[0], unreserve=o[1])
+        held = [p for o in owners for p in o[0]]
+        assert 0 not in held and len(held) == len(set(held)) and all(0 < p < 97 for p in held)
+        assert pool.reserved == sum(o[1] for o in owners)
+        assert pool.available == 96 - len(held) - pool.reserved >= 0
+    for o in owners:
+        pool.release(o[0], unreserve=o[1])
+    assert pool.available == 96 and pool.reserved == 0
