@@ -30,8 +30,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from . import _lib
-from ._lib import check, ptr, stream_ptr
+from ._lib import check, stream_ptr
 from .lm_engine import DecoderEngine, KVCache, SamplerSetup
 
 

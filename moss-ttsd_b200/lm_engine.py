@@ -19,9 +19,8 @@ HBM layout (one replica per GPU):
 from __future__ import annotations
 
 import ctypes
-import math
 import os
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional
 
 import numpy as np

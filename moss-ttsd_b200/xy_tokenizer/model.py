@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import os
 import math
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 import yaml
