@@ -78,3 +78,26 @@ def test_bench_stdout_is_one_json_line_even_when_a_library_writes_to_fd1():
     assert json.loads(out.stdout) == {"metric": "m", "value": 1.5}
     assert out.stdout.count("\n") == 1
     assert "NCCL version 0.0.0" in out.stderr and "chatter" in out.stderr
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """`bench.py --impl reference` launched the way the driver launches N > 1 (torchrun, one process per GPU): rank 0 alone
+    times the CPU port and prints the line, the other ranks exit 0 without work; the line carries the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29533", os.path.join(root, "bench.py"), "--impl", "reference",
+                          "--gpus", "2", "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=900,
+                         env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["metric"].startswith("audio-sec") and d["unit"] == "audio_s/s"
