@@ -201,8 +201,10 @@ def build_batch(scripts):
 
 def nccl_env():
     """NCCL's communicator lines are kept (the driver checks the rank count from them): INFO/INIT goes to a per-process
-    file unless the caller already configured NCCL_DEBUG; stdout stays one JSON line."""
-    if "NCCL_DEBUG" not in os.environ:
+    file unless the caller already asked for INFO or more itself; nccl_summary() echoes the lines to stderr and puts them
+    into the JSON line; stdout stays one JSON line."""
+    # absent, or preset to a level that carries no communicator lines (the GPU pool presets VERSION): raise it to INFO/INIT
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
         os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         d = os.path.join(ROOT, "gpurun_out")
@@ -222,14 +224,14 @@ def nccl_summary():
     import socket
     path = path.replace("%h", socket.gethostname()).replace("%p", str(os.getpid()))
     try:
-        with open(path) as f:
+        with open(path, errors="replace") as f:
             lines = [ln.strip() for ln in f if "nranks" in ln and ("comm" in ln or "Init" in ln)]
-    except OSError:
+        seen = sorted({int(m.group(1)) for ln in lines for m in [re.search(r"nranks (\d+)", ln)] if m})
+        for ln in lines[-4:]:
+            print(ln, file=sys.stderr)
+        return {"nranks_seen": seen, "lines": lines[-4:], "file": path}
+    except Exception:   # a log that cannot be read must never cost the bench line
         return None
-    seen = sorted({int(m.group(1)) for ln in lines for m in [re.search(r"nranks (\d+)", ln)] if m})
-    for ln in lines[-4:]:
-        print(ln, file=sys.stderr)
-    return {"nranks_seen": seen, "lines": lines[-4:], "file": path}
 
 
 # ------------------------------------------------------------------------------------------------ main arm
@@ -447,10 +449,11 @@ def main():
                                    "job_prefill_mean": job_prefill_ms, "job_decode_step_mean": job_decode_step_ms},
             "decode_step_latency": lat,
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "roofline_other": roof_other, "cpu_baseline": cpu,
-            "extras": extras, "nccl": (nccl_summary() or {"note": "NCCL_DEBUG was preset by the caller: NCCL's own init lines are wherever "
-                                                                    "that setting sends them", "NCCL_DEBUG": os.environ.get("NCCL_DEBUG"),
-                                                          "world_size": world, "ranks_counted_by_allreduce": int(ranks_seen),
-                                                          "nccl_version": ".".join(str(v) for v in torch.cuda.nccl.version())})
+            "extras": extras,
+            "nccl": dict(nccl_summary() or {"note": "NCCL_DEBUG was preset by the caller: NCCL's own init lines are wherever that "
+                                                    "setting sends them"},
+                         NCCL_DEBUG=os.environ.get("NCCL_DEBUG"), world_size=world, ranks_counted_by_allreduce=int(ranks_seen),
+                         nccl_version=".".join(str(v) for v in torch.cuda.nccl.version()))
             if world > 1 else None,
         })
     if world > 1:
